@@ -1,0 +1,58 @@
+"""Shared test-input builders (seeded, CPU-generated so CPU and GPU runs see identical bytes)."""
+import math
+
+import numpy as np
+import torch
+
+
+def gradcheck_like_scene(N=2, H=13, W=13, k3=2, M=4, seed=1112, fadescale=6.5, fadeexp=7.5):
+    """Small scene in the style of the reference's gradcheck inputs
+    (/root/reference/extensions/mvpraymarch/mvpraymarch.py:464-565): pinhole rays from z=-4, a k3^3 grid of
+    randomly rotated slabs around the origin, softplus payload, random tminmax."""
+    g = torch.Generator().manual_seed(seed)
+    K = k3 ** 3
+    focal = torch.tensor([[W * 4.0, W * 4.0]] * N)
+    princpt = torch.tensor([[W * 0.5, H * 0.5]] * N)
+    py, px = torch.meshgrid(torch.arange(H).float(), torch.arange(W).float(), indexing="ij")
+    pc = torch.stack([px, py], dim=-1)[None].repeat(N, 1, 1, 1)
+    rd = (pc - princpt[:, None, None, :]) / focal[:, None, None, :]
+    rd = torch.cat([rd, torch.ones_like(rd[..., :1])], dim=-1)
+    rd = rd / rd.norm(dim=-1, keepdim=True)
+    rp = torch.tensor([0.0, 0.0, -4.0])[None, None, None, :].repeat(N, H, W, 1)
+    max_len = 6.0
+    stepsize = max_len / 15.386928
+    tminmax = max_len * torch.arange(2, dtype=torch.float32)[None, None, None, :].repeat(N, H, W, 1) \
+        + torch.rand(N, H, W, 2, generator=g)
+    tpl = torch.nn.functional.softplus(1.5 * (torch.randn(N, K, M, M, M, 4, generator=g)
+                                              - torch.tensor([0, 0, 0, 3.5]))) * torch.tensor([1, 1, 1, 40.0])
+    lin = torch.linspace(-1.0, 1.0, k3)
+    gz, gy, gx = torch.meshgrid(lin, lin, lin, indexing="ij")
+    grid = torch.stack([gx, gy, gz], dim=-1).reshape(1, K, 3)
+    pos = 0.3 * (grid + 0.1 * torch.randn(N, K, 3, generator=g))
+    rv = torch.randn(N * K, 3, generator=g)
+    th = torch.sqrt(1e-5 + (rv ** 2).sum(-1, keepdim=True))
+    kx = rv / th
+    Kx = torch.zeros(N * K, 3, 3)
+    Kx[:, 0, 1], Kx[:, 0, 2], Kx[:, 1, 0] = -kx[:, 2], kx[:, 1], kx[:, 2]
+    Kx[:, 1, 2], Kx[:, 2, 0], Kx[:, 2, 1] = -kx[:, 0], -kx[:, 1], kx[:, 0]
+    rot = (torch.eye(3)[None] + torch.sin(th)[..., None] * Kx + (1 - torch.cos(th))[..., None] * (Kx @ Kx)).view(N, K, 3, 3)
+    scale = 2.2 * torch.exp(0.1 * torch.randn(N, K, 3, generator=g))
+    return dict(raypos=rp.contiguous(), raydir=rd.contiguous(), tminmax=tminmax.contiguous(), stepsize=stepsize,
+                primpos=pos.contiguous(), primrot=rot.contiguous(), primscale=scale.contiguous(),
+                template=tpl.contiguous(), fadescale=fadescale, fadeexp=fadeexp)
+
+
+def scene_args_np(s, dtype=np.float32):
+    """(positional args for oracle.forward, kwargs)."""
+    a = [s["raypos"].numpy().astype(dtype), s["raydir"].numpy().astype(dtype), float(s["stepsize"]),
+         s["tminmax"].numpy().astype(dtype), s["primpos"].numpy().astype(dtype), s["primrot"].numpy().astype(dtype),
+         s["primscale"].numpy().astype(dtype), s["template"].numpy().astype(dtype)]
+    kw = dict(fadescale=float(s.get("fadescale", 8.0)), fadeexp=float(s.get("fadeexp", 8.0)))
+    return a, kw
+
+
+def relerr(a, b):
+    """max|a-b| / max|b| -- the parity measure of SURVEY.md section 8d (the reference's own report format)."""
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))

@@ -1,0 +1,39 @@
+"""In-tree build of the C-ABI CUDA library (sm_100a only).  No torch headers, no JIT cache: the .so lives next to
+this file so it travels to the GPU box with the repo snapshot."""
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SRC = [os.path.join(HERE, "csrc", "mvp_kernels.cu")]
+HDR = [os.path.join(ROOT, "include", "mvpraymarch_b200.h")]
+LIB = os.path.join(HERE, "libmvpraymarch_b200.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo",
+    "-use_fast_math",                      # same math mode as the reference (extensions/mvpraymarch/setup.py:25)
+    "-Xcompiler", "-fPIC", "-shared",
+    "-I" + os.path.join(ROOT, "include"),
+]
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(f) > t for f in SRC + HDR + [os.path.abspath(__file__)])
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + SRC + ["-o", LIB]
+    subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    import sys
+    print(build(force="-f" in sys.argv, verbose="-v" in sys.argv))

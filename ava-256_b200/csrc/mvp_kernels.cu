@@ -1,0 +1,938 @@
+// mvp_kernels.cu -- B200 (sm_100a) volumetric-primitive raymarcher: accel build, forward, backward.
+//
+// Replaces (semantics, not code) /root/reference/extensions/mvpraymarch/{mvpraymarch_kernel.cu, bvh.cu,
+// mvpraymarch_subset_kernel.h, utils.h, primtransf.h, primsampler.h, primaccum.h}.  See DESIGN.md for the
+// data layout and the per-kernel rooflines.  Design in one paragraph:
+//
+//   * No BVH.  The reference finds each warp's candidate slabs by a DFS over a 2K-1 node AABB heap
+//     (utils.h:719-815), per warp, per kernel.  Here a view's camera is recovered from its ray field
+//     (fit_camera_kernel, verified against every ray), every slab OBB is projected to a pixel rectangle
+//     (prim_setup_kernel) and rectangles are bucketed into 4-pixel-high tile rows in DFS-rank order
+//     (row_lists_kernel).  A warp (= one 8x4 pixel tile, the reference's warp footprint) scans its row's
+//     bucket, keeps rectangles that overlap its 8 columns, and runs the reference's *exact* per-lane slab
+//     test on them -- so list membership, per-ray [t_enter,t_exit] and the 512 cap are the reference's.
+//     Views whose rays are not a pinhole grid fall back to "every slab is a candidate" (correct, slow).
+//   * Interval marching.  The reference re-transforms every listed slab at every step.  Here each list entry
+//     carries the warp's step interval [mlo,mhi]; a 16-step active mask is rebuilt by ballot and only active
+//     slabs are transformed.  Ray position and t advance incrementally in fp32 exactly as in the reference
+//     (mvpraymarch_subset_kernel.h:95-96) so validity decisions match bit for bit.
+//   * Backward is slab-major: forward records, per ray, the saturating sample (step, rank) and the alpha
+//     before it, which removes the only order dependence (primaccum.h:81-98).  Each warp then walks one slab
+//     at a time, keeps the 15 transform gradients in registers over all its steps, reduces them with a
+//     16-value butterfly and issues one atomic per value per (warp, slab); payload gradients go out as
+//     128-bit vector reductions (red.global.add.v4.f32) instead of 32 scalar atomics per sample.
+//
+// Arithmetic mirrors the reference's fp32 operation order where a step function of the result exists
+// (transform + strict validity, slab test, lattice snap, saturation); -use_fast_math is on like the reference.
+
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "mvpraymarch_b200.h"
+
+namespace {
+
+constexpr int kMaxHit = 512;      // utils.h:779-781 (template argument hard-wired at mvpraymarch_kernel.cu:33)
+constexpr int kTileW = 8;         // warp footprint of the reference's default block (8,16): 8 x 4 pixels
+constexpr int kTileH = 4;
+constexpr int kWarps = 4;         // warps (tiles) per CTA, arranged 2 x 2
+constexpr int kMaskSteps = 16;    // steps per active-mask rebuild
+constexpr int kRowCapMax = 2048;  // entries per tile-row bucket before the row falls back to scanning all slabs
+constexpr int kBig = 1 << 30;
+
+struct Cam {          // 64 B per view
+    float o[3];
+    int ok;           // fit succeeded (consumers also check bad[n] == 0)
+    float minv[9];    // pixel (w,h,1) ~ minv * (P - o)
+    float pad[3];
+};
+
+struct __align__(8) RowEntry { int k; unsigned xr; };   // xr = x0 | x1 << 16  (pixels, inclusive)
+
+struct Layout {
+    size_t cam, bad, pack, rx, ry, rowcnt, rowlist, total;
+    int R, rowcap;
+};
+
+__host__ __device__ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+__host__ inline Layout make_layout(const mvp_shape &s) {
+    Layout L;
+    L.R = (s.H + kTileH - 1) / kTileH;
+    L.rowcap = s.K < kRowCapMax ? s.K : kRowCapMax;
+    size_t off = 0;
+    L.cam = off;     off = align256(off + (size_t)s.N * sizeof(Cam));
+    L.bad = off;     off = align256(off + (size_t)s.N * sizeof(int));
+    L.pack = off;    off = align256(off + (size_t)s.N * s.K * 64);
+    L.rx = off;      off = align256(off + (size_t)s.N * s.K * 4);
+    L.ry = off;      off = align256(off + (size_t)s.N * s.K * 4);
+    L.rowcnt = off;  off = align256(off + (size_t)s.N * L.R * 4);
+    L.rowlist = off; off = align256(off + (size_t)s.N * L.R * L.rowcap * sizeof(RowEntry));
+    L.total = off;
+    return L;
+}
+
+// DFS leaf order of the reference's implicit heap (utils.h:740-742, 788): leaves are visited in the order
+// k = kstart, kstart+1, ..., K-1, 0, ..., kstart-1 with kstart = nextpow2(K) - K  (0 when K is a power of two).
+__host__ __device__ inline int dfs_kstart(int K) {
+    int P = 1;
+    while (P < K) P <<= 1;
+    return P - K;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// 1. camera fit: D(w,h) = A + B w + C h  with raydir(w,h) = normalize(D); verified on every ray.
+// ------------------------------------------------------------------------------------------------------
+constexpr int kFitThreads = 256;
+constexpr int kFitRaysPerThread = 8;
+
+__global__ void __launch_bounds__(kFitThreads) fit_camera_kernel(int H, int W, const float *__restrict__ raypos,
+                                                                 const float *__restrict__ raydir, Cam *cam, int *bad) {
+    const int n = blockIdx.y;
+    const size_t HW = (size_t)H * W;
+    const float *rp = raypos + (size_t)n * HW * 3;
+    const float *rd = raydir + (size_t)n * HW * 3;
+    __shared__ float s_minv[9];
+    __shared__ float s_o[3];
+    __shared__ int s_ok;
+    if (threadIdx.x == 0) {
+        int ok = (W >= 2 && H >= 2);
+        double mi[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        if (ok) {
+            double d00[3], d10[3], d01[3], d11[3];
+            const size_t i00 = 0, i10 = (size_t)(W - 1), i01 = (size_t)(H - 1) * W, i11 = HW - 1;
+            for (int i = 0; i < 3; ++i) {
+                d00[i] = rd[i00 * 3 + i]; d10[i] = rd[i10 * 3 + i]; d01[i] = rd[i01 * 3 + i]; d11[i] = rd[i11 * 3 + i];
+            }
+            // [d10 d01 -d00] (b,c,a)^T = d11
+            double m[9] = {d10[0], d01[0], -d00[0], d10[1], d01[1], -d00[1], d10[2], d01[2], -d00[2]};
+            double det = m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
+            if (!(fabs(det) > 1e-12)) ok = 0;
+            double b = 0, c = 0, a = 0;
+            if (ok) {
+                double id = 1.0 / det;
+                b = id * (d11[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (d11[1] * m[8] - m[5] * d11[2]) + m[2] * (d11[1] * m[7] - m[4] * d11[2]));
+                c = id * (m[0] * (d11[1] * m[8] - m[5] * d11[2]) - d11[0] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * d11[2] - d11[1] * m[6]));
+                a = id * (m[0] * (m[4] * d11[2] - d11[1] * m[7]) - m[1] * (m[3] * d11[2] - d11[1] * m[6]) + d11[0] * (m[3] * m[7] - m[4] * m[6]));
+                if (!(a > 1e-9 && b > 1e-9 && c > 1e-9) || !isfinite(a + b + c)) ok = 0;
+            }
+            if (ok) {
+                double A[3], B[3], C[3];
+                for (int i = 0; i < 3; ++i) {
+                    A[i] = a * d00[i];
+                    B[i] = (b * d10[i] - A[i]) / (double)(W - 1);
+                    C[i] = (c * d01[i] - A[i]) / (double)(H - 1);
+                }
+                // M = [B C A] (columns); invert
+                double M[9] = {B[0], C[0], A[0], B[1], C[1], A[1], B[2], C[2], A[2]};
+                double dm = M[0] * (M[4] * M[8] - M[5] * M[7]) - M[1] * (M[3] * M[8] - M[5] * M[6]) + M[2] * (M[3] * M[7] - M[4] * M[6]);
+                if (!(fabs(dm) > 1e-30) || !isfinite(dm)) ok = 0;
+                else {
+                    double im = 1.0 / dm;
+                    mi[0] = (M[4] * M[8] - M[5] * M[7]) * im; mi[1] = (M[2] * M[7] - M[1] * M[8]) * im; mi[2] = (M[1] * M[5] - M[2] * M[4]) * im;
+                    mi[3] = (M[5] * M[6] - M[3] * M[8]) * im; mi[4] = (M[0] * M[8] - M[2] * M[6]) * im; mi[5] = (M[2] * M[3] - M[0] * M[5]) * im;
+                    mi[6] = (M[3] * M[7] - M[4] * M[6]) * im; mi[7] = (M[1] * M[6] - M[0] * M[7]) * im; mi[8] = (M[0] * M[4] - M[1] * M[3]) * im;
+                    for (int i = 0; i < 9; ++i) if (!isfinite(mi[i])) ok = 0;
+                }
+            }
+        }
+        for (int i = 0; i < 9; ++i) s_minv[i] = (float)mi[i];
+        for (int i = 0; i < 3; ++i) s_o[i] = rp[i];
+        s_ok = ok;
+    }
+    __syncthreads();
+    int fail = 0;
+    if (s_ok) {
+        const float m0 = s_minv[0], m1 = s_minv[1], m2 = s_minv[2], m3 = s_minv[3], m4 = s_minv[4], m5 = s_minv[5],
+                    m6 = s_minv[6], m7 = s_minv[7], m8 = s_minv[8];
+        const float ox = s_o[0], oy = s_o[1], oz = s_o[2];
+        size_t base = (size_t)blockIdx.x * (kFitThreads * kFitRaysPerThread);
+#pragma unroll
+        for (int it = 0; it < kFitRaysPerThread; ++it) {
+            size_t r = base + (size_t)it * kFitThreads + threadIdx.x;
+            if (r < HW) {
+                float px_ = __ldg(rp + r * 3 + 0), py_ = __ldg(rp + r * 3 + 1), pz_ = __ldg(rp + r * 3 + 2);
+                float dx = __ldg(rd + r * 3 + 0), dy = __ldg(rd + r * 3 + 1), dz = __ldg(rd + r * 3 + 2);
+                int w = (int)(r % (size_t)W), h = (int)(r / (size_t)W);
+                float qx = m0 * dx + m1 * dy + m2 * dz, qy = m3 * dx + m4 * dy + m5 * dz, qz = m6 * dx + m7 * dy + m8 * dz;
+                float u = __fdiv_rn(qx, qz), v = __fdiv_rn(qy, qz);
+                bool good = (px_ == ox) && (py_ == oy) && (pz_ == oz) && (qz > 0.f) && (fabsf(u - (float)w) < 0.05f) &&
+                            (fabsf(v - (float)h) < 0.05f);
+                fail |= !good;
+            }
+        }
+    } else {
+        fail = 1;
+    }
+    fail = __syncthreads_or(fail);
+    if (threadIdx.x == 0) {
+        if (fail) atomicOr(bad + n, 1);
+        if (blockIdx.x == 0) {
+            Cam c;
+            for (int i = 0; i < 3; ++i) c.o[i] = s_o[i];
+            c.ok = s_ok;
+            for (int i = 0; i < 9; ++i) c.minv[i] = s_minv[i];
+            c.pad[0] = c.pad[1] = c.pad[2] = 0.f;
+            cam[n] = c;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// 2. per-slab record + pixel rectangle
+//    record (4 x float4): (pos.xyz, s.x) (R row0, s.y) (R row1, s.z) (R row2, 0)
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) prim_setup_kernel(int N, int K, int H, int W, const float *__restrict__ primpos,
+                                                         const float *__restrict__ primrot, const float *__restrict__ primscale,
+                                                         const Cam *__restrict__ cam, const int *__restrict__ bad,
+                                                         float4 *__restrict__ pack, unsigned *__restrict__ rx, unsigned *__restrict__ ry) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)N * K) return;
+    const int n = (int)(i / (size_t)K);
+    const float *pp = primpos + i * 3, *pr = primrot + i * 9, *ps = primscale + i * 3;
+    float p0 = pp[0], p1 = pp[1], p2 = pp[2];
+    float r[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) r[j] = pr[j];
+    float s0 = ps[0], s1 = ps[1], s2 = ps[2];
+    pack[i * 4 + 0] = make_float4(p0, p1, p2, s0);
+    pack[i * 4 + 1] = make_float4(r[0], r[1], r[2], s1);
+    pack[i * 4 + 2] = make_float4(r[3], r[4], r[5], s2);
+    pack[i * 4 + 3] = make_float4(r[6], r[7], r[8], 0.f);
+
+    // rectangle: full screen unless the view is a verified pinhole and all 8 corners are on one side of it
+    int x0 = 0, x1 = W - 1, y0 = 0, y1 = H - 1;
+    const Cam c = cam[n];
+    if (c.ok && bad[n] == 0) {
+        float e0 = __fdiv_rn(1.f, s0), e1 = __fdiv_rn(1.f, s1), e2 = __fdiv_rn(1.f, s2);
+        float umin = CUDART_INF_F, umax = -CUDART_INF_F, vmin = CUDART_INF_F, vmax = -CUDART_INF_F;
+        float zmin = CUDART_INF_F, zmax = -CUDART_INF_F;
+        bool nan = false;
+#pragma unroll
+        for (int cidx = 0; cidx < 8; ++cidx) {
+            float a = (cidx & 1) ? e0 : -e0, b = (cidx & 2) ? e1 : -e1, d = (cidx & 4) ? e2 : -e2;
+            // world corner = R (c / s) + pos   (primtransf.h:12-63)
+            float wx = r[0] * a + r[1] * b + r[2] * d + p0 - c.o[0];
+            float wy = r[3] * a + r[4] * b + r[5] * d + p1 - c.o[1];
+            float wz = r[6] * a + r[7] * b + r[8] * d + p2 - c.o[2];
+            float qx = c.minv[0] * wx + c.minv[1] * wy + c.minv[2] * wz;
+            float qy = c.minv[3] * wx + c.minv[4] * wy + c.minv[5] * wz;
+            float qz = c.minv[6] * wx + c.minv[7] * wy + c.minv[8] * wz;
+            float u = __fdiv_rn(qx, qz), v = __fdiv_rn(qy, qz);
+            nan |= !(u == u) || !(v == v) || !(qz == qz);
+            umin = fminf(umin, u); umax = fmaxf(umax, u); vmin = fminf(vmin, v); vmax = fmaxf(vmax, v);
+            zmin = fminf(zmin, qz); zmax = fmaxf(zmax, qz);
+        }
+        // lines, not half-lines (utils.h:747-755 has no t >= 0 clip): a slab entirely behind the pinhole projects
+        // through it just the same; only a slab straddling the plane qz = 0 has an unbounded footprint.
+        const float zeps = 1e-6f * fmaxf(fabsf(zmin), fabsf(zmax));
+        if (!nan && (zmin > zeps || zmax < -zeps)) {
+            float fx0 = fmaxf(floorf(umin) - 1.f, 0.f), fx1 = fminf(ceilf(umax) + 1.f, (float)(W - 1));
+            float fy0 = fmaxf(floorf(vmin) - 1.f, 0.f), fy1 = fminf(ceilf(vmax) + 1.f, (float)(H - 1));
+            if (fx0 > fx1 || fy0 > fy1) { x0 = 1; x1 = 0; y0 = 1; y1 = 0; }   // off screen: empty
+            else { x0 = (int)fx0; x1 = (int)fx1; y0 = (int)fy0; y1 = (int)fy1; }
+        }
+    }
+    rx[i] = (unsigned)x0 | ((unsigned)x1 << 16);
+    ry[i] = (unsigned)y0 | ((unsigned)y1 << 16);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// 3. tile-row buckets in DFS-rank order (deterministic ordered compaction; one CTA per (row, view))
+// ------------------------------------------------------------------------------------------------------
+constexpr int kRowThreads = 256;
+
+__global__ void __launch_bounds__(kRowThreads) row_lists_kernel(int K, int R, int rowcap, const unsigned *__restrict__ rx,
+                                                                const unsigned *__restrict__ ry, int *__restrict__ rowcnt,
+                                                                RowEntry *__restrict__ rowlist) {
+    const int row = blockIdx.x, n = blockIdx.y;
+    const int ylo = row * kTileH, yhi = ylo + kTileH - 1;
+    const unsigned *rxn = rx + (size_t)n * K, *ryn = ry + (size_t)n * K;
+    RowEntry *out = rowlist + ((size_t)n * R + row) * rowcap;
+    const int kstart = dfs_kstart(K);
+    __shared__ int s_wcnt[kRowThreads / 32];
+    __shared__ int s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (int j0 = 0; j0 < K; j0 += kRowThreads) {
+        const int j = j0 + threadIdx.x;
+        bool in = false;
+        int k = 0;
+        unsigned xr = 0;
+        if (j < K) {
+            k = j + kstart; if (k >= K) k -= K;
+            unsigned yr = __ldg(ryn + k);
+            int y0 = (int)(yr & 0xffffu), y1 = (int)(yr >> 16);
+            in = (y0 <= y1) && (y0 <= yhi) && (y1 >= ylo);
+            if (in) xr = __ldg(rxn + k);
+        }
+        unsigned b = __ballot_sync(0xffffffffu, in);
+        if (lane == 0) s_wcnt[warp] = __popc(b);
+        __syncthreads();
+        int pre = s_base;
+        for (int w = 0; w < warp; ++w) pre += s_wcnt[w];
+        int pos = pre + __popc(b & ((1u << lane) - 1u));
+        if (in && pos < rowcap) { RowEntry e; e.k = k; e.xr = xr; out[pos] = e; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int w = 0; w < kRowThreads / 32; ++w) t += s_wcnt[w];
+            s_base += t;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) rowcnt[(size_t)n * R + row] = s_base;   // may exceed rowcap: consumers then scan all slabs
+}
+
+// ------------------------------------------------------------------------------------------------------
+// device helpers shared by forward and backward
+// ------------------------------------------------------------------------------------------------------
+struct Prim {
+    float px, py, pz;
+    float r00, r01, r02, r10, r11, r12, r20, r21, r22;
+    float sx, sy, sz;
+};
+
+__device__ __forceinline__ Prim load_prim(const float4 *__restrict__ packn, int k) {
+    const float4 *p = packn + (size_t)k * 4;
+    float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
+    Prim q;
+    q.px = a.x; q.py = a.y; q.pz = a.z; q.sx = a.w;
+    q.r00 = b.x; q.r01 = b.y; q.r02 = b.z; q.sy = b.w;
+    q.r10 = c.x; q.r11 = c.y; q.r12 = c.z; q.sz = c.w;
+    q.r20 = d.x; q.r21 = d.y; q.r22 = d.z;
+    return q;
+}
+
+// (v . R)_j as the reference compiles it: fma(R2j, v.z, fma(R0j, v.x, R1j * v.y))   (primtransf.h:128-131)
+__device__ __forceinline__ float rowdot(float c0, float x, float c1, float y, float c2, float z) {
+    return __fmaf_rn(c2, z, __fmaf_rn(c0, x, __fmul_rn(c1, y)));
+}
+
+struct Ray {
+    float ox, oy, oz, dx, dy, dz, tmin, tmax;
+};
+
+// 1/x as the reference gets it under -use_fast_math (MUFU.RCP)
+__device__ __forceinline__ float fast_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// utils.h:744-755: line vs slab in slab coordinates.  Returns hit; lo/hi valid when hit.
+__device__ __forceinline__ bool slab_test(const Prim &q, const Ray &r, float &lo, float &hi) {
+    float xm = r.ox - q.px, ym = r.oy - q.py, zm = r.oz - q.pz;
+    float rx0 = rowdot(q.r00, xm, q.r10, ym, q.r20, zm), rd0 = rowdot(q.r00, r.dx, q.r10, r.dy, q.r20, r.dz);
+    float rx1 = rowdot(q.r01, xm, q.r11, ym, q.r21, zm), rd1 = rowdot(q.r01, r.dx, q.r11, r.dy, q.r21, r.dz);
+    float rx2 = rowdot(q.r02, xm, q.r12, ym, q.r22, zm), rd2 = rowdot(q.r02, r.dx, q.r12, r.dy, q.r22, r.dz);
+    float i0 = fast_rcp(__fmul_rn(q.sx, rd0)), i1 = fast_rcp(__fmul_rn(q.sy, rd1)), i2 = fast_rcp(__fmul_rn(q.sz, rd2));
+    float a0 = __fmul_rn(__fmaf_rn(q.sx, -rx0, -1.f), i0), b0 = __fmul_rn(__fmaf_rn(q.sx, -rx0, 1.f), i0);
+    float a1 = __fmul_rn(__fmaf_rn(q.sy, -rx1, -1.f), i1), b1 = __fmul_rn(__fmaf_rn(q.sy, -rx1, 1.f), i1);
+    float a2 = __fmul_rn(__fmaf_rn(q.sz, -rx2, -1.f), i2), b2 = __fmul_rn(__fmaf_rn(q.sz, -rx2, 1.f), i2);
+    lo = fmaxf(fmaxf(fminf(a0, b0), fminf(a1, b1)), fminf(a2, b2));
+    hi = fminf(fminf(fmaxf(a0, b0), fmaxf(a1, b1)), fmaxf(a2, b2));
+    return lo <= hi;
+}
+
+__device__ __forceinline__ int clamp_step(float v) {   // float -> step index, saturating, NaN -> +big
+    if (!(v == v)) return kBig;
+    return (int)fminf(fmaxf(v, -(float)kBig), (float)kBig);
+}
+
+struct TileCtx {
+    // per-lane
+    Ray ray;
+    bool inimg;
+    float rt0, rt1;     // own-hit [lo, hi] union (rtminmax, utils.h:757-761)
+    int off;            // lane step j = sweep m + off
+    // warp
+    int nl;             // list length
+};
+
+struct Params {
+    int N, H, W, K, TD, TH, TW;
+    float dt, fadescale, fadeexp;
+    const float *raypos, *raydir, *tminmax;
+    const float *tplate;
+    const float4 *pack;
+    const unsigned *rx, *ry;
+    const int *rowcnt;
+    const RowEntry *rowlist;
+    int R, rowcap;
+    int TXn, TYn;
+    // forward outputs
+    float *rayrgba, *raysat;
+    int4 *rayaux;
+    // backward
+    const float *grad_rayrgba;
+    const float *raysat_in;
+    const int4 *rayaux_in;
+    float *g_primpos, *g_primrot, *g_primscale, *g_tplate;
+};
+
+// Builds the warp's slab list (rank order, <= 512 entries, step intervals in sweep units) and each lane's rtminmax.
+// s_k/s_lo/s_hi: this warp's shared arrays.
+__device__ __forceinline__ void build_tile_list(const Params &p, float rdt, int n, int tx, int ty, int lane, TileCtx &c,
+                                                int *s_k, int *s_lo, int *s_hi) {
+    const int px = tx * kTileW + (lane & 7), py = ty * kTileH + (lane >> 3);
+    c.inimg = (px < p.W) && (py < p.H);
+    const int cx = min(px, p.W - 1), cy = min(py, p.H - 1);
+    const size_t r = ((size_t)n * p.H + cy) * p.W + cx;
+    c.ray.ox = __ldg(p.raypos + r * 3 + 0); c.ray.oy = __ldg(p.raypos + r * 3 + 1); c.ray.oz = __ldg(p.raypos + r * 3 + 2);
+    c.ray.dx = __ldg(p.raydir + r * 3 + 0); c.ray.dy = __ldg(p.raydir + r * 3 + 1); c.ray.dz = __ldg(p.raydir + r * 3 + 2);
+    const float2 tmm = __ldg(reinterpret_cast<const float2 *>(p.tminmax) + r);
+    c.ray.tmin = tmm.x; c.ray.tmax = tmm.y;
+    c.rt0 = CUDART_INF_F; c.rt1 = -CUDART_INF_F;
+
+    // warp-common sweep origin: lanes are aligned in depth, lane step j = m + off
+    float tref = c.inimg ? c.ray.tmin : CUDART_INF_F;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tref = fminf(tref, __shfl_xor_sync(0xffffffffu, tref, o));
+    c.off = clamp_step(ceilf((tref - c.ray.tmin) * rdt));
+
+    const float4 *packn = p.pack + (size_t)n * p.K * 4;
+    const int cnt = p.rowcnt[(size_t)n * p.R + ty];
+    const bool overflow = cnt > p.rowcap;
+    const int total = overflow ? p.K : cnt;
+    const RowEntry *rl = p.rowlist + ((size_t)n * p.R + ty) * p.rowcap;
+    const unsigned *rxn = p.rx + (size_t)n * p.K, *ryn = p.ry + (size_t)n * p.K;
+    const int tx0 = tx * kTileW, tx1 = tx0 + kTileW - 1, ty0 = ty * kTileH, ty1 = ty0 + kTileH - 1;
+    const int kstart = dfs_kstart(p.K);
+    int nl = 0;
+    for (int base = 0; base < total; base += 32) {
+        const int idx = base + lane;
+        int k = 0;
+        bool cand = false;
+        if (idx < total) {
+            unsigned xr;
+            if (!overflow) {
+                RowEntry e = rl[idx];
+                k = e.k; xr = e.xr;
+                cand = true;
+            } else {
+                k = idx + kstart; if (k >= p.K) k -= p.K;
+                xr = __ldg(rxn + k);
+                unsigned yr = __ldg(ryn + k);
+                int y0 = (int)(yr & 0xffffu), y1 = (int)(yr >> 16);
+                cand = (y0 <= y1) && (y0 <= ty1) && (y1 >= ty0);
+            }
+            int x0 = (int)(xr & 0xffffu), x1 = (int)(xr >> 16);
+            cand = cand && (x0 <= x1) && (x0 <= tx1) && (x1 >= tx0);
+        }
+        unsigned m = __ballot_sync(0xffffffffu, cand);
+        while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            const int kk = __shfl_sync(0xffffffffu, k, b);
+            const Prim q = load_prim(packn, kk);
+            float lo, hi;
+            bool hit = slab_test(q, c.ray, lo, hi) && c.inimg;
+            int jlo = kBig, jhi = -kBig;
+            if (hit) {
+                c.rt0 = fminf(c.rt0, lo); c.rt1 = fmaxf(c.rt1, hi);
+                jlo = clamp_step(floorf((lo - c.ray.tmin) * rdt) - 1.f) - c.off;
+                jhi = clamp_step(floorf((hi - c.ray.tmin) * rdt) + 2.f) - c.off;
+            }
+            const unsigned any = __ballot_sync(0xffffffffu, hit);
+            if (any) {
+                const int wlo = __reduce_min_sync(0xffffffffu, jlo), whi = __reduce_max_sync(0xffffffffu, jhi);
+                if (nl < kMaxHit) {
+                    if (lane == 0) { s_k[nl] = kk; s_lo[nl] = wlo; s_hi[nl] = whi; }
+                    ++nl;
+                }
+            }
+        }
+    }
+    __syncwarp();
+    c.nl = nl;
+}
+
+// Lattice snap (mvpraymarch_subset_kernel.h:63-72 as compiled).  Returns the first step index j0.
+__device__ __forceinline__ int lattice_start(const TileCtx &c, float dt, float rdt, float &t, float &x, float &y, float &z, float &r1e) {
+    const float r0 = fmaxf(c.rt0, c.ray.tmin), r1 = fminf(c.rt1, c.ray.tmax);
+    const float xs = __fmaf_rn(c.ray.dx, c.ray.tmin, c.ray.ox), ys = __fmaf_rn(c.ray.dy, c.ray.tmin, c.ray.oy),
+                zs = __fmaf_rn(c.ray.dz, c.ray.tmin, c.ray.oz);
+    const int incs = __float2int_rd(__fmul_rn(__fadd_rn(r0, -c.ray.tmin), rdt));
+    const float fi = (float)incs;
+    t = __fmaf_rn(fi, dt, c.ray.tmin);
+    x = __fmaf_rn(__fmul_rn(c.ray.dx, fi), dt, xs);
+    y = __fmaf_rn(__fmul_rn(c.ray.dy, fi), dt, ys);
+    z = __fmaf_rn(__fmul_rn(c.ray.dz, fi), dt, zs);
+    r1e = __fadd_rn(r1, 9.9999997473787516356e-06f);
+    return incs;
+}
+
+struct Sample {
+    float4 s;           // rgb, alpha*fade
+    float fade;
+    float wgt[8];
+    int idx[8];         // voxel index or -1
+    float x0, x1, y0, y1, z0, z1;
+};
+
+// primsampler.h:44-66 + utils.h:408-502
+template <bool kKeep>
+__device__ __forceinline__ float4 sample_slab(const float4 *__restrict__ slab, float y0, float y1, float y2, int TD, int TH, int TW,
+                                              float fadescale, float fadeexp, Sample *keep) {
+    const float fade = __expf(-fadescale * (__powf(fabsf(y0), fadeexp) + __powf(fabsf(y1), fadeexp) + __powf(fabsf(y2), fadeexp)));
+    const float fx = fmaxf(-100.f, fminf(100.f, (y0 + 1.f) * 0.5f)) * (float)(TW - 1);
+    const float fy = fmaxf(-100.f, fminf(100.f, (y1 + 1.f) * 0.5f)) * (float)(TH - 1);
+    const float fz = fmaxf(-100.f, fminf(100.f, (y2 + 1.f) * 0.5f)) * (float)(TD - 1);
+    const int ix = __float2int_rd(fx), iy = __float2int_rd(fy), iz = __float2int_rd(fz);
+    const float ax0 = fx - (float)ix, ax1 = (float)(ix + 1) - fx;
+    const float ay0 = fy - (float)iy, ay1 = (float)(iy + 1) - fy;
+    const float az0 = fz - (float)iz, az1 = (float)(iz + 1) - fz;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int cx = ix + (j & 1), cy = iy + ((j >> 1) & 1), cz = iz + ((j >> 2) & 1);
+        const bool inb = (cx >= 0) && (cx < TW) && (cy >= 0) && (cy < TH) && (cz >= 0) && (cz < TD);
+        const float w = ((j & 1) ? ax0 : ax1) * ((j & 2) ? ay0 : ay1) * ((j & 4) ? az0 : az1);
+        const int id = (cz * TH + cy) * TW + cx;
+        if (inb) {
+            const float4 v = __ldg(slab + id);
+            acc.x = __fmaf_rn(w, v.x, acc.x); acc.y = __fmaf_rn(w, v.y, acc.y);
+            acc.z = __fmaf_rn(w, v.z, acc.z); acc.w = __fmaf_rn(w, v.w, acc.w);
+        }
+        if (kKeep) { keep->wgt[j] = w; keep->idx[j] = inb ? id : -1; }
+    }
+    acc.w *= fade;
+    if (kKeep) {
+        keep->s = acc; keep->fade = fade;
+        keep->x0 = ax0; keep->x1 = ax1; keep->y0 = ay0; keep->y1 = ay1; keep->z0 = az0; keep->z1 = az1;
+    }
+    return acc;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// 4. forward
+// ------------------------------------------------------------------------------------------------------
+template <bool kGrad>
+__global__ void __launch_bounds__(kWarps * 32) render_forward_kernel(const Params p) {
+    __shared__ int s_k[kWarps][kMaxHit];
+    __shared__ int s_lo[kWarps][kMaxHit];
+    __shared__ int s_hi[kWarps][kMaxHit];
+    __shared__ unsigned s_mask[kWarps][kMaxHit / 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tx = blockIdx.x * 2 + (warp & 1), ty = blockIdx.y * 2 + (warp >> 1), n = blockIdx.z;
+    if (tx >= p.TXn || ty >= p.TYn) return;   // warps are independent: no CTA-wide barrier below
+
+    const float rdt = fast_rcp(p.dt);   // MUFU.RCP(stepsize), as the reference (SASS 0x16c0)
+    TileCtx c;
+    build_tile_list(p, rdt, n, tx, ty, lane, c, s_k[warp], s_lo[warp], s_hi[warp]);
+
+    const int px = tx * kTileW + (lane & 7), py = ty * kTileH + (lane >> 3);
+    const size_t r = ((size_t)n * p.H + min(py, p.H - 1)) * p.W + min(px, p.W - 1);
+
+    float t, x, y, z, r1e;
+    const bool hashit = c.inimg && (c.rt0 <= c.rt1);
+    int j0 = lattice_start(c, p.dt, rdt, t, x, y, z, r1e);
+    bool done = !hashit || (t > r1e);
+    int ms = done ? kBig : (j0 - c.off);      // sweep index at which this lane starts
+
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float sat0 = -1.f, sat1 = -1.f, sat2 = -1.f;
+    int jsat = 0x7fffffff, ranksat = 0, jlast = j0 - 1;
+    float abefore = 0.f;
+    bool sat = false;
+
+    const int nl = c.nl;
+    const int nwords = (nl + 31) >> 5;
+    const float4 *packn = p.pack + (size_t)n * p.K * 4;
+    const size_t slabsz = (size_t)p.TD * p.TH * p.TW;
+    const float4 *tpn = reinterpret_cast<const float4 *>(p.tplate) + (size_t)n * p.K * slabsz;
+
+    int m = __reduce_min_sync(0xffffffffu, ms);
+    if (nl > 0 && m < kBig) {
+        int mbase = m - kMaskSteps;   // force a rebuild on entry
+        unsigned anyactive = 0;
+        while (true) {
+            if (m - mbase >= kMaskSteps) {
+                mbase = m;
+                anyactive = 0;
+                for (int w = 0; w < nwords; ++w) {
+                    const int slot = w * 32 + lane;
+                    const bool a = (slot < nl) && (s_lo[warp][slot] <= m + (kMaskSteps - 1)) && (s_hi[warp][slot] >= m);
+                    const unsigned word = __ballot_sync(0xffffffffu, a);
+                    if (lane == 0) s_mask[warp][w] = word;
+                    anyactive |= word;
+                }
+                __syncwarp();
+            }
+            const bool on = !done && (m >= ms);
+            if (anyactive) {
+                for (int w = 0; w < nwords; ++w) {
+                    unsigned word = s_mask[warp][w];
+                    while (word) {
+                        const int b = __ffs(word) - 1;
+                        word &= word - 1;
+                        const int slot = w * 32 + b;
+                        if (s_lo[warp][slot] > m || s_hi[warp][slot] < m) continue;
+                        const int k = s_k[warp][slot];
+                        const Prim q = load_prim(packn, k);
+                        // primtransf.h:119-132
+                        const float xm = x - q.px, ym = y - q.py, zm = z - q.pz;
+                        const float y0 = __fmul_rn(q.sx, rowdot(q.r00, xm, q.r10, ym, q.r20, zm));
+                        const float y1 = __fmul_rn(q.sy, rowdot(q.r01, xm, q.r11, ym, q.r21, zm));
+                        const float y2 = __fmul_rn(q.sz, rowdot(q.r02, xm, q.r12, ym, q.r22, zm));
+                        const bool valid = (fabsf(y0) < 1.f) && (fabsf(y1) < 1.f) && (fabsf(y2) < 1.f);
+                        if (valid && on && !sat && (t < r1e)) {
+                            const float4 s = sample_slab<false>(tpn + (size_t)k * slabsz, y0, y1, y2, p.TD, p.TH, p.TW,
+                                                                p.fadescale, p.fadeexp, nullptr);
+                            // primaccum.h:63-79
+                            const float newa = __fmaf_rn(s.w, p.dt, acc.w);
+                            const float contrib = __fadd_rn(fminf(newa, 1.f), -acc.w);
+                            if (newa >= 1.f) {
+                                sat0 = s.x; sat1 = s.y; sat2 = s.z;
+                                sat = true;
+                                if (kGrad) {
+                                    jsat = m + c.off;
+                                    int rk = k - dfs_kstart(p.K); if (rk < 0) rk += p.K;
+                                    ranksat = rk;
+                                    abefore = acc.w;
+                                }
+                            }
+                            acc.x = __fmaf_rn(contrib, s.x, acc.x); acc.y = __fmaf_rn(contrib, s.y, acc.y);
+                            acc.z = __fmaf_rn(contrib, s.z, acc.z); acc.w = __fadd_rn(acc.w, contrib);
+                        }
+                    }
+                }
+            }
+            if (on) {
+                if (kGrad && (t < r1e)) jlast = m + c.off;
+                t = __fadd_rn(t, p.dt);
+                x = __fmaf_rn(c.ray.dx, p.dt, x); y = __fmaf_rn(c.ray.dy, p.dt, y); z = __fmaf_rn(c.ray.dz, p.dt, z);
+                done = (t > r1e) || sat;
+            }
+            ++m;
+            if (__all_sync(0xffffffffu, done)) break;
+        }
+    }
+    if (c.inimg) {
+        reinterpret_cast<float4 *>(p.rayrgba)[r] = acc;
+        if (kGrad) {
+            p.raysat[r * 3 + 0] = sat0; p.raysat[r * 3 + 1] = sat1; p.raysat[r * 3 + 2] = sat2;
+            p.rayaux[r] = make_int4(jsat, ranksat, __float_as_int(abefore), jlast);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// 5. backward (slab-major)
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(kWarps * 32) render_backward_kernel(const Params p) {
+    __shared__ int s_k[kWarps][kMaxHit];
+    __shared__ int s_lo[kWarps][kMaxHit];
+    __shared__ int s_hi[kWarps][kMaxHit];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tx = blockIdx.x * 2 + (warp & 1), ty = blockIdx.y * 2 + (warp >> 1), n = blockIdx.z;
+    if (tx >= p.TXn || ty >= p.TYn) return;
+
+    const float rdt = fast_rcp(p.dt);   // MUFU.RCP(stepsize), as the reference (SASS 0x16c0)
+    TileCtx c;
+    build_tile_list(p, rdt, n, tx, ty, lane, c, s_k[warp], s_lo[warp], s_hi[warp]);
+    const int nl = c.nl;
+    if (nl == 0) return;
+
+    const int px = tx * kTileW + (lane & 7), py = ty * kTileH + (lane >> 3);
+    const size_t r = ((size_t)n * p.H + min(py, p.H - 1)) * p.W + min(px, p.W - 1);
+
+    float t0, xs, ys, zs, r1e;
+    const bool hashit = c.inimg && (c.rt0 <= c.rt1);
+    const int j0 = lattice_start(c, p.dt, rdt, t0, xs, ys, zs, r1e);   // xs = position at step j0
+    const float4 dL = __ldg(reinterpret_cast<const float4 *>(p.grad_rayrgba) + r);
+    const float rs0 = __ldg(p.raysat_in + r * 3 + 0), rs1 = __ldg(p.raysat_in + r * 3 + 1), rs2 = __ldg(p.raysat_in + r * 3 + 2);
+    const int4 aux = __ldg(p.rayaux_in + r);
+    const int jsat = aux.x, ranksat = aux.y, jlast = hashit ? aux.w : (j0 - 1);
+    const float abefore = __int_as_float(aux.z);
+    const bool hassat = rs0 > -1.f;
+    const float sr = hassat ? rs0 : 0.f, sg = hassat ? rs1 : 0.f, sb = hassat ? rs2 : 0.f, sa = hassat ? 1.f : 0.f;
+
+    // lane's live sweep range
+    const int mfirst = hashit ? (j0 - c.off) : kBig;
+    const int mlast = hashit ? (min(jlast, jsat) - c.off) : -kBig;
+    const int wfirst = __reduce_min_sync(0xffffffffu, mfirst), wlast = __reduce_max_sync(0xffffffffu, mlast);
+    if (wfirst > wlast) return;
+
+    const float4 *packn = p.pack + (size_t)n * p.K * 4;
+    const size_t slabsz = (size_t)p.TD * p.TH * p.TW;
+    const float4 *tpn = reinterpret_cast<const float4 *>(p.tplate) + (size_t)n * p.K * slabsz;
+    float *gtn = p.g_tplate + (size_t)n * p.K * slabsz * 4;
+    float *gpn = p.g_primpos + (size_t)n * p.K * 3, *grn = p.g_primrot + (size_t)n * p.K * 9, *gsn = p.g_primscale + (size_t)n * p.K * 3;
+    const float gmx = (float)(p.TW - 1) * 0.5f, gmy = (float)(p.TH - 1) * 0.5f, gmz = (float)(p.TD - 1) * 0.5f;
+    const int kstart = dfs_kstart(p.K);
+
+    // Slabs are processed in the order of their first sweep step, 16-step chunk by chunk, so that each lane's
+    // position can be carried forward with the SAME fma sequence the forward kernel executed (bit-identical sample
+    // positions: the trilinear position gradient is discontinuous across voxel cells, so this matters).
+    float xb = xs, yb = ys, zb = zs;       // position at sweep step max(mcur, mfirst)
+    int mcur = wfirst;
+    const int nwords = (nl + 31) >> 5;
+    for (int cs = wfirst; cs <= wlast; cs += kMaskSteps) {
+        for (; mcur < cs; ++mcur) {
+            if (mcur >= mfirst) { xb = __fmaf_rn(c.ray.dx, p.dt, xb); yb = __fmaf_rn(c.ray.dy, p.dt, yb); zb = __fmaf_rn(c.ray.dz, p.dt, zb); }
+        }
+        for (int w = 0; w < nwords; ++w) {
+            const int myslot = w * 32 + lane;
+            bool pick = false;
+            if (myslot < nl) {
+                const int a0 = max(s_lo[warp][myslot], wfirst), b0 = min(s_hi[warp][myslot], wlast);
+                pick = (a0 <= b0) && (a0 >= cs) && (a0 < cs + kMaskSteps);
+            }
+            unsigned word = __ballot_sync(0xffffffffu, pick);
+            while (word) {
+                const int bit = __ffs(word) - 1;
+                word &= word - 1;
+                const int slot = w * 32 + bit;
+        const int k = s_k[warp][slot];
+        const int ma = max(s_lo[warp][slot], wfirst), mb = min(s_hi[warp][slot], wlast);
+        int rank = k - kstart; if (rank < 0) rank += p.K;
+        const Prim q = load_prim(packn, k);
+        const float4 *slab = tpn + (size_t)k * slabsz;
+        float *gslab = gtn + (size_t)k * slabsz * 4;
+        float g[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) g[i] = 0.f;
+        bool touched = false;
+        float x = xb, y = yb, z = zb;
+        for (int m = cs; m < ma; ++m) {
+            if (m >= mfirst) { x = __fmaf_rn(c.ray.dx, p.dt, x); y = __fmaf_rn(c.ray.dy, p.dt, y); z = __fmaf_rn(c.ray.dz, p.dt, z); }
+        }
+        for (int m = ma; m <= mb; ++m) {
+            const int j = m + c.off;
+            // the sample (j, rank) exists in forward iff the lane was marching at j and had not saturated before it
+            const bool live = hashit && (m >= mfirst) && (j <= jlast) && ((j < jsat) || (j == jsat && rank <= ranksat));
+            const float xm = x - q.px, ym = y - q.py, zm = z - q.pz;
+            if (m >= mfirst) { x = __fmaf_rn(c.ray.dx, p.dt, x); y = __fmaf_rn(c.ray.dy, p.dt, y); z = __fmaf_rn(c.ray.dz, p.dt, z); }
+            const float rx0 = rowdot(q.r00, xm, q.r10, ym, q.r20, zm);
+            const float rx1 = rowdot(q.r01, xm, q.r11, ym, q.r21, zm);
+            const float rx2 = rowdot(q.r02, xm, q.r12, ym, q.r22, zm);
+            const float y0 = __fmul_rn(q.sx, rx0), y1 = __fmul_rn(q.sy, rx1), y2 = __fmul_rn(q.sz, rx2);
+            const bool valid = (fabsf(y0) < 1.f) && (fabsf(y1) < 1.f) && (fabsf(y2) < 1.f);
+            if (!(valid && live)) continue;
+            touched = true;
+            Sample sm;
+            const float4 s = sample_slab<true>(slab, y0, y1, y2, p.TD, p.TH, p.TW, p.fadescale, p.fadeexp, &sm);
+            // primaccum.h:81-98 with the saturating sample known from forward
+            const bool issat = (j == jsat) && (rank == ranksat);
+            const float a = s.w * p.dt;
+            const float weight = issat ? (1.f - abefore) : a;
+            const float dLa = issat ? 0.f : p.dt * ((s.x - sr) * dL.x + (s.y - sg) * dL.y + (s.z - sb) * dL.z + (1.f - sa) * dL.w);
+            const float d0 = weight * dL.x, d1 = weight * dL.y, d2 = weight * dL.z;
+            // primsampler.h:68-91
+            const float cf = -(p.fadescale * p.fadeexp) * s.w * dLa;
+            float gy0 = cf * __powf(fabsf(y0), p.fadeexp - 1.f) * (y0 > 0.f ? 1.f : -1.f);
+            float gy1 = cf * __powf(fabsf(y1), p.fadeexp - 1.f) * (y1 > 0.f ? 1.f : -1.f);
+            float gy2 = cf * __powf(fabsf(y2), p.fadeexp - 1.f) * (y2 > 0.f ? 1.f : -1.f);
+            const float d3 = dLa * sm.fade;
+            // utils.h:504-643
+            float gix = 0.f, giy = 0.f, giz = 0.f;
+#pragma unroll
+            for (int cn = 0; cn < 8; ++cn) {
+                if (sm.idx[cn] >= 0) {
+                    const float w_ = sm.wgt[cn];
+                    red_add_v4(gslab + (size_t)sm.idx[cn] * 4, w_ * d0, w_ * d1, w_ * d2, w_ * d3);
+                    const float4 v = __ldg(slab + sm.idx[cn]);
+                    const float dp = v.x * d0 + v.y * d1 + v.z * d2 + v.w * d3;
+                    const float wx = (cn & 1) ? sm.x0 : sm.x1, wy = (cn & 2) ? sm.y0 : sm.y1, wz = (cn & 4) ? sm.z0 : sm.z1;
+                    gix += ((cn & 1) ? dp : -dp) * wy * wz;
+                    giy += ((cn & 2) ? dp : -dp) * wx * wz;
+                    giz += ((cn & 4) ? dp : -dp) * wx * wy;
+                }
+            }
+            gy0 += gmx * gix; gy1 += gmy * giy; gy2 += gmz * giz;
+            // primtransf.h:155-179
+            g[0] += rx0 * gy0; g[1] += rx1 * gy1; g[2] += rx2 * gy2;            // grad scale
+            const float h0 = gy0 * q.sx, h1 = gy1 * q.sy, h2 = gy2 * q.sz;
+            g[3] += xm * h0; g[4] += xm * h1; g[5] += xm * h2;                   // grad rot row 0
+            g[6] += ym * h0; g[7] += ym * h1; g[8] += ym * h2;                   // row 1
+            g[9] += zm * h0; g[10] += zm * h1; g[11] += zm * h2;                 // row 2
+            g[12] -= q.r00 * h0 + q.r01 * h1 + q.r02 * h2;                       // grad pos
+            g[13] -= q.r10 * h0 + q.r11 * h1 + q.r12 * h2;
+            g[14] -= q.r20 * h0 + q.r21 * h1 + q.r22 * h2;
+        }
+        if (!__any_sync(0xffffffffu, touched)) continue;
+        // 16-value butterfly: after the 5 stages lanes 2i and 2i+1 hold the warp total of g[i]
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const bool up = lane & 16;
+            const float send = up ? g[i] : g[i + 8];
+            const float keep = up ? g[i + 8] : g[i];
+            g[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const bool up = lane & 8;
+            const float send = up ? g[i] : g[i + 4];
+            const float keep = up ? g[i + 4] : g[i];
+            g[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const bool up = lane & 4;
+            const float send = up ? g[i] : g[i + 2];
+            const float keep = up ? g[i + 2] : g[i];
+            g[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+        {
+            const bool up = lane & 2;
+            const float send = up ? g[0] : g[1];
+            const float keep = up ? g[1] : g[0];
+            g[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        }
+        g[0] += __shfl_xor_sync(0xffffffffu, g[0], 1);
+        const int vi = lane >> 1;
+        if (!(lane & 1) && vi < 15) {
+            float *dst = vi < 3 ? (gsn + (size_t)k * 3 + vi) : (vi < 12 ? (grn + (size_t)k * 9 + (vi - 3)) : (gpn + (size_t)k * 3 + (vi - 12)));
+            atomicAdd(dst, g[0]);
+        }
+            }   // while (word)
+        }       // for (w)
+    }           // for (cs)
+}
+
+int check_shape(const mvp_shape &s) {
+    if (s.N < 1 || s.H < 1 || s.W < 1 || s.K < 1 || s.TD < 1 || s.TH < 1 || s.TW < 1) return MVP_ERR_SHAPE;
+    if (s.H >= 32768 || s.W >= 32768) return MVP_ERR_SHAPE;
+    if (s.N > 65535) return MVP_ERR_SHAPE;
+    if ((size_t)s.TD * s.TH * s.TW >= ((size_t)1 << 27)) return MVP_ERR_SHAPE;
+    return MVP_OK;
+}
+
+int launch_accel(const mvp_shape &s, const float *raypos, const float *raydir, const float *primpos, const float *primrot,
+                 const float *primscale, char *ws, const Layout &L, cudaStream_t st) {
+    Cam *cam = reinterpret_cast<Cam *>(ws + L.cam);
+    int *bad = reinterpret_cast<int *>(ws + L.bad);
+    cudaError_t e = cudaMemsetAsync(bad, 0, (size_t)s.N * sizeof(int), st);
+    if (e != cudaSuccess) return (int)e;
+    const size_t HW = (size_t)s.H * s.W;
+    dim3 gfit((unsigned)((HW + kFitThreads * kFitRaysPerThread - 1) / (kFitThreads * kFitRaysPerThread)), s.N);
+    fit_camera_kernel<<<gfit, kFitThreads, 0, st>>>(s.H, s.W, raypos, raydir, cam, bad);
+    const size_t NK = (size_t)s.N * s.K;
+    prim_setup_kernel<<<(unsigned)((NK + 127) / 128), 128, 0, st>>>(
+        s.N, s.K, s.H, s.W, primpos, primrot, primscale, cam, bad, reinterpret_cast<float4 *>(ws + L.pack),
+        reinterpret_cast<unsigned *>(ws + L.rx), reinterpret_cast<unsigned *>(ws + L.ry));
+    row_lists_kernel<<<dim3(L.R, s.N), kRowThreads, 0, st>>>(s.K, L.R, L.rowcap, reinterpret_cast<unsigned *>(ws + L.rx),
+                                                            reinterpret_cast<unsigned *>(ws + L.ry),
+                                                            reinterpret_cast<int *>(ws + L.rowcnt),
+                                                            reinterpret_cast<RowEntry *>(ws + L.rowlist));
+    e = cudaGetLastError();
+    return e == cudaSuccess ? MVP_OK : (int)e;
+}
+
+void fill_params(Params &p, const mvp_shape &s, float stepsize, float fadescale, float fadeexp, char *ws, const Layout &L) {
+    p.N = s.N; p.H = s.H; p.W = s.W; p.K = s.K; p.TD = s.TD; p.TH = s.TH; p.TW = s.TW;
+    p.dt = stepsize;
+    p.fadescale = fadescale; p.fadeexp = fadeexp;
+    p.pack = reinterpret_cast<const float4 *>(ws + L.pack);
+    p.rx = reinterpret_cast<const unsigned *>(ws + L.rx);
+    p.ry = reinterpret_cast<const unsigned *>(ws + L.ry);
+    p.rowcnt = reinterpret_cast<const int *>(ws + L.rowcnt);
+    p.rowlist = reinterpret_cast<const RowEntry *>(ws + L.rowlist);
+    p.R = L.R; p.rowcap = L.rowcap;
+    p.TXn = (s.W + kTileW - 1) / kTileW;
+    p.TYn = (s.H + kTileH - 1) / kTileH;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mvp_abi_version(void) { return MVP_ABI_VERSION; }
+
+const char *mvp_error_string(int code) {
+    switch (code) {
+        case MVP_OK: return "ok";
+        case MVP_ERR_NULL: return "required pointer is NULL";
+        case MVP_ERR_SHAPE: return "invalid or unsupported shape";
+        case MVP_ERR_STEPSIZE: return "stepsize must be finite and > 0";
+        case MVP_ERR_WORKSPACE: return "workspace too small or not 256-byte aligned";
+        case MVP_ERR_ALGO: return "unsupported algo";
+        default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
+    }
+}
+
+size_t mvp_workspace_bytes(const mvp_shape *shape) {
+    if (!shape || check_shape(*shape) != MVP_OK) return 0;
+    return make_layout(*shape).total;
+}
+
+int mvp_build_accel(const mvp_shape *shape, const float *raypos, const float *raydir, const float *primpos,
+                    const float *primrot, const float *primscale, void *workspace, size_t workspace_bytes, void *stream) {
+    if (!shape || !raypos || !raydir || !primpos || !primrot || !primscale || !workspace) return MVP_ERR_NULL;
+    int rc = check_shape(*shape);
+    if (rc != MVP_OK) return rc;
+    const Layout L = make_layout(*shape);
+    if (workspace_bytes < L.total || ((uintptr_t)workspace & 255)) return MVP_ERR_WORKSPACE;
+    return launch_accel(*shape, raypos, raydir, primpos, primrot, primscale, (char *)workspace, L, (cudaStream_t)stream);
+}
+
+int mvp_forward_launch_count(uint32_t flags) { return (flags & MVP_FLAG_ACCEL_VALID) ? 1 : 4; }
+int mvp_backward_launch_count(uint32_t flags) { return (flags & MVP_FLAG_ACCEL_VALID) ? 1 : 4; }
+
+int mvp_raymarch_forward(const mvp_forward_args *a, void *stream) {
+    if (!a) return MVP_ERR_NULL;
+    if (!a->raypos || !a->raydir || !a->tminmax || !a->primpos || !a->primrot || !a->primscale || !a->tplate || !a->rayrgba ||
+        !a->workspace)
+        return MVP_ERR_NULL;
+    if ((a->raysat == nullptr) != (a->rayaux == nullptr)) return MVP_ERR_NULL;
+    int rc = check_shape(a->shape);
+    if (rc != MVP_OK) return rc;
+    if (!(a->stepsize > 0.f) || !(a->stepsize < 3.0e38f)) return MVP_ERR_STEPSIZE;
+    const Layout L = make_layout(a->shape);
+    if (a->workspace_bytes < L.total || ((uintptr_t)a->workspace & 255)) return MVP_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    char *ws = (char *)a->workspace;
+    if (!(a->flags & MVP_FLAG_ACCEL_VALID)) {
+        rc = launch_accel(a->shape, a->raypos, a->raydir, a->primpos, a->primrot, a->primscale, ws, L, st);
+        if (rc != MVP_OK) return rc;
+    }
+    Params p{};
+    fill_params(p, a->shape, a->stepsize, a->fadescale, a->fadeexp, ws, L);
+    p.raypos = a->raypos; p.raydir = a->raydir; p.tminmax = a->tminmax; p.tplate = a->tplate;
+    p.rayrgba = a->rayrgba; p.raysat = a->raysat; p.rayaux = reinterpret_cast<int4 *>(a->rayaux);
+    dim3 grid((p.TXn + 1) / 2, (p.TYn + 1) / 2, a->shape.N);
+    if (grid.y > 65535) return MVP_ERR_SHAPE;
+    if (a->raysat) render_forward_kernel<true><<<grid, kWarps * 32, 0, st>>>(p);
+    else render_forward_kernel<false><<<grid, kWarps * 32, 0, st>>>(p);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? MVP_OK : (int)e;
+}
+
+int mvp_raymarch_backward(const mvp_backward_args *a, void *stream) {
+    if (!a) return MVP_ERR_NULL;
+    if (!a->raypos || !a->raydir || !a->tminmax || !a->primpos || !a->primrot || !a->primscale || !a->tplate ||
+        !a->grad_rayrgba || !a->raysat || !a->rayaux || !a->grad_primpos || !a->grad_primrot || !a->grad_primscale ||
+        !a->grad_tplate || !a->workspace)
+        return MVP_ERR_NULL;
+    int rc = check_shape(a->shape);
+    if (rc != MVP_OK) return rc;
+    if (!(a->stepsize > 0.f) || !(a->stepsize < 3.0e38f)) return MVP_ERR_STEPSIZE;
+    const Layout L = make_layout(a->shape);
+    if (a->workspace_bytes < L.total || ((uintptr_t)a->workspace & 255)) return MVP_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    char *ws = (char *)a->workspace;
+    if (!(a->flags & MVP_FLAG_ACCEL_VALID)) {
+        rc = launch_accel(a->shape, a->raypos, a->raydir, a->primpos, a->primrot, a->primscale, ws, L, st);
+        if (rc != MVP_OK) return rc;
+    }
+    Params p{};
+    fill_params(p, a->shape, a->stepsize, a->fadescale, a->fadeexp, ws, L);
+    p.raypos = a->raypos; p.raydir = a->raydir; p.tminmax = a->tminmax; p.tplate = a->tplate;
+    p.grad_rayrgba = a->grad_rayrgba; p.raysat_in = a->raysat; p.rayaux_in = reinterpret_cast<const int4 *>(a->rayaux);
+    p.g_primpos = a->grad_primpos; p.g_primrot = a->grad_primrot; p.g_primscale = a->grad_primscale; p.g_tplate = a->grad_tplate;
+    dim3 grid((p.TXn + 1) / 2, (p.TYn + 1) / 2, a->shape.N);
+    if (grid.y > 65535) return MVP_ERR_SHAPE;
+    render_backward_kernel<<<grid, kWarps * 32, 0, st>>>(p);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? MVP_OK : (int)e;
+}
+
+}  // extern "C"

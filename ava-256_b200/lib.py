@@ -1,0 +1,94 @@
+"""ctypes binding of the C-ABI in include/mvpraymarch_b200.h.  There is no fallback: if the CUDA library cannot be
+built or loaded, importing this module raises."""
+import ctypes
+import os
+
+from . import build as _build
+
+c_f = ctypes.c_void_p  # device pointers travel as plain addresses
+
+
+class Shape(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("N", "H", "W", "K", "TD", "TH", "TW")]
+
+
+class ForwardArgs(ctypes.Structure):
+    _fields_ = [
+        ("shape", Shape),
+        ("stepsize", ctypes.c_float), ("fadescale", ctypes.c_float), ("fadeexp", ctypes.c_float),
+        ("flags", ctypes.c_uint32),
+        ("raypos", c_f), ("raydir", c_f), ("tminmax", c_f),
+        ("primpos", c_f), ("primrot", c_f), ("primscale", c_f),
+        ("tplate", c_f),
+        ("rayrgba", c_f), ("raysat", c_f), ("rayaux", c_f),
+        ("workspace", c_f), ("workspace_bytes", ctypes.c_size_t),
+    ]
+
+
+class BackwardArgs(ctypes.Structure):
+    _fields_ = [
+        ("shape", Shape),
+        ("stepsize", ctypes.c_float), ("fadescale", ctypes.c_float), ("fadeexp", ctypes.c_float),
+        ("flags", ctypes.c_uint32),
+        ("raypos", c_f), ("raydir", c_f), ("tminmax", c_f),
+        ("primpos", c_f), ("primrot", c_f), ("primscale", c_f),
+        ("tplate", c_f),
+        ("grad_rayrgba", c_f), ("raysat", c_f), ("rayaux", c_f),
+        ("grad_primpos", c_f), ("grad_primrot", c_f), ("grad_primscale", c_f), ("grad_tplate", c_f),
+        ("workspace", c_f), ("workspace_bytes", ctypes.c_size_t),
+    ]
+
+
+FLAG_ACCEL_VALID = 1
+ABI_VERSION = 1
+
+EXPORTS = ("mvp_abi_version", "mvp_error_string", "mvp_workspace_bytes", "mvp_build_accel", "mvp_raymarch_forward",
+           "mvp_raymarch_backward", "mvp_forward_launch_count", "mvp_backward_launch_count")
+
+
+def _load():
+    path = _build.LIB
+    if _build.needs_build():
+        try:
+            _build.build()
+        except Exception as e:  # nvcc missing on the GPU box is fine as long as a prebuilt .so travelled with the repo
+            if not os.path.exists(path):
+                raise RuntimeError("mvpraymarch_b200: CUDA library missing and could not be built: %r" % (e,))
+    lib = ctypes.CDLL(path)
+    for name in EXPORTS:
+        if not hasattr(lib, name):
+            raise RuntimeError("mvpraymarch_b200: %s does not export %s" % (path, name))
+    lib.mvp_abi_version.restype = ctypes.c_int
+    lib.mvp_error_string.restype = ctypes.c_char_p
+    lib.mvp_error_string.argtypes = [ctypes.c_int]
+    lib.mvp_workspace_bytes.restype = ctypes.c_size_t
+    lib.mvp_workspace_bytes.argtypes = [ctypes.POINTER(Shape)]
+    lib.mvp_build_accel.restype = ctypes.c_int
+    lib.mvp_build_accel.argtypes = [ctypes.POINTER(Shape)] + [c_f] * 6 + [ctypes.c_size_t, c_f]
+    lib.mvp_raymarch_forward.restype = ctypes.c_int
+    lib.mvp_raymarch_forward.argtypes = [ctypes.POINTER(ForwardArgs), c_f]
+    lib.mvp_raymarch_backward.restype = ctypes.c_int
+    lib.mvp_raymarch_backward.argtypes = [ctypes.POINTER(BackwardArgs), c_f]
+    lib.mvp_forward_launch_count.restype = ctypes.c_int
+    lib.mvp_forward_launch_count.argtypes = [ctypes.c_uint32]
+    lib.mvp_backward_launch_count.restype = ctypes.c_int
+    lib.mvp_backward_launch_count.argtypes = [ctypes.c_uint32]
+    if lib.mvp_abi_version() != ABI_VERSION:
+        raise RuntimeError("mvpraymarch_b200: ABI version mismatch")
+    return lib
+
+
+LIB = _load()
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError("mvpraymarch_b200: %s (code %d)" % (LIB.mvp_error_string(rc).decode(), rc))
+
+
+def workspace_bytes(N, H, W, K, TD, TH, TW):
+    s = Shape(N, H, W, K, TD, TH, TW)
+    n = LIB.mvp_workspace_bytes(ctypes.byref(s))
+    if n == 0:
+        raise RuntimeError("mvpraymarch_b200: invalid shape %r" % ((N, H, W, K, TD, TH, TW),))
+    return n

@@ -1,0 +1,163 @@
+"""torch.autograd front-end of the B200 raymarcher: the host-side mirror of the reference's op
+(/root/reference/extensions/mvpraymarch/mvpraymarch.py:87-390) on top of the C-ABI in include/mvpraymarch_b200.h.
+
+Same contract as the reference: fp32 CUDA tensors, contiguous, caller-visible output rayrgba [N,H,W,4] that
+participates in autograd with gradients for primpos, primrot, primscale and template (None for everything else,
+mvpraymarch.py:279-292).  Differences that are deliberate:
+  * kernels run on torch's current stream (the reference launches on legacy stream 0, mvpraymarch.cpp:277);
+  * no allocation or sync inside the native call (the reference cudaMalloc/cudaFree's per forward, bvh.cu:261-293);
+  * the acceleration structure is a screen-space bucket list, not the BVH tensors of build_accel (:21-84);
+    it is kept for backward instead of being rebuilt;
+  * 64-bit indexing (the reference overflows int32 at N*K*T^3*4 >= 2^31, primsampler.h:31-36).
+"""
+import ctypes
+
+import torch
+from torch.autograd import Function
+
+from . import lib as _lib
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _check_f32_cuda(name, t):
+    if not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor" % name)          # mvpraymarch.cpp:102
+    if not t.is_contiguous():
+        raise RuntimeError("%s must be contiguous" % name)             # mvpraymarch.cpp:103
+    if t.dtype != torch.float32:
+        raise RuntimeError("%s must be float32" % name)
+
+
+class MVPRaymarch(Function):
+    """Custom Function for raymarching Mixture of Volumetric Primitives (reference: mvpraymarch.py:87-292)."""
+
+    @staticmethod
+    def forward(ctx, raypos, raydir, stepsize, tminmax, primpos, primrot, primscale, template, warp, rayterm,
+                gradmode, options):
+        algo = options["algo"]
+        if algo != 0 or warp is not None:
+            raise NotImplementedError("mvpraymarch_b200: algo=1 / warp fields are not implemented yet (SURVEY 8f #3)")
+        if options["usebvh"] != "fixedorder":
+            raise NotImplementedError("mvpraymarch_b200: only usebvh='fixedorder' (the default, and the only "
+                                      "self-consistent mode of the reference) is implemented")
+        # same shape contract as mvpraymarch.py:112-127
+        assert raypos.is_contiguous() and raypos.size(3) == 3
+        assert raydir.is_contiguous() and raydir.size(3) == 3
+        assert tminmax.is_contiguous() and tminmax.size(3) == 2
+        assert primpos.is_contiguous() and primpos.size(2) == 3
+        assert primrot.is_contiguous() and primrot.size(2) == 3
+        assert primscale.is_contiguous() and primscale.size(2) == 3
+        assert template.is_contiguous() and template.dim() == 6 and template.size(-1) == 4, \
+            "channels-last template [N,K,TD,TH,TW,4] required (the reference sampler is always channels-last, primsampler.h:16)"
+        for name, t in (("raypos", raypos), ("raydir", raydir), ("tminmax", tminmax), ("primpos", primpos),
+                        ("primrot", primrot), ("primscale", primscale), ("template", template)):
+            _check_f32_cuda(name, t)
+
+        N, H, W = raypos.shape[:3]
+        K = primpos.size(1)
+        TD, TH, TW = template.shape[2:5]
+        dev = raypos.device
+        with torch.cuda.device(dev):
+            wsbytes = _lib.workspace_bytes(N, H, W, K, TD, TH, TW)
+            workspace = torch.empty(wsbytes, dtype=torch.uint8, device=dev)
+            rayrgba = torch.empty((N, H, W, 4), dtype=torch.float32, device=dev)
+            if gradmode:
+                raysat = torch.empty((N, H, W, 3), dtype=torch.float32, device=dev)
+                rayaux = torch.empty((N, H, W, 4), dtype=torch.int32, device=dev)
+            else:
+                raysat = rayaux = None
+            a = _lib.ForwardArgs()
+            a.shape = _lib.Shape(N, H, W, K, TD, TH, TW)
+            a.stepsize, a.fadescale, a.fadeexp = float(stepsize), float(options["fadescale"]), float(options["fadeexp"])
+            a.flags = 0
+            a.raypos, a.raydir, a.tminmax = _ptr(raypos), _ptr(raydir), _ptr(tminmax)
+            a.primpos, a.primrot, a.primscale = _ptr(primpos), _ptr(primrot), _ptr(primscale)
+            a.tplate = _ptr(template)
+            a.rayrgba, a.raysat, a.rayaux = _ptr(rayrgba), _ptr(raysat), _ptr(rayaux)
+            a.workspace, a.workspace_bytes = _ptr(workspace), wsbytes
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(_lib.LIB.mvp_raymarch_forward(ctypes.byref(a), ctypes.c_void_p(stream)))
+
+        if gradmode:
+            ctx.save_for_backward(raypos, raydir, tminmax, primpos, primrot, primscale, template, raysat, rayaux, workspace)
+            ctx.options = options
+            ctx.stepsize = float(stepsize)
+        return rayrgba
+
+    @staticmethod
+    def backward(ctx, grad_rayrgba):
+        raypos, raydir, tminmax, primpos, primrot, primscale, template, raysat, rayaux, workspace = ctx.saved_tensors
+        options = ctx.options
+        N, H, W = raypos.shape[:3]
+        K = primpos.size(1)
+        TD, TH, TW = template.shape[2:5]
+        dev = raypos.device
+        with torch.cuda.device(dev):
+            grad_rayrgba = grad_rayrgba.contiguous()                   # mvpraymarch.py:264
+            grad_primpos = torch.zeros_like(primpos)                   # mvpraymarch.py:240-246
+            grad_primrot = torch.zeros_like(primrot)
+            grad_primscale = torch.zeros_like(primscale)
+            grad_template = torch.zeros_like(template)
+            a = _lib.BackwardArgs()
+            a.shape = _lib.Shape(N, H, W, K, TD, TH, TW)
+            a.stepsize, a.fadescale, a.fadeexp = ctx.stepsize, float(options["fadescale"]), float(options["fadeexp"])
+            a.flags = _lib.FLAG_ACCEL_VALID
+            a.raypos, a.raydir, a.tminmax = _ptr(raypos), _ptr(raydir), _ptr(tminmax)
+            a.primpos, a.primrot, a.primscale = _ptr(primpos), _ptr(primrot), _ptr(primscale)
+            a.tplate = _ptr(template)
+            a.grad_rayrgba, a.raysat, a.rayaux = _ptr(grad_rayrgba), _ptr(raysat), _ptr(rayaux)
+            a.grad_primpos, a.grad_primrot, a.grad_primscale = _ptr(grad_primpos), _ptr(grad_primrot), _ptr(grad_primscale)
+            a.grad_tplate = _ptr(grad_template)
+            a.workspace, a.workspace_bytes = _ptr(workspace), workspace.numel()
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(_lib.LIB.mvp_raymarch_backward(ctypes.byref(a), ctypes.c_void_p(stream)))
+        return (None, None, None, None, grad_primpos, grad_primrot, grad_primscale, grad_template, None, None, None, None)
+
+
+def mvpraymarch(
+    raypos,
+    raydir,
+    stepsize,
+    tminmax,
+    primtransf,
+    template,
+    warp,
+    rayterm=None,
+    algo=0,
+    usebvh="fixedorder",
+    sortprims=False,
+    randomorder=False,
+    maxhitboxes=512,
+    synchitboxes=True,
+    chlast=True,
+    fadescale=8.0,
+    fadeexp=8.0,
+    accum=0,
+    termthresh=0.0,
+    griddim=3,
+    blocksize=(8, 16),
+    bwdblocksize=(8, 16),
+):
+    """Drop-in for extensions.mvpraymarch.mvpraymarch.mvpraymarch (reference mvpraymarch.py:295-390).
+
+    Same parameters, same defaults.  `sortprims`, `randomorder`, `maxhitboxes`, `synchitboxes`, `chlast`, `accum`,
+    `termthresh`, `griddim`, `blocksize`, `bwdblocksize` and `rayterm` are accepted and, exactly like in the
+    reference kernels ("accepted but ignored"), have no effect on the result.
+    Returns rayrgba [N,H,W,4]."""
+    if isinstance(primtransf, tuple):
+        primpos, primrot, primscale = primtransf
+    else:                                                              # packed [N,K,5,3]  (mvpraymarch.py:353-360)
+        primpos = primtransf[:, :, 0, :].contiguous()
+        primrot = primtransf[:, :, 1:4, :].contiguous()
+        primscale = primtransf[:, :, 4, :].contiguous()
+    options = {
+        "algo": algo, "usebvh": usebvh, "sortprims": sortprims, "randomorder": randomorder,
+        "maxhitboxes": maxhitboxes, "synchitboxes": synchitboxes, "chlast": chlast, "fadescale": fadescale,
+        "fadeexp": fadeexp, "accum": accum, "termthresh": termthresh, "griddim": griddim, "blocksize": blocksize,
+        "bwdblocksize": bwdblocksize,
+    }
+    return MVPRaymarch.apply(raypos, raydir, stepsize, tminmax, primpos, primrot, primscale, template, warp, rayterm,
+                             torch.is_grad_enabled(), options)

@@ -1,0 +1,106 @@
+/*
+ * mvpraymarch_b200 -- C-ABI of the B200-native (sm_100a) MVP raymarcher.
+ *
+ * This is the drop-in boundary for ava-256's hot path: every entry point below replaces one function of
+ * the reference's pybind11 module `mvpraymarchlib` (reference paths relative to /root/reference):
+ *
+ *   mvp_raymarch_forward   <- raymarch_forward   extensions/mvpraymarch/mvpraymarch.cpp:180-280
+ *                             (+ compute_aabb    extensions/mvpraymarch/mvpraymarch.cpp:146-178, which the
+ *                              reference's Python calls right before it, mvpraymarch.py:81-82: building the
+ *                              acceleration structure is part of the forward call here)
+ *   mvp_raymarch_backward  <- raymarch_backward  extensions/mvpraymarch/mvpraymarch.cpp:282-396
+ *   mvp_build_accel        <- compute_aabb       extensions/mvpraymarch/mvpraymarch.cpp:146-178
+ *                             (stand-alone form, for callers that want to build once and march many times)
+ *   mvp_workspace_bytes    <- the tensors build_accel allocates, extensions/mvpraymarch/mvpraymarch.py:21-84
+ *
+ * Conventions (same ownership model as the reference: the caller owns every buffer, outputs are written in
+ * place; unlike the reference nothing is allocated inside and everything runs on the caller's stream):
+ *   - all pointers are DEVICE pointers to contiguous fp32 (or int32) arrays; no torch types;
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - return value: 0 = ok, < 0 = invalid argument (MVP_ERR_*), > 0 = a cudaError_t from the launch;
+ *   - thread-safe and re-entrant: no global state.
+ *
+ * Tensor layouts (SURVEY.md terminology table):
+ *   raypos, raydir [N,H,W,3]   tminmax [N,H,W,2]
+ *   primpos [N,K,3]  primrot [N,K,3,3] (row-major)  primscale [N,K,3] (inverse half-extents)
+ *   tplate  [N,K,TD,TH,TW,4] channels-last RGBA
+ *   rayrgba [N,H,W,4]  raysat [N,H,W,3]  rayaux [N,H,W,4] (int32, opaque; written by forward, read by backward)
+ */
+#ifndef MVPRAYMARCH_B200_H_
+#define MVPRAYMARCH_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVP_ABI_VERSION 1
+
+#define MVP_OK 0
+#define MVP_ERR_NULL (-1)      /* a required pointer is NULL */
+#define MVP_ERR_SHAPE (-2)     /* non-positive or unsupported dimension (H, W < 32768; K >= 1) */
+#define MVP_ERR_STEPSIZE (-3)  /* stepsize must be finite and > 0 */
+#define MVP_ERR_WORKSPACE (-4) /* workspace too small or misaligned (256 B) */
+#define MVP_ERR_ALGO (-5)      /* only algo 0 (no warp field) is implemented */
+
+typedef struct mvp_shape {
+    int32_t N, H, W, K, TD, TH, TW;
+} mvp_shape;
+
+/* flags */
+#define MVP_FLAG_ACCEL_VALID 1u /* workspace already holds the accel structure of these primitives+rays */
+
+typedef struct mvp_forward_args {
+    mvp_shape shape;
+    float stepsize, fadescale, fadeexp;
+    uint32_t flags;
+    const float *raypos, *raydir, *tminmax;
+    const float *primpos, *primrot, *primscale;
+    const float *tplate;
+    float *rayrgba;          /* out */
+    float *raysat;           /* out, NULL when no gradient will be taken (mvpraymarch.py:147-152) */
+    int32_t *rayaux;         /* out, NULL iff raysat is NULL */
+    void *workspace;         /* >= mvp_workspace_bytes(shape), 256-byte aligned */
+    size_t workspace_bytes;
+} mvp_forward_args;
+
+typedef struct mvp_backward_args {
+    mvp_shape shape;
+    float stepsize, fadescale, fadeexp;
+    uint32_t flags;          /* MVP_FLAG_ACCEL_VALID if `workspace` is the one the forward call filled */
+    const float *raypos, *raydir, *tminmax;
+    const float *primpos, *primrot, *primscale;
+    const float *tplate;
+    const float *grad_rayrgba; /* [N,H,W,4] */
+    const float *raysat;       /* from forward */
+    const int32_t *rayaux;     /* from forward */
+    float *grad_primpos, *grad_primrot, *grad_primscale; /* out, accumulated into: caller zero-fills */
+    float *grad_tplate;        /* out, accumulated into: caller zero-fills */
+    void *workspace;
+    size_t workspace_bytes;
+} mvp_backward_args;
+
+int mvp_abi_version(void);
+const char *mvp_error_string(int code);
+
+/* Bytes of scratch the accel structure + per-call state need for this shape (0 for an invalid shape). */
+size_t mvp_workspace_bytes(const mvp_shape *shape);
+
+/* Build the acceleration structure (camera fit, primitive records, screen rectangles, tile-row lists). */
+int mvp_build_accel(const mvp_shape *shape, const float *raypos, const float *raydir,
+                    const float *primpos, const float *primrot, const float *primscale,
+                    void *workspace, size_t workspace_bytes, void *stream);
+
+int mvp_raymarch_forward(const mvp_forward_args *args, void *stream);
+int mvp_raymarch_backward(const mvp_backward_args *args, void *stream);
+
+/* Number of kernels the last forward / backward call of this shape launches (for bench.py's gpu_launches). */
+int mvp_forward_launch_count(uint32_t flags);
+int mvp_backward_launch_count(uint32_t flags);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVPRAYMARCH_B200_H_ */

@@ -5,7 +5,7 @@ import numpy as np
 import torch
 
 
-def gradcheck_like_scene(N=2, H=13, W=13, k3=2, M=4, seed=1112, fadescale=6.5, fadeexp=7.5):
+def gradcheck_like_scene(N=2, H=13, W=13, k3=2, M=4, seed=1112, fadescale=6.5, fadeexp=7.5, alpha_gain=40.0):
     """Small scene in the style of the reference's gradcheck inputs
     (/root/reference/extensions/mvpraymarch/mvpraymarch.py:464-565): pinhole rays from z=-4, a k3^3 grid of
     randomly rotated slabs around the origin, softplus payload, random tminmax."""
@@ -24,7 +24,7 @@ def gradcheck_like_scene(N=2, H=13, W=13, k3=2, M=4, seed=1112, fadescale=6.5, f
     tminmax = max_len * torch.arange(2, dtype=torch.float32)[None, None, None, :].repeat(N, H, W, 1) \
         + torch.rand(N, H, W, 2, generator=g)
     tpl = torch.nn.functional.softplus(1.5 * (torch.randn(N, K, M, M, M, 4, generator=g)
-                                              - torch.tensor([0, 0, 0, 3.5]))) * torch.tensor([1, 1, 1, 40.0])
+                                              - torch.tensor([0, 0, 0, 3.5]))) * torch.tensor([1, 1, 1, alpha_gain])
     lin = torch.linspace(-1.0, 1.0, k3)
     gz, gy, gx = torch.meshgrid(lin, lin, lin, indexing="ij")
     grid = torch.stack([gx, gy, gz], dim=-1).reshape(1, K, 3)
@@ -56,3 +56,38 @@ def relerr(a, b):
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Named, seeded parity cases (inputs are regenerated from seeds; tests/golden/*.npz hold reference OUTPUTS)
+# ----------------------------------------------------------------------------------------------------------
+def _head_case(n_views, H, W, K, T, seed=1112, view_offset=0, alpha_mu=6.0, alpha_sigma=6.0, stepsize=None):
+    import sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    from ava256_b200 import scene
+    s = scene.make_scene(n_views, H, W, K, T, seed=seed, view_offset=view_offset, alpha_mu=alpha_mu,
+                         alpha_sigma=alpha_sigma, share_primitives=False)
+    if stepsize is not None:
+        s["stepsize"] = stepsize
+    s["fadescale"], s["fadeexp"] = 8.0, 8.0
+    return s
+
+
+CASES = {
+    # gradcheck-style (mvpraymarch.py:434-440 shapes scaled down), fade 6.5/7.5 like the reference's __main__ (:748-774)
+    "gradcheck_small": lambda: gradcheck_like_scene(N=2, H=24, W=20, k3=3, M=6, seed=1112, alpha_gain=8.0),
+    # odd image size (partial tiles in x and y), K not a power of two (rotated DFS order)
+    "gradcheck_ragged": lambda: gradcheck_like_scene(N=1, H=13, W=19, k3=3, M=4, seed=7, alpha_gain=8.0),
+    # head scene, C1-like but small: pinhole dome cameras, UV-grid slabs on an ellipsoid
+    "head_small": lambda: _head_case(2, 64, 42, 256, 8, stepsize=1.0 / 64, alpha_mu=2.0, alpha_sigma=3.0),
+    "head_t16": lambda: _head_case(1, 48, 32, 64, 16, stepsize=1.0 / 32, view_offset=11, alpha_mu=1.0, alpha_sigma=2.0),
+}
+
+
+def build_case(name):
+    s = CASES[name]()
+    g = torch.Generator().manual_seed(4242)
+    grad = torch.randn(*s["raypos"].shape[:3], 4, generator=g)
+    return s, grad

@@ -1,0 +1,106 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).  Every call goes through the public op
+(extensions.mvpraymarch.mvpraymarch.mvpraymarch -> ctypes -> C-ABI); the checkers are
+  (a) oracle/mvp_oracle.c on the same seeded inputs,
+  (b) the committed golden vectors produced by the unmodified reference CUDA extension (tests/golden/*.npz),
+  (c) the reference extension itself when oracle/_ref travelled to the box.
+Tolerances are the north star's: forward max|d|/max|ref| <= 1e-4, gradients <= 1e-3."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import CASES, build_case, relerr, scene_args_np
+
+pytestmark = pytest.mark.gpu
+
+FWD_TOL = 1e-4
+BWD_TOL = 1e-3
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def run_ours(s, grad=None):
+    from extensions.mvpraymarch.mvpraymarch import mvpraymarch
+    dev = "cuda"
+    t = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in s.items()}
+    leaves = [t[k].clone().requires_grad_(grad is not None) for k in ("primpos", "primrot", "primscale", "template")]
+    out = mvpraymarch(t["raypos"], t["raydir"], t["stepsize"], t["tminmax"], (leaves[0], leaves[1], leaves[2]), leaves[3],
+                      None, fadescale=s.get("fadescale", 8.0), fadeexp=s.get("fadeexp", 8.0))
+    if grad is None:
+        return out.detach().cpu().numpy(), None
+    out.backward(grad.to(dev))
+    torch.cuda.synchronize()
+    return out.detach().cpu().numpy(), [x.grad.cpu().numpy() for x in leaves]
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_forward_backward_vs_oracle(name):
+    from oracle import oracle
+    s, grad = build_case(name)
+    out, grads = run_ours(s, grad)
+    a, kw = scene_args_np(s)
+    ref, raysat = oracle.forward(*a, **kw)
+    assert relerr(out, ref) <= FWD_TOL
+    gref = oracle.backward(*a, grad.numpy(), raysat, **kw)
+    for nm, g, r in zip(("primpos", "primrot", "primscale", "template"), grads, gref):
+        assert relerr(g, r) <= BWD_TOL, nm
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_forward_backward_vs_golden(name):
+    path = os.path.join(GOLDEN, name + ".npz")
+    if not os.path.exists(path):
+        pytest.skip("golden vector %s not generated yet" % name)
+    gold = np.load(path)
+    s, grad = build_case(name)
+    out, grads = run_ours(s, grad)
+    assert relerr(out, gold["rayrgba"]) <= FWD_TOL
+    for nm, g in zip(("primpos", "primrot", "primscale", "template"), grads):
+        assert relerr(g, gold["grad_" + nm]) <= BWD_TOL, nm
+
+
+def test_nograd_forward_matches_grad_forward():
+    s, _ = build_case("head_small")
+    with torch.no_grad():
+        a, _ = run_ours(s)
+    b, _ = run_ours(s, torch.zeros(*s["raypos"].shape[:3], 4))
+    assert np.array_equal(a, b)
+
+
+def test_non_pinhole_rays_fall_back():
+    """Rays that are not a pinhole grid (shuffled pixels) must still render correctly via the all-slabs fallback."""
+    from oracle import oracle
+    s, grad = build_case("gradcheck_ragged")
+    g = torch.Generator().manual_seed(3)
+    N, H, W = s["raypos"].shape[:3]
+    perm = torch.randperm(H * W, generator=g)
+    for k in ("raypos", "raydir", "tminmax"):
+        v = s[k]
+        s[k] = v.reshape(N, H * W, -1)[:, perm].reshape(v.shape).contiguous()
+    out, grads = run_ours(s, grad)
+    a, kw = scene_args_np(s)
+    ref, raysat = oracle.forward(*a, **kw)
+    assert relerr(out, ref) <= FWD_TOL
+    gref = oracle.backward(*a, grad.numpy(), raysat, **kw)
+    for nm, g_, r in zip(("primpos", "primrot", "primscale", "template"), grads, gref):
+        assert relerr(g_, r) <= BWD_TOL, nm
+
+
+def test_reference_extension_side_by_side():
+    """Mid-size head scene against the reference kernels compiled for sm_100 (needs oracle/_ref on the box)."""
+    from tests import refext
+    if not refext.available():
+        pytest.skip("oracle/_ref/mvpraymarchlib.so not present")
+    from ava256_b200 import scene
+    s = scene.make_scene(2, 256, 168, 1024, 8, alpha_mu=3.0, alpha_sigma=3.0, share_primitives=False)
+    g = torch.Generator().manual_seed(99)
+    grad = torch.randn(2, 256, 168, 4, generator=g)
+    out, grads = run_ours(s, grad)
+    t = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in s.items()}
+    rgba, sat, st = refext.forward(t["raypos"], t["raydir"], t["stepsize"], t["tminmax"], t["primpos"], t["primrot"],
+                                   t["primscale"], t["template"])
+    gref = refext.backward(t["raypos"], t["raydir"], t["stepsize"], t["tminmax"], t["primpos"], t["primrot"],
+                           t["primscale"], t["template"], rgba, sat, st, grad.cuda())
+    assert relerr(out, rgba.cpu().numpy()) <= FWD_TOL
+    for nm, g_, r in zip(("primpos", "primrot", "primscale", "template"), grads, gref):
+        assert relerr(g_, r.cpu().numpy()) <= BWD_TOL, nm

@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py -- rendered MP/s (fwd+bwd) of the mvpraymarch hot path on N B200s.
+
+Metric (BASELINE.json): rendered megapixels (rays) per second, forward + backward, on synthetic
+80-view 1024x667 batches of a K=16384, 8^3-voxel subject, sharded over ranks by
+views with one NCCL all-reduce of the primitive gradients per step (section 8e).  One "step" = one
+forward + backward pass of the raymarcher over ALL 80 views (strong scaling: the 80 views are split over ranks).
+
+    python bench.py [--gpus N --steps K --warmup W]                 # our CUDA path, N=1 default
+    torchrun ... bench.py --gpus N --steps K --warmup W             # N>1: one rank per GPU
+    python bench.py --impl reference ...                            # the reference's own CPU autograd path
+
+JSON line keys: the base contract's + "roofline" (dominant kernel), "roofline_forward", "cpu_baseline", "e2e",
+"clocks", "gpu_launches".  `oracle/` is only touched in the cpu_baseline / --impl reference legs.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+# canonical workload
+VIEWS, H, W, K, T = 80, 1024, 667, 16384, 8
+ALPHA_MU, ALPHA_SIGMA = 3.0, 3.0
+
+
+def algorithmic_bytes(n_views, h, w, k, t):
+    """compulsory traffic per pass (every input read once, every output written once)."""
+    tpl = k * t ** 3 * 16
+    srt = k * 60
+    aabb = (2 * k - 1) * 24
+    rays_in = h * w * 32
+    out = h * w * 28
+    fwd = tpl + srt + rays_in + out + aabb
+    bwd = (tpl + srt + aabb + rays_in) + h * w * 28 + (tpl + srt)
+    return n_views * fwd, n_views * bwd
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU autograd path (mvpraymarch.py:567-633 restated in oracle/torch_ref.py)
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_autograd_sample(side=48, k=256, t=8, steps=1, warmup=0):
+    """Bounded sample of the same kind of workload (head scene, dome camera) on the host cores.
+    Returns (MP/s fwd+bwd, seconds per step, description)."""
+    from ava256_b200 import scene
+    from oracle import torch_ref
+    torch.set_num_threads(os.cpu_count() or 1)
+    s = scene.make_scene(1, side, side * 2 // 3, k, t, alpha_mu=ALPHA_MU, alpha_sigma=ALPHA_SIGMA)
+    hh, ww = s["raypos"].shape[1:3]
+    stepsize = 2.0 / 16.0          # keeps the autograd graph at ~16 steps
+    g = torch.randn(1, hh, ww, 4, generator=torch.Generator().manual_seed(1))
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        torch_ref.raymarch_torch_fwd_bwd(s["raypos"], s["raydir"], stepsize, s["tminmax"], s["primpos"], s["primrot"],
+                                         s["primscale"], s["template"], g)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    desc = "PyTorch autograd raymarch loop (reference mvpraymarch.py:567-633 restated), 1 view %dx%d, K=%d, %d^3, dt=2/16, fp32" % (hh, ww, k, t)
+    return hh * ww / sec / 1e6, sec, desc
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    mps, sec, desc = cpu_autograd_sample(steps=args.steps, warmup=args.warmup)
+    cores = torch.get_num_threads()
+    line = {
+        "impl": "reference", "metric": "rendered MP/s (fwd+bwd)", "value": mps, "unit": "MP/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C3: %d views %dx%d, K=%d, %d^3 RGBA (reference arm: bounded CPU sample of it)" % (VIEWS, H, W, K, T),
+                   "parallelism": "cpu threads"},
+        "cpu_baseline": {"value": mps, "unit": "MP/s", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": mps, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world):
+    from ava256_b200 import lib, parallel, scene
+    from ava256_b200.op import mvpraymarch
+    import ctypes
+
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    views, h, w, k, t = args.views, args.height, args.width, args.prims, args.voxels
+    assert views % world == 0, "views must divide over ranks"
+    nv = views // world                      # contiguous block of views per rank
+    s = scene.make_scene(nv, h, w, k, t, seed=1112, view_offset=rank * nv, device=dev, alpha_mu=ALPHA_MU, alpha_sigma=ALPHA_SIGMA)
+    stepsize = s["stepsize"]
+    gen = torch.Generator(device=dev).manual_seed(1112 + rank)
+    grad_out = torch.randn(nv, h, w, 4, device=dev, generator=gen)
+    leaves = [s[n].requires_grad_(True) for n in ("primpos", "primrot", "primscale", "template")]
+    flat = torch.zeros(k * t ** 3 * 4 + k * 15, device=dev)     # all-reduced primitive gradients of the subject
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        for x in leaves:
+            x.grad = None
+        out = mvpraymarch(s["raypos"], s["raydir"], stepsize, s["tminmax"], (leaves[0], leaves[1], leaves[2]), leaves[3], None)
+        out.backward(grad_out)
+        # views of a step share the subject's primitives: local sum over the rank's views, one all-reduce
+        parallel.reduce_primitive_grads(leaves[3].grad, leaves[0].grad, leaves[1].grad, leaves[2].grad, flat=flat)
+        return out
+
+    for _ in range(args.warmup):
+        out = step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    tms = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_step = float(tms.item()) / args.steps
+    value = views * h * w / (ms_step * 1e-3) / 1e6
+    sat_frac = float((out[..., 3] >= 0.999).float().mean())
+    cover = float((out[..., 3] > 0).float().mean())
+
+    # ---- kernel-only timing for the roofline (CUDA events on the launching stream; accel already built) ----
+    N_, H_, W_ = s["raypos"].shape[:3]
+    wsb = lib.workspace_bytes(N_, H_, W_, k, t, t, t)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    rgba = torch.empty(N_, H_, W_, 4, device=dev)
+    rsat = torch.empty(N_, H_, W_, 3, device=dev)
+    raux = torch.empty(N_, H_, W_, 4, dtype=torch.int32, device=dev)
+    fa = lib.ForwardArgs()
+    fa.shape = lib.Shape(N_, H_, W_, k, t, t, t)
+    fa.stepsize, fa.fadescale, fa.fadeexp, fa.flags = stepsize, 8.0, 8.0, 0
+    P = lambda x: ctypes.c_void_p(x.data_ptr())  # noqa: E731
+    tl = [x.detach() for x in leaves]
+    fa.raypos, fa.raydir, fa.tminmax = P(s["raypos"]), P(s["raydir"]), P(s["tminmax"])
+    fa.primpos, fa.primrot, fa.primscale, fa.tplate = P(tl[0]), P(tl[1]), P(tl[2]), P(tl[3])
+    fa.rayrgba, fa.raysat, fa.rayaux, fa.workspace, fa.workspace_bytes = P(rgba), P(rsat), P(raux), P(ws), wsb
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    lib.check(lib.LIB.mvp_raymarch_forward(ctypes.byref(fa), stream))          # builds accel
+    fa.flags = lib.FLAG_ACCEL_VALID
+    gs = [torch.zeros_like(x) for x in tl]
+    ba = lib.BackwardArgs()
+    ba.shape, ba.stepsize, ba.fadescale, ba.fadeexp, ba.flags = fa.shape, stepsize, 8.0, 8.0, lib.FLAG_ACCEL_VALID
+    ba.raypos, ba.raydir, ba.tminmax = fa.raypos, fa.raydir, fa.tminmax
+    ba.primpos, ba.primrot, ba.primscale, ba.tplate = fa.primpos, fa.primrot, fa.primscale, fa.tplate
+    ba.grad_rayrgba, ba.raysat, ba.rayaux = P(grad_out), P(rsat), P(raux)
+    ba.grad_primpos, ba.grad_primrot, ba.grad_primscale, ba.grad_tplate = P(gs[0]), P(gs[1]), P(gs[2]), P(gs[3])
+    ba.workspace, ba.workspace_bytes = P(ws), wsb
+
+    def time_kernel(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    reps = max(2, min(args.steps, 5))
+    fwd_ms = time_kernel(lambda: lib.check(lib.LIB.mvp_raymarch_forward(ctypes.byref(fa), stream)), reps)
+    bwd_ms = time_kernel(lambda: lib.check(lib.LIB.mvp_raymarch_backward(ctypes.byref(ba), stream)), reps)
+    del gs, ws
+
+    # ---- end-to-end through the public op with HOST buffers (pinned): H2D of the step's inputs, D2H of the results ----
+    e2e = None
+    if not args.no_e2e:
+        host_in = {n: s[n].detach().cpu().pin_memory() for n in ("raypos", "raydir", "tminmax")}
+        host_prim = {n: x.detach()[0].cpu().pin_memory() for n, x in zip(("primpos", "primrot", "primscale", "template"), leaves)}
+        host_grad = grad_out.cpu().pin_memory()
+        host_out = torch.empty(nv, h, w, 4).pin_memory()
+        host_flat = torch.empty(flat.numel()).pin_memory()
+        h2d = sum(x.numel() * 4 for x in host_in.values()) + sum(x.numel() * 4 for x in host_prim.values()) + host_grad.numel() * 4
+        d2h = host_out.numel() * 4 + host_flat.numel() * 4
+        del leaves, s
+        torch.cuda.empty_cache()
+
+        def e2e_step():
+            d = {n: x.to(dev, non_blocking=True) for n, x in host_in.items()}
+            pr = {n: x.to(dev, non_blocking=True) for n, x in host_prim.items()}
+            g = host_grad.to(dev, non_blocking=True)
+            lv = [pr[n][None].expand(nv, *pr[n].shape).contiguous().requires_grad_(True)
+                  for n in ("primpos", "primrot", "primscale", "template")]
+            o_ = mvpraymarch(d["raypos"], d["raydir"], stepsize, d["tminmax"], (lv[0], lv[1], lv[2]), lv[3], None)
+            o_.backward(g)
+            parallel.reduce_primitive_grads(lv[3].grad, lv[0].grad, lv[1].grad, lv[2].grad, flat=flat)
+            host_out.copy_(o_.detach(), non_blocking=True)
+            host_flat.copy_(flat, non_blocking=True)
+
+        e2e_step()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nrep = max(1, min(args.steps, 3))
+        a.record()
+        for _ in range(nrep):
+            e2e_step()
+        b.record()
+        barrier()
+        te = torch.tensor([a.elapsed_time(b) / nrep], device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": views * h * w / (float(te.item()) * 1e-3) / 1e6, "unit": "MP/s",
+               "h2d_bytes_per_step": int(h2d * world), "d2h_bytes_per_step": int(d2h * world),
+               "ms_per_step": float(te.item()),
+               "what": "pinned host rays + one subject's primitives + grad_out -> device, per-view expand, op fwd+bwd, "
+                       "view-sum (+all-reduce), rayrgba + reduced gradients -> pinned host"}
+
+    if rank != 0:
+        return
+    peak, peak_src = measured_peaks()
+    fb, bb = algorithmic_bytes(nv, h, w, k, t)
+    fwd_gbs, bwd_gbs = fb / (fwd_ms * 1e-3) / 1e9, bb / (bwd_ms * 1e-3) / 1e9
+    roof_f = {"kernel": "render_forward_kernel", "bound": "hbm", "achieved": fwd_gbs, "peak": peak, "unit": "GB/s",
+              "frac": fwd_gbs / peak, "traffic": None, "ms_per_launch": fwd_ms, "algorithmic_bytes_per_launch": fb,
+              "peak_source": peak_src}
+    roof_b = {"kernel": "render_backward_kernel", "bound": "hbm", "achieved": bwd_gbs, "peak": peak, "unit": "GB/s",
+              "frac": bwd_gbs / peak, "traffic": None, "ms_per_launch": bwd_ms, "algorithmic_bytes_per_launch": bb,
+              "peak_source": peak_src}
+    # traffic (dram bytes per launch) comes from the committed ncu capture of the same kernels, if present
+    tr = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr):
+        with open(tr) as f:
+            tj = json.load(f)
+        for r_ in (roof_f, roof_b):
+            per_view = tj.get(r_["kernel"], {}).get("dram_bytes_per_view")
+            if per_view and (h, w, k, t) == tuple(tj.get("shape", ())):
+                r_["traffic"] = per_view * nv
+    cpu_mps, cpu_sec, cpu_desc = (None, None, None)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu_mps, cpu_sec, cpu_desc = cpu_autograd_sample(side=48, steps=2, warmup=0)
+        cpu = {"value": cpu_mps, "unit": "MP/s", "cores": torch.get_num_threads(), "kind": "port", "sample": cpu_desc,
+               "seconds_per_sample_step": cpu_sec}
+    dominant = roof_b if bwd_ms >= fwd_ms else roof_f
+    line = {
+        "metric": "rendered MP/s (fwd+bwd)", "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C3: %d views %dx%d, K=%d, %d^3 RGBA, dt=1/256, one subject (template materialised per view); "
+                               "%d views per rank" % (views, h, w, k, t, nv),
+                   "parallelism": "views sharded over %d rank(s), 1 NCCL all-reduce of %.1f MB primitive grads per step" % (world, flat.numel() * 4 / 1e6),
+                   "l2": "inputs (%.1f GB template per rank) larger than the 126 MB L2; no explicit flush" % (nv * k * t ** 3 * 16 / 1e9),
+                   "scene": {"alpha_mu": ALPHA_MU, "alpha_sigma": ALPHA_SIGMA, "saturated_ray_frac": sat_frac, "covered_ray_frac": cover}},
+        "roofline": dominant, "roofline_forward": roof_f, "roofline_backward": roof_b,
+        "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+        "gpu_launches": args.steps * (lib.LIB.mvp_forward_launch_count(0) + lib.LIB.mvp_backward_launch_count(lib.FLAG_ACCEL_VALID)),
+        "kernel_ms": {"forward_all_views_per_rank": fwd_ms, "backward_all_views_per_rank": bwd_ms},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--views", type=int, default=VIEWS)
+    ap.add_argument("--height", type=int, default=H)
+    ap.add_argument("--width", type=int, default=W)
+    ap.add_argument("--prims", type=int, default=K)
+    ap.add_argument("--voxels", type=int, default=T)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", rank))))
+    try:
+        run_ours(args, rank, world)
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

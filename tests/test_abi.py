@@ -1,0 +1,117 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol include/*.h declares, validates
+arguments before touching a device, and the Python entry point keeps the reference's exact signature."""
+import ctypes
+import inspect
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+REFERENCE_PARAMS = (  # /root/reference/extensions/mvpraymarch/mvpraymarch.py:295-318
+    ("raypos", inspect.Parameter.empty), ("raydir", inspect.Parameter.empty), ("stepsize", inspect.Parameter.empty),
+    ("tminmax", inspect.Parameter.empty), ("primtransf", inspect.Parameter.empty), ("template", inspect.Parameter.empty),
+    ("warp", inspect.Parameter.empty), ("rayterm", None), ("algo", 0), ("usebvh", "fixedorder"), ("sortprims", False),
+    ("randomorder", False), ("maxhitboxes", 512), ("synchitboxes", True), ("chlast", True), ("fadescale", 8.0),
+    ("fadeexp", 8.0), ("accum", 0), ("termthresh", 0.0), ("griddim", 3), ("blocksize", (8, 16)), ("bwdblocksize", (8, 16)),
+)
+
+
+def test_header_symbols_are_exported():
+    from ava256_b200 import lib
+    hdr = open(os.path.join(ROOT, "include", "mvpraymarch_b200.h")).read()
+    names = re.findall(r"^\s*(?:int|size_t|const char \*)\s*\**\s*(mvp_\w+)\s*\(", hdr, flags=re.M)
+    assert set(names) >= {"mvp_raymarch_forward", "mvp_raymarch_backward", "mvp_build_accel", "mvp_workspace_bytes"}
+    for n in names:
+        assert hasattr(lib.LIB, n), n
+    assert sorted(names) == sorted(lib.EXPORTS)
+    assert lib.LIB.mvp_abi_version() == 1
+
+
+def test_workspace_bytes_and_shape_validation():
+    from ava256_b200 import lib
+    small = lib.workspace_bytes(1, 128, 128, 256, 8, 8, 8)
+    big = lib.workspace_bytes(80, 1024, 667, 16384, 8, 8, 8)
+    assert 0 < small < big < 2 ** 31
+    assert small % 256 == 0
+    bad = lib.Shape(1, 0, 128, 256, 8, 8, 8)
+    assert lib.LIB.mvp_workspace_bytes(ctypes.byref(bad)) == 0
+    with pytest.raises(RuntimeError):
+        lib.workspace_bytes(1, 40000, 128, 256, 8, 8, 8)
+
+
+def test_argument_errors_do_not_need_a_device():
+    from ava256_b200 import lib
+    a = lib.ForwardArgs()
+    a.shape = lib.Shape(1, 8, 8, 4, 2, 2, 2)
+    a.stepsize = 0.1
+    assert lib.LIB.mvp_raymarch_forward(ctypes.byref(a), None) == -1          # MVP_ERR_NULL
+    assert lib.LIB.mvp_raymarch_forward(None, None) == -1
+    dummy = ctypes.c_void_p(256)
+    for f in ("raypos", "raydir", "tminmax", "primpos", "primrot", "primscale", "tplate", "rayrgba", "workspace"):
+        setattr(a, f, dummy)
+    a.workspace_bytes = 16
+    assert lib.LIB.mvp_raymarch_forward(ctypes.byref(a), None) == -4          # MVP_ERR_WORKSPACE
+    a.workspace_bytes = 1 << 30
+    a.stepsize = 0.0
+    assert lib.LIB.mvp_raymarch_forward(ctypes.byref(a), None) == -3          # MVP_ERR_STEPSIZE
+    a.stepsize = float("nan")
+    assert lib.LIB.mvp_raymarch_forward(ctypes.byref(a), None) == -3
+    a.stepsize = 0.1
+    a.shape = lib.Shape(1, 8, 8, 0, 2, 2, 2)
+    assert lib.LIB.mvp_raymarch_forward(ctypes.byref(a), None) == -2          # MVP_ERR_SHAPE
+    a.shape = lib.Shape(1, 8, 8, 4, 2, 2, 2)
+    a.raysat = dummy                                                            # raysat without rayaux
+    assert lib.LIB.mvp_raymarch_forward(ctypes.byref(a), None) == -1
+    b = lib.BackwardArgs()
+    assert lib.LIB.mvp_raymarch_backward(ctypes.byref(b), None) == -1
+    assert b"workspace" in lib.LIB.mvp_error_string(-4)
+    with pytest.raises(RuntimeError):
+        lib.check(-2)
+
+
+def test_python_entry_point_signature_matches_reference():
+    from extensions.mvpraymarch.mvpraymarch import mvpraymarch
+    sig = inspect.signature(mvpraymarch)
+    got = tuple((p.name, p.default) for p in sig.parameters.values())
+    assert got == REFERENCE_PARAMS
+    # models/raymarchers/mvpraymarcher.py:45 filters renderoptions with this attribute
+    assert mvpraymarch.__code__.co_varnames[: len(REFERENCE_PARAMS)] == tuple(n for n, _ in REFERENCE_PARAMS)
+
+
+def test_op_rejects_cpu_tensors_loudly():
+    from extensions.mvpraymarch.mvpraymarch import mvpraymarch
+    from tests.helpers import build_case
+    s, _ = build_case("gradcheck_ragged")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        mvpraymarch(s["raypos"], s["raydir"], s["stepsize"], s["tminmax"], (s["primpos"], s["primrot"], s["primscale"]),
+                    s["template"], None)
+
+
+def test_unsupported_modes_raise():
+    from extensions.mvpraymarch.mvpraymarch import mvpraymarch
+    from tests.helpers import build_case
+    s, _ = build_case("gradcheck_ragged")
+    with pytest.raises(NotImplementedError):
+        mvpraymarch(s["raypos"], s["raydir"], s["stepsize"], s["tminmax"], (s["primpos"], s["primrot"], s["primscale"]),
+                    s["template"], None, algo=1)
+    with pytest.raises(NotImplementedError):
+        mvpraymarch(s["raypos"], s["raydir"], s["stepsize"], s["tminmax"], (s["primpos"], s["primrot"], s["primscale"]),
+                    s["template"], None, usebvh=True)
+
+
+def test_scene_generator_is_deterministic_and_pinhole():
+    from ava256_b200 import scene
+    a = scene.make_scene(2, 32, 20, 16, 4)
+    b = scene.make_scene(2, 32, 20, 16, 4)
+    for k in a:
+        if torch.is_tensor(a[k]):
+            assert torch.equal(a[k], b[k]), k
+    assert torch.allclose(a["raydir"].norm(dim=-1), torch.ones(2, 32, 20), atol=1e-5)
+    assert (a["raypos"][0] == a["raypos"][0, 0, 0]).all()
+    # rotations orthonormal, scales positive
+    r = a["primrot"][0]
+    assert torch.allclose(r @ r.transpose(1, 2), torch.eye(3).expand_as(r), atol=1e-4)
+    assert (a["primscale"] > 0).all() and (a["template"] >= 0).all()

@@ -32,6 +32,14 @@ VIEWS, H, W, K, T = 80, 1024, 667, 16384, 8
 ALPHA_MU, ALPHA_SIGMA = 3.0, 3.0
 
 
+_T0 = time.time()
+
+
+def log(msg):
+    """progress to stderr (stdout carries only the JSON line)"""
+    print("[bench %7.1fs] %s" % (time.time() - _T0, msg), file=sys.stderr, flush=True)
+
+
 def algorithmic_bytes(n_views, h, w, k, t):
     """compulsory traffic per pass (every input read once, every output written once)."""
     tpl = k * t ** 3 * 16
@@ -151,6 +159,7 @@ def run_ours(args, rank, world):
     nv = views // world                      # contiguous block of views per rank
     s = scene.make_scene(nv, h, w, k, t, seed=1112, view_offset=rank * nv, device=dev, alpha_mu=ALPHA_MU, alpha_sigma=ALPHA_SIGMA)
     stepsize = s["stepsize"]
+    log("scene ready: %d views/rank %dx%d K=%d T=%d" % (nv, h, w, k, t))
     gen = torch.Generator(device=dev).manual_seed(1112 + rank)
     grad_out = torch.randn(nv, h, w, 4, device=dev, generator=gen)
     leaves = [s[n].requires_grad_(True) for n in ("primpos", "primrot", "primscale", "template")]
@@ -170,8 +179,10 @@ def run_ours(args, rank, world):
         parallel.reduce_primitive_grads(leaves[3].grad, leaves[0].grad, leaves[1].grad, leaves[2].grad, flat=flat)
         return out
 
-    for _ in range(args.warmup):
+    for i in range(args.warmup):
         out = step()
+        torch.cuda.synchronize()
+        log("warmup step %d done" % i)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -184,6 +195,7 @@ def run_ours(args, rank, world):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    log("timed region: %.1f ms for %d steps" % (ms, args.steps))
     clocks = sampler.stop() if rank == 0 else None
     tms = torch.tensor([ms], device=dev)
     if world > 1:
@@ -235,6 +247,7 @@ def run_ours(args, rank, world):
     fwd_ms = time_kernel(lambda: lib.check(lib.LIB.mvp_raymarch_forward(ctypes.byref(fa), stream)), reps)
     bwd_ms = time_kernel(lambda: lib.check(lib.LIB.mvp_raymarch_backward(ctypes.byref(ba), stream)), reps)
     del gs, ws
+    log("kernel-only: fwd %.2f ms, bwd %.2f ms per launch (%d views)" % (fwd_ms, bwd_ms, nv))
 
     # ---- end-to-end through the public op with HOST buffers (pinned): H2D of the step's inputs, D2H of the results ----
     e2e = None
@@ -261,8 +274,10 @@ def run_ours(args, rank, world):
             host_out.copy_(o_.detach(), non_blocking=True)
             host_flat.copy_(flat, non_blocking=True)
 
+        log("e2e buffers pinned")
         e2e_step()
         barrier()
+        log("e2e warm-up step done")
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         nrep = max(1, min(args.steps, 3))
         a.record()
@@ -279,6 +294,7 @@ def run_ours(args, rank, world):
                "what": "pinned host rays + one subject's primitives + grad_out -> device, per-view expand, op fwd+bwd, "
                        "view-sum (+all-reduce), rayrgba + reduced gradients -> pinned host"}
 
+    log("e2e done")
     if rank != 0:
         return
     peak, peak_src = measured_peaks()

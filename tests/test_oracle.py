@@ -73,3 +73,33 @@ def test_oracle_aabb_contains_corners():
             p = rot[k] @ (sg / sc[k]) + pos[k]
             assert (p >= bb[K - 1 + k, 0] - 1e-12).all() and (p <= bb[K - 1 + k, 1] + 1e-12).all()
     assert (bb[0, 0] <= bb[K - 1:, 0].min(0) + 1e-12).all() and (bb[0, 1] >= bb[K - 1:, 1].max(0) - 1e-12).all()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Pin against the REFERENCE ITSELF: tests/golden/*.npz are outputs of the unmodified reference CUDA extension
+# (compiled for sm_100 by oracle/build_ref.py, run on a B200 by tests/golden/make_golden.py).
+# ---------------------------------------------------------------------------------------------------------
+import os  # noqa: E402
+
+import pytest  # noqa: E402
+
+from tests.helpers import CASES, build_case  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_oracle_f32_matches_reference_cuda_golden(name):
+    path = os.path.join(GOLDEN, name + ".npz")
+    assert os.path.exists(path), "golden vector missing: run tests/golden/make_golden.py on the GPU box"
+    gold = np.load(path)
+    s, grad = build_case(name)
+    a, kw = scene_args_np(s)
+    rgba, raysat = oracle.forward(*a, **kw)
+    assert relerr(rgba, gold["rayrgba"]) < 5e-6
+    # same rays saturate, same saturation colour
+    assert np.array_equal(raysat[..., 0] > -1, gold["raysat"][..., 0] > -1)
+    assert relerr(raysat, gold["raysat"]) < 5e-6
+    g = oracle.backward(*a, grad.numpy(), gold["raysat"], **kw)
+    for nm, x in zip(("primpos", "primrot", "primscale", "template"), g):
+        assert relerr(x, gold["grad_" + nm]) < 2e-5, nm

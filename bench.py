@@ -103,12 +103,13 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------
 # reference arm: the reference's own CPU autograd path (mvpraymarch.py:567-633 restated in oracle/torch_ref.py)
 # ----------------------------------------------------------------------------------------------------------------
-def cpu_autograd_sample(side=48, k=256, t=8, steps=1, warmup=0):
+def cpu_autograd_sample(side=96, k=64, t=8, steps=1, warmup=0):
     """Bounded sample of the same kind of workload (head scene, dome camera) on the host cores.
     Returns (MP/s fwd+bwd, seconds per step, description)."""
     from ava256_b200 import scene
     from oracle import torch_ref
-    torch.set_num_threads(os.cpu_count() or 1)
+    # the loop is ~10^4 small ATen ops: beyond ~16 threads the fork/join cost dominates and it gets slower
+    torch.set_num_threads(min(os.cpu_count() or 1, 16))
     s = scene.make_scene(1, side, side * 2 // 3, k, t, alpha_mu=ALPHA_MU, alpha_sigma=ALPHA_SIGMA)
     hh, ww = s["raypos"].shape[1:3]
     stepsize = 2.0 / 16.0          # SURVEY 8d: keeps the autograd graph at ~16 steps
@@ -318,7 +319,7 @@ def run_ours(args, rank, world):
     cpu_mps, cpu_sec, cpu_desc = (None, None, None)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cpu_mps, cpu_sec, cpu_desc = cpu_autograd_sample(side=48, steps=2, warmup=0)
+        cpu_mps, cpu_sec, cpu_desc = cpu_autograd_sample(steps=1, warmup=0)
         cpu = {"value": cpu_mps, "unit": "MP/s", "cores": torch.get_num_threads(), "kind": "port", "sample": cpu_desc,
                "seconds_per_sample_step": cpu_sec}
     dominant = roof_b if bwd_ms >= fwd_ms else roof_f

@@ -373,10 +373,15 @@ struct Params {
     float *g_primpos, *g_primrot, *g_primscale, *g_tplate;
 };
 
-// Builds the warp's slab list (rank order, <= 512 entries, step intervals in sweep units) and each lane's rtminmax.
-// s_k/s_lo/s_hi: this warp's shared arrays.
-__device__ __forceinline__ void build_tile_list(const Params &p, float rdt, int n, int tx, int ty, int lane, TileCtx &c,
-                                                int *s_k, int *s_lo, int *s_hi) {
+// Builds the warp's slab list (rank order, <= 512 entries) and each lane's rtminmax; then, with every lane's
+// first step j0 known, a second pass over the (short) list converts each slab's per-lane [t_enter, t_exit] into a
+// warp step interval in units of "steps since the lane's own first step" (sweep m = j - j0).  Aligning lanes on
+// their own first hit -- which is also what the reference's lock-step loop does (mvpraymarch_subset_kernel.h:63-76)
+// -- keeps the 32 rays of a tile in phase on a tilted surface, so more lanes are inside a slab at the same time.
+// Returns j0 (first step index) and the lattice start state of the lane.
+__device__ __forceinline__ int build_tile_list(const Params &p, float rdt, int n, int tx, int ty, int lane, TileCtx &c,
+                                                int *s_k, int *s_lo, int *s_hi, float &t, float &x, float &y, float &z,
+                                                float &r1e) {
     const int px = tx * kTileW + (lane & 7), py = ty * kTileH + (lane >> 3);
     c.inimg = (px < p.W) && (py < p.H);
     const int cx = min(px, p.W - 1), cy = min(py, p.H - 1);
@@ -386,12 +391,6 @@ __device__ __forceinline__ void build_tile_list(const Params &p, float rdt, int 
     const float2 tmm = __ldg(reinterpret_cast<const float2 *>(p.tminmax) + r);
     c.ray.tmin = tmm.x; c.ray.tmax = tmm.y;
     c.rt0 = CUDART_INF_F; c.rt1 = -CUDART_INF_F;
-
-    // warp-common sweep origin: lanes are aligned in depth, lane step j = m + off
-    float tref = c.inimg ? c.ray.tmin : CUDART_INF_F;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) tref = fminf(tref, __shfl_xor_sync(0xffffffffu, tref, o));
-    c.off = clamp_step(ceilf((tref - c.ray.tmin) * rdt));
 
     const float4 *packn = p.pack + (size_t)n * p.K * 4;
     const int cnt = p.rowcnt[(size_t)n * p.R + ty];
@@ -429,18 +428,11 @@ __device__ __forceinline__ void build_tile_list(const Params &p, float rdt, int 
             const int kk = __shfl_sync(0xffffffffu, k, b);
             const Prim q = load_prim(packn, kk);
             float lo, hi;
-            bool hit = slab_test(q, c.ray, lo, hi) && c.inimg;
-            int jlo = kBig, jhi = -kBig;
-            if (hit) {
-                c.rt0 = fminf(c.rt0, lo); c.rt1 = fmaxf(c.rt1, hi);
-                jlo = clamp_step(floorf((lo - c.ray.tmin) * rdt) - 1.f) - c.off;
-                jhi = clamp_step(floorf((hi - c.ray.tmin) * rdt) + 2.f) - c.off;
-            }
-            const unsigned any = __ballot_sync(0xffffffffu, hit);
-            if (any) {
-                const int wlo = __reduce_min_sync(0xffffffffu, jlo), whi = __reduce_max_sync(0xffffffffu, jhi);
+            const bool hit = slab_test(q, c.ray, lo, hi) && c.inimg;
+            if (hit) { c.rt0 = fminf(c.rt0, lo); c.rt1 = fmaxf(c.rt1, hi); }
+            if (__any_sync(0xffffffffu, hit)) {
                 if (nl < kMaxHit) {
-                    if (lane == 0) { s_k[nl] = kk; s_lo[nl] = wlo; s_hi[nl] = whi; }
+                    if (lane == 0) s_k[nl] = kk;
                     ++nl;
                 }
             }
@@ -448,61 +440,86 @@ __device__ __forceinline__ void build_tile_list(const Params &p, float rdt, int 
     }
     __syncwarp();
     c.nl = nl;
-}
-
-// Lattice snap (mvpraymarch_subset_kernel.h:63-72 as compiled).  Returns the first step index j0.
-__device__ __forceinline__ int lattice_start(const TileCtx &c, float dt, float rdt, float &t, float &x, float &y, float &z, float &r1e) {
+    // lattice snap (mvpraymarch_subset_kernel.h:63-72 as compiled)
     const float r0 = fmaxf(c.rt0, c.ray.tmin), r1 = fminf(c.rt1, c.ray.tmax);
     const float xs = __fmaf_rn(c.ray.dx, c.ray.tmin, c.ray.ox), ys = __fmaf_rn(c.ray.dy, c.ray.tmin, c.ray.oy),
                 zs = __fmaf_rn(c.ray.dz, c.ray.tmin, c.ray.oz);
     const int incs = __float2int_rd(__fmul_rn(__fadd_rn(r0, -c.ray.tmin), rdt));
     const float fi = (float)incs;
-    t = __fmaf_rn(fi, dt, c.ray.tmin);
-    x = __fmaf_rn(__fmul_rn(c.ray.dx, fi), dt, xs);
-    y = __fmaf_rn(__fmul_rn(c.ray.dy, fi), dt, ys);
-    z = __fmaf_rn(__fmul_rn(c.ray.dz, fi), dt, zs);
+    t = __fmaf_rn(fi, p.dt, c.ray.tmin);
+    x = __fmaf_rn(__fmul_rn(c.ray.dx, fi), p.dt, xs);
+    y = __fmaf_rn(__fmul_rn(c.ray.dy, fi), p.dt, ys);
+    z = __fmaf_rn(__fmul_rn(c.ray.dz, fi), p.dt, zs);
     r1e = __fadd_rn(r1, 9.9999997473787516356e-06f);
+    c.off = incs;
+    // pass 2: warp step intervals relative to each lane's own first step
+    for (int slot = 0; slot < nl; ++slot) {
+        const Prim q = load_prim(packn, s_k[slot]);
+        float lo, hi;
+        const bool hit = slab_test(q, c.ray, lo, hi) && c.inimg;
+        int jlo = kBig, jhi = -kBig;
+        if (hit) {
+            jlo = clamp_step(floorf((lo - c.ray.tmin) * rdt) - 1.f - fi);
+            jhi = clamp_step(floorf((hi - c.ray.tmin) * rdt) + 2.f - fi);
+        }
+        const int wlo = __reduce_min_sync(0xffffffffu, jlo), whi = __reduce_max_sync(0xffffffffu, jhi);
+        if (lane == 0) { s_lo[slot] = wlo; s_hi[slot] = whi; }
+    }
+    __syncwarp();
     return incs;
 }
 
 struct Sample {
     float4 s;           // rgb, alpha*fade
     float fade;
-    float wgt[8];
-    int idx[8];         // voxel index or -1
-    float x0, x1, y0, y1, z0, z1;
+    float x0, x1, y0, y1, z0, z1;   // trilinear factors
+    int base;                        // voxel index of the (clamped) lower corner
+    bool ex, ey, ez;                 // cell was clamped on this axis (index coordinate exactly T-1)
 };
 
-// primsampler.h:44-66 + utils.h:408-502
-template <bool kKeep>
+// primsampler.h:44-66 + utils.h:408-502.  T > 0: cubic slab with compile-time strides; T == 0: runtime dims.
+// The reference tests every corner against the slab bounds; for a valid sample (|y| < 1) the only corner that can
+// fall outside is ix+1 == TW when fx rounds to exactly TW-1 (weight exactly 0), so the cell is clamped to TW-2 and
+// the weights keep the un-clamped fractions: the same products are formed and the zero-weight term adds 0.
+template <int T, bool kKeep>
 __device__ __forceinline__ float4 sample_slab(const float4 *__restrict__ slab, float y0, float y1, float y2, int TD, int TH, int TW,
                                               float fadescale, float fadeexp, Sample *keep) {
+    const int td = T > 0 ? T : TD, th = T > 0 ? T : TH, tw = T > 0 ? T : TW;
     const float fade = __expf(-fadescale * (__powf(fabsf(y0), fadeexp) + __powf(fabsf(y1), fadeexp) + __powf(fabsf(y2), fadeexp)));
-    const float fx = fmaxf(-100.f, fminf(100.f, (y0 + 1.f) * 0.5f)) * (float)(TW - 1);
-    const float fy = fmaxf(-100.f, fminf(100.f, (y1 + 1.f) * 0.5f)) * (float)(TH - 1);
-    const float fz = fmaxf(-100.f, fminf(100.f, (y2 + 1.f) * 0.5f)) * (float)(TD - 1);
+    const float fx = fmaxf(-100.f, fminf(100.f, (y0 + 1.f) * 0.5f)) * (float)(tw - 1);
+    const float fy = fmaxf(-100.f, fminf(100.f, (y1 + 1.f) * 0.5f)) * (float)(th - 1);
+    const float fz = fmaxf(-100.f, fminf(100.f, (y2 + 1.f) * 0.5f)) * (float)(td - 1);
     const int ix = __float2int_rd(fx), iy = __float2int_rd(fy), iz = __float2int_rd(fz);
     const float ax0 = fx - (float)ix, ax1 = (float)(ix + 1) - fx;
     const float ay0 = fy - (float)iy, ay1 = (float)(iy + 1) - fy;
     const float az0 = fz - (float)iz, az1 = (float)(iz + 1) - fz;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int cx = ix + (j & 1), cy = iy + ((j >> 1) & 1), cz = iz + ((j >> 2) & 1);
-        const bool inb = (cx >= 0) && (cx < TW) && (cy >= 0) && (cy < TH) && (cz >= 0) && (cz < TD);
-        const float w = ((j & 1) ? ax0 : ax1) * ((j & 2) ? ay0 : ay1) * ((j & 4) ? az0 : az1);
-        const int id = (cz * TH + cy) * TW + cx;
-        if (inb) {
-            const float4 v = __ldg(slab + id);
-            acc.x = __fmaf_rn(w, v.x, acc.x); acc.y = __fmaf_rn(w, v.y, acc.y);
-            acc.z = __fmaf_rn(w, v.z, acc.z); acc.w = __fmaf_rn(w, v.w, acc.w);
-        }
-        if (kKeep) { keep->wgt[j] = w; keep->idx[j] = inb ? id : -1; }
-    }
+    // clamp the cell (degenerate 1-voxel axes: both corners are voxel 0, weights sum to 1)
+    const int cx = max(min(ix, tw - 2), 0), cy = max(min(iy, th - 2), 0), cz = max(min(iz, td - 2), 0);
+    const float bx0 = (ix > cx) ? 1.f : ax0, bx1 = (ix > cx) ? 0.f : ax1;
+    const float by0 = (iy > cy) ? 1.f : ay0, by1 = (iy > cy) ? 0.f : ay1;
+    const float bz0 = (iz > cz) ? 1.f : az0, bz1 = (iz > cz) ? 0.f : az1;
+    const int sx = tw > 1 ? 1 : 0, sy = th > 1 ? tw : 0, sz = td > 1 ? th * tw : 0;
+    const int base = (cz * th + cy) * tw + cx;
+    const float4 *pc = slab + base;
+    const float4 v000 = __ldg(pc), v001 = __ldg(pc + sx), v010 = __ldg(pc + sy), v011 = __ldg(pc + sy + sx);
+    const float4 v100 = __ldg(pc + sz), v101 = __ldg(pc + sz + sx), v110 = __ldg(pc + sz + sy), v111 = __ldg(pc + sz + sy + sx);
+    // (wx * wy) * wz, left-associated like the reference; corner order tnw,tne,tsw,tse,bnw,bne,bsw,bse
+    const float w00 = bx1 * by1, w01 = bx0 * by1, w10 = bx1 * by0, w11 = bx0 * by0;
+    float4 acc;
+    float w;
+    w = w00 * bz1; acc.x = w * v000.x; acc.y = w * v000.y; acc.z = w * v000.z; acc.w = w * v000.w;
+    w = w01 * bz1; acc.x = __fmaf_rn(w, v001.x, acc.x); acc.y = __fmaf_rn(w, v001.y, acc.y); acc.z = __fmaf_rn(w, v001.z, acc.z); acc.w = __fmaf_rn(w, v001.w, acc.w);
+    w = w10 * bz1; acc.x = __fmaf_rn(w, v010.x, acc.x); acc.y = __fmaf_rn(w, v010.y, acc.y); acc.z = __fmaf_rn(w, v010.z, acc.z); acc.w = __fmaf_rn(w, v010.w, acc.w);
+    w = w11 * bz1; acc.x = __fmaf_rn(w, v011.x, acc.x); acc.y = __fmaf_rn(w, v011.y, acc.y); acc.z = __fmaf_rn(w, v011.z, acc.z); acc.w = __fmaf_rn(w, v011.w, acc.w);
+    w = w00 * bz0; acc.x = __fmaf_rn(w, v100.x, acc.x); acc.y = __fmaf_rn(w, v100.y, acc.y); acc.z = __fmaf_rn(w, v100.z, acc.z); acc.w = __fmaf_rn(w, v100.w, acc.w);
+    w = w01 * bz0; acc.x = __fmaf_rn(w, v101.x, acc.x); acc.y = __fmaf_rn(w, v101.y, acc.y); acc.z = __fmaf_rn(w, v101.z, acc.z); acc.w = __fmaf_rn(w, v101.w, acc.w);
+    w = w10 * bz0; acc.x = __fmaf_rn(w, v110.x, acc.x); acc.y = __fmaf_rn(w, v110.y, acc.y); acc.z = __fmaf_rn(w, v110.z, acc.z); acc.w = __fmaf_rn(w, v110.w, acc.w);
+    w = w11 * bz0; acc.x = __fmaf_rn(w, v111.x, acc.x); acc.y = __fmaf_rn(w, v111.y, acc.y); acc.z = __fmaf_rn(w, v111.z, acc.z); acc.w = __fmaf_rn(w, v111.w, acc.w);
     acc.w *= fade;
     if (kKeep) {
-        keep->s = acc; keep->fade = fade;
-        keep->x0 = ax0; keep->x1 = ax1; keep->y0 = ay0; keep->y1 = ay1; keep->z0 = az0; keep->z1 = az1;
+        keep->s = acc; keep->fade = fade; keep->base = base;
+        keep->x0 = bx0; keep->x1 = bx1; keep->y0 = by0; keep->y1 = by1; keep->z0 = bz0; keep->z1 = bz1;
+        keep->ex = ix > cx; keep->ey = iy > cy; keep->ez = iz > cz;
     }
     return acc;
 }
@@ -510,28 +527,25 @@ __device__ __forceinline__ float4 sample_slab(const float4 *__restrict__ slab, f
 // ------------------------------------------------------------------------------------------------------
 // 4. forward
 // ------------------------------------------------------------------------------------------------------
-template <bool kGrad>
-__global__ void __launch_bounds__(kWarps * 32) render_forward_kernel(const Params p) {
+template <int T, bool kGrad>
+__global__ void __launch_bounds__(kWarps * 32, 8) render_forward_kernel(const Params p) {
     __shared__ int s_k[kWarps][kMaxHit];
     __shared__ int s_lo[kWarps][kMaxHit];
     __shared__ int s_hi[kWarps][kMaxHit];
-    __shared__ unsigned s_mask[kWarps][kMaxHit / 32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tx = blockIdx.x * 2 + (warp & 1), ty = blockIdx.y * 2 + (warp >> 1), n = blockIdx.z;
     if (tx >= p.TXn || ty >= p.TYn) return;   // warps are independent: no CTA-wide barrier below
 
     const float rdt = fast_rcp(p.dt);   // MUFU.RCP(stepsize), as the reference (SASS 0x16c0)
     TileCtx c;
-    build_tile_list(p, rdt, n, tx, ty, lane, c, s_k[warp], s_lo[warp], s_hi[warp]);
+    float t, x, y, z, r1e;
+    const int j0 = build_tile_list(p, rdt, n, tx, ty, lane, c, s_k[warp], s_lo[warp], s_hi[warp], t, x, y, z, r1e);
 
     const int px = tx * kTileW + (lane & 7), py = ty * kTileH + (lane >> 3);
     const size_t r = ((size_t)n * p.H + min(py, p.H - 1)) * p.W + min(px, p.W - 1);
 
-    float t, x, y, z, r1e;
     const bool hashit = c.inimg && (c.rt0 <= c.rt1);
-    int j0 = lattice_start(c, p.dt, rdt, t, x, y, z, r1e);
     bool done = !hashit || (t > r1e);
-    int ms = done ? kBig : (j0 - c.off);      // sweep index at which this lane starts
 
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     float sat0 = -1.f, sat1 = -1.f, sat2 = -1.f;
@@ -544,70 +558,64 @@ __global__ void __launch_bounds__(kWarps * 32) render_forward_kernel(const Param
     const float4 *packn = p.pack + (size_t)n * p.K * 4;
     const size_t slabsz = (size_t)p.TD * p.TH * p.TW;
     const float4 *tpn = reinterpret_cast<const float4 *>(p.tplate) + (size_t)n * p.K * slabsz;
+    const int kstart = dfs_kstart(p.K);
 
-    int m = __reduce_min_sync(0xffffffffu, ms);
-    if (nl > 0 && m < kBig) {
-        int mbase = m - kMaskSteps;   // force a rebuild on entry
-        unsigned anyactive = 0;
-        while (true) {
-            if (m - mbase >= kMaskSteps) {
-                mbase = m;
-                anyactive = 0;
-                for (int w = 0; w < nwords; ++w) {
+    if (nl > 0 && !__all_sync(0xffffffffu, done)) {
+        // each lane keeps the interval of list slots `lane` and `lane + 32` in registers (lists are rarely longer)
+        int lo0 = kBig, hi0 = -kBig, lo1 = kBig, hi1 = -kBig;
+        if (lane < nl) { lo0 = s_lo[warp][lane]; hi0 = s_hi[warp][lane]; }
+        if (lane + 32 < nl) { lo1 = s_lo[warp][lane + 32]; hi1 = s_hi[warp][lane + 32]; }
+        for (int m = 0;; ++m) {
+            for (int w = 0; w < nwords; ++w) {
+                bool a;
+                if (w == 0) a = (lo0 <= m) && (m <= hi0);
+                else if (w == 1) a = (lo1 <= m) && (m <= hi1);
+                else {
                     const int slot = w * 32 + lane;
-                    const bool a = (slot < nl) && (s_lo[warp][slot] <= m + (kMaskSteps - 1)) && (s_hi[warp][slot] >= m);
-                    const unsigned word = __ballot_sync(0xffffffffu, a);
-                    if (lane == 0) s_mask[warp][w] = word;
-                    anyactive |= word;
+                    a = (slot < nl) && (s_lo[warp][slot] <= m) && (m <= s_hi[warp][slot]);
                 }
-                __syncwarp();
-            }
-            const bool on = !done && (m >= ms);
-            if (anyactive) {
-                for (int w = 0; w < nwords; ++w) {
-                    unsigned word = s_mask[warp][w];
-                    while (word) {
-                        const int b = __ffs(word) - 1;
-                        word &= word - 1;
-                        const int slot = w * 32 + b;
-                        if (s_lo[warp][slot] > m || s_hi[warp][slot] < m) continue;
-                        const int k = s_k[warp][slot];
-                        const Prim q = load_prim(packn, k);
-                        // primtransf.h:119-132
-                        const float xm = x - q.px, ym = y - q.py, zm = z - q.pz;
-                        const float y0 = __fmul_rn(q.sx, rowdot(q.r00, xm, q.r10, ym, q.r20, zm));
-                        const float y1 = __fmul_rn(q.sy, rowdot(q.r01, xm, q.r11, ym, q.r21, zm));
-                        const float y2 = __fmul_rn(q.sz, rowdot(q.r02, xm, q.r12, ym, q.r22, zm));
-                        const bool valid = (fabsf(y0) < 1.f) && (fabsf(y1) < 1.f) && (fabsf(y2) < 1.f);
-                        if (valid && on && !sat && (t < r1e)) {
-                            const float4 s = sample_slab<false>(tpn + (size_t)k * slabsz, y0, y1, y2, p.TD, p.TH, p.TW,
-                                                                p.fadescale, p.fadeexp, nullptr);
-                            // primaccum.h:63-79
-                            const float newa = __fmaf_rn(s.w, p.dt, acc.w);
-                            const float contrib = __fadd_rn(fminf(newa, 1.f), -acc.w);
-                            if (newa >= 1.f) {
-                                sat0 = s.x; sat1 = s.y; sat2 = s.z;
-                                sat = true;
-                                if (kGrad) {
-                                    jsat = m + c.off;
-                                    int rk = k - dfs_kstart(p.K); if (rk < 0) rk += p.K;
-                                    ranksat = rk;
-                                    abefore = acc.w;
-                                }
+                unsigned word = __ballot_sync(0xffffffffu, a);
+                while (word) {
+                    const int b = __ffs(word) - 1;
+                    word &= word - 1;
+                    const int k = s_k[warp][w * 32 + b];
+                    const Prim q = load_prim(packn, k);
+                    // primtransf.h:119-132
+                    const float xm = x - q.px, ym = y - q.py, zm = z - q.pz;
+                    const float y0 = __fmul_rn(q.sx, rowdot(q.r00, xm, q.r10, ym, q.r20, zm));
+                    const float y1 = __fmul_rn(q.sy, rowdot(q.r01, xm, q.r11, ym, q.r21, zm));
+                    const float y2 = __fmul_rn(q.sz, rowdot(q.r02, xm, q.r12, ym, q.r22, zm));
+                    const bool valid = (fabsf(y0) < 1.f) && (fabsf(y1) < 1.f) && (fabsf(y2) < 1.f);
+                    if (valid && !done && (t < r1e)) {
+                        const float4 s = sample_slab<T, false>(tpn + (size_t)k * slabsz, y0, y1, y2, p.TD, p.TH, p.TW,
+                                                               p.fadescale, p.fadeexp, nullptr);
+                        // primaccum.h:63-79
+                        const float newa = __fmaf_rn(s.w, p.dt, acc.w);
+                        const float contrib = __fadd_rn(fminf(newa, 1.f), -acc.w);
+                        if (newa >= 1.f) {
+                            sat0 = s.x; sat1 = s.y; sat2 = s.z;
+                            sat = true;
+                            done = true;
+                            if (kGrad) {
+                                jsat = m + j0;
+                                int rk = k - kstart; if (rk < 0) rk += p.K;
+                                ranksat = rk;
+                                abefore = acc.w;
                             }
-                            acc.x = __fmaf_rn(contrib, s.x, acc.x); acc.y = __fmaf_rn(contrib, s.y, acc.y);
-                            acc.z = __fmaf_rn(contrib, s.z, acc.z); acc.w = __fadd_rn(acc.w, contrib);
                         }
+                        acc.x = __fmaf_rn(contrib, s.x, acc.x); acc.y = __fmaf_rn(contrib, s.y, acc.y);
+                        acc.z = __fmaf_rn(contrib, s.z, acc.z); acc.w = __fadd_rn(acc.w, contrib);
                     }
                 }
             }
-            if (on) {
-                if (kGrad && (t < r1e)) jlast = m + c.off;
+            if (!done) {
+                if (kGrad && (t < r1e)) jlast = m + j0;
                 t = __fadd_rn(t, p.dt);
                 x = __fmaf_rn(c.ray.dx, p.dt, x); y = __fmaf_rn(c.ray.dy, p.dt, y); z = __fmaf_rn(c.ray.dz, p.dt, z);
-                done = (t > r1e) || sat;
+                done = (t > r1e);
+            } else if (kGrad && sat && jlast < jsat) {
+                jlast = jsat;   // the saturating step itself was marched
             }
-            ++m;
             if (__all_sync(0xffffffffu, done)) break;
         }
     }
@@ -627,7 +635,8 @@ __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-__global__ void __launch_bounds__(kWarps * 32) render_backward_kernel(const Params p) {
+template <int T>
+__global__ void __launch_bounds__(kWarps * 32, 4) render_backward_kernel(const Params p) {
     __shared__ int s_k[kWarps][kMaxHit];
     __shared__ int s_lo[kWarps][kMaxHit];
     __shared__ int s_hi[kWarps][kMaxHit];
@@ -635,55 +644,55 @@ __global__ void __launch_bounds__(kWarps * 32) render_backward_kernel(const Para
     const int tx = blockIdx.x * 2 + (warp & 1), ty = blockIdx.y * 2 + (warp >> 1), n = blockIdx.z;
     if (tx >= p.TXn || ty >= p.TYn) return;
 
-    const float rdt = fast_rcp(p.dt);   // MUFU.RCP(stepsize), as the reference (SASS 0x16c0)
+    const float rdt = fast_rcp(p.dt);
     TileCtx c;
-    build_tile_list(p, rdt, n, tx, ty, lane, c, s_k[warp], s_lo[warp], s_hi[warp]);
+    float t0, xb, yb, zb, r1e;   // xb = position at sweep step mcur (starts at the lane's own first step)
+    const int j0 = build_tile_list(p, rdt, n, tx, ty, lane, c, s_k[warp], s_lo[warp], s_hi[warp], t0, xb, yb, zb, r1e);
     const int nl = c.nl;
     if (nl == 0) return;
 
     const int px = tx * kTileW + (lane & 7), py = ty * kTileH + (lane >> 3);
     const size_t r = ((size_t)n * p.H + min(py, p.H - 1)) * p.W + min(px, p.W - 1);
 
-    float t0, xs, ys, zs, r1e;
     const bool hashit = c.inimg && (c.rt0 <= c.rt1);
-    const int j0 = lattice_start(c, p.dt, rdt, t0, xs, ys, zs, r1e);   // xs = position at step j0
     const float4 dL = __ldg(reinterpret_cast<const float4 *>(p.grad_rayrgba) + r);
     const float rs0 = __ldg(p.raysat_in + r * 3 + 0), rs1 = __ldg(p.raysat_in + r * 3 + 1), rs2 = __ldg(p.raysat_in + r * 3 + 2);
     const int4 aux = __ldg(p.rayaux_in + r);
-    const int jsat = aux.x, ranksat = aux.y, jlast = hashit ? aux.w : (j0 - 1);
+    const int msat = aux.x == 0x7fffffff ? 0x7fffffff : aux.x - j0;   // in sweep units
+    const int ranksat = aux.y;
     const float abefore = __int_as_float(aux.z);
     const bool hassat = rs0 > -1.f;
     const float sr = hassat ? rs0 : 0.f, sg = hassat ? rs1 : 0.f, sb = hassat ? rs2 : 0.f, sa = hassat ? 1.f : 0.f;
 
-    // lane's live sweep range
-    const int mfirst = hashit ? (j0 - c.off) : kBig;
-    const int mlast = hashit ? (min(jlast, jsat) - c.off) : -kBig;
-    const int wfirst = __reduce_min_sync(0xffffffffu, mfirst), wlast = __reduce_max_sync(0xffffffffu, mlast);
-    if (wfirst > wlast) return;
+    // lane's live sweep range [0, mlast]
+    const int mlast = hashit ? (min(aux.w - j0, msat)) : -1;
+    const int wlast = __reduce_max_sync(0xffffffffu, mlast);
+    if (wlast < 0) return;
 
     const float4 *packn = p.pack + (size_t)n * p.K * 4;
     const size_t slabsz = (size_t)p.TD * p.TH * p.TW;
     const float4 *tpn = reinterpret_cast<const float4 *>(p.tplate) + (size_t)n * p.K * slabsz;
     float *gtn = p.g_tplate + (size_t)n * p.K * slabsz * 4;
     float *gpn = p.g_primpos + (size_t)n * p.K * 3, *grn = p.g_primrot + (size_t)n * p.K * 9, *gsn = p.g_primscale + (size_t)n * p.K * 3;
-    const float gmx = (float)(p.TW - 1) * 0.5f, gmy = (float)(p.TH - 1) * 0.5f, gmz = (float)(p.TD - 1) * 0.5f;
+    const int td = T > 0 ? T : p.TD, th = T > 0 ? T : p.TH, tw = T > 0 ? T : p.TW;
+    const float gmx = (float)(tw - 1) * 0.5f, gmy = (float)(th - 1) * 0.5f, gmz = (float)(td - 1) * 0.5f;
+    const int sx = tw > 1 ? 1 : 0, sy = th > 1 ? tw : 0, sz = td > 1 ? th * tw : 0;
     const int kstart = dfs_kstart(p.K);
 
     // Slabs are processed in the order of their first sweep step, 16-step chunk by chunk, so that each lane's
     // position can be carried forward with the SAME fma sequence the forward kernel executed (bit-identical sample
     // positions: the trilinear position gradient is discontinuous across voxel cells, so this matters).
-    float xb = xs, yb = ys, zb = zs;       // position at sweep step max(mcur, mfirst)
-    int mcur = wfirst;
+    int mcur = 0;
     const int nwords = (nl + 31) >> 5;
-    for (int cs = wfirst; cs <= wlast; cs += kMaskSteps) {
+    for (int cs = 0; cs <= wlast; cs += kMaskSteps) {
         for (; mcur < cs; ++mcur) {
-            if (mcur >= mfirst) { xb = __fmaf_rn(c.ray.dx, p.dt, xb); yb = __fmaf_rn(c.ray.dy, p.dt, yb); zb = __fmaf_rn(c.ray.dz, p.dt, zb); }
+            xb = __fmaf_rn(c.ray.dx, p.dt, xb); yb = __fmaf_rn(c.ray.dy, p.dt, yb); zb = __fmaf_rn(c.ray.dz, p.dt, zb);
         }
         for (int w = 0; w < nwords; ++w) {
             const int myslot = w * 32 + lane;
             bool pick = false;
             if (myslot < nl) {
-                const int a0 = max(s_lo[warp][myslot], wfirst), b0 = min(s_hi[warp][myslot], wlast);
+                const int a0 = max(s_lo[warp][myslot], 0), b0 = min(s_hi[warp][myslot], wlast);
                 pick = (a0 <= b0) && (a0 >= cs) && (a0 < cs + kMaskSteps);
             }
             unsigned word = __ballot_sync(0xffffffffu, pick);
@@ -691,108 +700,113 @@ __global__ void __launch_bounds__(kWarps * 32) render_backward_kernel(const Para
                 const int bit = __ffs(word) - 1;
                 word &= word - 1;
                 const int slot = w * 32 + bit;
-        const int k = s_k[warp][slot];
-        const int ma = max(s_lo[warp][slot], wfirst), mb = min(s_hi[warp][slot], wlast);
-        int rank = k - kstart; if (rank < 0) rank += p.K;
-        const Prim q = load_prim(packn, k);
-        const float4 *slab = tpn + (size_t)k * slabsz;
-        float *gslab = gtn + (size_t)k * slabsz * 4;
-        float g[16];
+                const int k = s_k[warp][slot];
+                const int ma = max(s_lo[warp][slot], 0), mb = min(s_hi[warp][slot], wlast);
+                int rank = k - kstart; if (rank < 0) rank += p.K;
+                const Prim q = load_prim(packn, k);
+                const float4 *slab = tpn + (size_t)k * slabsz;
+                float *gslab = gtn + (size_t)k * slabsz * 4;
+                float g[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) g[i] = 0.f;
-        bool touched = false;
-        float x = xb, y = yb, z = zb;
-        for (int m = cs; m < ma; ++m) {
-            if (m >= mfirst) { x = __fmaf_rn(c.ray.dx, p.dt, x); y = __fmaf_rn(c.ray.dy, p.dt, y); z = __fmaf_rn(c.ray.dz, p.dt, z); }
-        }
-        for (int m = ma; m <= mb; ++m) {
-            const int j = m + c.off;
-            // the sample (j, rank) exists in forward iff the lane was marching at j and had not saturated before it
-            const bool live = hashit && (m >= mfirst) && (j <= jlast) && ((j < jsat) || (j == jsat && rank <= ranksat));
-            const float xm = x - q.px, ym = y - q.py, zm = z - q.pz;
-            if (m >= mfirst) { x = __fmaf_rn(c.ray.dx, p.dt, x); y = __fmaf_rn(c.ray.dy, p.dt, y); z = __fmaf_rn(c.ray.dz, p.dt, z); }
-            const float rx0 = rowdot(q.r00, xm, q.r10, ym, q.r20, zm);
-            const float rx1 = rowdot(q.r01, xm, q.r11, ym, q.r21, zm);
-            const float rx2 = rowdot(q.r02, xm, q.r12, ym, q.r22, zm);
-            const float y0 = __fmul_rn(q.sx, rx0), y1 = __fmul_rn(q.sy, rx1), y2 = __fmul_rn(q.sz, rx2);
-            const bool valid = (fabsf(y0) < 1.f) && (fabsf(y1) < 1.f) && (fabsf(y2) < 1.f);
-            if (!(valid && live)) continue;
-            touched = true;
-            Sample sm;
-            const float4 s = sample_slab<true>(slab, y0, y1, y2, p.TD, p.TH, p.TW, p.fadescale, p.fadeexp, &sm);
-            // primaccum.h:81-98 with the saturating sample known from forward
-            const bool issat = (j == jsat) && (rank == ranksat);
-            const float a = s.w * p.dt;
-            const float weight = issat ? (1.f - abefore) : a;
-            const float dLa = issat ? 0.f : p.dt * ((s.x - sr) * dL.x + (s.y - sg) * dL.y + (s.z - sb) * dL.z + (1.f - sa) * dL.w);
-            const float d0 = weight * dL.x, d1 = weight * dL.y, d2 = weight * dL.z;
-            // primsampler.h:68-91
-            const float cf = -(p.fadescale * p.fadeexp) * s.w * dLa;
-            float gy0 = cf * __powf(fabsf(y0), p.fadeexp - 1.f) * (y0 > 0.f ? 1.f : -1.f);
-            float gy1 = cf * __powf(fabsf(y1), p.fadeexp - 1.f) * (y1 > 0.f ? 1.f : -1.f);
-            float gy2 = cf * __powf(fabsf(y2), p.fadeexp - 1.f) * (y2 > 0.f ? 1.f : -1.f);
-            const float d3 = dLa * sm.fade;
-            // utils.h:504-643
-            float gix = 0.f, giy = 0.f, giz = 0.f;
-#pragma unroll
-            for (int cn = 0; cn < 8; ++cn) {
-                if (sm.idx[cn] >= 0) {
-                    const float w_ = sm.wgt[cn];
-                    red_add_v4(gslab + (size_t)sm.idx[cn] * 4, w_ * d0, w_ * d1, w_ * d2, w_ * d3);
-                    const float4 v = __ldg(slab + sm.idx[cn]);
-                    const float dp = v.x * d0 + v.y * d1 + v.z * d2 + v.w * d3;
-                    const float wx = (cn & 1) ? sm.x0 : sm.x1, wy = (cn & 2) ? sm.y0 : sm.y1, wz = (cn & 4) ? sm.z0 : sm.z1;
-                    gix += ((cn & 1) ? dp : -dp) * wy * wz;
-                    giy += ((cn & 2) ? dp : -dp) * wx * wz;
-                    giz += ((cn & 4) ? dp : -dp) * wx * wy;
+                for (int i = 0; i < 16; ++i) g[i] = 0.f;
+                bool touched = false;
+                float x = xb, y = yb, z = zb;
+                for (int m = cs; m < ma; ++m) {
+                    x = __fmaf_rn(c.ray.dx, p.dt, x); y = __fmaf_rn(c.ray.dy, p.dt, y); z = __fmaf_rn(c.ray.dz, p.dt, z);
                 }
-            }
-            gy0 += gmx * gix; gy1 += gmy * giy; gy2 += gmz * giz;
-            // primtransf.h:155-179
-            g[0] += rx0 * gy0; g[1] += rx1 * gy1; g[2] += rx2 * gy2;            // grad scale
-            const float h0 = gy0 * q.sx, h1 = gy1 * q.sy, h2 = gy2 * q.sz;
-            g[3] += xm * h0; g[4] += xm * h1; g[5] += xm * h2;                   // grad rot row 0
-            g[6] += ym * h0; g[7] += ym * h1; g[8] += ym * h2;                   // row 1
-            g[9] += zm * h0; g[10] += zm * h1; g[11] += zm * h2;                 // row 2
-            g[12] -= q.r00 * h0 + q.r01 * h1 + q.r02 * h2;                       // grad pos
-            g[13] -= q.r10 * h0 + q.r11 * h1 + q.r12 * h2;
-            g[14] -= q.r20 * h0 + q.r21 * h1 + q.r22 * h2;
-        }
-        if (!__any_sync(0xffffffffu, touched)) continue;
-        // 16-value butterfly: after the 5 stages lanes 2i and 2i+1 hold the warp total of g[i]
+                for (int m = ma; m <= mb; ++m) {
+                    // the sample (m, rank) exists in forward iff the lane was marching at m and had not saturated before it
+                    const bool live = (m <= mlast) && ((m < msat) || (rank <= ranksat));
+                    const float xm = x - q.px, ym = y - q.py, zm = z - q.pz;
+                    x = __fmaf_rn(c.ray.dx, p.dt, x); y = __fmaf_rn(c.ray.dy, p.dt, y); z = __fmaf_rn(c.ray.dz, p.dt, z);
+                    const float rx0 = rowdot(q.r00, xm, q.r10, ym, q.r20, zm);
+                    const float rx1 = rowdot(q.r01, xm, q.r11, ym, q.r21, zm);
+                    const float rx2 = rowdot(q.r02, xm, q.r12, ym, q.r22, zm);
+                    const float y0 = __fmul_rn(q.sx, rx0), y1 = __fmul_rn(q.sy, rx1), y2 = __fmul_rn(q.sz, rx2);
+                    const bool valid = (fabsf(y0) < 1.f) && (fabsf(y1) < 1.f) && (fabsf(y2) < 1.f);
+                    if (!(valid && live)) continue;
+                    touched = true;
+                    Sample sm;
+                    const float4 s = sample_slab<T, true>(slab, y0, y1, y2, p.TD, p.TH, p.TW, p.fadescale, p.fadeexp, &sm);
+                    // primaccum.h:81-98 with the saturating sample known from forward
+                    const bool issat = (m == msat) && (rank == ranksat);
+                    const float a = s.w * p.dt;
+                    const float weight = issat ? (1.f - abefore) : a;
+                    const float dLa = issat ? 0.f : p.dt * ((s.x - sr) * dL.x + (s.y - sg) * dL.y + (s.z - sb) * dL.z + (1.f - sa) * dL.w);
+                    const float d0 = weight * dL.x, d1 = weight * dL.y, d2 = weight * dL.z;
+                    // primsampler.h:68-91
+                    const float cf = -(p.fadescale * p.fadeexp) * s.w * dLa;
+                    float gy0 = cf * __powf(fabsf(y0), p.fadeexp - 1.f) * (y0 > 0.f ? 1.f : -1.f);
+                    float gy1 = cf * __powf(fabsf(y1), p.fadeexp - 1.f) * (y1 > 0.f ? 1.f : -1.f);
+                    float gy2 = cf * __powf(fabsf(y2), p.fadeexp - 1.f) * (y2 > 0.f ? 1.f : -1.f);
+                    const float d3 = dLa * sm.fade;
+                    // utils.h:504-643: scatter w_c * dL_sample, gather dL/d(index) = sum_c dw_c <T_c, dL_sample>
+                    float gix = 0.f, giy = 0.f, giz = 0.f;
+                    const float4 *pc = slab + sm.base;
+                    float *gc = gslab + (size_t)sm.base * 4;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const bool up = lane & 16;
-            const float send = up ? g[i] : g[i + 8];
-            const float keep = up ? g[i + 8] : g[i];
-            g[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-        }
+                    for (int cn = 0; cn < 8; ++cn) {
+                        const int o = ((cn & 1) ? sx : 0) + ((cn & 2) ? sy : 0) + ((cn & 4) ? sz : 0);
+                        const float wx = (cn & 1) ? sm.x0 : sm.x1, wy = (cn & 2) ? sm.y0 : sm.y1, wz = (cn & 4) ? sm.z0 : sm.z1;
+                        const float w_ = wx * wy * wz;
+                        if (w_ != 0.f) red_add_v4(gc + (size_t)o * 4, w_ * d0, w_ * d1, w_ * d2, w_ * d3);
+                        const float4 v = __ldg(pc + o);
+                        const float dp = v.x * d0 + v.y * d1 + v.z * d2 + v.w * d3;
+                        // d(weight)/d(index): +1 on the upper corner, -1 on the lower one.  On a clamped axis the
+                        // reference sees the upper voxel as ITS lower corner (sign -1) and no other corner.
+                        const float gx = (cn & 1) ? (sm.ex ? -dp : dp) : (sm.ex ? 0.f : -dp);
+                        const float gy = (cn & 2) ? (sm.ey ? -dp : dp) : (sm.ey ? 0.f : -dp);
+                        const float gz = (cn & 4) ? (sm.ez ? -dp : dp) : (sm.ez ? 0.f : -dp);
+                        gix += gx * wy * wz;
+                        giy += gy * wx * wz;
+                        giz += gz * wx * wy;
+                    }
+                    gy0 += gmx * gix; gy1 += gmy * giy; gy2 += gmz * giz;
+                    // primtransf.h:155-179
+                    g[0] += rx0 * gy0; g[1] += rx1 * gy1; g[2] += rx2 * gy2;            // grad scale
+                    const float h0 = gy0 * q.sx, h1 = gy1 * q.sy, h2 = gy2 * q.sz;
+                    g[3] += xm * h0; g[4] += xm * h1; g[5] += xm * h2;                   // grad rot row 0
+                    g[6] += ym * h0; g[7] += ym * h1; g[8] += ym * h2;                   // row 1
+                    g[9] += zm * h0; g[10] += zm * h1; g[11] += zm * h2;                 // row 2
+                    g[12] -= q.r00 * h0 + q.r01 * h1 + q.r02 * h2;                       // grad pos
+                    g[13] -= q.r10 * h0 + q.r11 * h1 + q.r12 * h2;
+                    g[14] -= q.r20 * h0 + q.r21 * h1 + q.r22 * h2;
+                }
+                if (!__any_sync(0xffffffffu, touched)) continue;
+                // 16-value butterfly: after the 5 stages lanes 2i and 2i+1 hold the warp total of g[i]
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const bool up = lane & 8;
-            const float send = up ? g[i] : g[i + 4];
-            const float keep = up ? g[i + 4] : g[i];
-            g[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-        }
+                for (int i = 0; i < 8; ++i) {
+                    const bool up = lane & 16;
+                    const float send = up ? g[i] : g[i + 8];
+                    const float keep = up ? g[i + 8] : g[i];
+                    g[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                }
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const bool up = lane & 4;
-            const float send = up ? g[i] : g[i + 2];
-            const float keep = up ? g[i + 2] : g[i];
-            g[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-        }
-        {
-            const bool up = lane & 2;
-            const float send = up ? g[0] : g[1];
-            const float keep = up ? g[1] : g[0];
-            g[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-        }
-        g[0] += __shfl_xor_sync(0xffffffffu, g[0], 1);
-        const int vi = lane >> 1;
-        if (!(lane & 1) && vi < 15) {
-            float *dst = vi < 3 ? (gsn + (size_t)k * 3 + vi) : (vi < 12 ? (grn + (size_t)k * 9 + (vi - 3)) : (gpn + (size_t)k * 3 + (vi - 12)));
-            atomicAdd(dst, g[0]);
-        }
+                for (int i = 0; i < 4; ++i) {
+                    const bool up = lane & 8;
+                    const float send = up ? g[i] : g[i + 4];
+                    const float keep = up ? g[i + 4] : g[i];
+                    g[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                }
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const bool up = lane & 4;
+                    const float send = up ? g[i] : g[i + 2];
+                    const float keep = up ? g[i + 2] : g[i];
+                    g[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                }
+                {
+                    const bool up = lane & 2;
+                    const float send = up ? g[0] : g[1];
+                    const float keep = up ? g[1] : g[0];
+                    g[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+                }
+                g[0] += __shfl_xor_sync(0xffffffffu, g[0], 1);
+                const int vi = lane >> 1;
+                if (!(lane & 1) && vi < 15) {
+                    float *dst = vi < 3 ? (gsn + (size_t)k * 3 + vi) : (vi < 12 ? (grn + (size_t)k * 9 + (vi - 3)) : (gpn + (size_t)k * 3 + (vi - 12)));
+                    atomicAdd(dst, g[0]);
+                }
             }   // while (word)
         }       // for (w)
     }           // for (cs)
@@ -900,8 +914,16 @@ int mvp_raymarch_forward(const mvp_forward_args *a, void *stream) {
     p.rayrgba = a->rayrgba; p.raysat = a->raysat; p.rayaux = reinterpret_cast<int4 *>(a->rayaux);
     dim3 grid((p.TXn + 1) / 2, (p.TYn + 1) / 2, a->shape.N);
     if (grid.y > 65535) return MVP_ERR_SHAPE;
-    if (a->raysat) render_forward_kernel<true><<<grid, kWarps * 32, 0, st>>>(p);
-    else render_forward_kernel<false><<<grid, kWarps * 32, 0, st>>>(p);
+    const int cubic = (a->shape.TD == a->shape.TH && a->shape.TH == a->shape.TW) ? a->shape.TD : 0;
+#define MVP_LAUNCH_FWD(TT)                                                                   \
+    do {                                                                                     \
+        if (a->raysat) render_forward_kernel<TT, true><<<grid, kWarps * 32, 0, st>>>(p);     \
+        else render_forward_kernel<TT, false><<<grid, kWarps * 32, 0, st>>>(p);              \
+    } while (0)
+    if (cubic == 8) MVP_LAUNCH_FWD(8);
+    else if (cubic == 16) MVP_LAUNCH_FWD(16);
+    else MVP_LAUNCH_FWD(0);
+#undef MVP_LAUNCH_FWD
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? MVP_OK : (int)e;
 }
@@ -930,7 +952,10 @@ int mvp_raymarch_backward(const mvp_backward_args *a, void *stream) {
     p.g_primpos = a->grad_primpos; p.g_primrot = a->grad_primrot; p.g_primscale = a->grad_primscale; p.g_tplate = a->grad_tplate;
     dim3 grid((p.TXn + 1) / 2, (p.TYn + 1) / 2, a->shape.N);
     if (grid.y > 65535) return MVP_ERR_SHAPE;
-    render_backward_kernel<<<grid, kWarps * 32, 0, st>>>(p);
+    const int cubic = (a->shape.TD == a->shape.TH && a->shape.TH == a->shape.TW) ? a->shape.TD : 0;
+    if (cubic == 8) render_backward_kernel<8><<<grid, kWarps * 32, 0, st>>>(p);
+    else if (cubic == 16) render_backward_kernel<16><<<grid, kWarps * 32, 0, st>>>(p);
+    else render_backward_kernel<0><<<grid, kWarps * 32, 0, st>>>(p);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? MVP_OK : (int)e;
 }

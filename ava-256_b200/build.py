@@ -29,7 +29,8 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + SRC + ["-o", LIB]
+    extra = os.environ.get("MVP_NVCC_EXTRA", "").split()      # experiment knob, e.g. -DMVP_BWD_MINB=4
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + SRC + ["-o", LIB]
     subprocess.check_call(cmd)
     return LIB
 

@@ -28,6 +28,7 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "mvpraymarch_b200.h"
 
@@ -39,7 +40,14 @@ constexpr int kTileH = 4;
 constexpr int kWarps = 4;         // warps (tiles) per CTA, arranged 2 x 2
 constexpr int kMaskSteps = 16;    // steps per active-mask rebuild
 constexpr int kRowCapMax = 2048;  // entries per tile-row bucket before the row falls back to scanning all slabs
+constexpr int kFastCap = 96;     // shared-memory list capacity of the common-case render kernels
 constexpr int kBig = 1 << 30;
+#ifndef MVP_BWD_MINB
+#define MVP_BWD_MINB 4   // resident CTAs per SM the backward kernel is compiled for (register cap 65536 / (128 * MINB))
+#endif
+#ifndef MVP_FWD_MINB
+#define MVP_FWD_MINB 8
+#endif
 
 struct Cam {          // 64 B per view
     float o[3];
@@ -51,7 +59,7 @@ struct Cam {          // 64 B per view
 struct __align__(8) RowEntry { int k; unsigned xr; };   // xr = x0 | x1 << 16  (pixels, inclusive)
 
 struct Layout {
-    size_t cam, bad, pack, rx, ry, rowcnt, rowlist, total;
+    size_t cam, bad, pack, rx, ry, rowcnt, rowlist, tileflag, total;
     int R, rowcap;
 };
 
@@ -69,6 +77,7 @@ __host__ inline Layout make_layout(const mvp_shape &s) {
     L.ry = off;      off = align256(off + (size_t)s.N * s.K * 4);
     L.rowcnt = off;  off = align256(off + (size_t)s.N * L.R * 4);
     L.rowlist = off; off = align256(off + (size_t)s.N * L.R * L.rowcap * sizeof(RowEntry));
+    L.tileflag = off; off = align256(off + (size_t)s.N * ((s.H + kTileH - 1) / kTileH) * ((s.W + kTileW - 1) / kTileW));
     L.total = off;
     return L;
 }
@@ -243,9 +252,11 @@ __global__ void __launch_bounds__(128) prim_setup_kernel(int N, int K, int H, in
 // ------------------------------------------------------------------------------------------------------
 constexpr int kRowThreads = 256;
 
-__global__ void __launch_bounds__(kRowThreads) row_lists_kernel(int K, int R, int rowcap, const unsigned *__restrict__ rx,
-                                                                const unsigned *__restrict__ ry, int *__restrict__ rowcnt,
-                                                                RowEntry *__restrict__ rowlist) {
+__global__ void __launch_bounds__(kRowThreads) row_lists_kernel(int K, int R, int rowcap, int TXn, int fastcap,
+                                                                const unsigned *__restrict__ rx, const unsigned *__restrict__ ry,
+                                                                int *__restrict__ rowcnt, RowEntry *__restrict__ rowlist,
+                                                                unsigned char *__restrict__ tileflag) {
+    extern __shared__ int s_tilecnt[];   // [TXn] candidates (rectangle overlaps) per 8-pixel tile column of this row
     const int row = blockIdx.x, n = blockIdx.y;
     const int ylo = row * kTileH, yhi = ylo + kTileH - 1;
     const unsigned *rxn = rx + (size_t)n * K, *ryn = ry + (size_t)n * K;
@@ -255,6 +266,7 @@ __global__ void __launch_bounds__(kRowThreads) row_lists_kernel(int K, int R, in
     __shared__ int s_base;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_base = 0;
+    for (int i = threadIdx.x; i < TXn; i += kRowThreads) s_tilecnt[i] = 0;
     __syncthreads();
     for (int j0 = 0; j0 < K; j0 += kRowThreads) {
         const int j = j0 + threadIdx.x;
@@ -275,6 +287,13 @@ __global__ void __launch_bounds__(kRowThreads) row_lists_kernel(int K, int R, in
         for (int w = 0; w < warp; ++w) pre += s_wcnt[w];
         int pos = pre + __popc(b & ((1u << lane) - 1u));
         if (in && pos < rowcap) { RowEntry e; e.k = k; e.xr = xr; out[pos] = e; }
+        if (in) {
+            const int x0 = (int)(xr & 0xffffu), x1 = (int)(xr >> 16);
+            if (x0 <= x1) {
+                const int t1 = min(x1 / kTileW, TXn - 1);
+                for (int tcol = x0 / kTileW; tcol <= t1; ++tcol) atomicAdd(&s_tilecnt[tcol], 1);
+            }
+        }
         __syncthreads();
         if (threadIdx.x == 0) {
             int t = 0;
@@ -284,6 +303,11 @@ __global__ void __launch_bounds__(kRowThreads) row_lists_kernel(int K, int R, in
         __syncthreads();
     }
     if (threadIdx.x == 0) rowcnt[(size_t)n * R + row] = s_base;   // may exceed rowcap: consumers then scan all slabs
+    // A tile whose candidate count fits the fast kernel's shared-memory list can never overflow it (list <= candidates);
+    // everything else is rendered by the 512-entry variant.
+    __syncthreads();
+    unsigned char *fl = tileflag + ((size_t)n * R + row) * TXn;
+    for (int i = threadIdx.x; i < TXn; i += kRowThreads) fl[i] = (s_tilecnt[i] > fastcap) ? 1 : 0;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -363,6 +387,8 @@ struct Params {
     const RowEntry *rowlist;
     int R, rowcap;
     int TXn, TYn;
+    int align;
+    unsigned char *tileflag;
     // forward outputs
     float *rayrgba, *raysat;
     int4 *rayaux;
@@ -373,15 +399,19 @@ struct Params {
     float *g_primpos, *g_primrot, *g_primscale, *g_tplate;
 };
 
-// Builds the warp's slab list (rank order, <= 512 entries) and each lane's rtminmax; then, with every lane's
-// first step j0 known, a second pass over the (short) list converts each slab's per-lane [t_enter, t_exit] into a
-// warp step interval in units of "steps since the lane's own first step" (sweep m = j - j0).  Aligning lanes on
-// their own first hit -- which is also what the reference's lock-step loop does (mvpraymarch_subset_kernel.h:63-76)
-// -- keeps the 32 rays of a tile in phase on a tilted surface, so more lanes are inside a slab at the same time.
-// Returns j0 (first step index) and the lattice start state of the lane.
-__device__ __forceinline__ int build_tile_list(const Params &p, float rdt, int n, int tx, int ty, int lane, TileCtx &c,
+// Builds the warp's slab list (rank order, at most CAP entries in shared memory) and each lane's rtminmax; then,
+// with every lane's first step j0 known, chooses the lane <-> sweep alignment and, in a second pass over the (short)
+// list, converts each slab's per-lane [t_enter, t_exit] into a warp step interval in sweep units (lane step
+// j = sweep m + off).  Lanes only ever wait (sweep steps before their own first step are idle), so ANY alignment
+// gives the reference's result; a good one keeps the 32 rays of a tile inside the same slab at the same time:
+//   align 0: equal depth t (sweep planes perpendicular to the view direction)
+//   align 1: every lane starts at its own first hit (the reference's lock-step loop, subset_kernel.h:63-76)
+//   align 2: equal depth relative to a plane fitted to the tile's first-hit depths (compensates surface tilt)
+// Returns false when the list would exceed CAP (< 512): the tile is then left to the 512-entry kernel variant.
+template <int CAP>
+__device__ __forceinline__ bool build_tile_list(const Params &p, float rdt, int n, int tx, int ty, int lane, TileCtx &c,
                                                 int *s_k, int *s_lo, int *s_hi, float &t, float &x, float &y, float &z,
-                                                float &r1e) {
+                                                float &r1e, int &j0) {
     const int px = tx * kTileW + (lane & 7), py = ty * kTileH + (lane >> 3);
     c.inimg = (px < p.W) && (py < p.H);
     const int cx = min(px, p.W - 1), cy = min(py, p.H - 1);
@@ -431,9 +461,11 @@ __device__ __forceinline__ int build_tile_list(const Params &p, float rdt, int n
             const bool hit = slab_test(q, c.ray, lo, hi) && c.inimg;
             if (hit) { c.rt0 = fminf(c.rt0, lo); c.rt1 = fmaxf(c.rt1, hi); }
             if (__any_sync(0xffffffffu, hit)) {
-                if (nl < kMaxHit) {
+                if (nl < CAP) {
                     if (lane == 0) s_k[nl] = kk;
                     ++nl;
+                } else if (CAP < kMaxHit) {
+                    return false;          // warp-uniform
                 }
             }
         }
@@ -451,22 +483,70 @@ __device__ __forceinline__ int build_tile_list(const Params &p, float rdt, int n
     y = __fmaf_rn(__fmul_rn(c.ray.dy, fi), p.dt, ys);
     z = __fmaf_rn(__fmul_rn(c.ray.dz, fi), p.dt, zs);
     r1e = __fadd_rn(r1, 9.9999997473787516356e-06f);
-    c.off = incs;
-    // pass 2: warp step intervals relative to each lane's own first step
+    j0 = incs;
+    const bool hashit = c.inimg && (c.rt0 <= c.rt1);
+
+    // ---- alignment: off such that lane step j = m + off ----
+    int off = incs;                                   // align 1
+    if (p.align != 1) {
+        const float tsteps = c.ray.tmin * rdt;        // lattice origin of this lane in steps
+        float plane = 0.f;                            // depth (in steps) of the sweep origin at this lane
+        if (p.align == 2) {
+            // least-squares plane g ~ a + b u + c v through the first-hit depths of the front-most lanes
+            const float g = tsteps + fi;
+            float gmin = hashit ? g : CUDART_INF_F;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) gmin = fminf(gmin, __shfl_xor_sync(0xffffffffu, gmin, o));
+            const bool inl = hashit && (g <= gmin + 24.f);
+            const int u = lane & 7, v = lane >> 3;
+            const int gq = inl ? (int)((g - gmin) * 16.f) : 0;
+            const int w1 = inl ? 1 : 0;
+            const float S1 = (float)__reduce_add_sync(0xffffffffu, w1);
+            const float Su = (float)__reduce_add_sync(0xffffffffu, w1 * u), Sv = (float)__reduce_add_sync(0xffffffffu, w1 * v);
+            const float Suu = (float)__reduce_add_sync(0xffffffffu, w1 * u * u), Suv = (float)__reduce_add_sync(0xffffffffu, w1 * u * v);
+            const float Svv = (float)__reduce_add_sync(0xffffffffu, w1 * v * v);
+            const float Sg = (float)__reduce_add_sync(0xffffffffu, gq), Sug = (float)__reduce_add_sync(0xffffffffu, gq * u);
+            const float Svg = (float)__reduce_add_sync(0xffffffffu, gq * v);
+            const float det = S1 * (Suu * Svv - Suv * Suv) - Su * (Su * Svv - Suv * Sv) + Sv * (Su * Suv - Suu * Sv);
+            float pa = S1 > 0.f ? Sg / S1 : 0.f, pb = 0.f, pc = 0.f;
+            if (det > 0.5f) {
+                const float id = 1.f / det;
+                pa = id * (Sg * (Suu * Svv - Suv * Suv) - Su * (Sug * Svv - Suv * Svg) + Sv * (Sug * Suv - Suu * Svg));
+                pb = id * (S1 * (Sug * Svv - Svg * Suv) - Sg * (Su * Svv - Suv * Sv) + Sv * (Su * Svg - Sug * Sv));
+                pc = id * (S1 * (Suu * Svg - Suv * Sug) - Su * (Su * Svg - Sug * Sv) + Sg * (Su * Suv - Suu * Sv));
+                pb = fminf(fmaxf(pb, -128.f), 128.f); pc = fminf(fmaxf(pc, -128.f), 128.f);
+            }
+            plane = gmin + (pa + pb * (float)u + pc * (float)v) * (1.f / 16.f);
+            if (!(plane == plane) || gmin == CUDART_INF_F) plane = 0.f;
+        } else {
+            float tref = c.inimg ? tsteps : CUDART_INF_F;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) tref = fminf(tref, __shfl_xor_sync(0xffffffffu, tref, o));
+            plane = tref;
+        }
+        off = clamp_step(ceilf(plane - tsteps));
+    }
+    // normalise: the first lane to start does so at sweep step 0
+    int ms = hashit ? clamp_step((float)incs - (float)off) : kBig;
+    const int msmin = __reduce_min_sync(0xffffffffu, ms);
+    if (msmin < kBig) off += msmin;
+    c.off = off;
+    const float foff = (float)off;
+    // pass 2: warp step intervals in sweep units
     for (int slot = 0; slot < nl; ++slot) {
         const Prim q = load_prim(packn, s_k[slot]);
         float lo, hi;
         const bool hit = slab_test(q, c.ray, lo, hi) && c.inimg;
         int jlo = kBig, jhi = -kBig;
         if (hit) {
-            jlo = clamp_step(floorf((lo - c.ray.tmin) * rdt) - 1.f - fi);
-            jhi = clamp_step(floorf((hi - c.ray.tmin) * rdt) + 2.f - fi);
+            jlo = clamp_step(floorf((lo - c.ray.tmin) * rdt) - 1.f - foff);
+            jhi = clamp_step(floorf((hi - c.ray.tmin) * rdt) + 2.f - foff);
         }
         const int wlo = __reduce_min_sync(0xffffffffu, jlo), whi = __reduce_max_sync(0xffffffffu, jhi);
         if (lane == 0) { s_lo[slot] = wlo; s_hi[slot] = whi; }
     }
     __syncwarp();
-    return incs;
+    return true;
 }
 
 struct Sample {
@@ -478,26 +558,25 @@ struct Sample {
 };
 
 // primsampler.h:44-66 + utils.h:408-502.  T > 0: cubic slab with compile-time strides; T == 0: runtime dims.
-// The reference tests every corner against the slab bounds; for a valid sample (|y| < 1) the only corner that can
-// fall outside is ix+1 == TW when fx rounds to exactly TW-1 (weight exactly 0), so the cell is clamped to TW-2 and
-// the weights keep the un-clamped fractions: the same products are formed and the zero-weight term adds 0.
+// Only called for valid samples (|y| < 1), for which (a) the reference's +-100 clamp is a no-op and (b) the only
+// corner that can fall outside the slab is ix+1 == TW when fx rounds to exactly TW-1, with weight exactly 0.  The
+// cell is clamped to TW-2 instead and the fractions are taken against the clamped cell: identical products in all
+// other cases (fx - ix and (ix+1) - fx are the reference's expressions), weights (1, 0) in the edge case.
 template <int T, bool kKeep>
 __device__ __forceinline__ float4 sample_slab(const float4 *__restrict__ slab, float y0, float y1, float y2, int TD, int TH, int TW,
                                               float fadescale, float fadeexp, Sample *keep) {
     const int td = T > 0 ? T : TD, th = T > 0 ? T : TH, tw = T > 0 ? T : TW;
     const float fade = __expf(-fadescale * (__powf(fabsf(y0), fadeexp) + __powf(fabsf(y1), fadeexp) + __powf(fabsf(y2), fadeexp)));
-    const float fx = fmaxf(-100.f, fminf(100.f, (y0 + 1.f) * 0.5f)) * (float)(tw - 1);
-    const float fy = fmaxf(-100.f, fminf(100.f, (y1 + 1.f) * 0.5f)) * (float)(th - 1);
-    const float fz = fmaxf(-100.f, fminf(100.f, (y2 + 1.f) * 0.5f)) * (float)(td - 1);
+    const float fx = ((y0 + 1.f) * 0.5f) * (float)(tw - 1);
+    const float fy = ((y1 + 1.f) * 0.5f) * (float)(th - 1);
+    const float fz = ((y2 + 1.f) * 0.5f) * (float)(td - 1);
     const int ix = __float2int_rd(fx), iy = __float2int_rd(fy), iz = __float2int_rd(fz);
-    const float ax0 = fx - (float)ix, ax1 = (float)(ix + 1) - fx;
-    const float ay0 = fy - (float)iy, ay1 = (float)(iy + 1) - fy;
-    const float az0 = fz - (float)iz, az1 = (float)(iz + 1) - fz;
-    // clamp the cell (degenerate 1-voxel axes: both corners are voxel 0, weights sum to 1)
-    const int cx = max(min(ix, tw - 2), 0), cy = max(min(iy, th - 2), 0), cz = max(min(iz, td - 2), 0);
-    const float bx0 = (ix > cx) ? 1.f : ax0, bx1 = (ix > cx) ? 0.f : ax1;
-    const float by0 = (iy > cy) ? 1.f : ay0, by1 = (iy > cy) ? 0.f : ay1;
-    const float bz0 = (iz > cz) ? 1.f : az0, bz1 = (iz > cz) ? 0.f : az1;
+    int cx, cy, cz;
+    if (T >= 2) { cx = min(ix, T - 2); cy = min(iy, T - 2); cz = min(iz, T - 2); }
+    else { cx = max(min(ix, tw - 2), 0); cy = max(min(iy, th - 2), 0); cz = max(min(iz, td - 2), 0); }
+    const float bx0 = fx - (float)cx, bx1 = (float)(cx + 1) - fx;
+    const float by0 = fy - (float)cy, by1 = (float)(cy + 1) - fy;
+    const float bz0 = fz - (float)cz, bz1 = (float)(cz + 1) - fz;
     const int sx = tw > 1 ? 1 : 0, sy = th > 1 ? tw : 0, sz = td > 1 ? th * tw : 0;
     const int base = (cz * th + cy) * tw + cx;
     const float4 *pc = slab + base;
@@ -525,27 +604,40 @@ __device__ __forceinline__ float4 sample_slab(const float4 *__restrict__ slab, f
 }
 
 // ------------------------------------------------------------------------------------------------------
-// 4. forward
+// 4. forward.  CAP = shared-memory list capacity per warp.  The CAP < 512 variant handles every tile whose list
+//    fits (almost all) with a small shared-memory footprint (more L1 for the voxel gathers) and flags the rest;
+//    the CAP == 512 variant then renders only the flagged tiles.
 // ------------------------------------------------------------------------------------------------------
-template <int T, bool kGrad>
-__global__ void __launch_bounds__(kWarps * 32, 8) render_forward_kernel(const Params p) {
-    __shared__ int s_k[kWarps][kMaxHit];
-    __shared__ int s_lo[kWarps][kMaxHit];
-    __shared__ int s_hi[kWarps][kMaxHit];
+template <int T, bool kGrad, int CAP>
+__global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit) ? MVP_FWD_MINB : 4) render_forward_kernel(const Params p) {
+    __shared__ int s_k[kWarps][CAP];
+    __shared__ int s_lo[kWarps][CAP];
+    __shared__ int s_hi[kWarps][CAP];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tx = blockIdx.x * 2 + (warp & 1), ty = blockIdx.y * 2 + (warp >> 1), n = blockIdx.z;
-    if (tx >= p.TXn || ty >= p.TYn) return;   // warps are independent: no CTA-wide barrier below
+    if (tx >= p.TXn || ty >= p.TYn) return;   // warps are independent: no CTA-wide barrier below (exited warps count as arrived)
+    // Programmatic dependent launch: the 512-entry variant (few, long-running tiles) is launched first and lets the
+    // fast variant start while it is still running; the fast variant waits for it only at its very end.
+    if (CAP == kMaxHit) asm volatile("griddepcontrol.launch_dependents;");
+    const bool heavy = p.tileflag[((size_t)n * p.TYn + ty) * p.TXn + tx] != 0;
+    if ((CAP == kMaxHit) != heavy) {
+        if (CAP < kMaxHit) asm volatile("griddepcontrol.wait;" ::: "memory");
+        return;
+    }
 
     const float rdt = fast_rcp(p.dt);   // MUFU.RCP(stepsize), as the reference (SASS 0x16c0)
     TileCtx c;
     float t, x, y, z, r1e;
-    const int j0 = build_tile_list(p, rdt, n, tx, ty, lane, c, s_k[warp], s_lo[warp], s_hi[warp], t, x, y, z, r1e);
+    int j0;
+    const bool fits = build_tile_list<CAP>(p, rdt, n, tx, ty, lane, c, s_k[warp], s_lo[warp], s_hi[warp], t, x, y, z, r1e, j0);
+    (void)fits;   // cannot fail: the tile's candidate count was checked against CAP when the accel was built
 
     const int px = tx * kTileW + (lane & 7), py = ty * kTileH + (lane >> 3);
     const size_t r = ((size_t)n * p.H + min(py, p.H - 1)) * p.W + min(px, p.W - 1);
 
     const bool hashit = c.inimg && (c.rt0 <= c.rt1);
     bool done = !hashit || (t > r1e);
+    const int ms = done ? kBig : (j0 - c.off);   // sweep step at which this lane starts marching
 
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     float sat0 = -1.f, sat1 = -1.f, sat2 = -1.f;
@@ -566,6 +658,7 @@ __global__ void __launch_bounds__(kWarps * 32, 8) render_forward_kernel(const Pa
         if (lane < nl) { lo0 = s_lo[warp][lane]; hi0 = s_hi[warp][lane]; }
         if (lane + 32 < nl) { lo1 = s_lo[warp][lane + 32]; hi1 = s_hi[warp][lane + 32]; }
         for (int m = 0;; ++m) {
+            const bool on = !done && (m >= ms);
             for (int w = 0; w < nwords; ++w) {
                 bool a;
                 if (w == 0) a = (lo0 <= m) && (m <= hi0);
@@ -586,7 +679,7 @@ __global__ void __launch_bounds__(kWarps * 32, 8) render_forward_kernel(const Pa
                     const float y1 = __fmul_rn(q.sy, rowdot(q.r01, xm, q.r11, ym, q.r21, zm));
                     const float y2 = __fmul_rn(q.sz, rowdot(q.r02, xm, q.r12, ym, q.r22, zm));
                     const bool valid = (fabsf(y0) < 1.f) && (fabsf(y1) < 1.f) && (fabsf(y2) < 1.f);
-                    if (valid && !done && (t < r1e)) {
+                    if (valid && on && !sat && (t < r1e)) {
                         const float4 s = sample_slab<T, false>(tpn + (size_t)k * slabsz, y0, y1, y2, p.TD, p.TH, p.TW,
                                                                p.fadescale, p.fadeexp, nullptr);
                         // primaccum.h:63-79
@@ -595,9 +688,8 @@ __global__ void __launch_bounds__(kWarps * 32, 8) render_forward_kernel(const Pa
                         if (newa >= 1.f) {
                             sat0 = s.x; sat1 = s.y; sat2 = s.z;
                             sat = true;
-                            done = true;
                             if (kGrad) {
-                                jsat = m + j0;
+                                jsat = m + c.off;
                                 int rk = k - kstart; if (rk < 0) rk += p.K;
                                 ranksat = rk;
                                 abefore = acc.w;
@@ -608,13 +700,11 @@ __global__ void __launch_bounds__(kWarps * 32, 8) render_forward_kernel(const Pa
                     }
                 }
             }
-            if (!done) {
-                if (kGrad && (t < r1e)) jlast = m + j0;
+            if (on) {
+                if (kGrad && (t < r1e)) jlast = m + c.off;
                 t = __fadd_rn(t, p.dt);
                 x = __fmaf_rn(c.ray.dx, p.dt, x); y = __fmaf_rn(c.ray.dy, p.dt, y); z = __fmaf_rn(c.ray.dz, p.dt, z);
-                done = (t > r1e);
-            } else if (kGrad && sat && jlast < jsat) {
-                jlast = jsat;   // the saturating step itself was marched
+                done = (t > r1e) || sat;
             }
             if (__all_sync(0xffffffffu, done)) break;
         }
@@ -626,30 +716,39 @@ __global__ void __launch_bounds__(kWarps * 32, 8) render_forward_kernel(const Pa
             p.rayaux[r] = make_int4(jsat, ranksat, __float_as_int(abefore), jlast);
         }
     }
+    if (CAP < kMaxHit) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------------------------------------
 // 5. backward (slab-major)
 // ------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+    // no "memory" clobber: the gradient buffer is never read in this kernel, loads must stay free to move
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d));
 }
 
-template <int T>
-__global__ void __launch_bounds__(kWarps * 32, 4) render_backward_kernel(const Params p) {
-    __shared__ int s_k[kWarps][kMaxHit];
-    __shared__ int s_lo[kWarps][kMaxHit];
-    __shared__ int s_hi[kWarps][kMaxHit];
+template <int T, int CAP>
+__global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit) ? MVP_BWD_MINB : 4) render_backward_kernel(const Params p) {
+    __shared__ int s_k[kWarps][CAP];
+    __shared__ int s_lo[kWarps][CAP];
+    __shared__ int s_hi[kWarps][CAP];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tx = blockIdx.x * 2 + (warp & 1), ty = blockIdx.y * 2 + (warp >> 1), n = blockIdx.z;
     if (tx >= p.TXn || ty >= p.TYn) return;
+    if (CAP == kMaxHit) asm volatile("griddepcontrol.launch_dependents;");
+    const bool heavy = p.tileflag[((size_t)n * p.TYn + ty) * p.TXn + tx] != 0;
+    if ((CAP == kMaxHit) != heavy) {
+        if (CAP < kMaxHit) asm volatile("griddepcontrol.wait;" ::: "memory");
+        return;
+    }
 
     const float rdt = fast_rcp(p.dt);
     TileCtx c;
-    float t0, xb, yb, zb, r1e;   // xb = position at sweep step mcur (starts at the lane's own first step)
-    const int j0 = build_tile_list(p, rdt, n, tx, ty, lane, c, s_k[warp], s_lo[warp], s_hi[warp], t0, xb, yb, zb, r1e);
+    float t0, xb, yb, zb, r1e;   // xb = position at sweep step max(mcur, ms)
+    int j0;
+    build_tile_list<CAP>(p, rdt, n, tx, ty, lane, c, s_k[warp], s_lo[warp], s_hi[warp], t0, xb, yb, zb, r1e, j0);
     const int nl = c.nl;
-    if (nl == 0) return;
+    if (nl == 0) { if (CAP < kMaxHit) asm volatile("griddepcontrol.wait;" ::: "memory"); return; }
 
     const int px = tx * kTileW + (lane & 7), py = ty * kTileH + (lane >> 3);
     const size_t r = ((size_t)n * p.H + min(py, p.H - 1)) * p.W + min(px, p.W - 1);
@@ -658,16 +757,18 @@ __global__ void __launch_bounds__(kWarps * 32, 4) render_backward_kernel(const P
     const float4 dL = __ldg(reinterpret_cast<const float4 *>(p.grad_rayrgba) + r);
     const float rs0 = __ldg(p.raysat_in + r * 3 + 0), rs1 = __ldg(p.raysat_in + r * 3 + 1), rs2 = __ldg(p.raysat_in + r * 3 + 2);
     const int4 aux = __ldg(p.rayaux_in + r);
-    const int msat = aux.x == 0x7fffffff ? 0x7fffffff : aux.x - j0;   // in sweep units
+    const int msat = aux.x == 0x7fffffff ? 0x7fffffff : aux.x - c.off;   // in sweep units
     const int ranksat = aux.y;
     const float abefore = __int_as_float(aux.z);
     const bool hassat = rs0 > -1.f;
     const float sr = hassat ? rs0 : 0.f, sg = hassat ? rs1 : 0.f, sb = hassat ? rs2 : 0.f, sa = hassat ? 1.f : 0.f;
 
-    // lane's live sweep range [0, mlast]
-    const int mlast = hashit ? (min(aux.w - j0, msat)) : -1;
+    // lane's live sweep range [ms, mlast]
+    const int ms = hashit ? (j0 - c.off) : kBig;
+    const int mlast = hashit ? (min(aux.w - c.off, msat)) : -1;
+    const float foff = (float)c.off;
     const int wlast = __reduce_max_sync(0xffffffffu, mlast);
-    if (wlast < 0) return;
+    if (wlast < 0) { if (CAP < kMaxHit) asm volatile("griddepcontrol.wait;" ::: "memory"); return; }
 
     const float4 *packn = p.pack + (size_t)n * p.K * 4;
     const size_t slabsz = (size_t)p.TD * p.TH * p.TW;
@@ -686,7 +787,7 @@ __global__ void __launch_bounds__(kWarps * 32, 4) render_backward_kernel(const P
     const int nwords = (nl + 31) >> 5;
     for (int cs = 0; cs <= wlast; cs += kMaskSteps) {
         for (; mcur < cs; ++mcur) {
-            xb = __fmaf_rn(c.ray.dx, p.dt, xb); yb = __fmaf_rn(c.ray.dy, p.dt, yb); zb = __fmaf_rn(c.ray.dz, p.dt, zb);
+            if (mcur >= ms) { xb = __fmaf_rn(c.ray.dx, p.dt, xb); yb = __fmaf_rn(c.ray.dy, p.dt, yb); zb = __fmaf_rn(c.ray.dz, p.dt, zb); }
         }
         for (int w = 0; w < nwords; ++w) {
             const int myslot = w * 32 + lane;
@@ -701,22 +802,39 @@ __global__ void __launch_bounds__(kWarps * 32, 4) render_backward_kernel(const P
                 word &= word - 1;
                 const int slot = w * 32 + bit;
                 const int k = s_k[warp][slot];
-                const int ma = max(s_lo[warp][slot], 0), mb = min(s_hi[warp][slot], wlast);
                 int rank = k - kstart; if (rank < 0) rank += p.K;
                 const Prim q = load_prim(packn, k);
+                // Slab-major order needs no cross-lane alignment: every lane walks ITS OWN step interval of this slab
+                // (recomputed from the reference's slab test), so all rays that cross the slab are busy together.
+                float lo, hi;
+                const bool hit = slab_test(q, c.ray, lo, hi) && hashit;
+                int la = kBig, lb = -kBig;               // lane's candidate sweep steps [la, lb]
+                if (hit) {
+                    la = max(clamp_step(floorf((lo - c.ray.tmin) * rdt) - foff), max(ms, cs));
+                    lb = min(clamp_step(floorf((hi - c.ray.tmin) * rdt) + 1.f - foff), mlast);
+                    if (rank > ranksat) lb = min(lb, msat - 1);      // samples after the saturating one do not exist
+                }
+                const int len = lb - la + 1;
+                const int maxlen = __reduce_max_sync(0xffffffffu, len);
+                if (maxlen <= 0) continue;
                 const float4 *slab = tpn + (size_t)k * slabsz;
                 float *gslab = gtn + (size_t)k * slabsz * 4;
                 float g[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) g[i] = 0.f;
                 bool touched = false;
+                // carry the lane's position from the chunk base (step max(cs, ms)) to its first candidate step
                 float x = xb, y = yb, z = zb;
-                for (int m = cs; m < ma; ++m) {
-                    x = __fmaf_rn(c.ray.dx, p.dt, x); y = __fmaf_rn(c.ray.dy, p.dt, y); z = __fmaf_rn(c.ray.dz, p.dt, z);
+                {
+                    const int adv = (len > 0) ? (la - max(cs, ms)) : 0;
+                    const int maxadv = __reduce_max_sync(0xffffffffu, adv);
+                    for (int i = 0; i < maxadv; ++i) {
+                        if (i < adv) { x = __fmaf_rn(c.ray.dx, p.dt, x); y = __fmaf_rn(c.ray.dy, p.dt, y); z = __fmaf_rn(c.ray.dz, p.dt, z); }
+                    }
                 }
-                for (int m = ma; m <= mb; ++m) {
-                    // the sample (m, rank) exists in forward iff the lane was marching at m and had not saturated before it
-                    const bool live = (m <= mlast) && ((m < msat) || (rank <= ranksat));
+                for (int i = 0; i < maxlen; ++i) {
+                    const bool live = i < len;
+                    const int m = la + i;
                     const float xm = x - q.px, ym = y - q.py, zm = z - q.pz;
                     x = __fmaf_rn(c.ray.dx, p.dt, x); y = __fmaf_rn(c.ray.dy, p.dt, y); z = __fmaf_rn(c.ray.dz, p.dt, z);
                     const float rx0 = rowdot(q.r00, xm, q.r10, ym, q.r20, zm);
@@ -726,43 +844,71 @@ __global__ void __launch_bounds__(kWarps * 32, 4) render_backward_kernel(const P
                     const bool valid = (fabsf(y0) < 1.f) && (fabsf(y1) < 1.f) && (fabsf(y2) < 1.f);
                     if (!(valid && live)) continue;
                     touched = true;
-                    Sample sm;
-                    const float4 s = sample_slab<T, true>(slab, y0, y1, y2, p.TD, p.TH, p.TW, p.fadescale, p.fadeexp, &sm);
-                    // primaccum.h:81-98 with the saturating sample known from forward
+                    // ---- forward sample (primsampler.h:44-66) keeping what the adjoint needs ----
+                    const float e1 = p.fadeexp - 1.f;
+                    const float pw0 = __powf(fabsf(y0), e1), pw1 = __powf(fabsf(y1), e1), pw2 = __powf(fabsf(y2), e1);
+                    const float fade = __expf(-p.fadescale * (pw0 * fabsf(y0) + pw1 * fabsf(y1) + pw2 * fabsf(y2)));
+                    const float fx = ((y0 + 1.f) * 0.5f) * (float)(tw - 1);
+                    const float fy = ((y1 + 1.f) * 0.5f) * (float)(th - 1);
+                    const float fz = ((y2 + 1.f) * 0.5f) * (float)(td - 1);
+                    const int ix = __float2int_rd(fx), iy = __float2int_rd(fy), iz = __float2int_rd(fz);
+                    int cx, cy, cz;
+                    if (T >= 2) { cx = min(ix, T - 2); cy = min(iy, T - 2); cz = min(iz, T - 2); }
+                    else { cx = max(min(ix, tw - 2), 0); cy = max(min(iy, th - 2), 0); cz = max(min(iz, td - 2), 0); }
+                    const float bx0 = fx - (float)cx, bx1 = (float)(cx + 1) - fx;
+                    const float by0 = fy - (float)cy, by1 = (float)(cy + 1) - fy;
+                    const float bz0 = fz - (float)cz, bz1 = (float)(cz + 1) - fz;
+                    const bool ex = ix > cx, ey = iy > cy, ez = iz > cz;
+                    const int base = (cz * th + cy) * tw + cx;
+                    const float4 *pc = slab + base;
+                    // One pass over the 8 corners.  dL/d(sample) = (A dL.rgb, B) with A, B known only after the sample is
+                    // complete, but <T_c, dL/d(sample)> = A <T_c.rgb, dL.rgb> + B T_c.a is linear in (A, B): accumulate
+                    // the index-gradient sums for both parts now and combine afterwards (no corner stays live).
+                    const float wx_[2] = {bx1, bx0}, wy_[2] = {by1, by0}, wz_[2] = {bz1, bz0};
+                    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+                    float gpU[3] = {0.f, 0.f, 0.f}, gpL[3] = {0.f, 0.f, 0.f};   // rgb part: upper / lower corner sums per axis
+                    float gaU[3] = {0.f, 0.f, 0.f}, gaL[3] = {0.f, 0.f, 0.f};   // alpha part
+                    float wgt[8];
+#pragma unroll
+                    for (int cn = 0; cn < 8; ++cn) {
+                        const int bx = cn & 1, byy = (cn >> 1) & 1, bz = (cn >> 2) & 1;
+                        const float4 v = __ldg(pc + ((bx ? sx : 0) + (byy ? sy : 0) + (bz ? sz : 0)));
+                        const float w_ = (wx_[bx] * wy_[byy]) * wz_[bz];
+                        wgt[cn] = w_;
+                        s.x = __fmaf_rn(w_, v.x, s.x); s.y = __fmaf_rn(w_, v.y, s.y);
+                        s.z = __fmaf_rn(w_, v.z, s.z); s.w = __fmaf_rn(w_, v.w, s.w);
+                        const float pr = v.x * dL.x + v.y * dL.y + v.z * dL.z;
+                        const float wyz = wy_[byy] * wz_[bz], wxz = wx_[bx] * wz_[bz], wxy = wx_[bx] * wy_[byy];
+                        if (bx) { gpU[0] += pr * wyz; gaU[0] += v.w * wyz; } else { gpL[0] += pr * wyz; gaL[0] += v.w * wyz; }
+                        if (byy) { gpU[1] += pr * wxz; gaU[1] += v.w * wxz; } else { gpL[1] += pr * wxz; gaL[1] += v.w * wxz; }
+                        if (bz) { gpU[2] += pr * wxy; gaU[2] += v.w * wxy; } else { gpL[2] += pr * wxy; gaL[2] += v.w * wxy; }
+                    }
+                    s.w *= fade;
+                    // ---- primaccum.h:81-98 with the saturating sample known from forward ----
                     const bool issat = (m == msat) && (rank == ranksat);
-                    const float a = s.w * p.dt;
-                    const float weight = issat ? (1.f - abefore) : a;
+                    const float A = issat ? (1.f - abefore) : s.w * p.dt;       // weight of dL.rgb
                     const float dLa = issat ? 0.f : p.dt * ((s.x - sr) * dL.x + (s.y - sg) * dL.y + (s.z - sb) * dL.z + (1.f - sa) * dL.w);
-                    const float d0 = weight * dL.x, d1 = weight * dL.y, d2 = weight * dL.z;
-                    // primsampler.h:68-91
+                    const float B = dLa * fade;                                  // dL/d(alpha0)
+                    const float d0 = A * dL.x, d1 = A * dL.y, d2 = A * dL.z, d3 = B;
+                    // ---- primsampler.h:68-91 ----
                     const float cf = -(p.fadescale * p.fadeexp) * s.w * dLa;
-                    float gy0 = cf * __powf(fabsf(y0), p.fadeexp - 1.f) * (y0 > 0.f ? 1.f : -1.f);
-                    float gy1 = cf * __powf(fabsf(y1), p.fadeexp - 1.f) * (y1 > 0.f ? 1.f : -1.f);
-                    float gy2 = cf * __powf(fabsf(y2), p.fadeexp - 1.f) * (y2 > 0.f ? 1.f : -1.f);
-                    const float d3 = dLa * sm.fade;
-                    // utils.h:504-643: scatter w_c * dL_sample, gather dL/d(index) = sum_c dw_c <T_c, dL_sample>
-                    float gix = 0.f, giy = 0.f, giz = 0.f;
-                    const float4 *pc = slab + sm.base;
-                    float *gc = gslab + (size_t)sm.base * 4;
+                    float gy0 = cf * pw0 * (y0 > 0.f ? 1.f : -1.f);
+                    float gy1 = cf * pw1 * (y1 > 0.f ? 1.f : -1.f);
+                    float gy2 = cf * pw2 * (y2 > 0.f ? 1.f : -1.f);
+                    // ---- utils.h:504-643: scatter w_c * dL_sample (zero-weight corners add 0) ----
+                    float *gc = gslab + (size_t)base * 4;
 #pragma unroll
                     for (int cn = 0; cn < 8; ++cn) {
                         const int o = ((cn & 1) ? sx : 0) + ((cn & 2) ? sy : 0) + ((cn & 4) ? sz : 0);
-                        const float wx = (cn & 1) ? sm.x0 : sm.x1, wy = (cn & 2) ? sm.y0 : sm.y1, wz = (cn & 4) ? sm.z0 : sm.z1;
-                        const float w_ = wx * wy * wz;
-                        if (w_ != 0.f) red_add_v4(gc + (size_t)o * 4, w_ * d0, w_ * d1, w_ * d2, w_ * d3);
-                        const float4 v = __ldg(pc + o);
-                        const float dp = v.x * d0 + v.y * d1 + v.z * d2 + v.w * d3;
-                        // d(weight)/d(index): +1 on the upper corner, -1 on the lower one.  On a clamped axis the
-                        // reference sees the upper voxel as ITS lower corner (sign -1) and no other corner.
-                        const float gx = (cn & 1) ? (sm.ex ? -dp : dp) : (sm.ex ? 0.f : -dp);
-                        const float gy = (cn & 2) ? (sm.ey ? -dp : dp) : (sm.ey ? 0.f : -dp);
-                        const float gz = (cn & 4) ? (sm.ez ? -dp : dp) : (sm.ez ? 0.f : -dp);
-                        gix += gx * wy * wz;
-                        giy += gy * wx * wz;
-                        giz += gz * wx * wy;
+                        red_add_v4(gc + (size_t)o * 4, wgt[cn] * d0, wgt[cn] * d1, wgt[cn] * d2, wgt[cn] * d3);
                     }
+                    // dL/d(index): d(weight)/d(index) is +1 on the upper corner, -1 on the lower one; on a clamped axis the
+                    // reference sees the upper voxel as ITS lower corner (sign -1) and no other corner.
+                    const float gix = ex ? -(A * gpU[0] + B * gaU[0]) : (A * (gpU[0] - gpL[0]) + B * (gaU[0] - gaL[0]));
+                    const float giy = ey ? -(A * gpU[1] + B * gaU[1]) : (A * (gpU[1] - gpL[1]) + B * (gaU[1] - gaL[1]));
+                    const float giz = ez ? -(A * gpU[2] + B * gaU[2]) : (A * (gpU[2] - gpL[2]) + B * (gaU[2] - gaL[2]));
                     gy0 += gmx * gix; gy1 += gmy * giy; gy2 += gmz * giz;
-                    // primtransf.h:155-179
+                    // ---- primtransf.h:155-179 ----
                     g[0] += rx0 * gy0; g[1] += rx1 * gy1; g[2] += rx2 * gy2;            // grad scale
                     const float h0 = gy0 * q.sx, h1 = gy1 * q.sy, h2 = gy2 * q.sz;
                     g[3] += xm * h0; g[4] += xm * h1; g[5] += xm * h2;                   // grad rot row 0
@@ -810,6 +956,24 @@ __global__ void __launch_bounds__(kWarps * 32, 4) render_backward_kernel(const P
             }   // while (word)
         }       // for (w)
     }           // for (cs)
+    if (CAP < kMaxHit) asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+// Launches `kern` as a programmatic dependent of the previous kernel in the stream (it may start before that kernel has
+// finished; it executes griddepcontrol.wait before exiting, so it never completes first).
+template <typename KernT>
+cudaError_t launch_dependent(KernT kern, dim3 grid, int threads, cudaStream_t st, const Params &p) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, p);
 }
 
 int check_shape(const mvp_shape &s) {
@@ -833,10 +997,11 @@ int launch_accel(const mvp_shape &s, const float *raypos, const float *raydir, c
     prim_setup_kernel<<<(unsigned)((NK + 127) / 128), 128, 0, st>>>(
         s.N, s.K, s.H, s.W, primpos, primrot, primscale, cam, bad, reinterpret_cast<float4 *>(ws + L.pack),
         reinterpret_cast<unsigned *>(ws + L.rx), reinterpret_cast<unsigned *>(ws + L.ry));
-    row_lists_kernel<<<dim3(L.R, s.N), kRowThreads, 0, st>>>(s.K, L.R, L.rowcap, reinterpret_cast<unsigned *>(ws + L.rx),
-                                                            reinterpret_cast<unsigned *>(ws + L.ry),
-                                                            reinterpret_cast<int *>(ws + L.rowcnt),
-                                                            reinterpret_cast<RowEntry *>(ws + L.rowlist));
+    const int TXn = (s.W + kTileW - 1) / kTileW;
+    row_lists_kernel<<<dim3(L.R, s.N), kRowThreads, (size_t)TXn * sizeof(int), st>>>(
+        s.K, L.R, L.rowcap, TXn, kFastCap, reinterpret_cast<unsigned *>(ws + L.rx), reinterpret_cast<unsigned *>(ws + L.ry),
+        reinterpret_cast<int *>(ws + L.rowcnt), reinterpret_cast<RowEntry *>(ws + L.rowlist),
+        reinterpret_cast<unsigned char *>(ws + L.tileflag));
     e = cudaGetLastError();
     return e == cudaSuccess ? MVP_OK : (int)e;
 }
@@ -853,6 +1018,9 @@ void fill_params(Params &p, const mvp_shape &s, float stepsize, float fadescale,
     p.R = L.R; p.rowcap = L.rowcap;
     p.TXn = (s.W + kTileW - 1) / kTileW;
     p.TYn = (s.H + kTileH - 1) / kTileH;
+    p.tileflag = reinterpret_cast<unsigned char *>(ws + L.tileflag);
+    const char *al = getenv("MVP_ALIGN");   // experiment knob: 0 depth (default, fastest measured), 1 first hit, 2 fitted plane
+    p.align = al ? atoi(al) : 0;
 }
 
 }  // namespace
@@ -888,8 +1056,8 @@ int mvp_build_accel(const mvp_shape *shape, const float *raypos, const float *ra
     return launch_accel(*shape, raypos, raydir, primpos, primrot, primscale, (char *)workspace, L, (cudaStream_t)stream);
 }
 
-int mvp_forward_launch_count(uint32_t flags) { return (flags & MVP_FLAG_ACCEL_VALID) ? 1 : 4; }
-int mvp_backward_launch_count(uint32_t flags) { return (flags & MVP_FLAG_ACCEL_VALID) ? 1 : 4; }
+int mvp_forward_launch_count(uint32_t flags) { return (flags & MVP_FLAG_ACCEL_VALID) ? 2 : 5; }
+int mvp_backward_launch_count(uint32_t flags) { return (flags & MVP_FLAG_ACCEL_VALID) ? 2 : 5; }
 
 int mvp_raymarch_forward(const mvp_forward_args *a, void *stream) {
     if (!a) return MVP_ERR_NULL;
@@ -915,10 +1083,15 @@ int mvp_raymarch_forward(const mvp_forward_args *a, void *stream) {
     dim3 grid((p.TXn + 1) / 2, (p.TYn + 1) / 2, a->shape.N);
     if (grid.y > 65535) return MVP_ERR_SHAPE;
     const int cubic = (a->shape.TD == a->shape.TH && a->shape.TH == a->shape.TW) ? a->shape.TD : 0;
-#define MVP_LAUNCH_FWD(TT)                                                                   \
-    do {                                                                                     \
-        if (a->raysat) render_forward_kernel<TT, true><<<grid, kWarps * 32, 0, st>>>(p);     \
-        else render_forward_kernel<TT, false><<<grid, kWarps * 32, 0, st>>>(p);              \
+#define MVP_LAUNCH_FWD(TT)                                                                                   \
+    do {                                                                                                     \
+        if (a->raysat) {                                                                                     \
+            render_forward_kernel<TT, true, kMaxHit><<<grid, kWarps * 32, 0, st>>>(p);                       \
+            launch_dependent(render_forward_kernel<TT, true, kFastCap>, grid, kWarps * 32, st, p);           \
+        } else {                                                                                             \
+            render_forward_kernel<TT, false, kMaxHit><<<grid, kWarps * 32, 0, st>>>(p);                      \
+            launch_dependent(render_forward_kernel<TT, false, kFastCap>, grid, kWarps * 32, st, p);          \
+        }                                                                                                    \
     } while (0)
     if (cubic == 8) MVP_LAUNCH_FWD(8);
     else if (cubic == 16) MVP_LAUNCH_FWD(16);
@@ -953,9 +1126,15 @@ int mvp_raymarch_backward(const mvp_backward_args *a, void *stream) {
     dim3 grid((p.TXn + 1) / 2, (p.TYn + 1) / 2, a->shape.N);
     if (grid.y > 65535) return MVP_ERR_SHAPE;
     const int cubic = (a->shape.TD == a->shape.TH && a->shape.TH == a->shape.TW) ? a->shape.TD : 0;
-    if (cubic == 8) render_backward_kernel<8><<<grid, kWarps * 32, 0, st>>>(p);
-    else if (cubic == 16) render_backward_kernel<16><<<grid, kWarps * 32, 0, st>>>(p);
-    else render_backward_kernel<0><<<grid, kWarps * 32, 0, st>>>(p);
+#define MVP_LAUNCH_BWD(TT)                                                                       \
+    do {                                                                                         \
+        render_backward_kernel<TT, kMaxHit><<<grid, kWarps * 32, 0, st>>>(p);                    \
+        launch_dependent(render_backward_kernel<TT, kFastCap>, grid, kWarps * 32, st, p);        \
+    } while (0)
+    if (cubic == 8) MVP_LAUNCH_BWD(8);
+    else if (cubic == 16) MVP_LAUNCH_BWD(16);
+    else MVP_LAUNCH_BWD(0);
+#undef MVP_LAUNCH_BWD
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? MVP_OK : (int)e;
 }

@@ -29,7 +29,7 @@ import torch.distributed as dist  # noqa: E402
 
 # canonical workload
 VIEWS, H, W, K, T = 80, 1024, 667, 16384, 8
-ALPHA_MU, ALPHA_SIGMA = 3.0, 3.0
+ALPHA_MU, ALPHA_SIGMA = 17.0, 6.0   # ~50 % of the object rays saturate, measured 0.135 / 0.275
 
 
 _T0 = time.time()

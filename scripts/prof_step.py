@@ -11,7 +11,8 @@ from extensions.mvpraymarch.mvpraymarch import mvpraymarch  # noqa: E402
 
 a = [int(x) for x in sys.argv[1:]]
 N, H, W, K, T, iters = (a + [2, 1024, 667, 16384, 8, 2][len(a):])[:6]
-s = scene.make_scene(N, H, W, K, T, alpha_mu=3.0, alpha_sigma=3.0, device="cuda")
+import os as _os
+s = scene.make_scene(N, H, W, K, T, alpha_mu=float(_os.environ.get("ALPHA_MU", "3.0")), alpha_sigma=float(_os.environ.get("ALPHA_SIGMA", "3.0")), device="cuda")
 leaves = [s[k].clone().requires_grad_(True) for k in ("primpos", "primrot", "primscale", "template")]
 grad = torch.randn(N, H, W, 4, device="cuda")
 for _ in range(iters):

@@ -5,7 +5,7 @@ import numpy as np
 import torch
 
 
-def gradcheck_like_scene(N=2, H=13, W=13, k3=2, M=4, seed=1112, fadescale=6.5, fadeexp=7.5, alpha_gain=40.0):
+def gradcheck_like_scene(N=2, H=13, W=13, k3=2, M=4, seed=1112, fadescale=6.5, fadeexp=7.5, alpha_gain=40.0, scale=2.2):
     """Small scene in the style of the reference's gradcheck inputs
     (/root/reference/extensions/mvpraymarch/mvpraymarch.py:464-565): pinhole rays from z=-4, a k3^3 grid of
     randomly rotated slabs around the origin, softplus payload, random tminmax."""
@@ -36,7 +36,7 @@ def gradcheck_like_scene(N=2, H=13, W=13, k3=2, M=4, seed=1112, fadescale=6.5, f
     Kx[:, 0, 1], Kx[:, 0, 2], Kx[:, 1, 0] = -kx[:, 2], kx[:, 1], kx[:, 2]
     Kx[:, 1, 2], Kx[:, 2, 0], Kx[:, 2, 1] = -kx[:, 0], -kx[:, 1], kx[:, 0]
     rot = (torch.eye(3)[None] + torch.sin(th)[..., None] * Kx + (1 - torch.cos(th))[..., None] * (Kx @ Kx)).view(N, K, 3, 3)
-    scale = 2.2 * torch.exp(0.1 * torch.randn(N, K, 3, generator=g))
+    scale = scale * torch.exp(0.1 * torch.randn(N, K, 3, generator=g))
     return dict(raypos=rp.contiguous(), raydir=rd.contiguous(), tminmax=tminmax.contiguous(), stepsize=stepsize,
                 primpos=pos.contiguous(), primrot=rot.contiguous(), primscale=scale.contiguous(),
                 template=tpl.contiguous(), fadescale=fadescale, fadeexp=fadeexp)
@@ -82,6 +82,8 @@ CASES = {
     "gradcheck_ragged": lambda: gradcheck_like_scene(N=1, H=13, W=19, k3=3, M=4, seed=7, alpha_gain=8.0),
     # head scene, C1-like but small: pinhole dome cameras, UV-grid slabs on an ellipsoid
     "head_small": lambda: _head_case(2, 64, 42, 256, 8, stepsize=1.0 / 64, alpha_mu=2.0, alpha_sigma=3.0),
+    # 125 large overlapping slabs: every tile sees > 96 candidates -> exercises the 512-entry kernel variant
+    "many_overlaps": lambda: gradcheck_like_scene(N=1, H=12, W=20, k3=5, M=4, seed=3, alpha_gain=0.4, scale=1.1),
     "head_t16": lambda: _head_case(1, 48, 32, 64, 16, stepsize=1.0 / 32, view_offset=11, alpha_mu=1.0, alpha_sigma=2.0),
 }
 

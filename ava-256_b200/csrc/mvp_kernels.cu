@@ -399,15 +399,16 @@ struct Params {
     float *g_primpos, *g_primrot, *g_primscale, *g_tplate;
 };
 
-// Builds the warp's slab list (rank order, at most CAP entries in shared memory) and each lane's rtminmax; then,
-// with every lane's first step j0 known, chooses the lane <-> sweep alignment and, in a second pass over the (short)
-// list, converts each slab's per-lane [t_enter, t_exit] into a warp step interval in sweep units (lane step
-// j = sweep m + off).  Lanes only ever wait (sweep steps before their own first step are idle), so ANY alignment
-// gives the reference's result; a good one keeps the 32 rays of a tile inside the same slab at the same time:
-//   align 0: equal depth t (sweep planes perpendicular to the view direction)
-//   align 1: every lane starts at its own first hit (the reference's lock-step loop, subset_kernel.h:63-76)
-//   align 2: equal depth relative to a plane fitted to the tile's first-hit depths (compensates surface tilt)
-// Returns false when the list would exceed CAP (< 512): the tile is then left to the 512-entry kernel variant.
+// Builds the warp's slab list (rank order, at most CAP entries in shared memory), each slab's warp step interval and
+// each lane's rtminmax, in one pass over the tile row's bucket.
+//
+// Lane <-> sweep alignment: lane step j = sweep m + off with off = ceil((tref - tmin) / dt), tref = min tmin of the
+// tile, i.e. all lanes of a tile are at (nearly) the same depth t at the same sweep step.  Lanes only ever wait (sweep
+// steps before their own first step are idle), so any alignment reproduces the reference; measured on B200, equal
+// depth beats both "every lane starts at its own first hit" (the reference's lock-step loop) and a plane fitted to
+// the first-hit depths (0.57 vs 0.70 ms per 1024x667 view) because neighbouring slabs sit at randomly different
+// depths while the sweep planes stay coherent.
+// Returns false when the list would exceed CAP (< 512); cannot happen for tiles classified "fast" at accel build.
 template <int CAP>
 __device__ __forceinline__ bool build_tile_list(const Params &p, float rdt, int n, int tx, int ty, int lane, TileCtx &c,
                                                 int *s_k, int *s_lo, int *s_hi, float &t, float &x, float &y, float &z,
@@ -421,6 +422,13 @@ __device__ __forceinline__ bool build_tile_list(const Params &p, float rdt, int 
     const float2 tmm = __ldg(reinterpret_cast<const float2 *>(p.tminmax) + r);
     c.ray.tmin = tmm.x; c.ray.tmax = tmm.y;
     c.rt0 = CUDART_INF_F; c.rt1 = -CUDART_INF_F;
+
+    const float tsteps = c.ray.tmin * rdt;            // lattice origin of this lane, in steps
+    float tref = c.inimg ? tsteps : CUDART_INF_F;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tref = fminf(tref, __shfl_xor_sync(0xffffffffu, tref, o));
+    c.off = clamp_step(ceilf(tref - tsteps));
+    const float foff = (float)c.off;
 
     const float4 *packn = p.pack + (size_t)n * p.K * 4;
     const int cnt = p.rowcnt[(size_t)n * p.R + ty];
@@ -459,10 +467,18 @@ __device__ __forceinline__ bool build_tile_list(const Params &p, float rdt, int 
             const Prim q = load_prim(packn, kk);
             float lo, hi;
             const bool hit = slab_test(q, c.ray, lo, hi) && c.inimg;
-            if (hit) { c.rt0 = fminf(c.rt0, lo); c.rt1 = fmaxf(c.rt1, hi); }
+            int jlo = kBig, jhi = -kBig;
+            if (hit) {
+                c.rt0 = fminf(c.rt0, lo); c.rt1 = fmaxf(c.rt1, hi);
+                // lattice steps that can lie inside [lo, hi]: floor((lo-tmin)/dt) .. floor((hi-tmin)/dt) + 1 (one step of
+                // slack on each side covers the fp difference between this quotient and the incremental t of the march)
+                jlo = clamp_step(floorf(lo * rdt - tsteps) - foff);
+                jhi = clamp_step(floorf(hi * rdt - tsteps) + 1.f - foff);
+            }
             if (__any_sync(0xffffffffu, hit)) {
+                const int wlo = __reduce_min_sync(0xffffffffu, jlo), whi = __reduce_max_sync(0xffffffffu, jhi);
                 if (nl < CAP) {
-                    if (lane == 0) s_k[nl] = kk;
+                    if (lane == 0) { s_k[nl] = kk; s_lo[nl] = wlo; s_hi[nl] = whi; }
                     ++nl;
                 } else if (CAP < kMaxHit) {
                     return false;          // warp-uniform
@@ -484,68 +500,6 @@ __device__ __forceinline__ bool build_tile_list(const Params &p, float rdt, int 
     z = __fmaf_rn(__fmul_rn(c.ray.dz, fi), p.dt, zs);
     r1e = __fadd_rn(r1, 9.9999997473787516356e-06f);
     j0 = incs;
-    const bool hashit = c.inimg && (c.rt0 <= c.rt1);
-
-    // ---- alignment: off such that lane step j = m + off ----
-    int off = incs;                                   // align 1
-    if (p.align != 1) {
-        const float tsteps = c.ray.tmin * rdt;        // lattice origin of this lane in steps
-        float plane = 0.f;                            // depth (in steps) of the sweep origin at this lane
-        if (p.align == 2) {
-            // least-squares plane g ~ a + b u + c v through the first-hit depths of the front-most lanes
-            const float g = tsteps + fi;
-            float gmin = hashit ? g : CUDART_INF_F;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) gmin = fminf(gmin, __shfl_xor_sync(0xffffffffu, gmin, o));
-            const bool inl = hashit && (g <= gmin + 24.f);
-            const int u = lane & 7, v = lane >> 3;
-            const int gq = inl ? (int)((g - gmin) * 16.f) : 0;
-            const int w1 = inl ? 1 : 0;
-            const float S1 = (float)__reduce_add_sync(0xffffffffu, w1);
-            const float Su = (float)__reduce_add_sync(0xffffffffu, w1 * u), Sv = (float)__reduce_add_sync(0xffffffffu, w1 * v);
-            const float Suu = (float)__reduce_add_sync(0xffffffffu, w1 * u * u), Suv = (float)__reduce_add_sync(0xffffffffu, w1 * u * v);
-            const float Svv = (float)__reduce_add_sync(0xffffffffu, w1 * v * v);
-            const float Sg = (float)__reduce_add_sync(0xffffffffu, gq), Sug = (float)__reduce_add_sync(0xffffffffu, gq * u);
-            const float Svg = (float)__reduce_add_sync(0xffffffffu, gq * v);
-            const float det = S1 * (Suu * Svv - Suv * Suv) - Su * (Su * Svv - Suv * Sv) + Sv * (Su * Suv - Suu * Sv);
-            float pa = S1 > 0.f ? Sg / S1 : 0.f, pb = 0.f, pc = 0.f;
-            if (det > 0.5f) {
-                const float id = 1.f / det;
-                pa = id * (Sg * (Suu * Svv - Suv * Suv) - Su * (Sug * Svv - Suv * Svg) + Sv * (Sug * Suv - Suu * Svg));
-                pb = id * (S1 * (Sug * Svv - Svg * Suv) - Sg * (Su * Svv - Suv * Sv) + Sv * (Su * Svg - Sug * Sv));
-                pc = id * (S1 * (Suu * Svg - Suv * Sug) - Su * (Su * Svg - Sug * Sv) + Sg * (Su * Suv - Suu * Sv));
-                pb = fminf(fmaxf(pb, -128.f), 128.f); pc = fminf(fmaxf(pc, -128.f), 128.f);
-            }
-            plane = gmin + (pa + pb * (float)u + pc * (float)v) * (1.f / 16.f);
-            if (!(plane == plane) || gmin == CUDART_INF_F) plane = 0.f;
-        } else {
-            float tref = c.inimg ? tsteps : CUDART_INF_F;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) tref = fminf(tref, __shfl_xor_sync(0xffffffffu, tref, o));
-            plane = tref;
-        }
-        off = clamp_step(ceilf(plane - tsteps));
-    }
-    // normalise: the first lane to start does so at sweep step 0
-    int ms = hashit ? clamp_step((float)incs - (float)off) : kBig;
-    const int msmin = __reduce_min_sync(0xffffffffu, ms);
-    if (msmin < kBig) off += msmin;
-    c.off = off;
-    const float foff = (float)off;
-    // pass 2: warp step intervals in sweep units
-    for (int slot = 0; slot < nl; ++slot) {
-        const Prim q = load_prim(packn, s_k[slot]);
-        float lo, hi;
-        const bool hit = slab_test(q, c.ray, lo, hi) && c.inimg;
-        int jlo = kBig, jhi = -kBig;
-        if (hit) {
-            jlo = clamp_step(floorf((lo - c.ray.tmin) * rdt) - 1.f - foff);
-            jhi = clamp_step(floorf((hi - c.ray.tmin) * rdt) + 2.f - foff);
-        }
-        const int wlo = __reduce_min_sync(0xffffffffu, jlo), whi = __reduce_max_sync(0xffffffffu, jhi);
-        if (lane == 0) { s_lo[slot] = wlo; s_hi[slot] = whi; }
-    }
-    __syncwarp();
     return true;
 }
 
@@ -652,13 +606,15 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit) ? MVP_FWD_MINB : 
     const float4 *tpn = reinterpret_cast<const float4 *>(p.tplate) + (size_t)n * p.K * slabsz;
     const int kstart = dfs_kstart(p.K);
 
-    if (nl > 0 && !__all_sync(0xffffffffu, done)) {
+    const int mstart = __reduce_min_sync(0xffffffffu, ms);
+    if (nl > 0 && mstart < kBig) {
         // each lane keeps the interval of list slots `lane` and `lane + 32` in registers (lists are rarely longer)
         int lo0 = kBig, hi0 = -kBig, lo1 = kBig, hi1 = -kBig;
         if (lane < nl) { lo0 = s_lo[warp][lane]; hi0 = s_hi[warp][lane]; }
         if (lane + 32 < nl) { lo1 = s_lo[warp][lane + 32]; hi1 = s_hi[warp][lane + 32]; }
-        for (int m = 0;; ++m) {
+        for (int m = mstart;; ++m) {
             const bool on = !done && (m >= ms);
+            bool anyslab = false;
             for (int w = 0; w < nwords; ++w) {
                 bool a;
                 if (w == 0) a = (lo0 <= m) && (m <= hi0);
@@ -668,6 +624,7 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit) ? MVP_FWD_MINB : 
                     a = (slot < nl) && (s_lo[warp][slot] <= m) && (m <= s_hi[warp][slot]);
                 }
                 unsigned word = __ballot_sync(0xffffffffu, a);
+                anyslab |= (word != 0);
                 while (word) {
                     const int b = __ffs(word) - 1;
                     word &= word - 1;
@@ -707,6 +664,29 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit) ? MVP_FWD_MINB : 
                 done = (t > r1e) || sat;
             }
             if (__all_sync(0xffffffffu, done)) break;
+            if (!anyslab) {
+                // nothing is active at this step: run ahead to the next step at which a slab becomes active, carrying
+                // t and the position with the same per-step fma sequence (the result must not depend on the skipping)
+                int nxt = kBig;
+                if (lo0 > m) nxt = lo0;
+                if (lo1 > m) nxt = min(nxt, lo1);
+                for (int w = 2; w < nwords; ++w) {
+                    const int slot = w * 32 + lane;
+                    if (slot < nl) { const int l = s_lo[warp][slot]; if (l > m) nxt = min(nxt, l); }
+                }
+                nxt = __reduce_min_sync(0xffffffffu, nxt);
+                if (nxt == kBig) break;          // no slab starts later: nothing left to sample for any lane
+                for (int mm = m + 1; mm < nxt; ++mm) {
+                    if (!done && (mm >= ms)) {
+                        if (kGrad && (t < r1e)) jlast = mm + c.off;
+                        t = __fadd_rn(t, p.dt);
+                        x = __fmaf_rn(c.ray.dx, p.dt, x); y = __fmaf_rn(c.ray.dy, p.dt, y); z = __fmaf_rn(c.ray.dz, p.dt, z);
+                        done = (t > r1e);
+                    }
+                }
+                m = nxt - 1;
+                if (__all_sync(0xffffffffu, done)) break;
+            }
         }
     }
     if (c.inimg) {
@@ -768,7 +748,8 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit) ? MVP_BWD_MINB : 
     const int mlast = hashit ? (min(aux.w - c.off, msat)) : -1;
     const float foff = (float)c.off;
     const int wlast = __reduce_max_sync(0xffffffffu, mlast);
-    if (wlast < 0) { if (CAP < kMaxHit) asm volatile("griddepcontrol.wait;" ::: "memory"); return; }
+    const int wfirst = __reduce_min_sync(0xffffffffu, ms);
+    if (wlast < wfirst || wfirst >= kBig) { if (CAP < kMaxHit) asm volatile("griddepcontrol.wait;" ::: "memory"); return; }
 
     const float4 *packn = p.pack + (size_t)n * p.K * 4;
     const size_t slabsz = (size_t)p.TD * p.TH * p.TW;
@@ -783,9 +764,9 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit) ? MVP_BWD_MINB : 
     // Slabs are processed in the order of their first sweep step, 16-step chunk by chunk, so that each lane's
     // position can be carried forward with the SAME fma sequence the forward kernel executed (bit-identical sample
     // positions: the trilinear position gradient is discontinuous across voxel cells, so this matters).
-    int mcur = 0;
+    int mcur = wfirst;
     const int nwords = (nl + 31) >> 5;
-    for (int cs = 0; cs <= wlast; cs += kMaskSteps) {
+    for (int cs = wfirst; cs <= wlast; cs += kMaskSteps) {
         for (; mcur < cs; ++mcur) {
             if (mcur >= ms) { xb = __fmaf_rn(c.ray.dx, p.dt, xb); yb = __fmaf_rn(c.ray.dy, p.dt, yb); zb = __fmaf_rn(c.ray.dz, p.dt, zb); }
         }
@@ -793,7 +774,7 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit) ? MVP_BWD_MINB : 
             const int myslot = w * 32 + lane;
             bool pick = false;
             if (myslot < nl) {
-                const int a0 = max(s_lo[warp][myslot], 0), b0 = min(s_hi[warp][myslot], wlast);
+                const int a0 = max(s_lo[warp][myslot], wfirst), b0 = min(s_hi[warp][myslot], wlast);
                 pick = (a0 <= b0) && (a0 >= cs) && (a0 < cs + kMaskSteps);
             }
             unsigned word = __ballot_sync(0xffffffffu, pick);
@@ -1019,8 +1000,7 @@ void fill_params(Params &p, const mvp_shape &s, float stepsize, float fadescale,
     p.TXn = (s.W + kTileW - 1) / kTileW;
     p.TYn = (s.H + kTileH - 1) / kTileH;
     p.tileflag = reinterpret_cast<unsigned char *>(ws + L.tileflag);
-    const char *al = getenv("MVP_ALIGN");   // experiment knob: 0 depth (default, fastest measured), 1 first hit, 2 fitted plane
-    p.align = al ? atoi(al) : 0;
+    p.align = 0;
 }
 
 }  // namespace

@@ -40,6 +40,7 @@ constexpr int kTileH = 4;
 constexpr int kWarps = 4;         // warps (tiles) per CTA, arranged 2 x 2
 constexpr int kMaskSteps = 16;    // steps per active-mask rebuild
 constexpr int kRowCapMax = 2048;  // entries per tile-row bucket before the row falls back to scanning all slabs
+constexpr int kRing = 64;        // backward sample ring (entries per warp, power of two, >= 2 * 32)
 constexpr int kFastCap = 96;     // shared-memory list capacity of the common-case render kernels
 constexpr int kBig = 1 << 30;
 #ifndef MVP_BWD_MINB
@@ -712,6 +713,7 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit) ? MVP_BWD_MINB : 
     __shared__ int s_k[kWarps][CAP];
     __shared__ int s_lo[kWarps][CAP];
     __shared__ int s_hi[kWarps][CAP];
+    __shared__ float4 s_q[kWarps][kRing];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tx = blockIdx.x * 2 + (warp & 1), ty = blockIdx.y * 2 + (warp >> 1), n = blockIdx.z;
     if (tx >= p.TXn || ty >= p.TYn) return;
@@ -800,9 +802,12 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit) ? MVP_BWD_MINB : 
                 if (maxlen <= 0) continue;
                 const float4 *slab = tpn + (size_t)k * slabsz;
                 float *gslab = gtn + (size_t)k * slabsz * 4;
-                float g[16];
+                // transform-gradient accumulators of THIS lane for this slab: Gx[i][j] = sum xm_i * dL/dy_j and
+                // Gy[j] = sum dL/dy_j; grad_rot/scale/pos are linear in them (derived once per slab, before the reduction)
+                float gx[9], gsum[3];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) g[i] = 0.f;
+                for (int i = 0; i < 9; ++i) gx[i] = 0.f;
+                gsum[0] = gsum[1] = gsum[2] = 0.f;
                 bool touched = false;
                 // carry the lane's position from the chunk base (step max(cs, ms)) to its first candidate step
                 float x = xb, y = yb, z = zb;
@@ -813,93 +818,142 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit) ? MVP_BWD_MINB : 
                         if (i < adv) { x = __fmaf_rn(c.ray.dx, p.dt, x); y = __fmaf_rn(c.ray.dy, p.dt, y); z = __fmaf_rn(c.ray.dz, p.dt, z); }
                     }
                 }
-                for (int i = 0; i < maxlen; ++i) {
-                    const bool live = i < len;
-                    const int m = la + i;
-                    const float xm = x - q.px, ym = y - q.py, zm = z - q.pz;
-                    x = __fmaf_rn(c.ray.dx, p.dt, x); y = __fmaf_rn(c.ray.dy, p.dt, y); z = __fmaf_rn(c.ray.dz, p.dt, z);
-                    const float rx0 = rowdot(q.r00, xm, q.r10, ym, q.r20, zm);
-                    const float rx1 = rowdot(q.r01, xm, q.r11, ym, q.r21, zm);
-                    const float rx2 = rowdot(q.r02, xm, q.r12, ym, q.r22, zm);
-                    const float y0 = __fmul_rn(q.sx, rx0), y1 = __fmul_rn(q.sy, rx1), y2 = __fmul_rn(q.sz, rx2);
-                    const bool valid = (fabsf(y0) < 1.f) && (fabsf(y1) < 1.f) && (fabsf(y2) < 1.f);
-                    if (!(valid && live)) continue;
-                    touched = true;
-                    // ---- forward sample (primsampler.h:44-66) keeping what the adjoint needs ----
-                    const float e1 = p.fadeexp - 1.f;
-                    const float pw0 = __powf(fabsf(y0), e1), pw1 = __powf(fabsf(y1), e1), pw2 = __powf(fabsf(y2), e1);
-                    const float fade = __expf(-p.fadescale * (pw0 * fabsf(y0) + pw1 * fabsf(y1) + pw2 * fabsf(y2)));
-                    const float fx = ((y0 + 1.f) * 0.5f) * (float)(tw - 1);
-                    const float fy = ((y1 + 1.f) * 0.5f) * (float)(th - 1);
-                    const float fz = ((y2 + 1.f) * 0.5f) * (float)(td - 1);
-                    const int ix = __float2int_rd(fx), iy = __float2int_rd(fy), iz = __float2int_rd(fz);
-                    int cx, cy, cz;
-                    if (T >= 2) { cx = min(ix, T - 2); cy = min(iy, T - 2); cz = min(iz, T - 2); }
-                    else { cx = max(min(ix, tw - 2), 0); cy = max(min(iy, th - 2), 0); cz = max(min(iz, td - 2), 0); }
-                    const float bx0 = fx - (float)cx, bx1 = (float)(cx + 1) - fx;
-                    const float by0 = fy - (float)cy, by1 = (float)(cy + 1) - fy;
-                    const float bz0 = fz - (float)cz, bz1 = (float)(cz + 1) - fz;
-                    const bool ex = ix > cx, ey = iy > cy, ez = iz > cz;
-                    const int base = (cz * th + cy) * tw + cx;
-                    const float4 *pc = slab + base;
-                    // One pass over the 8 corners.  dL/d(sample) = (A dL.rgb, B) with A, B known only after the sample is
-                    // complete, but <T_c, dL/d(sample)> = A <T_c.rgb, dL.rgb> + B T_c.a is linear in (A, B): accumulate
-                    // the index-gradient sums for both parts now and combine afterwards (no corner stays live).
-                    const float wx_[2] = {bx1, bx0}, wy_[2] = {by1, by0}, wz_[2] = {bz1, bz0};
-                    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-                    float gpU[3] = {0.f, 0.f, 0.f}, gpL[3] = {0.f, 0.f, 0.f};   // rgb part: upper / lower corner sums per axis
-                    float gaU[3] = {0.f, 0.f, 0.f}, gaL[3] = {0.f, 0.f, 0.f};   // alpha part
-                    float wgt[8];
-#pragma unroll
-                    for (int cn = 0; cn < 8; ++cn) {
-                        const int bx = cn & 1, byy = (cn >> 1) & 1, bz = (cn >> 2) & 1;
-                        const float4 v = __ldg(pc + ((bx ? sx : 0) + (byy ? sy : 0) + (bz ? sz : 0)));
-                        const float w_ = (wx_[bx] * wy_[byy]) * wz_[bz];
-                        wgt[cn] = w_;
-                        s.x = __fmaf_rn(w_, v.x, s.x); s.y = __fmaf_rn(w_, v.y, s.y);
-                        s.z = __fmaf_rn(w_, v.z, s.z); s.w = __fmaf_rn(w_, v.w, s.w);
-                        const float pr = v.x * dL.x + v.y * dL.y + v.z * dL.z;
-                        const float wyz = wy_[byy] * wz_[bz], wxz = wx_[bx] * wz_[bz], wxy = wx_[bx] * wy_[byy];
-                        if (bx) { gpU[0] += pr * wyz; gaU[0] += v.w * wyz; } else { gpL[0] += pr * wyz; gaL[0] += v.w * wyz; }
-                        if (byy) { gpU[1] += pr * wxz; gaU[1] += v.w * wxz; } else { gpL[1] += pr * wxz; gaL[1] += v.w * wxz; }
-                        if (bz) { gpU[2] += pr * wxy; gaU[2] += v.w * wxy; } else { gpL[2] += pr * wxy; gaL[2] += v.w * wxy; }
+                // Sample compaction: lanes enumerate their own valid steps (cheap transform + test) and push the sample
+                // position into a ring; the expensive adjoint runs on full batches of 32 samples, each computed by
+                // whichever lane pops it (per-ray data comes from the owner lane by shuffle; the per-slab gradient sums are
+                // reduced over the warp afterwards, so it does not matter which lane accumulates a sample).
+                int qhead = 0, qn = 0;
+                float4 *ring = s_q[warp];
+                for (int i = 0; i <= maxlen; ++i) {
+                    const bool flush = (i == maxlen);
+                    if (!flush) {
+                        const bool live = i < len;
+                        const float xm = x - q.px, ym = y - q.py, zm = z - q.pz;
+                        x = __fmaf_rn(c.ray.dx, p.dt, x); y = __fmaf_rn(c.ray.dy, p.dt, y); z = __fmaf_rn(c.ray.dz, p.dt, z);
+                        const float y0 = __fmul_rn(q.sx, rowdot(q.r00, xm, q.r10, ym, q.r20, zm));
+                        const float y1 = __fmul_rn(q.sy, rowdot(q.r01, xm, q.r11, ym, q.r21, zm));
+                        const float y2 = __fmul_rn(q.sz, rowdot(q.r02, xm, q.r12, ym, q.r22, zm));
+                        const bool valid = live && (fabsf(y0) < 1.f) && (fabsf(y1) < 1.f) && (fabsf(y2) < 1.f);
+                        const unsigned vm = __ballot_sync(0xffffffffu, valid);
+                        if (vm) {
+                            if (valid) {
+                                const int pos = (qhead + qn + __popc(vm & ((1u << lane) - 1u))) & (kRing - 1);
+                                const bool issat = ((la + i) == msat) && (rank == ranksat);
+                                ring[pos] = make_float4(xm, ym, zm, __int_as_float(lane | (issat ? 256 : 0)));
+                            }
+                            qn += __popc(vm);
+                            __syncwarp();
+                        }
                     }
-                    s.w *= fade;
-                    // ---- primaccum.h:81-98 with the saturating sample known from forward ----
-                    const bool issat = (m == msat) && (rank == ranksat);
-                    const float A = issat ? (1.f - abefore) : s.w * p.dt;       // weight of dL.rgb
-                    const float dLa = issat ? 0.f : p.dt * ((s.x - sr) * dL.x + (s.y - sg) * dL.y + (s.z - sb) * dL.z + (1.f - sa) * dL.w);
-                    const float B = dLa * fade;                                  // dL/d(alpha0)
-                    const float d0 = A * dL.x, d1 = A * dL.y, d2 = A * dL.z, d3 = B;
-                    // ---- primsampler.h:68-91 ----
-                    const float cf = -(p.fadescale * p.fadeexp) * s.w * dLa;
-                    float gy0 = cf * pw0 * (y0 > 0.f ? 1.f : -1.f);
-                    float gy1 = cf * pw1 * (y1 > 0.f ? 1.f : -1.f);
-                    float gy2 = cf * pw2 * (y2 > 0.f ? 1.f : -1.f);
-                    // ---- utils.h:504-643: scatter w_c * dL_sample (zero-weight corners add 0) ----
-                    float *gc = gslab + (size_t)base * 4;
+                    while (qn >= 32 || (flush && qn > 0)) {
+                        const int cnt = min(qn, 32);
+                        const bool act = lane < cnt;
+                        const float4 rec = ring[(qhead + (act ? lane : 0)) & (kRing - 1)];
+                        qhead = (qhead + cnt) & (kRing - 1);
+                        qn -= cnt;
+                        __syncwarp();
+                        const int meta = __float_as_int(rec.w);
+                        const int owner = meta & 31;
+                        const bool issat = (meta & 256) != 0;
+                        // per-ray data of the owner lane
+                        const float oLx = __shfl_sync(0xffffffffu, dL.x, owner), oLy = __shfl_sync(0xffffffffu, dL.y, owner);
+                        const float oLz = __shfl_sync(0xffffffffu, dL.z, owner), oLw = __shfl_sync(0xffffffffu, dL.w, owner);
+                        const float osr = __shfl_sync(0xffffffffu, sr, owner), osg = __shfl_sync(0xffffffffu, sg, owner);
+                        const float osb = __shfl_sync(0xffffffffu, sb, owner), osa = __shfl_sync(0xffffffffu, sa, owner);
+                        const float oab = __shfl_sync(0xffffffffu, abefore, owner);
+                        if (!act) continue;
+                        touched = true;
+                        const float xm = rec.x, ym = rec.y, zm = rec.z;
+                        const float rx0 = rowdot(q.r00, xm, q.r10, ym, q.r20, zm);
+                        const float rx1 = rowdot(q.r01, xm, q.r11, ym, q.r21, zm);
+                        const float rx2 = rowdot(q.r02, xm, q.r12, ym, q.r22, zm);
+                        const float y0 = __fmul_rn(q.sx, rx0), y1 = __fmul_rn(q.sy, rx1), y2 = __fmul_rn(q.sz, rx2);
+                        // ---- forward sample (primsampler.h:44-66) keeping what the adjoint needs ----
+                        const float e1 = p.fadeexp - 1.f;
+                        const float pw0 = __powf(fabsf(y0), e1), pw1 = __powf(fabsf(y1), e1), pw2 = __powf(fabsf(y2), e1);
+                        const float fade = __expf(-p.fadescale * (pw0 * fabsf(y0) + pw1 * fabsf(y1) + pw2 * fabsf(y2)));
+                        const float fx = ((y0 + 1.f) * 0.5f) * (float)(tw - 1);
+                        const float fy = ((y1 + 1.f) * 0.5f) * (float)(th - 1);
+                        const float fz = ((y2 + 1.f) * 0.5f) * (float)(td - 1);
+                        const int ix = __float2int_rd(fx), iy = __float2int_rd(fy), iz = __float2int_rd(fz);
+                        int cx, cy, cz;
+                        if (T >= 2) { cx = min(ix, T - 2); cy = min(iy, T - 2); cz = min(iz, T - 2); }
+                        else { cx = max(min(ix, tw - 2), 0); cy = max(min(iy, th - 2), 0); cz = max(min(iz, td - 2), 0); }
+                        const float bx0 = fx - (float)cx, bx1 = (float)(cx + 1) - fx;
+                        const float by0 = fy - (float)cy, by1 = (float)(cy + 1) - fy;
+                        const float bz0 = fz - (float)cz, bz1 = (float)(cz + 1) - fz;
+                        const bool ex = ix > cx, ey = iy > cy, ez = iz > cz;
+                        const int base = (cz * th + cy) * tw + cx;
+                        const float4 *pc = slab + base;
+                        // One pass over the 8 corners.  dL/d(sample) = (A dL.rgb, B) with A, B known only after the sample
+                        // is complete, but <T_c, dL/d(sample)> = A <T_c.rgb, dL.rgb> + B T_c.a is linear in (A, B):
+                        // accumulate the index-gradient sums for both parts now and combine afterwards.
+                        const float wx_[2] = {bx1, bx0}, wy_[2] = {by1, by0}, wz_[2] = {bz1, bz0};
+                        float4 sv = make_float4(0.f, 0.f, 0.f, 0.f);
+                        float gpU[3] = {0.f, 0.f, 0.f}, gpL[3] = {0.f, 0.f, 0.f};   // rgb part: upper / lower corner sums per axis
+                        float gaU[3] = {0.f, 0.f, 0.f}, gaL[3] = {0.f, 0.f, 0.f};   // alpha part
+                        float wgt[8];
 #pragma unroll
-                    for (int cn = 0; cn < 8; ++cn) {
-                        const int o = ((cn & 1) ? sx : 0) + ((cn & 2) ? sy : 0) + ((cn & 4) ? sz : 0);
-                        red_add_v4(gc + (size_t)o * 4, wgt[cn] * d0, wgt[cn] * d1, wgt[cn] * d2, wgt[cn] * d3);
+                        for (int cn = 0; cn < 8; ++cn) {
+                            const int bx = cn & 1, byy = (cn >> 1) & 1, bz = (cn >> 2) & 1;
+                            const float4 v = __ldg(pc + ((bx ? sx : 0) + (byy ? sy : 0) + (bz ? sz : 0)));
+                            const float w_ = (wx_[bx] * wy_[byy]) * wz_[bz];
+                            wgt[cn] = w_;
+                            sv.x = __fmaf_rn(w_, v.x, sv.x); sv.y = __fmaf_rn(w_, v.y, sv.y);
+                            sv.z = __fmaf_rn(w_, v.z, sv.z); sv.w = __fmaf_rn(w_, v.w, sv.w);
+                            const float pr = v.x * oLx + v.y * oLy + v.z * oLz;
+                            const float wyz = wy_[byy] * wz_[bz], wxz = wx_[bx] * wz_[bz], wxy = wx_[bx] * wy_[byy];
+                            if (bx) { gpU[0] += pr * wyz; gaU[0] += v.w * wyz; } else { gpL[0] += pr * wyz; gaL[0] += v.w * wyz; }
+                            if (byy) { gpU[1] += pr * wxz; gaU[1] += v.w * wxz; } else { gpL[1] += pr * wxz; gaL[1] += v.w * wxz; }
+                            if (bz) { gpU[2] += pr * wxy; gaU[2] += v.w * wxy; } else { gpL[2] += pr * wxy; gaL[2] += v.w * wxy; }
+                        }
+                        sv.w *= fade;
+                        // ---- primaccum.h:81-98 with the saturating sample known from forward ----
+                        const float A = issat ? (1.f - oab) : sv.w * p.dt;             // weight of dL.rgb
+                        const float dLa = issat ? 0.f : p.dt * ((sv.x - osr) * oLx + (sv.y - osg) * oLy + (sv.z - osb) * oLz + (1.f - osa) * oLw);
+                        const float B = dLa * fade;                                     // dL/d(alpha0)
+                        const float d0 = A * oLx, d1 = A * oLy, d2 = A * oLz;
+                        // ---- primsampler.h:68-91 ----
+                        const float cf = -(p.fadescale * p.fadeexp) * sv.w * dLa;
+                        float gy0 = cf * pw0 * (y0 > 0.f ? 1.f : -1.f);
+                        float gy1 = cf * pw1 * (y1 > 0.f ? 1.f : -1.f);
+                        float gy2 = cf * pw2 * (y2 > 0.f ? 1.f : -1.f);
+                        // ---- utils.h:504-643: scatter w_c * dL_sample (zero-weight corners add 0) ----
+                        float *gc = gslab + (size_t)base * 4;
+#pragma unroll
+                        for (int cn = 0; cn < 8; ++cn) {
+                            const int o = ((cn & 1) ? sx : 0) + ((cn & 2) ? sy : 0) + ((cn & 4) ? sz : 0);
+                            red_add_v4(gc + (size_t)o * 4, wgt[cn] * d0, wgt[cn] * d1, wgt[cn] * d2, wgt[cn] * B);
+                        }
+                        // dL/d(index): d(weight)/d(index) is +1 on the upper corner, -1 on the lower one; on a clamped axis
+                        // the reference sees the upper voxel as ITS lower corner (sign -1) and no other corner.
+                        const float gix = ex ? -(A * gpU[0] + B * gaU[0]) : (A * (gpU[0] - gpL[0]) + B * (gaU[0] - gaL[0]));
+                        const float giy = ey ? -(A * gpU[1] + B * gaU[1]) : (A * (gpU[1] - gpL[1]) + B * (gaU[1] - gaL[1]));
+                        const float giz = ez ? -(A * gpU[2] + B * gaU[2]) : (A * (gpU[2] - gpL[2]) + B * (gaU[2] - gaL[2]));
+                        gy0 += gmx * gix; gy1 += gmy * giy; gy2 += gmz * giz;
+                        // ---- primtransf.h:155-179, accumulated in factored form ----
+                        gx[0] += xm * gy0; gx[1] += xm * gy1; gx[2] += xm * gy2;
+                        gx[3] += ym * gy0; gx[4] += ym * gy1; gx[5] += ym * gy2;
+                        gx[6] += zm * gy0; gx[7] += zm * gy1; gx[8] += zm * gy2;
+                        gsum[0] += gy0; gsum[1] += gy1; gsum[2] += gy2;
                     }
-                    // dL/d(index): d(weight)/d(index) is +1 on the upper corner, -1 on the lower one; on a clamped axis the
-                    // reference sees the upper voxel as ITS lower corner (sign -1) and no other corner.
-                    const float gix = ex ? -(A * gpU[0] + B * gaU[0]) : (A * (gpU[0] - gpL[0]) + B * (gaU[0] - gaL[0]));
-                    const float giy = ey ? -(A * gpU[1] + B * gaU[1]) : (A * (gpU[1] - gpL[1]) + B * (gaU[1] - gaL[1]));
-                    const float giz = ez ? -(A * gpU[2] + B * gaU[2]) : (A * (gpU[2] - gpL[2]) + B * (gaU[2] - gaL[2]));
-                    gy0 += gmx * gix; gy1 += gmy * giy; gy2 += gmz * giz;
-                    // ---- primtransf.h:155-179 ----
-                    g[0] += rx0 * gy0; g[1] += rx1 * gy1; g[2] += rx2 * gy2;            // grad scale
-                    const float h0 = gy0 * q.sx, h1 = gy1 * q.sy, h2 = gy2 * q.sz;
-                    g[3] += xm * h0; g[4] += xm * h1; g[5] += xm * h2;                   // grad rot row 0
-                    g[6] += ym * h0; g[7] += ym * h1; g[8] += ym * h2;                   // row 1
-                    g[9] += zm * h0; g[10] += zm * h1; g[11] += zm * h2;                 // row 2
-                    g[12] -= q.r00 * h0 + q.r01 * h1 + q.r02 * h2;                       // grad pos
-                    g[13] -= q.r10 * h0 + q.r11 * h1 + q.r12 * h2;
-                    g[14] -= q.r20 * h0 + q.r21 * h1 + q.r22 * h2;
                 }
                 if (!__any_sync(0xffffffffu, touched)) continue;
+                // grad_scale_j = sum_i R[i][j] Gx[i][j];  grad_rot[i][j] = s_j Gx[i][j];  grad_pos = -R (s * Gy)
+                float g[16];
+                g[0] = q.r00 * gx[0] + q.r10 * gx[3] + q.r20 * gx[6];
+                g[1] = q.r01 * gx[1] + q.r11 * gx[4] + q.r21 * gx[7];
+                g[2] = q.r02 * gx[2] + q.r12 * gx[5] + q.r22 * gx[8];
+                g[3] = q.sx * gx[0]; g[4] = q.sy * gx[1]; g[5] = q.sz * gx[2];
+                g[6] = q.sx * gx[3]; g[7] = q.sy * gx[4]; g[8] = q.sz * gx[5];
+                g[9] = q.sx * gx[6]; g[10] = q.sy * gx[7]; g[11] = q.sz * gx[8];
+                {
+                    const float h0 = q.sx * gsum[0], h1 = q.sy * gsum[1], h2 = q.sz * gsum[2];
+                    g[12] = -(q.r00 * h0 + q.r01 * h1 + q.r02 * h2);
+                    g[13] = -(q.r10 * h0 + q.r11 * h1 + q.r12 * h2);
+                    g[14] = -(q.r20 * h0 + q.r21 * h1 + q.r22 * h2);
+                }
+                g[15] = 0.f;
                 // 16-value butterfly: after the 5 stages lanes 2i and 2i+1 hold the warp total of g[i]
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {

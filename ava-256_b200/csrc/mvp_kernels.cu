@@ -41,7 +41,10 @@ constexpr int kWarps = 4;         // warps (tiles) per CTA, arranged 2 x 2
 constexpr int kMaskSteps = 16;    // steps per active-mask rebuild
 constexpr int kRowCapMax = 2048;  // entries per tile-row bucket before the row falls back to scanning all slabs
 constexpr int kRing = 64;        // backward sample ring (entries per warp, power of two, >= 2 * 32)
-constexpr int kFastCap = 96;     // shared-memory list capacity of the common-case render kernels
+#ifndef MVP_FASTCAP
+#define MVP_FASTCAP 384
+#endif
+constexpr int kFastCap = MVP_FASTCAP;   // shared-memory list capacity of the common-case render kernels
 constexpr int kBig = 1 << 30;
 #ifndef MVP_BWD_MINB
 #define MVP_BWD_MINB 4   // resident CTAs per SM the backward kernel is compiled for (register cap 65536 / (128 * MINB))
@@ -367,6 +370,15 @@ __device__ __forceinline__ int clamp_step(float v) {   // float -> step index, s
     return (int)fminf(fmaxf(v, -(float)kBig), (float)kBig);
 }
 
+// warp step interval of a list entry, packed as two int16 (lo | hi << 16); the extreme values mean "unbounded", so
+// clamping an interval that does not fit only ever widens it (a superset of active steps is always correct)
+__device__ __forceinline__ int pack_iv(int lo, int hi) {
+    lo = max(min(lo, 32767), -32768); hi = max(min(hi, 32767), -32768);
+    return (lo & 0xffff) | (hi << 16);
+}
+__device__ __forceinline__ int iv_lo(int v) { const int l = (int)(short)(v & 0xffff); return l == -32768 ? -kBig : l; }
+__device__ __forceinline__ int iv_hi(int v) { const int h = v >> 16; return h == 32767 ? kBig : h; }
+
 struct TileCtx {
     // per-lane
     Ray ray;
@@ -412,7 +424,7 @@ struct Params {
 // Returns false when the list would exceed CAP (< 512); cannot happen for tiles classified "fast" at accel build.
 template <int CAP>
 __device__ __forceinline__ bool build_tile_list(const Params &p, float rdt, int n, int tx, int ty, int lane, TileCtx &c,
-                                                int *s_k, int *s_lo, int *s_hi, float &t, float &x, float &y, float &z,
+                                                int *s_k, int *s_iv, float &t, float &x, float &y, float &z,
                                                 float &r1e, int &j0) {
     const int px = tx * kTileW + (lane & 7), py = ty * kTileH + (lane >> 3);
     c.inimg = (px < p.W) && (py < p.H);
@@ -479,7 +491,7 @@ __device__ __forceinline__ bool build_tile_list(const Params &p, float rdt, int 
             if (__any_sync(0xffffffffu, hit)) {
                 const int wlo = __reduce_min_sync(0xffffffffu, jlo), whi = __reduce_max_sync(0xffffffffu, jhi);
                 if (nl < CAP) {
-                    if (lane == 0) { s_k[nl] = kk; s_lo[nl] = wlo; s_hi[nl] = whi; }
+                    if (lane == 0) { s_k[nl] = kk; s_iv[nl] = pack_iv(wlo, whi); }
                     ++nl;
                 } else if (CAP < kMaxHit) {
                     return false;          // warp-uniform
@@ -566,8 +578,7 @@ __device__ __forceinline__ float4 sample_slab(const float4 *__restrict__ slab, f
 template <int T, bool kGrad, int CAP>
 __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit) ? MVP_FWD_MINB : 4) render_forward_kernel(const Params p) {
     __shared__ int s_k[kWarps][CAP];
-    __shared__ int s_lo[kWarps][CAP];
-    __shared__ int s_hi[kWarps][CAP];
+    __shared__ int s_iv[kWarps][CAP];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tx = blockIdx.x * 2 + (warp & 1), ty = blockIdx.y * 2 + (warp >> 1), n = blockIdx.z;
     if (tx >= p.TXn || ty >= p.TYn) return;   // warps are independent: no CTA-wide barrier below (exited warps count as arrived)
@@ -584,7 +595,7 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit) ? MVP_FWD_MINB : 
     TileCtx c;
     float t, x, y, z, r1e;
     int j0;
-    const bool fits = build_tile_list<CAP>(p, rdt, n, tx, ty, lane, c, s_k[warp], s_lo[warp], s_hi[warp], t, x, y, z, r1e, j0);
+    const bool fits = build_tile_list<CAP>(p, rdt, n, tx, ty, lane, c, s_k[warp], s_iv[warp], t, x, y, z, r1e, j0);
     (void)fits;   // cannot fail: the tile's candidate count was checked against CAP when the accel was built
 
     const int px = tx * kTileW + (lane & 7), py = ty * kTileH + (lane >> 3);
@@ -611,8 +622,8 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit) ? MVP_FWD_MINB : 
     if (nl > 0 && mstart < kBig) {
         // each lane keeps the interval of list slots `lane` and `lane + 32` in registers (lists are rarely longer)
         int lo0 = kBig, hi0 = -kBig, lo1 = kBig, hi1 = -kBig;
-        if (lane < nl) { lo0 = s_lo[warp][lane]; hi0 = s_hi[warp][lane]; }
-        if (lane + 32 < nl) { lo1 = s_lo[warp][lane + 32]; hi1 = s_hi[warp][lane + 32]; }
+        if (lane < nl) { const int v = s_iv[warp][lane]; lo0 = iv_lo(v); hi0 = iv_hi(v); }
+        if (lane + 32 < nl) { const int v = s_iv[warp][lane + 32]; lo1 = iv_lo(v); hi1 = iv_hi(v); }
         for (int m = mstart;; ++m) {
             const bool on = !done && (m >= ms);
             bool anyslab = false;
@@ -622,7 +633,7 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit) ? MVP_FWD_MINB : 
                 else if (w == 1) a = (lo1 <= m) && (m <= hi1);
                 else {
                     const int slot = w * 32 + lane;
-                    a = (slot < nl) && (s_lo[warp][slot] <= m) && (m <= s_hi[warp][slot]);
+                    if (slot < nl) { const int v = s_iv[warp][slot]; a = (iv_lo(v) <= m) && (m <= iv_hi(v)); } else a = false;
                 }
                 unsigned word = __ballot_sync(0xffffffffu, a);
                 anyslab |= (word != 0);
@@ -673,7 +684,7 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit) ? MVP_FWD_MINB : 
                 if (lo1 > m) nxt = min(nxt, lo1);
                 for (int w = 2; w < nwords; ++w) {
                     const int slot = w * 32 + lane;
-                    if (slot < nl) { const int l = s_lo[warp][slot]; if (l > m) nxt = min(nxt, l); }
+                    if (slot < nl) { const int l = iv_lo(s_iv[warp][slot]); if (l > m) nxt = min(nxt, l); }
                 }
                 nxt = __reduce_min_sync(0xffffffffu, nxt);
                 if (nxt == kBig) break;          // no slab starts later: nothing left to sample for any lane
@@ -711,8 +722,7 @@ __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float 
 template <int T, int CAP>
 __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit) ? MVP_BWD_MINB : 4) render_backward_kernel(const Params p) {
     __shared__ int s_k[kWarps][CAP];
-    __shared__ int s_lo[kWarps][CAP];
-    __shared__ int s_hi[kWarps][CAP];
+    __shared__ int s_iv[kWarps][CAP];
     __shared__ float4 s_q[kWarps][kRing];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tx = blockIdx.x * 2 + (warp & 1), ty = blockIdx.y * 2 + (warp >> 1), n = blockIdx.z;
@@ -728,7 +738,7 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit) ? MVP_BWD_MINB : 
     TileCtx c;
     float t0, xb, yb, zb, r1e;   // xb = position at sweep step max(mcur, ms)
     int j0;
-    build_tile_list<CAP>(p, rdt, n, tx, ty, lane, c, s_k[warp], s_lo[warp], s_hi[warp], t0, xb, yb, zb, r1e, j0);
+    build_tile_list<CAP>(p, rdt, n, tx, ty, lane, c, s_k[warp], s_iv[warp], t0, xb, yb, zb, r1e, j0);
     const int nl = c.nl;
     if (nl == 0) { if (CAP < kMaxHit) asm volatile("griddepcontrol.wait;" ::: "memory"); return; }
 
@@ -776,7 +786,8 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit) ? MVP_BWD_MINB : 
             const int myslot = w * 32 + lane;
             bool pick = false;
             if (myslot < nl) {
-                const int a0 = max(s_lo[warp][myslot], wfirst), b0 = min(s_hi[warp][myslot], wlast);
+                const int v = s_iv[warp][myslot];
+                const int a0 = max(iv_lo(v), wfirst), b0 = min(iv_hi(v), wlast);
                 pick = (a0 <= b0) && (a0 >= cs) && (a0 < cs + kMaskSteps);
             }
             unsigned word = __ballot_sync(0xffffffffu, pick);

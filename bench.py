@@ -72,7 +72,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -251,6 +251,10 @@ def run_ours(args, rank, world):
     log("kernel-only: fwd %.2f ms, bwd %.2f ms per launch (%d views)" % (fwd_ms, bwd_ms, nv))
 
     # ---- end-to-end through the public op with HOST buffers (pinned): H2D of the step's inputs, D2H of the results ----
+    # The host hands over, every step: the rays of all views, one subject's primitives/payload and the image
+    # gradient; it gets back the rendered images and the view-summed (all-reduced) primitive gradients.  Views are
+    # streamed in chunks: H2D of chunk i+1 (copy stream) overlaps fwd+bwd of chunk i (compute stream) and D2H of chunk
+    # i-1 (second copy stream) -- all inside the timed region.
     e2e = None
     if not args.no_e2e:
         host_in = {n: s[n].detach().cpu().pin_memory() for n in ("raypos", "raydir", "tminmax")}
@@ -260,20 +264,51 @@ def run_ours(args, rank, world):
         host_flat = torch.empty(flat.numel()).pin_memory()
         h2d = sum(x.numel() * 4 for x in host_in.values()) + sum(x.numel() * 4 for x in host_prim.values()) + host_grad.numel() * 4
         d2h = host_out.numel() * 4 + host_flat.numel() * 4
-        del leaves, s
+        dev_in = {n: s[n] for n in host_in}            # device staging buffers (reused, overwritten every step)
+        dev_grad = grad_out
+        del leaves, tl
         torch.cuda.empty_cache()
+        chunk = max(1, min(nv, args.e2e_chunk))
+        bounds = [(i, min(i + chunk, nv)) for i in range(0, nv, chunk)]
+        s_in, s_out, s_cmp = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.current_stream()
+        names = ("primpos", "primrot", "primscale", "template")
 
         def e2e_step():
-            d = {n: x.to(dev, non_blocking=True) for n, x in host_in.items()}
-            pr = {n: x.to(dev, non_blocking=True) for n, x in host_prim.items()}
-            g = host_grad.to(dev, non_blocking=True)
-            lv = [pr[n][None].expand(nv, *pr[n].shape).contiguous().requires_grad_(True)
-                  for n in ("primpos", "primrot", "primscale", "template")]
-            o_ = mvpraymarch(d["raypos"], d["raydir"], stepsize, d["tminmax"], (lv[0], lv[1], lv[2]), lv[3], None)
-            o_.backward(g)
-            parallel.reduce_primitive_grads(lv[3].grad, lv[0].grad, lv[1].grad, lv[2].grad, flat=flat)
-            host_out.copy_(o_.detach(), non_blocking=True)
+            ev_in = []
+            with torch.cuda.stream(s_in):
+                s_in.wait_stream(s_cmp)
+                pr = {n: x.to(dev, non_blocking=True) for n, x in host_prim.items()}
+                for (a0, a1) in bounds:
+                    for n in dev_in:
+                        dev_in[n][a0:a1].copy_(host_in[n][a0:a1], non_blocking=True)
+                    dev_grad[a0:a1].copy_(host_grad[a0:a1], non_blocking=True)
+                    e = torch.cuda.Event()
+                    e.record(s_in)
+                    ev_in.append(e)
+            flat.zero_()
+            for ci, (a0, a1) in enumerate(bounds):
+                s_cmp.wait_event(ev_in[ci])
+                nvc = a1 - a0
+                lv = [pr[n][None].expand(nvc, *pr[n].shape).contiguous().requires_grad_(True) for n in names]
+                o_ = mvpraymarch(dev_in["raypos"][a0:a1], dev_in["raydir"][a0:a1], stepsize, dev_in["tminmax"][a0:a1],
+                                 (lv[0], lv[1], lv[2]), lv[3], None)
+                o_.backward(dev_grad[a0:a1])
+                off = 0
+                for x in (lv[3], lv[0], lv[1], lv[2]):
+                    n_ = x[0].numel()
+                    flat[off:off + n_] += x.grad.view(nvc, n_).sum(dim=0)
+                    off += n_
+                od = o_.detach()
+                e = torch.cuda.Event()
+                e.record(s_cmp)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(e)
+                    host_out[a0:a1].copy_(od, non_blocking=True)
+                    od.record_stream(s_out)
+            if world > 1:
+                dist.all_reduce(flat)
             host_flat.copy_(flat, non_blocking=True)
+            s_cmp.wait_stream(s_out)
 
         log("e2e buffers pinned")
         e2e_step()
@@ -293,7 +328,8 @@ def run_ours(args, rank, world):
                "h2d_bytes_per_step": int(h2d * world), "d2h_bytes_per_step": int(d2h * world),
                "ms_per_step": float(te.item()),
                "what": "pinned host rays + one subject's primitives + grad_out -> device, per-view expand, op fwd+bwd, "
-                       "view-sum (+all-reduce), rayrgba + reduced gradients -> pinned host"}
+                       "view-sum (+all-reduce), rayrgba + reduced gradients -> pinned host; views streamed in chunks of %d "
+                       "(H2D / compute / D2H overlapped on three streams)" % chunk}
 
     log("e2e done")
     if rank != 0:
@@ -352,6 +388,7 @@ def main():
     ap.add_argument("--prims", type=int, default=K)
     ap.add_argument("--voxels", type=int, default=T)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-chunk", type=int, default=8, help="views per pipelined chunk in the e2e measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

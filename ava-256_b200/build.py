@@ -5,17 +5,19 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-SRC = [os.path.join(HERE, "csrc", "mvp_kernels.cu")]
+SRC = [os.path.join(HERE, "csrc", "mvp_kernels.cu"), os.path.join(HERE, "csrc", "raydirs.cu")]
+# raydirs.cu mirrors the reference's utils extension, which is NOT built with -use_fast_math
+NO_FAST_MATH = {"raydirs.cu"}
 HDR = [os.path.join(ROOT, "include", "mvpraymarch_b200.h")]
 LIB = os.path.join(HERE, "libmvpraymarch_b200.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
-    "-use_fast_math",                      # same math mode as the reference (extensions/mvpraymarch/setup.py:25)
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
     "-I" + os.path.join(ROOT, "include"),
 ]
+FAST_MATH = ["-use_fast_math"]             # same math mode as the reference (extensions/mvpraymarch/setup.py:25)
 
 
 def needs_build():
@@ -30,8 +32,13 @@ def build(force=False, verbose=False):
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     extra = os.environ.get("MVP_NVCC_EXTRA", "").split()      # experiment knob, e.g. -DMVP_BWD_MINB=4
-    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + SRC + ["-o", LIB]
-    subprocess.check_call(cmd)
+    objs = []
+    for src in SRC:
+        obj = os.path.join(HERE, "csrc", os.path.basename(src)[:-3] + ".o")
+        fm = [] if os.path.basename(src) in NO_FAST_MATH else FAST_MATH
+        subprocess.check_call([nvcc] + NVCC_FLAGS + fm + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj])
+        objs.append(obj)
+    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a"] + objs + ["-o", LIB])
     return LIB
 
 

@@ -1,0 +1,61 @@
+// raydirs.cu -- pinhole ray generation + unit-cube clip, the step right before the raymarcher
+// (SURVEY.md section 8f row 1).  Replaces /root/reference/extensions/utils/utils_kernel.cu:12-52
+// (compute_raydirs_forward_kernel); the reference's backward kernel is an empty stub and its Python backward returns
+// None for every input (extensions/utils/utils.py:45-46), so there is nothing else to build.
+//
+// Compiled WITHOUT -use_fast_math, like the reference's utils extension (extensions/utils/setup.py has no such flag):
+// IEEE division, rnorm3df for the normalisation.  Pure streaming kernel: 32 B written per ray, no reads to speak of
+// -> HBM-write bound; one thread per ray, x fastest for coalesced 12/12/8-byte stores.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mvpraymarch_b200.h"
+
+namespace {
+
+__global__ void __launch_bounds__(256) compute_raydirs_kernel(int N, int H, int W, const float *__restrict__ viewpos,
+                                                              const float *__restrict__ viewrot, const float *__restrict__ focal,
+                                                              const float *__restrict__ princpt, const float2 *__restrict__ pixelcoords,
+                                                              float volradius, float *__restrict__ raypos, float *__restrict__ raydir,
+                                                              float2 *__restrict__ tminmax) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    const int h = blockIdx.y;
+    const int n = blockIdx.z;
+    if (w >= W) return;
+    // raypos = viewpos / volradius                                           utils_kernel.cu:32
+    const float rx = viewpos[n * 3 + 0] / volradius, ry = viewpos[n * 3 + 1] / volradius, rz = viewpos[n * 3 + 2] / volradius;
+    const float *R = viewrot + n * 9;
+    const size_t r = ((size_t)n * H + h) * W + w;
+    float2 pc = pixelcoords ? __ldg(pixelcoords + r) : make_float2((float)w, (float)h);
+    pc.x = (pc.x - princpt[n * 2 + 0]) / focal[n * 2 + 0];                    // :36-37
+    pc.y = (pc.y - princpt[n * 2 + 1]) / focal[n * 2 + 1];
+    // raydir = viewrot0 * x + viewrot1 * y + viewrot2 * 1                     :38-39
+    float dx = R[0] * pc.x + R[3] * pc.y + R[6] * 1.f;
+    float dy = R[1] * pc.x + R[4] * pc.y + R[7] * 1.f;
+    float dz = R[2] * pc.x + R[5] * pc.y + R[8] * 1.f;
+    const float inv = rnorm3df(dx, dy, dz);                                    // :40 normalize = v * rnorm(v)
+    dx *= inv; dy *= inv; dz *= inv;
+    // unit-cube slab test                                                     :42-46
+    const float t1x = (-1.f - rx) / dx, t1y = (-1.f - ry) / dy, t1z = (-1.f - rz) / dz;
+    const float t2x = (1.f - rx) / dx, t2y = (1.f - ry) / dy, t2z = (1.f - rz) / dz;
+    const float tmin = fmaxf(fminf(t1x, t2x), fmaxf(fminf(t1y, t2y), fminf(t1z, t2z)));
+    const float tmax = fminf(fmaxf(t1x, t2x), fminf(fmaxf(t1y, t2y), fmaxf(t1z, t2z)));
+    raypos[r * 3 + 0] = rx; raypos[r * 3 + 1] = ry; raypos[r * 3 + 2] = rz;
+    raydir[r * 3 + 0] = dx; raydir[r * 3 + 1] = dy; raydir[r * 3 + 2] = dz;
+    tminmax[r] = make_float2(fmaxf(tmin, 0.f), tmax);
+}
+
+}  // namespace
+
+extern "C" int mvp_compute_raydirs(int32_t N, int32_t H, int32_t W, const float *viewpos, const float *viewrot, const float *focal,
+                                   const float *princpt, const float *pixelcoords, float volradius, float *raypos, float *raydir,
+                                   float *tminmax, void *stream) {
+    if (!viewpos || !viewrot || !focal || !princpt || !raypos || !raydir || !tminmax) return MVP_ERR_NULL;
+    if (N < 1 || H < 1 || W < 1 || H > 65535 || N > 65535) return MVP_ERR_SHAPE;
+    dim3 grid((W + 255) / 256, H, N);
+    compute_raydirs_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(N, H, W, viewpos, viewrot, focal, princpt,
+                                                                  reinterpret_cast<const float2 *>(pixelcoords), volradius, raypos,
+                                                                  raydir, reinterpret_cast<float2 *>(tminmax));
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? MVP_OK : (int)e;
+}

@@ -43,7 +43,7 @@ FLAG_ACCEL_VALID = 1
 ABI_VERSION = 1
 
 EXPORTS = ("mvp_abi_version", "mvp_error_string", "mvp_workspace_bytes", "mvp_build_accel", "mvp_raymarch_forward",
-           "mvp_raymarch_backward", "mvp_forward_launch_count", "mvp_backward_launch_count")
+           "mvp_raymarch_backward", "mvp_compute_raydirs", "mvp_forward_launch_count", "mvp_backward_launch_count")
 
 
 def _load():
@@ -69,6 +69,8 @@ def _load():
     lib.mvp_raymarch_forward.argtypes = [ctypes.POINTER(ForwardArgs), c_f]
     lib.mvp_raymarch_backward.restype = ctypes.c_int
     lib.mvp_raymarch_backward.argtypes = [ctypes.POINTER(BackwardArgs), c_f]
+    lib.mvp_compute_raydirs.restype = ctypes.c_int
+    lib.mvp_compute_raydirs.argtypes = [ctypes.c_int32] * 3 + [c_f] * 5 + [ctypes.c_float] + [c_f] * 4
     lib.mvp_forward_launch_count.restype = ctypes.c_int
     lib.mvp_forward_launch_count.argtypes = [ctypes.c_uint32]
     lib.mvp_backward_launch_count.restype = ctypes.c_int

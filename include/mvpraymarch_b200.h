@@ -12,6 +12,8 @@
  *   mvp_build_accel        <- compute_aabb       extensions/mvpraymarch/mvpraymarch.cpp:146-178
  *                             (stand-alone form, for callers that want to build once and march many times)
  *   mvp_workspace_bytes    <- the tensors build_accel allocates, extensions/mvpraymarch/mvpraymarch.py:21-84
+ *   mvp_compute_raydirs    <- compute_raydirs_forward  extensions/utils/utils.cpp:46-82 (pybind module `utilslib`;
+ *                             the step right before the raymarcher)
  *
  * Conventions (same ownership model as the reference: the caller owns every buffer, outputs are written in
  * place; unlike the reference nothing is allocated inside and everything runs on the caller's stream):
@@ -95,6 +97,13 @@ int mvp_build_accel(const mvp_shape *shape, const float *raypos, const float *ra
 
 int mvp_raymarch_forward(const mvp_forward_args *args, void *stream);
 int mvp_raymarch_backward(const mvp_backward_args *args, void *stream);
+
+/* Pinhole ray generation + unit-cube clip (reference: extensions/utils/utils_kernel.cu:12-52).
+ * viewpos [N,3], viewrot [N,3,3], focal [N,2], princpt [N,2], pixelcoords [N,H,W,2] or NULL (integer grid);
+ * outputs raypos, raydir [N,H,W,3], tminmax [N,H,W,2]. */
+int mvp_compute_raydirs(int32_t N, int32_t H, int32_t W, const float *viewpos, const float *viewrot, const float *focal,
+                        const float *princpt, const float *pixelcoords, float volradius, float *raypos, float *raydir,
+                        float *tminmax, void *stream);
 
 /* Number of kernels the last forward / backward call of this shape launches (for bench.py's gpu_launches). */
 int mvp_forward_launch_count(uint32_t flags);

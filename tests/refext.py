@@ -68,3 +68,30 @@ def backward(raypos, raydir, stepsize, tminmax, primpos, primrot, primscale, tem
                         0, False, 512, True, True, fadescale, fadeexp, 0, 0.0, 3, blocksize[0], blocksize[1])
     torch.cuda.synchronize()
     return tuple(g)
+
+
+# ---- reference ray generator (extensions/utils -> utilslib), for the compute_raydirs parity test ----
+_USO = os.path.join(os.path.dirname(_SO), "utilslib", "utilslib.so")
+_umod = None
+
+
+def utils_available():
+    return os.path.exists(_USO) and torch.cuda.is_available()
+
+
+def compute_raydirs(viewpos, viewrot, focal, princpt, pixelcoords, H, W, volradius):
+    """Calls the reference's compute_raydirs_forward (utils.cpp:46-82); pixelcoords may be None."""
+    global _umod
+    if _umod is None:
+        spec = importlib.util.spec_from_file_location("utilslib", _USO)
+        _umod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(_umod)
+    N = viewpos.shape[0]
+    dev = viewpos.device
+    raypos = torch.empty((N, H, W, 3), device=dev)
+    raydir = torch.empty((N, H, W, 3), device=dev)
+    tminmax = torch.empty((N, H, W, 2), device=dev)
+    torch.cuda.synchronize()
+    _umod.compute_raydirs_forward(viewpos, viewrot, focal, princpt, pixelcoords, W, H, volradius, raypos, raydir, tminmax)
+    torch.cuda.synchronize()
+    return raypos, raydir, tminmax

@@ -45,7 +45,7 @@ constexpr int kRing = 64;        // backward sample ring (entries per warp, powe
 #define MVP_PREFETCH 1
 #endif
 #ifndef MVP_FASTCAP
-#define MVP_FASTCAP 384
+#define MVP_FASTCAP 256
 #endif
 constexpr int kFastCap = MVP_FASTCAP;   // shared-memory list capacity of the common-case render kernels
 constexpr int kBig = 1 << 30;
@@ -594,6 +594,9 @@ template <int T, bool kGrad, int CAP>
 __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit) ? MVP_FWD_MINB : 4) render_forward_kernel(const Params p) {
     __shared__ int s_k[kWarps][CAP];
     __shared__ int s_iv[kWarps][CAP];
+    __shared__ float4 s_ring[kWarps][kRing];   // sample queue: (y0, y1, y2, owner | slot << 5) -> (r, g, b, same) once sampled
+    __shared__ float s_ra[kWarps][kRing];      // sampled alpha * fade
+    __shared__ int s_rm[kWarps][kGrad ? kRing : 1];   // sweep step of the queued sample (needed to record the saturating one)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tx = blockIdx.x * 2 + (warp & 1), ty = blockIdx.y * 2 + (warp >> 1), n = blockIdx.z;
     if (tx >= p.TXn || ty >= p.TYn) return;   // warps are independent: no CTA-wide barrier below (exited warps count as arrived)
@@ -633,6 +636,66 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit) ? MVP_FWD_MINB : 
     const float4 *tpn = reinterpret_cast<const float4 *>(p.tplate) + (size_t)n * p.K * slabsz;
     const int kstart = dfs_kstart(p.K);
 
+    // Sample compaction.  At one (step, slab) event only ~10 of the 32 rays of a tile are inside the slab, so the valid
+    // samples are queued (sample coordinates + owner lane + list slot) and the expensive gather/interpolation runs on
+    // full batches of 32 queued samples, one per lane, whichever ray they belong to.  The results go back through shared
+    // memory and every ray composites ITS samples in queue order = (step, rank) order, so the arithmetic and its order
+    // are exactly the reference's.  A ray that saturates only learns so at the next flush; what it queued in between is
+    // sampled in vain and then ignored.  (Measured: neutral at 8^3 / K=16384, -15 % forward time at 16^3 / K=4096.)
+    int qn = 0;
+    unsigned ownlo = 0, ownhi = 0;   // queue positions (0..63) holding this lane's pending samples
+    float4 *ring = s_ring[warp];
+    float *ra = s_ra[warp];
+    int *rm = s_rm[warp];
+    auto flush = [&](int cnt) {
+        const bool act = lane < cnt;
+        const float4 rec = ring[act ? lane : 0];
+        float4 sres = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (act) {
+            const int kk = s_k[warp][(__float_as_int(rec.w) >> 5) & 1023];
+            sres = sample_slab<T, false>(tpn + (size_t)kk * slabsz, rec.x, rec.y, rec.z, p.TD, p.TH, p.TW, p.fadescale, p.fadeexp, nullptr);
+        }
+        __syncwarp();
+        if (act) { ring[lane] = make_float4(sres.x, sres.y, sres.z, rec.w); ra[lane] = sres.w; }
+        __syncwarp();
+        unsigned mine = ownlo & (cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u));
+        while (mine) {
+            const int b = __ffs(mine) - 1;
+            mine &= mine - 1;
+            if (!sat) {
+                const float4 rr = ring[b];
+                const float aw = ra[b];
+                // primaccum.h:63-79
+                const float newa = __fmaf_rn(aw, p.dt, acc.w);
+                const float contrib = __fadd_rn(fminf(newa, 1.f), -acc.w);
+                if (newa >= 1.f) {
+                    sat0 = rr.x; sat1 = rr.y; sat2 = rr.z;
+                    sat = true;
+                    if (kGrad) {
+                        jsat = rm[b] + c.off;
+                        int rk = s_k[warp][(__float_as_int(rr.w) >> 5) & 1023] - kstart; if (rk < 0) rk += p.K;
+                        ranksat = rk;
+                        abefore = acc.w;
+                    }
+                }
+                acc.x = __fmaf_rn(contrib, rr.x, acc.x); acc.y = __fmaf_rn(contrib, rr.y, acc.y);
+                acc.z = __fmaf_rn(contrib, rr.z, acc.z); acc.w = __fadd_rn(acc.w, contrib);
+            }
+        }
+        __syncwarp();
+        // move what is left of the queue to the front
+        const int n2 = qn - cnt;
+        float4 mv = make_float4(0.f, 0.f, 0.f, 0.f);
+        int mvm = 0;
+        if (lane < n2) { mv = ring[32 + lane]; if (kGrad) mvm = rm[32 + lane]; }
+        __syncwarp();
+        if (lane < n2) { ring[lane] = mv; if (kGrad) rm[lane] = mvm; }
+        __syncwarp();
+        ownlo = ownhi; ownhi = 0;
+        qn = n2;
+        if (sat) done = true;
+    };
+
     const int mstart = __reduce_min_sync(0xffffffffu, ms);
     if (nl > 0 && mstart < kBig) {
         // each lane keeps the interval of list slots `lane` and `lane + 32` in registers (lists are rarely longer)
@@ -663,24 +726,18 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit) ? MVP_FWD_MINB : 
                     const float y1 = __fmul_rn(q.sy, rowdot(q.r01, xm, q.r11, ym, q.r21, zm));
                     const float y2 = __fmul_rn(q.sz, rowdot(q.r02, xm, q.r12, ym, q.r22, zm));
                     const bool valid = (fabsf(y0) < 1.f) && (fabsf(y1) < 1.f) && (fabsf(y2) < 1.f);
-                    if (valid && on && !sat && (t < r1e)) {
-                        const float4 s = sample_slab<T, false>(tpn + (size_t)k * slabsz, y0, y1, y2, p.TD, p.TH, p.TW,
-                                                               p.fadescale, p.fadeexp, nullptr);
-                        // primaccum.h:63-79
-                        const float newa = __fmaf_rn(s.w, p.dt, acc.w);
-                        const float contrib = __fadd_rn(fminf(newa, 1.f), -acc.w);
-                        if (newa >= 1.f) {
-                            sat0 = s.x; sat1 = s.y; sat2 = s.z;
-                            sat = true;
-                            if (kGrad) {
-                                jsat = m + c.off;
-                                int rk = k - kstart; if (rk < 0) rk += p.K;
-                                ranksat = rk;
-                                abefore = acc.w;
-                            }
+                    const bool want = valid && on && !sat && (t < r1e);
+                    const unsigned vm = __ballot_sync(0xffffffffu, want);
+                    if (vm) {
+                        if (want) {
+                            const int pos = qn + __popc(vm & ((1u << lane) - 1u));
+                            ring[pos] = make_float4(y0, y1, y2, __int_as_float(lane | ((w * 32 + b) << 5)));
+                            if (kGrad) rm[pos] = m;
+                            if (pos < 32) ownlo |= 1u << pos; else ownhi |= 1u << (pos - 32);
                         }
-                        acc.x = __fmaf_rn(contrib, s.x, acc.x); acc.y = __fmaf_rn(contrib, s.y, acc.y);
-                        acc.z = __fmaf_rn(contrib, s.z, acc.z); acc.w = __fadd_rn(acc.w, contrib);
+                        qn += __popc(vm);
+                        __syncwarp();
+                        if (qn >= 32) flush(32);
                     }
                 }
             }
@@ -716,6 +773,7 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit) ? MVP_FWD_MINB : 
             }
         }
     }
+    if (qn > 0) flush(qn);
     if (c.inimg) {
         reinterpret_cast<float4 *>(p.rayrgba)[r] = acc;
         if (kGrad) {

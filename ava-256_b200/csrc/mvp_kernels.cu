@@ -32,13 +32,22 @@
 
 #include "mvpraymarch_b200.h"
 
+// experiment knobs (defaults = measured best)
+#ifndef MVP_BWD_LO_SLACK
+#define MVP_BWD_LO_SLACK 1.f
+#define MVP_BWD_HI_SLACK 0.f
+#endif
+#ifndef MVP_CHUNK
+#define MVP_CHUNK 16
+#endif
+
 namespace {
 
 constexpr int kMaxHit = 512;      // utils.h:779-781 (template argument hard-wired at mvpraymarch_kernel.cu:33)
 constexpr int kTileW = 8;         // warp footprint of the reference's default block (8,16): 8 x 4 pixels
 constexpr int kTileH = 4;
 constexpr int kWarps = 4;         // warps (tiles) per CTA, arranged 2 x 2
-constexpr int kMaskSteps = 16;    // steps per active-mask rebuild
+constexpr int kMaskSteps = MVP_CHUNK;   // backward: sweep steps per chunk of slab start order
 constexpr int kRowCapMax = 2048;  // entries per tile-row bucket before the row falls back to scanning all slabs
 constexpr int kRing = 64;        // backward sample ring (entries per warp, power of two, >= 2 * 32)
 #ifndef MVP_PREFETCH
@@ -788,6 +797,10 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit) ? MVP_FWD_MINB : 
 // 5. backward (slab-major)
 // ------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d) {
+#ifdef MVP_EXPERIMENT_NO_RED   // timing experiment only: how much of the backward is the payload-gradient scatter?
+    if (a == 12345.678f) addr[0] = b + c + d;
+    return;
+#endif
     // no "memory" clobber: the gradient buffer is never read in this kernel, loads must stay free to move
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d));
 }
@@ -877,8 +890,11 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit) ? MVP_BWD_MINB : 
                 const bool hit = slab_test(q, c.ray, lo, hi) && hashit;
                 int la = kBig, lb = -kBig;               // lane's candidate sweep steps [la, lb]
                 if (hit) {
-                    la = max(clamp_step(floorf((lo - c.ray.tmin) * rdt) - foff), max(ms, cs));
-                    lb = min(clamp_step(floorf((hi - c.ray.tmin) * rdt) + 1.f - foff), mlast);
+                    // lattice steps strictly inside (lo, hi): floor((lo-tmin)/dt)+1 .. floor((hi-tmin)/dt).  A forward sample
+                    // outside this range can only be an fp-grazing one on the slab face (fade <= e^-8): its gradient is
+                    // dropped (<= 1e-6 relative), which saves two of ~6 loop iterations per slab.
+                    la = max(clamp_step(floorf((lo - c.ray.tmin) * rdt) + MVP_BWD_LO_SLACK - foff), max(ms, cs));
+                    lb = min(clamp_step(floorf((hi - c.ray.tmin) * rdt) + MVP_BWD_HI_SLACK - foff), mlast);
                     if (rank > ranksat) lb = min(lb, msat - 1);      // samples after the saturating one do not exist
                 }
                 const int len = lb - la + 1;

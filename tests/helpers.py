@@ -5,7 +5,7 @@ import numpy as np
 import torch
 
 
-def gradcheck_like_scene(N=2, H=13, W=13, k3=2, M=4, seed=1112, fadescale=6.5, fadeexp=7.5, alpha_gain=40.0, scale=2.2):
+def gradcheck_like_scene(N=2, H=13, W=13, k3=2, M=4, seed=1112, fadescale=6.5, fadeexp=7.5, alpha_gain=40.0, scale=2.2, dims=None):
     """Small scene in the style of the reference's gradcheck inputs
     (/root/reference/extensions/mvpraymarch/mvpraymarch.py:464-565): pinhole rays from z=-4, a k3^3 grid of
     randomly rotated slabs around the origin, softplus payload, random tminmax."""
@@ -23,7 +23,8 @@ def gradcheck_like_scene(N=2, H=13, W=13, k3=2, M=4, seed=1112, fadescale=6.5, f
     stepsize = max_len / 15.386928
     tminmax = max_len * torch.arange(2, dtype=torch.float32)[None, None, None, :].repeat(N, H, W, 1) \
         + torch.rand(N, H, W, 2, generator=g)
-    tpl = torch.nn.functional.softplus(1.5 * (torch.randn(N, K, M, M, M, 4, generator=g)
+    TD, TH, TW = dims if dims is not None else (M, M, M)
+    tpl = torch.nn.functional.softplus(1.5 * (torch.randn(N, K, TD, TH, TW, 4, generator=g)
                                               - torch.tensor([0, 0, 0, 3.5]))) * torch.tensor([1, 1, 1, alpha_gain])
     lin = torch.linspace(-1.0, 1.0, k3)
     gz, gy, gx = torch.meshgrid(lin, lin, lin, indexing="ij")
@@ -84,6 +85,10 @@ CASES = {
     "head_small": lambda: _head_case(2, 64, 42, 256, 8, stepsize=1.0 / 64, alpha_mu=2.0, alpha_sigma=3.0),
     # 125 large overlapping slabs: every tile sees > 96 candidates -> exercises the 512-entry kernel variant
     "many_overlaps": lambda: gradcheck_like_scene(N=1, H=12, W=20, k3=5, M=4, seed=3, alpha_gain=0.4, scale=1.1),
+    # non-cubic payload (runtime-stride sampler path) incl. a 1-voxel axis
+    "noncubic": lambda: gradcheck_like_scene(N=1, H=14, W=17, k3=2, seed=21, alpha_gain=30.0, dims=(3, 1, 5)),
+    # image smaller than one 8x4 tile, a single slab
+    "tiny": lambda: gradcheck_like_scene(N=2, H=3, W=5, k3=1, M=2, seed=5, alpha_gain=15.0, scale=1.0),
     "head_t16": lambda: _head_case(1, 48, 32, 64, 16, stepsize=1.0 / 32, view_offset=11, alpha_mu=1.0, alpha_sigma=2.0),
 }
 

@@ -51,7 +51,7 @@ constexpr int kMaskSteps = MVP_CHUNK;   // backward: sweep steps per chunk of sl
 constexpr int kRowCapMax = 2048;  // entries per tile-row bucket before the row falls back to scanning all slabs
 constexpr int kRing = 64;        // backward sample ring (entries per warp, power of two, >= 2 * 32)
 #ifndef MVP_PREFETCH
-#define MVP_PREFETCH 1
+#define MVP_PREFETCH 0   // measured: +1 % forward speed but +50 % DRAM reads (slabs of rays that saturate earlier are fetched in vain)
 #endif
 #ifndef MVP_FASTCAP
 #define MVP_FASTCAP 256

@@ -84,7 +84,7 @@ __host__ __device__ inline size_t align256(size_t x) { return (x + 255) & ~(size
 __host__ inline Layout make_layout(const mvp_shape &s) {
     Layout L;
     L.R = (s.H + kTileH - 1) / kTileH;
-    L.rowcap = s.K < kRowCapMax ? s.K : kRowCapMax;
+    L.rowcap = ((s.K < kRowCapMax ? s.K : kRowCapMax) + 1) & ~1;   // even: 16-byte aligned buckets (TMA bulk copies)
     size_t off = 0;
     L.cam = off;     off = align256(off + (size_t)s.N * sizeof(Cam));
     L.bad = off;     off = align256(off + (size_t)s.N * sizeof(int));
@@ -391,6 +391,33 @@ __device__ __forceinline__ int pack_iv(int lo, int hi) {
 __device__ __forceinline__ int iv_lo(int v) { const int l = (int)(short)(v & 0xffff); return l == -32768 ? -kBig : l; }
 __device__ __forceinline__ int iv_hi(int v) { const int h = v >> 16; return h == 32767 ? kBig : h; }
 
+// ---- TMA bulk copy (cp.async.bulk, global -> shared) + mbarrier, used to stage the tile row's bucket ----
+constexpr int kStage = 32;   // bucket entries per staged chunk (256 B), double buffered per warp
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+// Make the (generic-proxy) mbarrier initialisation visible to the async proxy of this CTA.  Deliberately NOT
+// fence.mbarrier_init.release.cluster: a cluster-scope fence compiles to CCTL.IVALL, which invalidates the SM's whole
+// L1D -- fatal for a kernel that lives off L1 hits and starts a new tile per warp all the time.
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+
 struct TileCtx {
     // per-lane
     Ray ray;
@@ -437,8 +464,8 @@ struct Params {
 // Returns false when the list would exceed CAP (< 512); cannot happen for tiles classified "fast" at accel build.
 template <int CAP, bool kPrefetch>
 __device__ __forceinline__ bool build_tile_list(const Params &p, float rdt, int n, int tx, int ty, int lane, TileCtx &c,
-                                                int *s_k, int *s_iv, float &t, float &x, float &y, float &z,
-                                                float &r1e, int &j0) {
+                                                int *s_k, int *s_iv, RowEntry *s_stage, unsigned long long *s_bar, float &t,
+                                                float &x, float &y, float &z, float &r1e, int &j0) {
     const int px = tx * kTileW + (lane & 7), py = ty * kTileH + (lane >> 3);
     c.inimg = (px < p.W) && (py < p.H);
     const int cx = min(px, p.W - 1), cy = min(py, p.H - 1);
@@ -465,14 +492,32 @@ __device__ __forceinline__ bool build_tile_list(const Params &p, float rdt, int 
     const int tx0 = tx * kTileW, tx1 = tx0 + kTileW - 1, ty0 = ty * kTileH, ty1 = ty0 + kTileH - 1;
     const int kstart = dfs_kstart(p.K);
     int nl = 0;
+    // The bucket is streamed through shared memory by the TMA engine in 256-byte chunks, double buffered: chunk c+1 is
+    // in flight while the (long) exact slab tests of chunk c run, so the bucket's load latency is never exposed.
+    auto stage_issue = [&](int ch) {
+        if (lane == 0) {
+            const int cntc = min(kStage, total - ch * kStage);
+            tma_load_1d(s_stage + (ch & 1) * kStage, rl + (size_t)ch * kStage, (unsigned)(((cntc + 1) & ~1) * sizeof(RowEntry)), s_bar + (ch & 1));
+        }
+    };
+    if (!overflow && total > 0) {
+        if (lane == 0) { mbar_init(s_bar, 1); mbar_init(s_bar + 1, 1); mbar_fence_init(); }
+        __syncwarp();
+        stage_issue(0);
+    }
     for (int base = 0; base < total; base += 32) {
         const int idx = base + lane;
         int k = 0;
         bool cand = false;
+        const int ch = base / kStage;
+        if (!overflow) {
+            if (base + kStage < total) stage_issue(ch + 1);   // its buffer was last read two chunks ago (warp-synced since)
+            mbar_wait(s_bar + (ch & 1), (unsigned)((ch >> 1) & 1));
+        }
         if (idx < total) {
             unsigned xr;
             if (!overflow) {
-                RowEntry e = rl[idx];
+                RowEntry e = s_stage[(ch & 1) * kStage + lane];
                 k = e.k; xr = e.xr;
                 cand = true;
             } else {
@@ -511,6 +556,7 @@ __device__ __forceinline__ bool build_tile_list(const Params &p, float rdt, int 
                 }
             }
         }
+        __syncwarp();   // every lane has consumed this chunk before its buffer is refilled
     }
     __syncwarp();
     c.nl = nl;
@@ -603,6 +649,8 @@ template <int T, bool kGrad, int CAP>
 __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit) ? MVP_FWD_MINB : 4) render_forward_kernel(const Params p) {
     __shared__ int s_k[kWarps][CAP];
     __shared__ int s_iv[kWarps][CAP];
+    __shared__ __align__(16) RowEntry s_stage[kWarps][2 * kStage];   // TMA-staged chunks of the tile row's bucket
+    __shared__ __align__(8) unsigned long long s_bar[kWarps][2];
     __shared__ float4 s_ring[kWarps][kRing];   // sample queue: (y0, y1, y2, owner | slot << 5) -> (r, g, b, same) once sampled
     __shared__ float s_ra[kWarps][kRing];      // sampled alpha * fade
     __shared__ int s_rm[kWarps][kGrad ? kRing : 1];   // sweep step of the queued sample (needed to record the saturating one)
@@ -622,7 +670,7 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit) ? MVP_FWD_MINB : 
     TileCtx c;
     float t, x, y, z, r1e;
     int j0;
-    const bool fits = build_tile_list<CAP, true>(p, rdt, n, tx, ty, lane, c, s_k[warp], s_iv[warp], t, x, y, z, r1e, j0);
+    const bool fits = build_tile_list<CAP, true>(p, rdt, n, tx, ty, lane, c, s_k[warp], s_iv[warp], s_stage[warp], s_bar[warp], t, x, y, z, r1e, j0);
     (void)fits;   // cannot fail: the tile's candidate count was checked against CAP when the accel was built
 
     const int px = tx * kTileW + (lane & 7), py = ty * kTileH + (lane >> 3);
@@ -810,6 +858,8 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit) ? MVP_BWD_MINB : 
     __shared__ int s_k[kWarps][CAP];
     __shared__ int s_iv[kWarps][CAP];
     __shared__ float4 s_q[kWarps][kRing];
+    __shared__ __align__(16) RowEntry s_stage[kWarps][2 * kStage];   // TMA-staged chunks of the tile row's bucket
+    __shared__ __align__(8) unsigned long long s_bar[kWarps][2];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tx = blockIdx.x * 2 + (warp & 1), ty = blockIdx.y * 2 + (warp >> 1), n = blockIdx.z;
     if (tx >= p.TXn || ty >= p.TYn) return;
@@ -824,7 +874,7 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit) ? MVP_BWD_MINB : 
     TileCtx c;
     float t0, xb, yb, zb, r1e;   // xb = position at sweep step max(mcur, ms)
     int j0;
-    build_tile_list<CAP, false>(p, rdt, n, tx, ty, lane, c, s_k[warp], s_iv[warp], t0, xb, yb, zb, r1e, j0);   // measured: the prefetch only pays in forward
+    build_tile_list<CAP, false>(p, rdt, n, tx, ty, lane, c, s_k[warp], s_iv[warp], s_stage[warp], s_bar[warp], t0, xb, yb, zb, r1e, j0);   // measured: the prefetch only pays in forward
     const int nl = c.nl;
     if (nl == 0) { if (CAP < kMaxHit) asm volatile("griddepcontrol.wait;" ::: "memory"); return; }
 

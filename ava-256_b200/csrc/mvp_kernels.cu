@@ -13,14 +13,17 @@
 //     test on them -- so list membership, per-ray [t_enter,t_exit] and the 512 cap are the reference's.
 //     Views whose rays are not a pinhole grid fall back to "every slab is a candidate" (correct, slow).
 //   * Interval marching.  The reference re-transforms every listed slab at every step.  Here each list entry
-//     carries the warp's step interval [mlo,mhi]; a 16-step active mask is rebuilt by ballot and only active
-//     slabs are transformed.  Ray position and t advance incrementally in fp32 exactly as in the reference
-//     (mvpraymarch_subset_kernel.h:95-96) so validity decisions match bit for bit.
-//   * Backward is slab-major: forward records, per ray, the saturating sample (step, rank) and the alpha
-//     before it, which removes the only order dependence (primaccum.h:81-98).  Each warp then walks one slab
-//     at a time, keeps the 15 transform gradients in registers over all its steps, reduces them with a
-//     16-value butterfly and issues one atomic per value per (warp, slab); payload gradients go out as
-//     128-bit vector reductions (red.global.add.v4.f32) instead of 32 scalar atomics per sample.
+//     carries the warp's step interval; per step one ballot per 32 list slots finds the active slabs and only those
+//     are transformed; stretches without an active slab are skipped.  Ray position and t advance incrementally in
+//     fp32 exactly as in the reference (mvpraymarch_subset_kernel.h:95-96) so validity decisions match bit for bit.
+//   * Sample compaction.  Valid samples are queued in shared memory and the gather/interpolation (forward) or the
+//     whole adjoint (backward) runs on full batches of 32 samples; forward composites per ray in queue order.
+//   * Backward is slab-major: forward records, per ray, the saturating sample (step, rank) and the alpha before it,
+//     which removes the only order dependence (primaccum.h:81-98).  Each warp walks one slab at a time (every lane its
+//     own step interval), keeps factored transform gradients in registers, reduces them with a 16-value butterfly and
+//     issues one atomic per value per (warp, slab); payload gradients go out as 128-bit vector reductions
+//     (red.global.add.v4.f32) instead of 32 scalar atomics per sample.
+//   * The tile row's bucket is staged through shared memory by the TMA engine (cp.async.bulk + mbarrier).
 //
 // Arithmetic mirrors the reference's fp32 operation order where a step function of the result exists
 // (transform + strict validity, slab test, lattice snap, saturation); -use_fast_math is on like the reference.
@@ -439,7 +442,6 @@ struct Params {
     const RowEntry *rowlist;
     int R, rowcap;
     int TXn, TYn;
-    int align;
     unsigned slab_bytes;          // TD*TH*TW*16
     unsigned char *tileflag;
     // forward outputs
@@ -586,22 +588,14 @@ __device__ __forceinline__ bool build_tile_list(const Params &p, float rdt, int 
     return true;
 }
 
-struct Sample {
-    float4 s;           // rgb, alpha*fade
-    float fade;
-    float x0, x1, y0, y1, z0, z1;   // trilinear factors
-    int base;                        // voxel index of the (clamped) lower corner
-    bool ex, ey, ez;                 // cell was clamped on this axis (index coordinate exactly T-1)
-};
-
 // primsampler.h:44-66 + utils.h:408-502.  T > 0: cubic slab with compile-time strides; T == 0: runtime dims.
 // Only called for valid samples (|y| < 1), for which (a) the reference's +-100 clamp is a no-op and (b) the only
 // corner that can fall outside the slab is ix+1 == TW when fx rounds to exactly TW-1, with weight exactly 0.  The
 // cell is clamped to TW-2 instead and the fractions are taken against the clamped cell: identical products in all
 // other cases (fx - ix and (ix+1) - fx are the reference's expressions), weights (1, 0) in the edge case.
-template <int T, bool kKeep>
+template <int T>
 __device__ __forceinline__ float4 sample_slab(const float4 *__restrict__ slab, float y0, float y1, float y2, int TD, int TH, int TW,
-                                              float fadescale, float fadeexp, Sample *keep) {
+                                              float fadescale, float fadeexp) {
     const int td = T > 0 ? T : TD, th = T > 0 ? T : TH, tw = T > 0 ? T : TW;
     const float fade = __expf(-fadescale * (__powf(fabsf(y0), fadeexp) + __powf(fabsf(y1), fadeexp) + __powf(fabsf(y2), fadeexp)));
     const float fx = ((y0 + 1.f) * 0.5f) * (float)(tw - 1);
@@ -632,11 +626,6 @@ __device__ __forceinline__ float4 sample_slab(const float4 *__restrict__ slab, f
     w = w10 * bz0; acc.x = __fmaf_rn(w, v110.x, acc.x); acc.y = __fmaf_rn(w, v110.y, acc.y); acc.z = __fmaf_rn(w, v110.z, acc.z); acc.w = __fmaf_rn(w, v110.w, acc.w);
     w = w11 * bz0; acc.x = __fmaf_rn(w, v111.x, acc.x); acc.y = __fmaf_rn(w, v111.y, acc.y); acc.z = __fmaf_rn(w, v111.z, acc.z); acc.w = __fmaf_rn(w, v111.w, acc.w);
     acc.w *= fade;
-    if (kKeep) {
-        keep->s = acc; keep->fade = fade; keep->base = base;
-        keep->x0 = bx0; keep->x1 = bx1; keep->y0 = by0; keep->y1 = by1; keep->z0 = bz0; keep->z1 = bz1;
-        keep->ex = ix > cx; keep->ey = iy > cy; keep->ez = iz > cz;
-    }
     return acc;
 }
 
@@ -710,7 +699,7 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit) ? MVP_FWD_MINB : 
         float4 sres = make_float4(0.f, 0.f, 0.f, 0.f);
         if (act) {
             const int kk = s_k[warp][(__float_as_int(rec.w) >> 5) & 1023];
-            sres = sample_slab<T, false>(tpn + (size_t)kk * slabsz, rec.x, rec.y, rec.z, p.TD, p.TH, p.TW, p.fadescale, p.fadeexp, nullptr);
+            sres = sample_slab<T>(tpn + (size_t)kk * slabsz, rec.x, rec.y, rec.z, p.TD, p.TH, p.TW, p.fadescale, p.fadeexp);
         }
         __syncwarp();
         if (act) { ring[lane] = make_float4(sres.x, sres.y, sres.z, rec.w); ra[lane] = sres.w; }
@@ -1204,7 +1193,6 @@ void fill_params(Params &p, const mvp_shape &s, float stepsize, float fadescale,
     p.TXn = (s.W + kTileW - 1) / kTileW;
     p.TYn = (s.H + kTileH - 1) / kTileH;
     p.tileflag = reinterpret_cast<unsigned char *>(ws + L.tileflag);
-    p.align = 0;
     p.slab_bytes = (unsigned)((size_t)s.TD * s.TH * s.TW * 16);
 }
 

@@ -32,7 +32,7 @@ def build(force: bool = False) -> str:
 class _Cfg(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ("N", "H", "W", "K", "TD", "TH", "TW", "bsx", "bsy", "maxhitboxes")] + [
         (n, ctypes.c_double) for n in ("stepsize", "fadescale", "fadeexp")
-    ]
+    ] + [(n, ctypes.c_int32) for n in ("WD", "WH", "WW")]
 
 
 _lib = None
@@ -49,11 +49,12 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
 
 
-def _cfg(raypos, primpos, template, stepsize, fadescale, fadeexp, blocksize, maxhitboxes):
+def _cfg(raypos, primpos, template, stepsize, fadescale, fadeexp, blocksize, maxhitboxes, warp=None):
     N, H, W = raypos.shape[:3]
     K = primpos.shape[1]
     TD, TH, TW = template.shape[2:5]
-    return _Cfg(N, H, W, K, TD, TH, TW, blocksize[0], blocksize[1], maxhitboxes, stepsize, fadescale, fadeexp)
+    WD, WH, WW = warp.shape[2:5] if warp is not None else (0, 0, 0)
+    return _Cfg(N, H, W, K, TD, TH, TW, blocksize[0], blocksize[1], maxhitboxes, stepsize, fadescale, fadeexp, WD, WH, WW)
 
 
 def _prep(dtype, *arrs):
@@ -61,13 +62,16 @@ def _prep(dtype, *arrs):
 
 
 def forward(raypos, raydir, stepsize, tminmax, primpos, primrot, primscale, template, fadescale=8.0, fadeexp=8.0,
-            blocksize=(8, 16), maxhitboxes=512, dtype=np.float32, want_raysat=True, return_stats=False):
-    """Reference-semantics forward on the CPU.  Returns (rayrgba, raysat[, stats])."""
+            blocksize=(8, 16), maxhitboxes=512, dtype=np.float32, want_raysat=True, return_stats=False, warp=None):
+    """Reference-semantics forward on the CPU.  Returns (rayrgba, raysat[, stats]).
+    warp: optional [N,K,WD,WH,WW,3] channels-last warp field (algo 1)."""
     lib = _load()
     suf = "f32" if dtype == np.float32 else "f64"
     raypos, raydir, tminmax, primpos, primrot, primscale, template = _prep(
         dtype, raypos, raydir, tminmax, primpos, primrot, primscale, template)
-    cfg = _cfg(raypos, primpos, template, stepsize, fadescale, fadeexp, blocksize, maxhitboxes)
+    if warp is not None:
+        warp = np.ascontiguousarray(warp, dtype=dtype)
+    cfg = _cfg(raypos, primpos, template, stepsize, fadescale, fadeexp, blocksize, maxhitboxes, warp)
     N, H, W = raypos.shape[:3]
     rayrgba = np.empty((N, H, W, 4), dtype)
     raysat = np.full((N, H, W, 3), -1, dtype) if want_raysat else None
@@ -75,7 +79,7 @@ def forward(raypos, raydir, stepsize, tminmax, primpos, primrot, primscale, temp
     fn = getattr(lib, "mvp_oracle_forward_" + suf)
     fn.restype = ctypes.c_int
     rc = fn(ctypes.byref(cfg), _p(raypos), _p(raydir), _p(tminmax), _p(primpos), _p(primrot), _p(primscale),
-            _p(template), _p(rayrgba), _p(raysat), _p(stats))
+            _p(template), _p(warp), _p(rayrgba), _p(raysat), _p(stats))
     assert rc == 0
     if return_stats:
         return rayrgba, raysat, dict(samples=int(stats[0]), warp_steps=int(stats[1]), list_entries=int(stats[2]),
@@ -84,20 +88,24 @@ def forward(raypos, raydir, stepsize, tminmax, primpos, primrot, primscale, temp
 
 
 def backward(raypos, raydir, stepsize, tminmax, primpos, primrot, primscale, template, grad_rayrgba, raysat,
-             fadescale=8.0, fadeexp=8.0, blocksize=(8, 16), maxhitboxes=512, dtype=np.float32):
-    """Reference-semantics backward.  Returns float64 (grad_primpos, grad_primrot, grad_primscale, grad_template)."""
+             fadescale=8.0, fadeexp=8.0, blocksize=(8, 16), maxhitboxes=512, dtype=np.float32, warp=None):
+    """Reference-semantics backward.  Returns float64 (grad_primpos, grad_primrot, grad_primscale, grad_template)
+    and, when `warp` is given, grad_warp as a fifth element."""
     lib = _load()
     suf = "f32" if dtype == np.float32 else "f64"
     raypos, raydir, tminmax, primpos, primrot, primscale, template, grad_rayrgba, raysat = _prep(
         dtype, raypos, raydir, tminmax, primpos, primrot, primscale, template, grad_rayrgba, raysat)
-    cfg = _cfg(raypos, primpos, template, stepsize, fadescale, fadeexp, blocksize, maxhitboxes)
+    if warp is not None:
+        warp = np.ascontiguousarray(warp, dtype=dtype)
+    cfg = _cfg(raypos, primpos, template, stepsize, fadescale, fadeexp, blocksize, maxhitboxes, warp)
     g = [np.zeros(a.shape, np.float64) for a in (primpos, primrot, primscale, template)]
+    gw = np.zeros(warp.shape, np.float64) if warp is not None else None
     fn = getattr(lib, "mvp_oracle_backward_" + suf)
     fn.restype = ctypes.c_int
     rc = fn(ctypes.byref(cfg), _p(raypos), _p(raydir), _p(tminmax), _p(primpos), _p(primrot), _p(primscale),
-            _p(template), _p(grad_rayrgba), _p(raysat), _p(g[0]), _p(g[1]), _p(g[2]), _p(g[3]))
+            _p(template), _p(warp), _p(grad_rayrgba), _p(raysat), _p(g[0]), _p(g[1]), _p(g[2]), _p(g[3]), _p(gw))
     assert rc == 0
-    return tuple(g)
+    return tuple(g) + ((gw,) if warp is not None else ())
 
 
 def aabb(primpos, primrot, primscale, dtype=np.float32):

@@ -23,7 +23,7 @@ import torch.nn.functional as F
 
 
 def raymarch_torch(raypos, raydir, stepsize, tminmax, primpos, primrot, primscale, template,
-                   fadescale=8.0, fadeexp=8.0, max_steps=None):
+                   fadescale=8.0, fadeexp=8.0, max_steps=None, warp=None):
     """Returns rayrgba [N,H,W,4].  Differentiable w.r.t. primpos, primrot, primscale, template.
 
     raypos, raydir: [N,H,W,3]; tminmax: [N,H,W,2]; primpos/primscale: [N,K,3]; primrot: [N,K,3,3];
@@ -32,6 +32,7 @@ def raymarch_torch(raypos, raydir, stepsize, tminmax, primpos, primrot, primscal
     N, H, W = raypos.shape[:3]
     K = primpos.shape[1]
     tplate = template.permute(0, 1, 5, 2, 3, 4)  # [N,K,4,TD,TH,TW]  (mvpraymarch.py:600 expects ch-first)
+    wfield = warp.permute(0, 1, 5, 2, 3, 4) if warp is not None else None   # [N,K,3,WD,WH,WW]  (:594-597, dowarp)
 
     rayrgba = torch.zeros((N, H, W, 4), dtype=raypos.dtype, device=raypos.device)
     raypos_t = raypos + raydir * tminmax[:, :, :, 0, None]          # :571
@@ -52,7 +53,10 @@ def raymarch_torch(raypos, raydir, stepsize, tminmax, primpos, primrot, primscal
                 * primscale[:, k, None, None, :]
             )                                                       # :583-589
             fade = torch.exp(-fadescale * torch.sum(torch.abs(y0) ** fadeexp, dim=-1, keepdim=True))  # :591
-            y1 = y0
+            if wfield is not None:                                  # :593-597
+                y1 = F.grid_sample(wfield[:, k], y0[:, None, :, :, :], align_corners=True)[:, :, 0, :, :].permute(0, 2, 3, 1)
+            else:
+                y1 = y0
             sample = F.grid_sample(tplate[:, k], y1[:, None, :, :, :], align_corners=True)[
                 :, :, 0, :, :
             ].permute(0, 2, 3, 1)                                   # :600-602
@@ -71,9 +75,11 @@ def raymarch_torch(raypos, raydir, stepsize, tminmax, primpos, primrot, primscal
 
 
 def raymarch_torch_fwd_bwd(raypos, raydir, stepsize, tminmax, primpos, primrot, primscale, template,
-                           grad_rayrgba, fadescale=8.0, fadeexp=8.0):
-    """Forward + autograd backward; returns (rayrgba, grad_primpos, grad_primrot, grad_primscale, grad_template)."""
+                           grad_rayrgba, fadescale=8.0, fadeexp=8.0, warp=None):
+    """Forward + autograd backward; returns (rayrgba, grad_primpos, grad_primrot, grad_primscale, grad_template
+    [, grad_warp])."""
     leaves = [x.detach().clone().requires_grad_(True) for x in (primpos, primrot, primscale, template)]
-    out = raymarch_torch(raypos, raydir, stepsize, tminmax, *leaves, fadescale=fadescale, fadeexp=fadeexp)
+    wl = warp.detach().clone().requires_grad_(True) if warp is not None else None
+    out = raymarch_torch(raypos, raydir, stepsize, tminmax, *leaves, fadescale=fadescale, fadeexp=fadeexp, warp=wl)
     out.backward(grad_rayrgba)
-    return (out.detach(),) + tuple(x.grad for x in leaves)
+    return (out.detach(),) + tuple(x.grad for x in leaves) + ((wl.grad,) if wl is not None else ())

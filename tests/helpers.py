@@ -43,6 +43,16 @@ def gradcheck_like_scene(N=2, H=13, W=13, k3=2, M=4, seed=1112, fadescale=6.5, f
                 template=tpl.contiguous(), fadescale=fadescale, fadeexp=fadeexp)
 
 
+def make_warp(N, K, WD, WH, WW, seed=77, amp=0.05):
+    """Warp field like the reference gradcheck's (mvpraymarch.py:498-510): identity grid + small noise; channels-last
+    [N,K,WD,WH,WW,3] with channel order (x, y, z) = (W, H, D) axes."""
+    g = torch.Generator().manual_seed(seed)
+    lz, ly, lx = (torch.linspace(-1.0, 1.0, n) if n > 1 else torch.zeros(1) for n in (WD, WH, WW))
+    gz, gy, gx = torch.meshgrid(lz, ly, lx, indexing="ij")
+    grid = torch.stack([gx, gy, gz], dim=-1)[None, None]
+    return (grid + amp * torch.randn(N, K, WD, WH, WW, 3, generator=g)).contiguous()
+
+
 def scene_args_np(s, dtype=np.float32):
     """(positional args for oracle.forward, kwargs)."""
     a = [s["raypos"].numpy().astype(dtype), s["raydir"].numpy().astype(dtype), float(s["stepsize"]),

@@ -103,3 +103,26 @@ def test_oracle_f32_matches_reference_cuda_golden(name):
     g = oracle.backward(*a, grad.numpy(), gold["raysat"], **kw)
     for nm, x in zip(("primpos", "primrot", "primscale", "template"), g):
         assert relerr(x, gold["grad_" + nm]) < 2e-5, nm
+
+
+def test_oracle_f64_warp_field_matches_torch_autograd_loop():
+    """algo 1 (PrimSamplerTW<true>, primsampler.h:53-58, 82-88): payload sampled at a warp-field-displaced position."""
+    from tests.helpers import make_warp
+    s = gradcheck_like_scene(N=1, H=11, W=10, k3=2, M=4, alpha_gain=25.0)
+    warp = make_warp(1, 8, 3, 3, 3, amp=0.15)      # large noise: warped positions leave [-1,1] (zero-padding path)
+    g = torch.Generator().manual_seed(9)
+    grad = torch.randn(1, 11, 10, 4, generator=g)
+    t = {k: (v.double() if torch.is_tensor(v) else v) for k, v in s.items()}
+    ref = torch_ref.raymarch_torch_fwd_bwd(t["raypos"], t["raydir"], t["stepsize"], t["tminmax"], t["primpos"], t["primrot"],
+                                           t["primscale"], t["template"], grad.double(), fadescale=s["fadescale"],
+                                           fadeexp=s["fadeexp"], warp=warp.double())
+    a, kw = scene_args_np(s, np.float64)
+    rgba, raysat = oracle.forward(*a, dtype=np.float64, warp=warp.numpy().astype(np.float64), **kw)
+    assert 5 < int((raysat[..., 0] > -1).sum()) < 105
+    assert relerr(rgba, ref[0].numpy()) < 1e-11
+    grads = oracle.backward(*a, grad.numpy().astype(np.float64), raysat, dtype=np.float64, warp=warp.numpy().astype(np.float64), **kw)
+    for name, mine, theirs in zip(("primpos", "primrot", "primscale", "template", "warp"), grads, ref[1:]):
+        assert relerr(mine, theirs.numpy()) < 1e-9, name
+    # and it is really a different image than without the warp
+    plain, _ = oracle.forward(*a, dtype=np.float64, **kw)
+    assert relerr(rgba, plain) > 1e-3

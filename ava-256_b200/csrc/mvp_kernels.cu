@@ -452,6 +452,10 @@ struct Params {
     const float *raysat_in;
     const int4 *rayaux_in;
     float *g_primpos, *g_primrot, *g_primscale, *g_tplate;
+    // algo 1: warp field [N,K,WD,WH,WW,3] (primsampler.h:53-58) and its gradient
+    const float *warp;
+    float *g_warp;
+    int WD, WH, WW;
 };
 
 // Builds the warp's slab list (rank order, at most CAP entries in shared memory), each slab's warp step interval and
@@ -629,13 +633,66 @@ __device__ __forceinline__ float4 sample_slab(const float4 *__restrict__ slab, f
     return acc;
 }
 
+// ---- generic trilinear cell for an ARBITRARY position (utils.h:408-502: +-100 clamp, corners outside the grid
+//      contribute nothing); used by the warp-field path (algo 1), where the warped position may leave the slab ----
+struct CellG {
+    int idx[8];        // voxel index of each corner, -1 if outside
+    float w[8];        // trilinear weight of each corner
+    float x0, x1, y0, y1, z0, z1;
+};
+__device__ __forceinline__ CellG cell_generic(float a0, float a1, float a2, int D, int H, int W) {
+    CellG c;
+    const float fx = fmaxf(-100.f, fminf(100.f, (a0 + 1.f) * 0.5f)) * (float)(W - 1);
+    const float fy = fmaxf(-100.f, fminf(100.f, (a1 + 1.f) * 0.5f)) * (float)(H - 1);
+    const float fz = fmaxf(-100.f, fminf(100.f, (a2 + 1.f) * 0.5f)) * (float)(D - 1);
+    const int ix = __float2int_rd(fx), iy = __float2int_rd(fy), iz = __float2int_rd(fz);
+    c.x0 = fx - (float)ix; c.x1 = (float)(ix + 1) - fx;
+    c.y0 = fy - (float)iy; c.y1 = (float)(iy + 1) - fy;
+    c.z0 = fz - (float)iz; c.z1 = (float)(iz + 1) - fz;
+#pragma unroll
+    for (int cn = 0; cn < 8; ++cn) {
+        const int x = ix + (cn & 1), y = iy + ((cn >> 1) & 1), z = iz + ((cn >> 2) & 1);
+        const bool inb = (x >= 0) && (x < W) && (y >= 0) && (y < H) && (z >= 0) && (z < D);
+        c.idx[cn] = inb ? (z * H + y) * W + x : -1;
+        c.w[cn] = (((cn & 1) ? c.x0 : c.x1) * ((cn & 2) ? c.y0 : c.y1)) * ((cn & 4) ? c.z0 : c.z1);
+    }
+    return c;
+}
+
+// primsampler.h:44-66 with dowarp = true: fade from y, warp field sampled at y, payload sampled at the warped position
+__device__ __forceinline__ float4 sample_slab_warped(const float4 *__restrict__ slab, const float *__restrict__ wk, float y0, float y1,
+                                                     float y2, const Params &p) {
+    const float fade = __expf(-p.fadescale * (__powf(fabsf(y0), p.fadeexp) + __powf(fabsf(y1), p.fadeexp) + __powf(fabsf(y2), p.fadeexp)));
+    const CellG cw = cell_generic(y0, y1, y2, p.WD, p.WH, p.WW);
+    float q0 = 0.f, q1 = 0.f, q2 = 0.f;
+#pragma unroll
+    for (int cn = 0; cn < 8; ++cn) {
+        if (cw.idx[cn] >= 0) {
+            const float *v = wk + (size_t)cw.idx[cn] * 3;
+            q0 = __fmaf_rn(cw.w[cn], __ldg(v), q0); q1 = __fmaf_rn(cw.w[cn], __ldg(v + 1), q1); q2 = __fmaf_rn(cw.w[cn], __ldg(v + 2), q2);
+        }
+    }
+    const CellG ct = cell_generic(q0, q1, q2, p.TD, p.TH, p.TW);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int cn = 0; cn < 8; ++cn) {
+        if (ct.idx[cn] >= 0) {
+            const float4 v = __ldg(slab + ct.idx[cn]);
+            acc.x = __fmaf_rn(ct.w[cn], v.x, acc.x); acc.y = __fmaf_rn(ct.w[cn], v.y, acc.y);
+            acc.z = __fmaf_rn(ct.w[cn], v.z, acc.z); acc.w = __fmaf_rn(ct.w[cn], v.w, acc.w);
+        }
+    }
+    acc.w *= fade;
+    return acc;
+}
+
 // ------------------------------------------------------------------------------------------------------
 // 4. forward.  CAP = shared-memory list capacity per warp.  The CAP < 512 variant handles every tile whose list
 //    fits (almost all) with a small shared-memory footprint (more L1 for the voxel gathers) and flags the rest;
 //    the CAP == 512 variant then renders only the flagged tiles.
 // ------------------------------------------------------------------------------------------------------
-template <int T, bool kGrad, int CAP>
-__global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit) ? MVP_FWD_MINB : 4) render_forward_kernel(const Params p) {
+template <int T, bool kGrad, int CAP, bool kWarp>
+__global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? MVP_FWD_MINB : 4) render_forward_kernel(const Params p) {
     __shared__ int s_k[kWarps][CAP];
     __shared__ int s_iv[kWarps][CAP];
     __shared__ __align__(16) RowEntry s_stage[kWarps][2 * kStage];   // TMA-staged chunks of the tile row's bucket
@@ -699,7 +756,8 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit) ? MVP_FWD_MINB : 
         float4 sres = make_float4(0.f, 0.f, 0.f, 0.f);
         if (act) {
             const int kk = s_k[warp][(__float_as_int(rec.w) >> 5) & 1023];
-            sres = sample_slab<T>(tpn + (size_t)kk * slabsz, rec.x, rec.y, rec.z, p.TD, p.TH, p.TW, p.fadescale, p.fadeexp);
+            if (kWarp) sres = sample_slab_warped(tpn + (size_t)kk * slabsz, p.warp + ((size_t)n * p.K + kk) * ((size_t)p.WD * p.WH * p.WW * 3), rec.x, rec.y, rec.z, p);
+            else sres = sample_slab<T>(tpn + (size_t)kk * slabsz, rec.x, rec.y, rec.z, p.TD, p.TH, p.TW, p.fadescale, p.fadeexp);
         }
         __syncwarp();
         if (act) { ring[lane] = make_float4(sres.x, sres.y, sres.z, rec.w); ra[lane] = sres.w; }
@@ -842,8 +900,8 @@ __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d));
 }
 
-template <int T, int CAP>
-__global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit) ? MVP_BWD_MINB : 4) render_backward_kernel(const Params p) {
+template <int T, int CAP, bool kWarp>
+__global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? MVP_BWD_MINB : 3) render_backward_kernel(const Params p) {
     __shared__ int s_k[kWarps][CAP];
     __shared__ int s_iv[kWarps][CAP];
     __shared__ float4 s_q[kWarps][kRing];
@@ -1007,6 +1065,8 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit) ? MVP_BWD_MINB : 
                         const float rx1 = rowdot(q.r01, xm, q.r11, ym, q.r21, zm);
                         const float rx2 = rowdot(q.r02, xm, q.r12, ym, q.r22, zm);
                         const float y0 = __fmul_rn(q.sx, rx0), y1 = __fmul_rn(q.sy, rx1), y2 = __fmul_rn(q.sz, rx2);
+                        float gy0, gy1, gy2;   // dL/dy0 of this sample
+                        if (!kWarp) {
                         // ---- forward sample (primsampler.h:44-66) keeping what the adjoint needs ----
                         const float e1 = p.fadeexp - 1.f;
                         const float pw0 = __powf(fabsf(y0), e1), pw1 = __powf(fabsf(y1), e1), pw2 = __powf(fabsf(y2), e1);
@@ -1054,9 +1114,9 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit) ? MVP_BWD_MINB : 
                         const float d0 = A * oLx, d1 = A * oLy, d2 = A * oLz;
                         // ---- primsampler.h:68-91 ----
                         const float cf = -(p.fadescale * p.fadeexp) * sv.w * dLa;
-                        float gy0 = cf * pw0 * (y0 > 0.f ? 1.f : -1.f);
-                        float gy1 = cf * pw1 * (y1 > 0.f ? 1.f : -1.f);
-                        float gy2 = cf * pw2 * (y2 > 0.f ? 1.f : -1.f);
+                        gy0 = cf * pw0 * (y0 > 0.f ? 1.f : -1.f);
+                        gy1 = cf * pw1 * (y1 > 0.f ? 1.f : -1.f);
+                        gy2 = cf * pw2 * (y2 > 0.f ? 1.f : -1.f);
                         // ---- utils.h:504-643: scatter w_c * dL_sample (zero-weight corners add 0) ----
                         float *gc = gslab + (size_t)base * 4;
 #pragma unroll
@@ -1070,6 +1130,70 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit) ? MVP_BWD_MINB : 
                         const float giy = ey ? -(A * gpU[1] + B * gaU[1]) : (A * (gpU[1] - gpL[1]) + B * (gaU[1] - gaL[1]));
                         const float giz = ez ? -(A * gpU[2] + B * gaU[2]) : (A * (gpU[2] - gpL[2]) + B * (gaU[2] - gaL[2]));
                         gy0 += gmx * gix; gy1 += gmy * giy; gy2 += gmz * giz;
+                        } else {
+                        // ---- algo 1 (PrimSamplerTW<true>): payload sampled at the warp-field-displaced position ----
+                        const size_t wsl = (size_t)p.WD * p.WH * p.WW * 3;
+                        const float *wk = p.warp + ((size_t)n * p.K + k) * wsl;
+                        float *gwk = p.g_warp + ((size_t)n * p.K + k) * wsl;
+                        const float e1 = p.fadeexp - 1.f;
+                        const float pw0 = __powf(fabsf(y0), e1), pw1 = __powf(fabsf(y1), e1), pw2 = __powf(fabsf(y2), e1);
+                        const float fade = __expf(-p.fadescale * (pw0 * fabsf(y0) + pw1 * fabsf(y1) + pw2 * fabsf(y2)));
+                        const CellG cw = cell_generic(y0, y1, y2, p.WD, p.WH, p.WW);
+                        float u0 = 0.f, u1 = 0.f, u2 = 0.f;                    // warped position (primsampler.h:53-58)
+#pragma unroll
+                        for (int cn = 0; cn < 8; ++cn) {
+                            if (cw.idx[cn] >= 0) {
+                                const float *v = wk + (size_t)cw.idx[cn] * 3;
+                                u0 = __fmaf_rn(cw.w[cn], __ldg(v), u0); u1 = __fmaf_rn(cw.w[cn], __ldg(v + 1), u1); u2 = __fmaf_rn(cw.w[cn], __ldg(v + 2), u2);
+                            }
+                        }
+                        const CellG ct = cell_generic(u0, u1, u2, p.TD, p.TH, p.TW);
+                        float4 sv = make_float4(0.f, 0.f, 0.f, 0.f);
+                        float gp0 = 0.f, gp1 = 0.f, gp2 = 0.f, ga0 = 0.f, ga1 = 0.f, ga2 = 0.f;   // signed index-gradient sums (rgb / alpha part)
+#pragma unroll
+                        for (int cn = 0; cn < 8; ++cn) {
+                            if (ct.idx[cn] >= 0) {
+                                const float4 v = __ldg(slab + ct.idx[cn]);
+                                sv.x = __fmaf_rn(ct.w[cn], v.x, sv.x); sv.y = __fmaf_rn(ct.w[cn], v.y, sv.y);
+                                sv.z = __fmaf_rn(ct.w[cn], v.z, sv.z); sv.w = __fmaf_rn(ct.w[cn], v.w, sv.w);
+                                const float pr = v.x * oLx + v.y * oLy + v.z * oLz;
+                                const float wx = (cn & 1) ? ct.x0 : ct.x1, wy = (cn & 2) ? ct.y0 : ct.y1, wz = (cn & 4) ? ct.z0 : ct.z1;
+                                const float sxg = (cn & 1) ? 1.f : -1.f, syg = (cn & 2) ? 1.f : -1.f, szg = (cn & 4) ? 1.f : -1.f;
+                                gp0 += sxg * pr * (wy * wz); ga0 += sxg * v.w * (wy * wz);
+                                gp1 += syg * pr * (wx * wz); ga1 += syg * v.w * (wx * wz);
+                                gp2 += szg * pr * (wx * wy); ga2 += szg * v.w * (wx * wy);
+                            }
+                        }
+                        sv.w *= fade;
+                        const float A = issat ? (1.f - oab) : sv.w * p.dt;
+                        const float dLa = issat ? 0.f : p.dt * ((sv.x - osr) * oLx + (sv.y - osg) * oLy + (sv.z - osb) * oLz + (1.f - osa) * oLw);
+                        const float B = dLa * fade;
+                        const float d0 = A * oLx, d1 = A * oLy, d2 = A * oLz;
+                        const float cf = -(p.fadescale * p.fadeexp) * sv.w * dLa;
+                        gy0 = cf * pw0 * (y0 > 0.f ? 1.f : -1.f);
+                        gy1 = cf * pw1 * (y1 > 0.f ? 1.f : -1.f);
+                        gy2 = cf * pw2 * (y2 > 0.f ? 1.f : -1.f);
+#pragma unroll
+                        for (int cn = 0; cn < 8; ++cn)
+                            if (ct.idx[cn] >= 0) red_add_v4(gslab + (size_t)ct.idx[cn] * 4, ct.w[cn] * d0, ct.w[cn] * d1, ct.w[cn] * d2, ct.w[cn] * B);
+                        // dL/d(warped position)  (utils.h:591-642), then through the warp field (primsampler.h:82-88)
+                        const float e0 = gmx * (A * gp0 + B * ga0), e1_ = gmy * (A * gp1 + B * ga1), e2 = gmz * (A * gp2 + B * ga2);
+                        float h0 = 0.f, h1 = 0.f, h2 = 0.f;
+#pragma unroll
+                        for (int cn = 0; cn < 8; ++cn) {
+                            if (cw.idx[cn] >= 0) {
+                                const float *v = wk + (size_t)cw.idx[cn] * 3;
+                                float *gv = gwk + (size_t)cw.idx[cn] * 3;
+                                atomicAdd(gv, cw.w[cn] * e0); atomicAdd(gv + 1, cw.w[cn] * e1_); atomicAdd(gv + 2, cw.w[cn] * e2);
+                                const float dpw = __ldg(v) * e0 + __ldg(v + 1) * e1_ + __ldg(v + 2) * e2;
+                                const float wx = (cn & 1) ? cw.x0 : cw.x1, wy = (cn & 2) ? cw.y0 : cw.y1, wz = (cn & 4) ? cw.z0 : cw.z1;
+                                h0 += ((cn & 1) ? dpw : -dpw) * (wy * wz);
+                                h1 += ((cn & 2) ? dpw : -dpw) * (wx * wz);
+                                h2 += ((cn & 4) ? dpw : -dpw) * (wx * wy);
+                            }
+                        }
+                        gy0 += ((float)(p.WW - 1) * 0.5f) * h0; gy1 += ((float)(p.WH - 1) * 0.5f) * h1; gy2 += ((float)(p.WD - 1) * 0.5f) * h2;
+                        }
                         // ---- primtransf.h:155-179, accumulated in factored form ----
                         gx[0] += xm * gy0; gx[1] += xm * gy1; gx[2] += xm * gy2;
                         gx[3] += ym * gy0; gx[4] += ym * gy1; gx[5] += ym * gy2;
@@ -1240,6 +1364,8 @@ int mvp_raymarch_forward(const mvp_forward_args *a, void *stream) {
     if ((a->raysat == nullptr) != (a->rayaux == nullptr)) return MVP_ERR_NULL;
     int rc = check_shape(a->shape);
     if (rc != MVP_OK) return rc;
+    if (a->algo != 0 && a->algo != 1) return MVP_ERR_ALGO;
+    if (a->algo == 1 && (!a->warp || a->WD < 1 || a->WH < 1 || a->WW < 1)) return a->warp ? MVP_ERR_SHAPE : MVP_ERR_NULL;
     if (!(a->stepsize > 0.f) || !(a->stepsize < 3.0e38f)) return MVP_ERR_STEPSIZE;
     const Layout L = make_layout(a->shape);
     if (a->workspace_bytes < L.total || ((uintptr_t)a->workspace & 255)) return MVP_ERR_WORKSPACE;
@@ -1253,22 +1379,24 @@ int mvp_raymarch_forward(const mvp_forward_args *a, void *stream) {
     fill_params(p, a->shape, a->stepsize, a->fadescale, a->fadeexp, ws, L);
     p.raypos = a->raypos; p.raydir = a->raydir; p.tminmax = a->tminmax; p.tplate = a->tplate;
     p.rayrgba = a->rayrgba; p.raysat = a->raysat; p.rayaux = reinterpret_cast<int4 *>(a->rayaux);
+    p.warp = a->warp; p.WD = a->WD; p.WH = a->WH; p.WW = a->WW;
     dim3 grid((p.TXn + 1) / 2, (p.TYn + 1) / 2, a->shape.N);
     if (grid.y > 65535) return MVP_ERR_SHAPE;
     const int cubic = (a->shape.TD == a->shape.TH && a->shape.TH == a->shape.TW) ? a->shape.TD : 0;
-#define MVP_LAUNCH_FWD(TT)                                                                                   \
+#define MVP_LAUNCH_FWD(TT, WW_)                                                                              \
     do {                                                                                                     \
         if (a->raysat) {                                                                                     \
-            render_forward_kernel<TT, true, kMaxHit><<<grid, kWarps * 32, 0, st>>>(p);                       \
-            launch_dependent(render_forward_kernel<TT, true, kFastCap>, grid, kWarps * 32, st, p);           \
+            render_forward_kernel<TT, true, kMaxHit, WW_><<<grid, kWarps * 32, 0, st>>>(p);                  \
+            launch_dependent(render_forward_kernel<TT, true, kFastCap, WW_>, grid, kWarps * 32, st, p);      \
         } else {                                                                                             \
-            render_forward_kernel<TT, false, kMaxHit><<<grid, kWarps * 32, 0, st>>>(p);                      \
-            launch_dependent(render_forward_kernel<TT, false, kFastCap>, grid, kWarps * 32, st, p);          \
+            render_forward_kernel<TT, false, kMaxHit, WW_><<<grid, kWarps * 32, 0, st>>>(p);                 \
+            launch_dependent(render_forward_kernel<TT, false, kFastCap, WW_>, grid, kWarps * 32, st, p);     \
         }                                                                                                    \
     } while (0)
-    if (cubic == 8) MVP_LAUNCH_FWD(8);
-    else if (cubic == 16) MVP_LAUNCH_FWD(16);
-    else MVP_LAUNCH_FWD(0);
+    if (a->algo == 1) MVP_LAUNCH_FWD(0, true);
+    else if (cubic == 8) MVP_LAUNCH_FWD(8, false);
+    else if (cubic == 16) MVP_LAUNCH_FWD(16, false);
+    else MVP_LAUNCH_FWD(0, false);
 #undef MVP_LAUNCH_FWD
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? MVP_OK : (int)e;
@@ -1282,6 +1410,8 @@ int mvp_raymarch_backward(const mvp_backward_args *a, void *stream) {
         return MVP_ERR_NULL;
     int rc = check_shape(a->shape);
     if (rc != MVP_OK) return rc;
+    if (a->algo != 0 && a->algo != 1) return MVP_ERR_ALGO;
+    if (a->algo == 1 && (!a->warp || !a->grad_warp || a->WD < 1 || a->WH < 1 || a->WW < 1)) return (a->warp && a->grad_warp) ? MVP_ERR_SHAPE : MVP_ERR_NULL;
     if (!(a->stepsize > 0.f) || !(a->stepsize < 3.0e38f)) return MVP_ERR_STEPSIZE;
     const Layout L = make_layout(a->shape);
     if (a->workspace_bytes < L.total || ((uintptr_t)a->workspace & 255)) return MVP_ERR_WORKSPACE;
@@ -1296,17 +1426,19 @@ int mvp_raymarch_backward(const mvp_backward_args *a, void *stream) {
     p.raypos = a->raypos; p.raydir = a->raydir; p.tminmax = a->tminmax; p.tplate = a->tplate;
     p.grad_rayrgba = a->grad_rayrgba; p.raysat_in = a->raysat; p.rayaux_in = reinterpret_cast<const int4 *>(a->rayaux);
     p.g_primpos = a->grad_primpos; p.g_primrot = a->grad_primrot; p.g_primscale = a->grad_primscale; p.g_tplate = a->grad_tplate;
+    p.warp = a->warp; p.g_warp = a->grad_warp; p.WD = a->WD; p.WH = a->WH; p.WW = a->WW;
     dim3 grid((p.TXn + 1) / 2, (p.TYn + 1) / 2, a->shape.N);
     if (grid.y > 65535) return MVP_ERR_SHAPE;
     const int cubic = (a->shape.TD == a->shape.TH && a->shape.TH == a->shape.TW) ? a->shape.TD : 0;
-#define MVP_LAUNCH_BWD(TT)                                                                       \
+#define MVP_LAUNCH_BWD(TT, WW_)                                                                  \
     do {                                                                                         \
-        render_backward_kernel<TT, kMaxHit><<<grid, kWarps * 32, 0, st>>>(p);                    \
-        launch_dependent(render_backward_kernel<TT, kFastCap>, grid, kWarps * 32, st, p);        \
+        render_backward_kernel<TT, kMaxHit, WW_><<<grid, kWarps * 32, 0, st>>>(p);               \
+        launch_dependent(render_backward_kernel<TT, kFastCap, WW_>, grid, kWarps * 32, st, p);   \
     } while (0)
-    if (cubic == 8) MVP_LAUNCH_BWD(8);
-    else if (cubic == 16) MVP_LAUNCH_BWD(16);
-    else MVP_LAUNCH_BWD(0);
+    if (a->algo == 1) MVP_LAUNCH_BWD(0, true);
+    else if (cubic == 8) MVP_LAUNCH_BWD(8, false);
+    else if (cubic == 16) MVP_LAUNCH_BWD(16, false);
+    else MVP_LAUNCH_BWD(0, false);
 #undef MVP_LAUNCH_BWD
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? MVP_OK : (int)e;

@@ -22,6 +22,7 @@ class ForwardArgs(ctypes.Structure):
         ("tplate", c_f),
         ("rayrgba", c_f), ("raysat", c_f), ("rayaux", c_f),
         ("workspace", c_f), ("workspace_bytes", ctypes.c_size_t),
+        ("warp", c_f), ("WD", ctypes.c_int32), ("WH", ctypes.c_int32), ("WW", ctypes.c_int32), ("algo", ctypes.c_int32),
     ]
 
 
@@ -36,11 +37,13 @@ class BackwardArgs(ctypes.Structure):
         ("grad_rayrgba", c_f), ("raysat", c_f), ("rayaux", c_f),
         ("grad_primpos", c_f), ("grad_primrot", c_f), ("grad_primscale", c_f), ("grad_tplate", c_f),
         ("workspace", c_f), ("workspace_bytes", ctypes.c_size_t),
+        ("warp", c_f), ("grad_warp", c_f), ("WD", ctypes.c_int32), ("WH", ctypes.c_int32), ("WW", ctypes.c_int32),
+        ("algo", ctypes.c_int32),
     ]
 
 
 FLAG_ACCEL_VALID = 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 EXPORTS = ("mvp_abi_version", "mvp_error_string", "mvp_workspace_bytes", "mvp_build_accel", "mvp_raymarch_forward",
            "mvp_raymarch_backward", "mvp_compute_raydirs", "mvp_forward_launch_count", "mvp_backward_launch_count")

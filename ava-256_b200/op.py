@@ -2,8 +2,8 @@
 (/root/reference/extensions/mvpraymarch/mvpraymarch.py:87-390) on top of the C-ABI in include/mvpraymarch_b200.h.
 
 Same contract as the reference: fp32 CUDA tensors, contiguous, caller-visible output rayrgba [N,H,W,4] that
-participates in autograd with gradients for primpos, primrot, primscale and template (None for everything else,
-mvpraymarch.py:279-292).  Differences that are deliberate:
+participates in autograd with gradients for primpos, primrot, primscale, template and (algo 1) warp, None for
+everything else (mvpraymarch.py:279-292).  Differences that are deliberate:
   * kernels run on torch's current stream (the reference launches on legacy stream 0, mvpraymarch.cpp:277);
   * no allocation or sync inside the native call (the reference cudaMalloc/cudaFree's per forward, bvh.cu:261-293);
   * the acceleration structure is a screen-space bucket list, not the BVH tensors of build_accel (:21-84);
@@ -38,8 +38,11 @@ class MVPRaymarch(Function):
     def forward(ctx, raypos, raydir, stepsize, tminmax, primpos, primrot, primscale, template, warp, rayterm,
                 gradmode, options):
         algo = options["algo"]
-        if algo != 0 or warp is not None:
-            raise NotImplementedError("mvpraymarch_b200: algo=1 / warp fields are not implemented yet (SURVEY 8f #3)")
+        if algo not in (0, 1):
+            raise NotImplementedError("mvpraymarch_b200: algo must be 0 or 1 (the reference launches nothing for other "
+                                      "values, mvpraymarch_kernel.cu:104-105)")
+        if algo == 1 and warp is None:
+            raise RuntimeError("mvpraymarch_b200: algo=1 samples a warp field (PrimSamplerTW<true>); pass `warp`")
         if options["usebvh"] != "fixedorder":
             raise NotImplementedError("mvpraymarch_b200: only usebvh='fixedorder' (the default, and the only "
                                       "self-consistent mode of the reference) is implemented")
@@ -55,6 +58,11 @@ class MVPRaymarch(Function):
         for name, t in (("raypos", raypos), ("raydir", raydir), ("tminmax", tminmax), ("primpos", primpos),
                         ("primrot", primrot), ("primscale", primscale), ("template", template)):
             _check_f32_cuda(name, t)
+        if warp is not None:                                           # mvpraymarch.py:124
+            assert warp.is_contiguous() and warp.dim() == 6 and warp.size(-1) == 3, \
+                "channels-last warp field [N,K,WD,WH,WW,3] required"
+            _check_f32_cuda("warp", warp)
+        usewarp = algo == 1                                            # algo 0 ignores a warp field, like the reference
 
         N, H, W = raypos.shape[:3]
         K = primpos.size(1)
@@ -78,18 +86,22 @@ class MVPRaymarch(Function):
             a.tplate = _ptr(template)
             a.rayrgba, a.raysat, a.rayaux = _ptr(rayrgba), _ptr(raysat), _ptr(rayaux)
             a.workspace, a.workspace_bytes = _ptr(workspace), wsbytes
+            a.algo = 1 if usewarp else 0
+            if usewarp:
+                a.warp = _ptr(warp)
+                a.WD, a.WH, a.WW = warp.shape[2:5]
             stream = torch.cuda.current_stream(dev).cuda_stream
             _lib.check(_lib.LIB.mvp_raymarch_forward(ctypes.byref(a), ctypes.c_void_p(stream)))
 
         if gradmode:
-            ctx.save_for_backward(raypos, raydir, tminmax, primpos, primrot, primscale, template, raysat, rayaux, workspace)
+            ctx.save_for_backward(raypos, raydir, tminmax, primpos, primrot, primscale, template, raysat, rayaux, workspace, warp)
             ctx.options = options
             ctx.stepsize = float(stepsize)
         return rayrgba
 
     @staticmethod
     def backward(ctx, grad_rayrgba):
-        raypos, raydir, tminmax, primpos, primrot, primscale, template, raysat, rayaux, workspace = ctx.saved_tensors
+        raypos, raydir, tminmax, primpos, primrot, primscale, template, raysat, rayaux, workspace, warp = ctx.saved_tensors
         options = ctx.options
         N, H, W = raypos.shape[:3]
         K = primpos.size(1)
@@ -101,6 +113,8 @@ class MVPRaymarch(Function):
             grad_primrot = torch.zeros_like(primrot)
             grad_primscale = torch.zeros_like(primscale)
             grad_template = torch.zeros_like(template)
+            grad_warp = torch.zeros_like(warp) if warp is not None else None     # mvpraymarch.py:246
+            usewarp = options["algo"] == 1
             a = _lib.BackwardArgs()
             a.shape = _lib.Shape(N, H, W, K, TD, TH, TW)
             a.stepsize, a.fadescale, a.fadeexp = ctx.stepsize, float(options["fadescale"]), float(options["fadeexp"])
@@ -112,9 +126,13 @@ class MVPRaymarch(Function):
             a.grad_primpos, a.grad_primrot, a.grad_primscale = _ptr(grad_primpos), _ptr(grad_primrot), _ptr(grad_primscale)
             a.grad_tplate = _ptr(grad_template)
             a.workspace, a.workspace_bytes = _ptr(workspace), workspace.numel()
+            a.algo = 1 if usewarp else 0
+            if usewarp:
+                a.warp, a.grad_warp = _ptr(warp), _ptr(grad_warp)
+                a.WD, a.WH, a.WW = warp.shape[2:5]
             stream = torch.cuda.current_stream(dev).cuda_stream
             _lib.check(_lib.LIB.mvp_raymarch_backward(ctypes.byref(a), ctypes.c_void_p(stream)))
-        return (None, None, None, None, grad_primpos, grad_primrot, grad_primscale, grad_template, None, None, None, None)
+        return (None, None, None, None, grad_primpos, grad_primrot, grad_primscale, grad_template, grad_warp, None, None, None)
 
 
 def mvpraymarch(

@@ -25,7 +25,7 @@
  * Tensor layouts (SURVEY.md terminology table):
  *   raypos, raydir [N,H,W,3]   tminmax [N,H,W,2]
  *   primpos [N,K,3]  primrot [N,K,3,3] (row-major)  primscale [N,K,3] (inverse half-extents)
- *   tplate  [N,K,TD,TH,TW,4] channels-last RGBA
+ *   tplate  [N,K,TD,TH,TW,4] channels-last RGBA      warp [N,K,WD,WH,WW,3] channels-last (algo 1)
  *   rayrgba [N,H,W,4]  raysat [N,H,W,3]  rayaux [N,H,W,4] (int32, opaque; written by forward, read by backward)
  */
 #ifndef MVPRAYMARCH_B200_H_
@@ -38,14 +38,14 @@
 extern "C" {
 #endif
 
-#define MVP_ABI_VERSION 1
+#define MVP_ABI_VERSION 2
 
 #define MVP_OK 0
 #define MVP_ERR_NULL (-1)      /* a required pointer is NULL */
 #define MVP_ERR_SHAPE (-2)     /* non-positive or unsupported dimension (H, W < 32768; K >= 1) */
 #define MVP_ERR_STEPSIZE (-3)  /* stepsize must be finite and > 0 */
 #define MVP_ERR_WORKSPACE (-4) /* workspace too small or misaligned (256 B) */
-#define MVP_ERR_ALGO (-5)      /* only algo 0 (no warp field) is implemented */
+#define MVP_ERR_ALGO (-5)      /* algo must be 0 (no warp field) or 1 (warp field, primsampler.h:53-58) */
 
 typedef struct mvp_shape {
     int32_t N, H, W, K, TD, TH, TW;
@@ -66,6 +66,11 @@ typedef struct mvp_forward_args {
     int32_t *rayaux;         /* out, NULL iff raysat is NULL */
     void *workspace;         /* >= mvp_workspace_bytes(shape), 256-byte aligned */
     size_t workspace_bytes;
+    /* algo 1 only (reference: PrimSamplerTW<true>): warp field [N,K,WD,WH,WW,3] channels-last, sampled at the slab
+     * coordinate; the payload is then sampled at the warped position (zero outside the slab).  algo 0 ignores these. */
+    const float *warp;
+    int32_t WD, WH, WW;
+    int32_t algo;            /* 0 or 1 (mvpraymarch.py:303) */
 } mvp_forward_args;
 
 typedef struct mvp_backward_args {
@@ -82,6 +87,10 @@ typedef struct mvp_backward_args {
     float *grad_tplate;        /* out, accumulated into: caller zero-fills */
     void *workspace;
     size_t workspace_bytes;
+    const float *warp;         /* algo 1 only */
+    float *grad_warp;          /* algo 1 only; out, accumulated into: caller zero-fills */
+    int32_t WD, WH, WW;
+    int32_t algo;
 } mvp_backward_args;
 
 int mvp_abi_version(void);

@@ -26,13 +26,15 @@ def main(outdir):
         dev = "cuda"
         t = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in s.items()}
         fs, fe = s.get("fadescale", 8.0), s.get("fadeexp", 8.0)
+        w = t.get("warp")
         rgba, sat, st = refext.forward(t["raypos"], t["raydir"], t["stepsize"], t["tminmax"], t["primpos"], t["primrot"],
-                                       t["primscale"], t["template"], fs, fe)
+                                       t["primscale"], t["template"], fs, fe, warp=w)
         g = refext.backward(t["raypos"], t["raydir"], t["stepsize"], t["tminmax"], t["primpos"], t["primrot"],
-                            t["primscale"], t["template"], rgba, sat, st, grad.to(dev), fs, fe)
+                            t["primscale"], t["template"], rgba, sat, st, grad.to(dev), fs, fe, warp=w)
+        extra = {"grad_warp": g[4].cpu().numpy()} if w is not None else {}
         np.savez_compressed(os.path.join(outdir, name + ".npz"), rayrgba=rgba.cpu().numpy(), raysat=sat.cpu().numpy(),
                             grad_primpos=g[0].cpu().numpy(), grad_primrot=g[1].cpu().numpy(),
-                            grad_primscale=g[2].cpu().numpy(), grad_template=g[3].cpu().numpy())
+                            grad_primscale=g[2].cpu().numpy(), grad_template=g[3].cpu().numpy(), **extra)
         print(name, "saved; saturated rays:", int((sat[..., 0] > -1).sum()), "of", sat[..., 0].numel())
 
 

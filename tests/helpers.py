@@ -59,6 +59,8 @@ def scene_args_np(s, dtype=np.float32):
          s["tminmax"].numpy().astype(dtype), s["primpos"].numpy().astype(dtype), s["primrot"].numpy().astype(dtype),
          s["primscale"].numpy().astype(dtype), s["template"].numpy().astype(dtype)]
     kw = dict(fadescale=float(s.get("fadescale", 8.0)), fadeexp=float(s.get("fadeexp", 8.0)))
+    if s.get("warp") is not None:
+        kw["warp"] = s["warp"].numpy().astype(dtype)
     return a, kw
 
 
@@ -99,6 +101,11 @@ CASES = {
     "noncubic": lambda: gradcheck_like_scene(N=1, H=14, W=17, k3=2, seed=21, alpha_gain=30.0, dims=(3, 1, 5)),
     # image smaller than one 8x4 tile, a single slab
     "tiny": lambda: gradcheck_like_scene(N=2, H=3, W=5, k3=1, M=2, seed=5, alpha_gain=15.0, scale=1.0),
+    # algo 1: warp field (PrimSamplerTW<true>); large noise so warped positions leave the slab (zero padding)
+    "warp_small": lambda: dict(gradcheck_like_scene(N=2, H=20, W=18, k3=2, M=6, seed=31, alpha_gain=60.0),
+                               warp=make_warp(2, 8, 3, 4, 5, seed=5, amp=0.12)),
+    "warp_head": lambda: dict(_head_case(1, 48, 32, 64, 8, stepsize=1.0 / 32, alpha_mu=2.0, alpha_sigma=2.0),
+                              warp=make_warp(1, 64, 4, 4, 4, seed=9, amp=0.05)),
     "head_t16": lambda: _head_case(1, 48, 32, 64, 16, stepsize=1.0 / 32, view_offset=11, alpha_mu=1.0, alpha_sigma=2.0),
 }
 

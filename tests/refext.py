@@ -37,7 +37,7 @@ def _tree(N, K, dev):
 
 
 def forward(raypos, raydir, stepsize, tminmax, primpos, primrot, primscale, template, fadescale=8.0, fadeexp=8.0,
-            blocksize=(8, 16)):
+            blocksize=(8, 16), warp=None):
     """Returns (rayrgba, raysat, state) from the reference kernels (one call; N*K*T^3*4 must stay < 2^31)."""
     m = module()
     N, H, W = raypos.shape[:3]
@@ -51,23 +51,25 @@ def forward(raypos, raydir, stepsize, tminmax, primpos, primrot, primscale, temp
     rayrgba = torch.empty((N, H, W, 4), device=dev)
     raysat = torch.full((N, H, W, 3), -1.0, device=dev)
     m.raymarch_forward(raypos, raydir, stepsize, tminmax, sortedobjid, nodechildren, nodeaabb, primpos, primrot, primscale,
-                       template, None, rayrgba, raysat, None, 0, False, 512, True, True, fadescale, fadeexp, 0, 0.0, 3,
-                       blocksize[0], blocksize[1])
+                       template, warp, rayrgba, raysat, None, 1 if warp is not None else 0, False, 512, True, True, fadescale,
+                       fadeexp, 0, 0.0, 3, blocksize[0], blocksize[1])
     torch.cuda.synchronize()
     return rayrgba, raysat, (sortedobjid, nodechildren, nodeaabb)
 
 
 def backward(raypos, raydir, stepsize, tminmax, primpos, primrot, primscale, template, rayrgba, raysat, state,
-             grad_rayrgba, fadescale=8.0, fadeexp=8.0, blocksize=(8, 16)):
+             grad_rayrgba, fadescale=8.0, fadeexp=8.0, blocksize=(8, 16), warp=None):
     m = module()
     sortedobjid, nodechildren, nodeaabb = state
     g = [torch.zeros_like(t) for t in (primpos, primrot, primscale, template)]
+    gw = torch.zeros_like(warp) if warp is not None else None
     torch.cuda.synchronize()
     m.raymarch_backward(raypos, raydir, stepsize, tminmax, sortedobjid, nodechildren, nodeaabb, primpos, g[0], primrot,
-                        g[1], primscale, g[2], template, g[3], None, None, rayrgba, grad_rayrgba.contiguous(), raysat, None,
-                        0, False, 512, True, True, fadescale, fadeexp, 0, 0.0, 3, blocksize[0], blocksize[1])
+                        g[1], primscale, g[2], template, g[3], warp, gw, rayrgba, grad_rayrgba.contiguous(), raysat, None,
+                        1 if warp is not None else 0, False, 512, True, True, fadescale, fadeexp, 0, 0.0, 3, blocksize[0],
+                        blocksize[1])
     torch.cuda.synchronize()
-    return tuple(g)
+    return tuple(g) + ((gw,) if warp is not None else ())
 
 
 # ---- reference ray generator (extensions/utils -> utilslib), for the compute_raydirs parity test ----

@@ -27,7 +27,7 @@ def test_header_symbols_are_exported():
     for n in names:
         assert hasattr(lib.LIB, n), n
     assert sorted(names) == sorted(lib.EXPORTS)
-    assert lib.LIB.mvp_abi_version() == 1
+    assert lib.LIB.mvp_abi_version() == 2
 
 
 def test_workspace_bytes_and_shape_validation():
@@ -94,9 +94,12 @@ def test_unsupported_modes_raise():
     from extensions.mvpraymarch.mvpraymarch import mvpraymarch
     from tests.helpers import build_case
     s, _ = build_case("gradcheck_ragged")
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="warp"):
         mvpraymarch(s["raypos"], s["raydir"], s["stepsize"], s["tminmax"], (s["primpos"], s["primrot"], s["primscale"]),
                     s["template"], None, algo=1)
+    with pytest.raises(NotImplementedError):
+        mvpraymarch(s["raypos"], s["raydir"], s["stepsize"], s["tminmax"], (s["primpos"], s["primrot"], s["primscale"]),
+                    s["template"], None, algo=2)
     with pytest.raises(NotImplementedError):
         mvpraymarch(s["raypos"], s["raydir"], s["stepsize"], s["tminmax"], (s["primpos"], s["primrot"], s["primscale"]),
                     s["template"], None, usebvh=True)

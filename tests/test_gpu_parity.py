@@ -24,8 +24,12 @@ def run_ours(s, grad=None):
     dev = "cuda"
     t = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in s.items()}
     leaves = [t[k].clone().requires_grad_(grad is not None) for k in ("primpos", "primrot", "primscale", "template")]
+    warp = t.get("warp")
+    if warp is not None:
+        warp = warp.clone().requires_grad_(grad is not None)
+        leaves.append(warp)
     out = mvpraymarch(t["raypos"], t["raydir"], t["stepsize"], t["tminmax"], (leaves[0], leaves[1], leaves[2]), leaves[3],
-                      None, fadescale=s.get("fadescale", 8.0), fadeexp=s.get("fadeexp", 8.0))
+                      warp, algo=1 if warp is not None else 0, fadescale=s.get("fadescale", 8.0), fadeexp=s.get("fadeexp", 8.0))
     if grad is None:
         return out.detach().cpu().numpy(), None
     out.backward(grad.to(dev))
@@ -42,7 +46,8 @@ def test_forward_backward_vs_oracle(name):
     ref, raysat = oracle.forward(*a, **kw)
     assert relerr(out, ref) <= FWD_TOL
     gref = oracle.backward(*a, grad.numpy(), raysat, **kw)
-    for nm, g, r in zip(("primpos", "primrot", "primscale", "template"), grads, gref):
+    assert len(grads) == len(gref)
+    for nm, g, r in zip(("primpos", "primrot", "primscale", "template", "warp"), grads, gref):
         assert relerr(g, r) <= BWD_TOL, nm
 
 
@@ -55,7 +60,7 @@ def test_forward_backward_vs_golden(name):
     s, grad = build_case(name)
     out, grads = run_ours(s, grad)
     assert relerr(out, gold["rayrgba"]) <= FWD_TOL
-    for nm, g in zip(("primpos", "primrot", "primscale", "template"), grads):
+    for nm, g in zip(("primpos", "primrot", "primscale", "template", "warp"), grads):
         assert relerr(g, gold["grad_" + nm]) <= BWD_TOL, nm
 
 

@@ -101,7 +101,7 @@ def test_oracle_f32_matches_reference_cuda_golden(name):
     assert np.array_equal(raysat[..., 0] > -1, gold["raysat"][..., 0] > -1)
     assert relerr(raysat, gold["raysat"]) < 5e-6
     g = oracle.backward(*a, grad.numpy(), gold["raysat"], **kw)
-    for nm, x in zip(("primpos", "primrot", "primscale", "template"), g):
+    for nm, x in zip(("primpos", "primrot", "primscale", "template", "warp"), g):
         assert relerr(x, gold["grad_" + nm]) < 2e-5, nm
 
 

@@ -49,7 +49,12 @@ namespace {
 constexpr int kMaxHit = 512;      // utils.h:779-781 (template argument hard-wired at mvpraymarch_kernel.cu:33)
 constexpr int kTileW = 8;         // warp footprint of the reference's default block (8,16): 8 x 4 pixels
 constexpr int kTileH = 4;
-constexpr int kWarps = 4;         // warps (tiles) per CTA, arranged 2 x 2
+#ifndef MVP_BLK_TX
+#define MVP_BLK_TX 2
+#endif
+constexpr int kWarps = 4;         // warps (tiles) per CTA
+constexpr int kBlkTX = MVP_BLK_TX;   // ... arranged kBlkTX x kBlkTY tiles (2 x 2 = 16 x 8 pixels: measured best)
+constexpr int kBlkTY = kWarps / kBlkTX;
 constexpr int kMaskSteps = MVP_CHUNK;   // backward: sweep steps per chunk of slab start order
 constexpr int kRowCapMax = 2048;  // entries per tile-row bucket before the row falls back to scanning all slabs
 constexpr int kRing = 64;        // backward sample ring (entries per warp, power of two, >= 2 * 32)
@@ -701,7 +706,7 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? MVP_F
     __shared__ float s_ra[kWarps][kRing];      // sampled alpha * fade
     __shared__ int s_rm[kWarps][kGrad ? kRing : 1];   // sweep step of the queued sample (needed to record the saturating one)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tx = blockIdx.x * 2 + (warp & 1), ty = blockIdx.y * 2 + (warp >> 1), n = blockIdx.z;
+    const int tx = blockIdx.x * kBlkTX + (warp % kBlkTX), ty = blockIdx.y * kBlkTY + (warp / kBlkTX), n = blockIdx.z;
     if (tx >= p.TXn || ty >= p.TYn) return;   // warps are independent: no CTA-wide barrier below (exited warps count as arrived)
     // Programmatic dependent launch: the 512-entry variant (few, long-running tiles) is launched first and lets the
     // fast variant start while it is still running; the fast variant waits for it only at its very end.
@@ -908,7 +913,7 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? MVP_B
     __shared__ __align__(16) RowEntry s_stage[kWarps][2 * kStage];   // TMA-staged chunks of the tile row's bucket
     __shared__ __align__(8) unsigned long long s_bar[kWarps][2];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tx = blockIdx.x * 2 + (warp & 1), ty = blockIdx.y * 2 + (warp >> 1), n = blockIdx.z;
+    const int tx = blockIdx.x * kBlkTX + (warp % kBlkTX), ty = blockIdx.y * kBlkTY + (warp / kBlkTX), n = blockIdx.z;
     if (tx >= p.TXn || ty >= p.TYn) return;
     if (CAP == kMaxHit) asm volatile("griddepcontrol.launch_dependents;");
     const bool heavy = p.tileflag[((size_t)n * p.TYn + ty) * p.TXn + tx] != 0;
@@ -1380,7 +1385,7 @@ int mvp_raymarch_forward(const mvp_forward_args *a, void *stream) {
     p.raypos = a->raypos; p.raydir = a->raydir; p.tminmax = a->tminmax; p.tplate = a->tplate;
     p.rayrgba = a->rayrgba; p.raysat = a->raysat; p.rayaux = reinterpret_cast<int4 *>(a->rayaux);
     p.warp = a->warp; p.WD = a->WD; p.WH = a->WH; p.WW = a->WW;
-    dim3 grid((p.TXn + 1) / 2, (p.TYn + 1) / 2, a->shape.N);
+    dim3 grid((p.TXn + kBlkTX - 1) / kBlkTX, (p.TYn + kBlkTY - 1) / kBlkTY, a->shape.N);
     if (grid.y > 65535) return MVP_ERR_SHAPE;
     const int cubic = (a->shape.TD == a->shape.TH && a->shape.TH == a->shape.TW) ? a->shape.TD : 0;
 #define MVP_LAUNCH_FWD(TT, WW_)                                                                              \
@@ -1427,7 +1432,7 @@ int mvp_raymarch_backward(const mvp_backward_args *a, void *stream) {
     p.grad_rayrgba = a->grad_rayrgba; p.raysat_in = a->raysat; p.rayaux_in = reinterpret_cast<const int4 *>(a->rayaux);
     p.g_primpos = a->grad_primpos; p.g_primrot = a->grad_primrot; p.g_primscale = a->grad_primscale; p.g_tplate = a->grad_tplate;
     p.warp = a->warp; p.g_warp = a->grad_warp; p.WD = a->WD; p.WH = a->WH; p.WW = a->WW;
-    dim3 grid((p.TXn + 1) / 2, (p.TYn + 1) / 2, a->shape.N);
+    dim3 grid((p.TXn + kBlkTX - 1) / kBlkTX, (p.TYn + kBlkTY - 1) / kBlkTY, a->shape.N);
     if (grid.y > 65535) return MVP_ERR_SHAPE;
     const int cubic = (a->shape.TD == a->shape.TH && a->shape.TH == a->shape.TW) ? a->shape.TD : 0;
 #define MVP_LAUNCH_BWD(TT, WW_)                                                                  \

@@ -118,3 +118,23 @@ def test_scene_generator_is_deterministic_and_pinhole():
     r = a["primrot"][0]
     assert torch.allclose(r @ r.transpose(1, 2), torch.eye(3).expand_as(r), atol=1e-4)
     assert (a["primscale"] > 0).all() and (a["template"] >= 0).all()
+
+
+def test_overlay_resolves_from_unmodified_reference_modules():
+    """With this repo in front of an unmodified ava-256 checkout, the reference's own modules import OUR op and ray
+    generator.  Needs /root/reference (absent on the GPU box -> skipped there)."""
+    import subprocess
+    import sys
+    ref = "/root/reference"
+    if not os.path.isdir(os.path.join(ref, "models", "raymarchers")):
+        pytest.skip("reference checkout not available")
+    code = ("import models.raymarchers.mvpraymarcher as m, extensions.utils.utils as u, inspect;"
+            "print(inspect.getsourcefile(m.mvpraymarch)); print(inspect.getsourcefile(u.compute_raydirs));"
+            "r = m.Raymarcher(256.0); print(r.dt)")
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + ref)
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd="/tmp")
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = out.stdout.strip().splitlines()
+    assert lines[0].startswith(ROOT) and "ava-256_b200" in lines[0]
+    assert lines[1].startswith(ROOT) and "ava-256_b200" in lines[1]
+    assert abs(float(lines[2]) - 1.0 / 256.0) < 1e-12

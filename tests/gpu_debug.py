@@ -14,7 +14,7 @@ from tests import refext  # noqa: E402
 from tests.helpers import CASES, build_case, relerr, scene_args_np  # noqa: E402
 from tests.test_gpu_parity import run_ours  # noqa: E402
 
-names = ("primpos", "primrot", "primscale", "template")
+names = ("primpos", "primrot", "primscale", "template", "warp")
 for name in CASES:
     s, grad = build_case(name)
     out, grads = run_ours(s, grad)
@@ -29,9 +29,9 @@ for name in CASES:
         t = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in s.items()}
         fs, fe = s.get("fadescale", 8.0), s.get("fadeexp", 8.0)
         rgba, sat, st = refext.forward(t["raypos"], t["raydir"], t["stepsize"], t["tminmax"], t["primpos"], t["primrot"],
-                                       t["primscale"], t["template"], fs, fe)
+                                       t["primscale"], t["template"], fs, fe, warp=t.get("warp"))
         g2 = refext.backward(t["raypos"], t["raydir"], t["stepsize"], t["tminmax"], t["primpos"], t["primrot"],
-                             t["primscale"], t["template"], rgba, sat, st, grad.cuda(), fs, fe)
+                             t["primscale"], t["template"], rgba, sat, st, grad.cuda(), fs, fe, warp=t.get("warp"))
         line = "%-18s vs refext: fwd %.2e" % (name, relerr(out, rgba.cpu().numpy()))
         for nm, g, r in zip(names, grads, g2):
             line += " | %s %.2e" % (nm, relerr(g, r.cpu().numpy()))

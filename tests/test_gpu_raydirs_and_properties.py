@@ -134,3 +134,37 @@ def test_full_size_properties(cfg):
         assert scale > 0, n_
         # atomics reorder fp32 sums between runs: compare to 1e-4 of the tensor's scale
         assert float((x2 - 2.0 * x1).abs().max()) <= 1e-4 * 2.0 * scale, n_
+
+
+def test_forward_is_cuda_graph_capturable():
+    """No allocation, no sync, caller's stream inside the native call: the whole forward,
+    including the accel build and the programmatic-dependent-launch pair, can be captured and replayed."""
+    from ava256_b200 import lib, scene
+    s = scene.make_scene(1, 64, 48, 256, 8, alpha_mu=4.0, alpha_sigma=3.0, device="cuda")
+    eager, _ = _abi_forward(s, 0)
+    N, H, W = s["raypos"].shape[:3]
+    P = lambda x: ctypes.c_void_p(x.data_ptr())  # noqa: E731
+    wsb = lib.workspace_bytes(N, H, W, 256, 8, 8, 8)
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    out = torch.zeros(N, H, W, 4, device="cuda")
+    a = lib.ForwardArgs()
+    a.shape = lib.Shape(N, H, W, 256, 8, 8, 8)
+    a.stepsize, a.fadescale, a.fadeexp, a.flags = s["stepsize"], 8.0, 8.0, 0
+    a.raypos, a.raydir, a.tminmax = P(s["raypos"]), P(s["raydir"]), P(s["tminmax"])
+    a.primpos, a.primrot, a.primscale, a.tplate = P(s["primpos"]), P(s["primrot"]), P(s["primscale"]), P(s["template"])
+    a.rayrgba, a.raysat, a.rayaux, a.workspace, a.workspace_bytes = P(out), None, None, P(ws), wsb
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            lib.check(lib.LIB.mvp_raymarch_forward(ctypes.byref(a), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.current_stream().wait_stream(side)
+    out.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, eager)
+    out.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, eager)

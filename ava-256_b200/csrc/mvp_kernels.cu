@@ -910,6 +910,7 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? MVP_B
     __shared__ int s_k[kWarps][CAP];
     __shared__ int s_iv[kWarps][CAP];
     __shared__ float4 s_q[kWarps][kRing];
+    __shared__ float s_ray[kWarps][9 * 32];   // per-ray adjoint constants: dL.xyzw, saturation colour + flag, alpha before saturation
     __shared__ __align__(16) RowEntry s_stage[kWarps][2 * kStage];   // TMA-staged chunks of the tile row's bucket
     __shared__ __align__(8) unsigned long long s_bar[kWarps][2];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -934,14 +935,22 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? MVP_B
     const size_t r = ((size_t)n * p.H + min(py, p.H - 1)) * p.W + min(px, p.W - 1);
 
     const bool hashit = c.inimg && (c.rt0 <= c.rt1);
-    const float4 dL = __ldg(reinterpret_cast<const float4 *>(p.grad_rayrgba) + r);
-    const float rs0 = __ldg(p.raysat_in + r * 3 + 0), rs1 = __ldg(p.raysat_in + r * 3 + 1), rs2 = __ldg(p.raysat_in + r * 3 + 2);
     const int4 aux = __ldg(p.rayaux_in + r);
     const int msat = aux.x == 0x7fffffff ? 0x7fffffff : aux.x - c.off;   // in sweep units
     const int ranksat = aux.y;
-    const float abefore = __int_as_float(aux.z);
-    const bool hassat = rs0 > -1.f;
-    const float sr = hassat ? rs0 : 0.f, sg = hassat ? rs1 : 0.f, sb = hassat ? rs2 : 0.f, sa = hassat ? 1.f : 0.f;
+    {
+        // per-ray constants of the adjoint live in shared memory ([field][lane]: a batch reads them by owner lane,
+        // conflict-free, instead of holding 9 registers per thread for the whole kernel)
+        const float4 dL = __ldg(reinterpret_cast<const float4 *>(p.grad_rayrgba) + r);
+        const float rs0 = __ldg(p.raysat_in + r * 3 + 0), rs1 = __ldg(p.raysat_in + r * 3 + 1), rs2 = __ldg(p.raysat_in + r * 3 + 2);
+        const bool hassat = rs0 > -1.f;
+        float *pr_ = s_ray[warp];
+        pr_[0 * 32 + lane] = dL.x; pr_[1 * 32 + lane] = dL.y; pr_[2 * 32 + lane] = dL.z; pr_[3 * 32 + lane] = dL.w;
+        pr_[4 * 32 + lane] = hassat ? rs0 : 0.f; pr_[5 * 32 + lane] = hassat ? rs1 : 0.f; pr_[6 * 32 + lane] = hassat ? rs2 : 0.f;
+        pr_[7 * 32 + lane] = hassat ? 1.f : 0.f;
+        pr_[8 * 32 + lane] = __int_as_float(aux.z);      // alpha before the saturating sample
+        __syncwarp();
+    }
 
     // lane's live sweep range [ms, mlast]
     const int ms = hashit ? (j0 - c.off) : kBig;
@@ -1058,12 +1067,10 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? MVP_B
                         const int owner = meta & 31;
                         const bool issat = (meta & 256) != 0;
                         // per-ray data of the owner lane
-                        const float oLx = __shfl_sync(0xffffffffu, dL.x, owner), oLy = __shfl_sync(0xffffffffu, dL.y, owner);
-                        const float oLz = __shfl_sync(0xffffffffu, dL.z, owner), oLw = __shfl_sync(0xffffffffu, dL.w, owner);
-                        const float osr = __shfl_sync(0xffffffffu, sr, owner), osg = __shfl_sync(0xffffffffu, sg, owner);
-                        const float osb = __shfl_sync(0xffffffffu, sb, owner), osa = __shfl_sync(0xffffffffu, sa, owner);
-                        const float oab = __shfl_sync(0xffffffffu, abefore, owner);
                         if (!act) continue;
+                        const float *pr_ = s_ray[warp] + owner;
+                        const float oLx = pr_[0 * 32], oLy = pr_[1 * 32], oLz = pr_[2 * 32], oLw = pr_[3 * 32];
+                        const float osr = pr_[4 * 32], osg = pr_[5 * 32], osb = pr_[6 * 32], osa = pr_[7 * 32], oab = pr_[8 * 32];
                         touched = true;
                         const float xm = rec.x, ym = rec.y, zm = rec.z;
                         const float rx0 = rowdot(q.r00, xm, q.r10, ym, q.r20, zm);

@@ -94,7 +94,7 @@ CASES = {
     # odd image size (partial tiles in x and y), K not a power of two (rotated DFS order)
     "gradcheck_ragged": lambda: gradcheck_like_scene(N=1, H=13, W=19, k3=3, M=4, seed=7, alpha_gain=8.0),
     # head scene, C1-like but small: pinhole dome cameras, UV-grid slabs on an ellipsoid
-    "head_small": lambda: _head_case(2, 64, 42, 256, 8, stepsize=1.0 / 64, alpha_mu=2.0, alpha_sigma=3.0),
+    "head_small": lambda: _head_case(2, 64, 42, 64, 8, stepsize=1.0 / 64, alpha_mu=1.0, alpha_sigma=2.0),
     # 125 large overlapping slabs: every tile sees > 96 candidates -> exercises the 512-entry kernel variant
     "many_overlaps": lambda: gradcheck_like_scene(N=1, H=12, W=20, k3=5, M=4, seed=3, alpha_gain=0.4, scale=1.1),
     # non-cubic payload (runtime-stride sampler path) incl. a 1-voxel axis
@@ -106,7 +106,7 @@ CASES = {
                                warp=make_warp(2, 8, 3, 4, 5, seed=5, amp=0.12)),
     "warp_head": lambda: dict(_head_case(1, 48, 32, 64, 8, stepsize=1.0 / 32, alpha_mu=2.0, alpha_sigma=2.0),
                               warp=make_warp(1, 64, 4, 4, 4, seed=9, amp=0.05)),
-    "head_t16": lambda: _head_case(1, 48, 32, 64, 16, stepsize=1.0 / 32, view_offset=11, alpha_mu=1.0, alpha_sigma=2.0),
+    "head_t16": lambda: _head_case(1, 48, 32, 16, 16, stepsize=1.0 / 32, view_offset=11, alpha_mu=0.5, alpha_sigma=1.0),
 }
 
 

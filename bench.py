@@ -400,9 +400,9 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     if world > 1:
-        # keep stdout to the single JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # keep stdout to the single JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION and above
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
+            os.environ["NCCL_DEBUG"] = "NONE"
         dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", rank))))
     try:
         run_ours(args, rank, world)

@@ -57,7 +57,7 @@ constexpr int kBlkTX = MVP_BLK_TX;   // ... arranged kBlkTX x kBlkTY tiles (2 x 
 constexpr int kBlkTY = kWarps / kBlkTX;
 constexpr int kMaskSteps = MVP_CHUNK;   // backward: sweep steps per chunk of slab start order
 constexpr int kRowCapMax = 2048;  // entries per tile-row bucket before the row falls back to scanning all slabs
-constexpr int kRing = 64;        // backward sample ring (entries per warp, power of two, >= 2 * 32)
+constexpr int kRing = 64;        // sample queue / ring per warp (forward and backward; power of two, >= 2 * 32)
 #ifndef MVP_PREFETCH
 #define MVP_PREFETCH 0   // measured: +1 % forward speed but +50 % DRAM reads (slabs of rays that saturate earlier are fetched in vain)
 #endif

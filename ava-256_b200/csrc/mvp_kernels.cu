@@ -52,7 +52,10 @@ constexpr int kTileH = 4;
 #ifndef MVP_BLK_TX
 #define MVP_BLK_TX 2
 #endif
-constexpr int kWarps = 4;         // warps (tiles) per CTA
+#ifndef MVP_WARPS
+#define MVP_WARPS 4
+#endif
+constexpr int kWarps = MVP_WARPS;   // warps (tiles) per CTA: 2 measured 4-5 % slower (fwd and bwd); 8 overflows the 48 KB static smem of the CAP=512 variants
 constexpr int kBlkTX = MVP_BLK_TX;   // ... arranged kBlkTX x kBlkTY tiles (2 x 2 = 16 x 8 pixels: measured best)
 constexpr int kBlkTY = kWarps / kBlkTX;
 constexpr int kMaskSteps = MVP_CHUNK;   // backward: sweep steps per chunk of slab start order
@@ -697,7 +700,7 @@ __device__ __forceinline__ float4 sample_slab_warped(const float4 *__restrict__ 
 //    the CAP == 512 variant then renders only the flagged tiles.
 // ------------------------------------------------------------------------------------------------------
 template <int T, bool kGrad, int CAP, bool kWarp>
-__global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? MVP_FWD_MINB : 4) render_forward_kernel(const Params p) {
+__global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_FWD_MINB * 4) / kWarps : 16 / kWarps) render_forward_kernel(const Params p) {
     __shared__ int s_k[kWarps][CAP];
     __shared__ int s_iv[kWarps][CAP];
     __shared__ __align__(16) RowEntry s_stage[kWarps][2 * kStage];   // TMA-staged chunks of the tile row's bucket
@@ -906,7 +909,7 @@ __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float 
 }
 
 template <int T, int CAP, bool kWarp>
-__global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? MVP_BWD_MINB : 3) render_backward_kernel(const Params p) {
+__global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_BWD_MINB * 4) / kWarps : 12 / kWarps) render_backward_kernel(const Params p) {
     __shared__ int s_k[kWarps][CAP];
     __shared__ int s_iv[kWarps][CAP];
     __shared__ float4 s_q[kWarps][kRing];

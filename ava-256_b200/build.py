@@ -5,10 +5,11 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-SRC = [os.path.join(HERE, "csrc", "mvp_kernels.cu"), os.path.join(HERE, "csrc", "raydirs.cu")]
-# raydirs.cu mirrors the reference's utils extension, which is NOT built with -use_fast_math
-NO_FAST_MATH = {"raydirs.cu"}
-HDR = [os.path.join(ROOT, "include", "mvpraymarch_b200.h")]
+SRC = [os.path.join(HERE, "csrc", n) for n in ("mvp_kernels.cu", "raydirs.cu", "epilogue.cu")]
+# raydirs.cu mirrors the reference's utils extension, which is NOT built with -use_fast_math; epilogue.cu replaces
+# eager PyTorch expressions and keeps their IEEE single-rounding arithmetic
+NO_FAST_MATH = {"raydirs.cu", "epilogue.cu"}
+HDR = [os.path.join(ROOT, "include", "mvpraymarch_b200.h"), os.path.join(HERE, "csrc", "epilogue_body.h")]
 LIB = os.path.join(HERE, "libmvpraymarch_b200.so")
 
 NVCC_FLAGS = [

@@ -1,0 +1,188 @@
+// epilogue.cu -- the two streaming kernels either side of the raymarcher:
+//
+//   mvp_composite_{forward,backward}        rayrgba [N,H,W,4] -> NCHW rgb (+ colour calibration + background matting)
+//                                           and alpha, replacing the permute / 2x contiguous / mul / add / mul / add
+//                                           chain of models/raymarchers/mvpraymarcher.py:50-51,
+//                                           models/colorcals/colorcal.py:26-29, models/autoencoder.py:262-270
+//   mvp_assemble_payload_{forward,backward} decoder images -> channels-last slabs with the relu(x*25+100) / relu
+//                                           de-normalisation fused in, replacing the view / permute / reshape / cat /
+//                                           relu chain of models/decoders/rgb.py:128-143, geometry.py:180-185,
+//                                           assembler.py:261
+//
+// Both are pure layout + elementwise work: HBM-bound, every byte touched once.  Bytes per unit (what the roofline
+// counts): composite fwd 16 B in + 16 B out per ray (+12 B with a background); bwd 16 B in (+16 B rayrgba, +12 B bg)
+// + 16 B out; payload 16 B in + 16 B out per texel forward, 32 B in + 16 B out backward.  Threads walk 4 consecutive
+// pixels / columns so every global access is a 16-byte vector and a warp's request covers whole 128-byte lines on the
+// planar side and 64 B per lane on the channels-last side; a scalar variant covers shapes that are not multiples of 4.
+//
+// Compiled WITHOUT -use_fast_math: the bodies use explicit single-rounding intrinsics so the forward results are
+// bit-identical to the eager PyTorch expressions they replace.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "epilogue_body.h"
+#include "mvpraymarch_b200.h"
+
+namespace {
+
+using namespace mvp_epi;
+constexpr int kThreads = 256;
+
+template <int V>
+__global__ void __launch_bounds__(kThreads) composite_forward_kernel(CompositeFwd a) {
+    const size_t px = ((size_t)blockIdx.x * kThreads + threadIdx.x) * V;
+    if (px < a.HW) composite_fwd<V>(a, (int)blockIdx.y, px);
+}
+
+template <int V>
+__global__ void __launch_bounds__(kThreads) composite_backward_kernel(CompositeBwd a, float *__restrict__ grad_ccw,
+                                                                     float *__restrict__ grad_ccb) {
+    const int n = (int)blockIdx.y;
+    const size_t px = ((size_t)blockIdx.x * kThreads + threadIdx.x) * V;
+    float part[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (px < a.HW) composite_bwd<V>(a, n, px, part);
+    if (a.want_cc) {   // uniform across the grid: every thread takes part in the reduction
+        __shared__ float s_part[kThreads / 32][6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) part[i] += __shfl_xor_sync(0xffffffffu, part[i], off);
+        }
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) s_part[warp][i] = part[i];
+        }
+        __syncthreads();
+        if (threadIdx.x < 6) {
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < kThreads / 32; ++w) t += s_part[w][threadIdx.x];
+            float *dst = threadIdx.x < 3 ? grad_ccw + n * 3 + threadIdx.x : grad_ccb + n * 3 + (threadIdx.x - 3);
+            atomicAdd(dst, t);
+        }
+    }
+}
+
+template <int V, int BT>
+__global__ void __launch_bounds__(kThreads) payload_forward_kernel(PayloadArgs a, size_t total) {
+    const size_t e = (size_t)blockIdx.x * kThreads + threadIdx.x;
+    if (e < total) payload_fwd<V, BT>(a, e);
+}
+
+template <int V, int BT>
+__global__ void __launch_bounds__(kThreads) payload_backward_kernel(PayloadArgs a, size_t total) {
+    const size_t e = (size_t)blockIdx.x * kThreads + threadIdx.x;
+    if (e < total) payload_bwd<V, BT>(a, e);
+}
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+inline int finish() {
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? MVP_OK : (int)e;
+}
+
+}  // namespace
+
+extern "C" int mvp_composite_forward(int32_t N, int32_t H, int32_t W, const float *rayrgba, const float *ccw, const float *ccb,
+                                     const float *bg, float *irgbrec, float *rayalpha, void *stream) {
+    if (!rayrgba || !irgbrec) return MVP_ERR_NULL;
+    if ((ccw == nullptr) != (ccb == nullptr)) return MVP_ERR_NULL;
+    if (N < 1 || H < 1 || W < 1 || N > 65535 || H >= 32768 || W >= 32768) return MVP_ERR_SHAPE;
+    if (!aligned16(rayrgba)) return MVP_ERR_ALIGN;
+    CompositeFwd a;
+    a.HW = (size_t)H * W;
+    a.rayrgba = rayrgba; a.ccw = ccw; a.ccb = ccb; a.bg = bg; a.irgbrec = irgbrec; a.rayalpha = rayalpha;
+    const bool vec = a.HW % 4 == 0 && aligned16(irgbrec) && (!bg || aligned16(bg)) && (!rayalpha || aligned16(rayalpha));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (vec) {
+        dim3 grid((unsigned)((a.HW / 4 + kThreads - 1) / kThreads), N);
+        composite_forward_kernel<4><<<grid, kThreads, 0, st>>>(a);
+    } else {
+        dim3 grid((unsigned)((a.HW + kThreads - 1) / kThreads), N);
+        composite_forward_kernel<1><<<grid, kThreads, 0, st>>>(a);
+    }
+    return finish();
+}
+
+extern "C" int mvp_composite_backward(int32_t N, int32_t H, int32_t W, const float *rayrgba, const float *ccw, const float *bg,
+                                      const float *grad_irgbrec, const float *grad_rayalpha, float *grad_rayrgba,
+                                      float *grad_ccw, float *grad_ccb, float *grad_bg, void *stream) {
+    if (!grad_irgbrec || !grad_rayrgba) return MVP_ERR_NULL;
+    if ((grad_ccw == nullptr) != (grad_ccb == nullptr)) return MVP_ERR_NULL;
+    if (grad_bg && !bg) return MVP_ERR_NULL;
+    if ((grad_ccw || grad_bg) && !rayrgba) return MVP_ERR_NULL;
+    if (N < 1 || H < 1 || W < 1 || N > 65535 || H >= 32768 || W >= 32768) return MVP_ERR_SHAPE;
+    if (!aligned16(grad_rayrgba) || (rayrgba && !aligned16(rayrgba))) return MVP_ERR_ALIGN;
+    CompositeBwd a;
+    a.HW = (size_t)H * W;
+    a.rayrgba = rayrgba; a.ccw = ccw; a.bg = bg; a.grad_irgbrec = grad_irgbrec; a.grad_rayalpha = grad_rayalpha;
+    a.grad_rayrgba = grad_rayrgba; a.grad_bg = grad_bg; a.want_cc = grad_ccw != nullptr;
+    const bool vec = a.HW % 4 == 0 && aligned16(grad_irgbrec) && (!bg || aligned16(bg)) &&
+                     (!grad_rayalpha || aligned16(grad_rayalpha)) && (!grad_bg || aligned16(grad_bg));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (vec) {
+        dim3 grid((unsigned)((a.HW / 4 + kThreads - 1) / kThreads), N);
+        composite_backward_kernel<4><<<grid, kThreads, 0, st>>>(a, grad_ccw, grad_ccb);
+    } else {
+        dim3 grid((unsigned)((a.HW + kThreads - 1) / kThreads), N);
+        composite_backward_kernel<1><<<grid, kThreads, 0, st>>>(a, grad_ccw, grad_ccb);
+    }
+    return finish();
+}
+
+namespace {
+
+// Elements (threads) of a payload launch, or 0 when the shape is unsupported.
+inline size_t payload_elements(int32_t N, int32_t hb, int32_t wb, int32_t B, int V) {
+    if (N < 1 || hb < 1 || wb < 1 || B < 1 || B > 64) return 0;
+    const size_t total = (size_t)N * hb * B * B * ((size_t)wb * B);
+    const size_t e = total / V;
+    if ((e + kThreads - 1) / kThreads > 0x7fffffffull) return 0;
+    return e;
+}
+
+template <bool kBwd>
+int launch_payload(int32_t N, int32_t hb, int32_t wb, int32_t B, const PayloadArgs &a, bool vec, cudaStream_t st) {
+    const int V = vec ? 4 : 1;
+    const size_t total = payload_elements(N, hb, wb, B, V);
+    if (total == 0) return MVP_ERR_SHAPE;
+    const unsigned grid = (unsigned)((total + kThreads - 1) / kThreads);
+    if (vec && B == 8) {
+        if (kBwd) payload_backward_kernel<4, 8><<<grid, kThreads, 0, st>>>(a, total);
+        else payload_forward_kernel<4, 8><<<grid, kThreads, 0, st>>>(a, total);
+    } else if (vec) {
+        if (kBwd) payload_backward_kernel<4, 0><<<grid, kThreads, 0, st>>>(a, total);
+        else payload_forward_kernel<4, 0><<<grid, kThreads, 0, st>>>(a, total);
+    } else {
+        if (kBwd) payload_backward_kernel<1, 0><<<grid, kThreads, 0, st>>>(a, total);
+        else payload_forward_kernel<1, 0><<<grid, kThreads, 0, st>>>(a, total);
+    }
+    return finish();
+}
+
+}  // namespace
+
+extern "C" int mvp_assemble_payload_forward(int32_t N, int32_t hb, int32_t wb, int32_t B, const float *tex, const float *opacity,
+                                            float rgb_scale, float rgb_bias, float *tplate, void *stream) {
+    if (!tex || !opacity || !tplate) return MVP_ERR_NULL;
+    if (!aligned16(tplate)) return MVP_ERR_ALIGN;
+    PayloadArgs a = {};
+    a.hb = hb; a.wb = wb; a.B = B; a.rgb_scale = rgb_scale; a.rgb_bias = rgb_bias;
+    a.tex = tex; a.opacity = opacity; a.tplate = tplate;
+    const bool vec = B > 0 && B % 4 == 0 && aligned16(tex) && aligned16(opacity);
+    return launch_payload<false>(N, hb, wb, B, a, vec, (cudaStream_t)stream);
+}
+
+extern "C" int mvp_assemble_payload_backward(int32_t N, int32_t hb, int32_t wb, int32_t B, const float *tplate,
+                                             const float *grad_tplate, float rgb_scale, float *grad_tex, float *grad_opacity,
+                                             void *stream) {
+    if (!tplate || !grad_tplate || !grad_tex || !grad_opacity) return MVP_ERR_NULL;
+    if (!aligned16(tplate) || !aligned16(grad_tplate)) return MVP_ERR_ALIGN;
+    PayloadArgs a = {};
+    a.hb = hb; a.wb = wb; a.B = B; a.rgb_scale = rgb_scale;
+    a.tplate_in = tplate; a.grad_tplate = grad_tplate; a.grad_tex = grad_tex; a.grad_opacity = grad_opacity;
+    const bool vec = B > 0 && B % 4 == 0 && aligned16(grad_tex) && aligned16(grad_opacity);
+    return launch_payload<true>(N, hb, wb, B, a, vec, (cudaStream_t)stream);
+}

@@ -1349,6 +1349,7 @@ const char *mvp_error_string(int code) {
         case MVP_ERR_STEPSIZE: return "stepsize must be finite and > 0";
         case MVP_ERR_WORKSPACE: return "workspace too small or not 256-byte aligned";
         case MVP_ERR_ALGO: return "unsupported algo";
+        case MVP_ERR_ALIGN: return "channels-last buffer is not 16-byte aligned";
         default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
     }
 }

@@ -43,10 +43,12 @@ class BackwardArgs(ctypes.Structure):
 
 
 FLAG_ACCEL_VALID = 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 EXPORTS = ("mvp_abi_version", "mvp_error_string", "mvp_workspace_bytes", "mvp_build_accel", "mvp_raymarch_forward",
-           "mvp_raymarch_backward", "mvp_compute_raydirs", "mvp_forward_launch_count", "mvp_backward_launch_count")
+           "mvp_raymarch_backward", "mvp_compute_raydirs", "mvp_forward_launch_count", "mvp_backward_launch_count",
+           "mvp_composite_forward", "mvp_composite_backward", "mvp_assemble_payload_forward",
+           "mvp_assemble_payload_backward")
 
 
 def _load():
@@ -74,6 +76,14 @@ def _load():
     lib.mvp_raymarch_backward.argtypes = [ctypes.POINTER(BackwardArgs), c_f]
     lib.mvp_compute_raydirs.restype = ctypes.c_int
     lib.mvp_compute_raydirs.argtypes = [ctypes.c_int32] * 3 + [c_f] * 5 + [ctypes.c_float] + [c_f] * 4
+    lib.mvp_composite_forward.restype = ctypes.c_int
+    lib.mvp_composite_forward.argtypes = [ctypes.c_int32] * 3 + [c_f] * 7
+    lib.mvp_composite_backward.restype = ctypes.c_int
+    lib.mvp_composite_backward.argtypes = [ctypes.c_int32] * 3 + [c_f] * 10
+    lib.mvp_assemble_payload_forward.restype = ctypes.c_int
+    lib.mvp_assemble_payload_forward.argtypes = [ctypes.c_int32] * 4 + [c_f] * 2 + [ctypes.c_float] * 2 + [c_f] * 2
+    lib.mvp_assemble_payload_backward.restype = ctypes.c_int
+    lib.mvp_assemble_payload_backward.argtypes = [ctypes.c_int32] * 4 + [c_f] * 2 + [ctypes.c_float] + [c_f] * 3
     lib.mvp_forward_launch_count.restype = ctypes.c_int
     lib.mvp_forward_launch_count.argtypes = [ctypes.c_uint32]
     lib.mvp_backward_launch_count.restype = ctypes.c_int

@@ -15,6 +15,14 @@
  *   mvp_compute_raydirs    <- compute_raydirs_forward  extensions/utils/utils.cpp:46-82 (pybind module `utilslib`;
  *                             the step right before the raymarcher)
  *
+ * and two entry points that replace eager PyTorch chains of the callers either side of the path (no native reference
+ * counterpart):
+ *
+ *   mvp_composite_*        <- models/raymarchers/mvpraymarcher.py:50-51 (NHWC -> NCHW rgb / alpha split),
+ *                             models/colorcals/colorcal.py:26-29 (w * rgb + b), models/autoencoder.py:262-270 (matting)
+ *   mvp_assemble_payload_* <- models/decoders/rgb.py:128-143, models/decoders/geometry.py:180-185 (image -> slab
+ *                             re-layout), models/decoders/assembler.py:261 (relu(rgb * 25 + 100), relu(alpha), cat)
+ *
  * Conventions (same ownership model as the reference: the caller owns every buffer, outputs are written in
  * place; unlike the reference nothing is allocated inside and everything runs on the caller's stream):
  *   - all pointers are DEVICE pointers to contiguous fp32 (or int32) arrays; no torch types;
@@ -38,7 +46,7 @@
 extern "C" {
 #endif
 
-#define MVP_ABI_VERSION 2
+#define MVP_ABI_VERSION 3
 
 #define MVP_OK 0
 #define MVP_ERR_NULL (-1)      /* a required pointer is NULL */
@@ -46,6 +54,7 @@ extern "C" {
 #define MVP_ERR_STEPSIZE (-3)  /* stepsize must be finite and > 0 */
 #define MVP_ERR_WORKSPACE (-4) /* workspace too small or misaligned (256 B) */
 #define MVP_ERR_ALGO (-5)      /* algo must be 0 (no warp field) or 1 (warp field, primsampler.h:53-58) */
+#define MVP_ERR_ALIGN (-6)     /* a channels-last (float4-accessed) buffer is not 16-byte aligned */
 
 typedef struct mvp_shape {
     int32_t N, H, W, K, TD, TH, TW;
@@ -113,6 +122,30 @@ int mvp_raymarch_backward(const mvp_backward_args *args, void *stream);
 int mvp_compute_raydirs(int32_t N, int32_t H, int32_t W, const float *viewpos, const float *viewrot, const float *focal,
                         const float *princpt, const float *pixelcoords, float volradius, float *raypos, float *raydir,
                         float *tminmax, void *stream);
+
+/* Image epilogue.  rayrgba [N,H,W,4] (16-byte aligned) ->
+ *   irgbrec  [N,3,H,W] = (ccw[n,c] * rgb + ccb[n,c]) + (1 - alpha) * bg[n,c,h,w]      (each op rounded once, like eager torch)
+ *   rayalpha [N,1,H,W] = alpha                                                        (optional)
+ * ccw, ccb [N,3]: per-view colour calibration, both NULL for none; bg [N,3,H,W] or NULL for a black background. */
+int mvp_composite_forward(int32_t N, int32_t H, int32_t W, const float *rayrgba, const float *ccw, const float *ccb,
+                          const float *bg, float *irgbrec, float *rayalpha, void *stream);
+/* Adjoint of the above.  grad_rayrgba [N,H,W,4] is written (not accumulated) contiguous channels-last, which is what
+ * mvp_raymarch_backward takes.  grad_ccw / grad_ccb [N,3] (both or neither) are ACCUMULATED into: caller zero-fills;
+ * grad_bg [N,3,H,W] is written.  rayrgba is needed only when grad_ccw or grad_bg is requested. */
+int mvp_composite_backward(int32_t N, int32_t H, int32_t W, const float *rayrgba, const float *ccw, const float *bg,
+                           const float *grad_irgbrec, const float *grad_rayalpha, float *grad_rayrgba, float *grad_ccw,
+                           float *grad_ccb, float *grad_bg, void *stream);
+
+/* Payload hand-off.  tex [N, B*3, hb*B, wb*B] (channel d*3+c), opacity [N, B, hb*B, wb*B]
+ * (channel d) -> tplate [N, hb*wb, B, B, B, 4] with
+ *   tplate[n, i*wb+j, d, y, x, c<3] = relu(tex[n, d*3+c, i*B+y, j*B+x] * rgb_scale + rgb_bias),
+ *   tplate[n, i*wb+j, d, y, x, 3]   = relu(opacity[n, d, i*B+y, j*B+x]).
+ * The reference hard-codes rgb_scale = 25, rgb_bias = 100 (assembler.py:261).  1 <= B <= 64. */
+int mvp_assemble_payload_forward(int32_t N, int32_t hb, int32_t wb, int32_t B, const float *tex, const float *opacity,
+                                 float rgb_scale, float rgb_bias, float *tplate, void *stream);
+/* Adjoint: grad_tex / grad_opacity (same shapes as tex / opacity) are written; `tplate` is the forward output (relu mask). */
+int mvp_assemble_payload_backward(int32_t N, int32_t hb, int32_t wb, int32_t B, const float *tplate, const float *grad_tplate,
+                                  float rgb_scale, float *grad_tex, float *grad_opacity, void *stream);
 
 /* Number of kernels the last forward / backward call of this shape launches (for bench.py's gpu_launches). */
 int mvp_forward_launch_count(uint32_t flags);

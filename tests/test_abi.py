@@ -27,7 +27,7 @@ def test_header_symbols_are_exported():
     for n in names:
         assert hasattr(lib.LIB, n), n
     assert sorted(names) == sorted(lib.EXPORTS)
-    assert lib.LIB.mvp_abi_version() == 2
+    assert lib.LIB.mvp_abi_version() == 3
 
 
 def test_workspace_bytes_and_shape_validation():

@@ -43,9 +43,10 @@ class MVPRaymarch(Function):
                                       "values, mvpraymarch_kernel.cu:104-105)")
         if algo == 1 and warp is None:
             raise RuntimeError("mvpraymarch_b200: algo=1 samples a warp field (PrimSamplerTW<true>); pass `warp`")
-        if options["usebvh"] != "fixedorder":
-            raise NotImplementedError("mvpraymarch_b200: only usebvh='fixedorder' (the default, and the only "
-                                      "self-consistent mode of the reference) is implemented")
+        if options["usebvh"] != "fixedorder":                            # usebvh=True is resolved in mvpraymarch() below
+            raise NotImplementedError("mvpraymarch_b200: MVPRaymarch marches primitives in index order; use "
+                                      "mvpraymarch(usebvh=True) for Morton order.  usebvh=False passes a null BVH to "
+                                      "the reference kernels (mvpraymarch.py:132-134) and is not a usable mode there either")
         # same shape contract as mvpraymarch.py:112-127
         assert raypos.is_contiguous() and raypos.size(3) == 3
         assert raydir.is_contiguous() and raydir.size(3) == 3
@@ -135,6 +136,38 @@ class MVPRaymarch(Function):
         return (None, None, None, None, grad_primpos, grad_primrot, grad_primscale, grad_template, grad_warp, None, None, None)
 
 
+def morton_codes(primpos):
+    """30-bit Morton codes of the primitive centres, normalised per view to their bounding box: the reference's
+    build_accel (mvpraymarch.py:46-53) + morton3D / expand_bits (bvh.cu:20-41).  [N,K] int64."""
+    cmax = primpos.max(dim=1, keepdim=True)[0]
+    cmin = primpos.min(dim=1, keepdim=True)[0]
+    c = (primpos - cmin) / (cmax - cmin).clamp(min=1e-8)                       # mvpraymarch.py:50
+    q = (c * 1024.0).clamp(0.0, 1023.0).to(torch.int64)                        # bvh.cu:33-35, (unsigned int) truncates
+
+    def expand_bits(v):                                                        # bvh.cu:22-28 (uint32 arithmetic)
+        v = (v * 0x00010001) & 0xFF0000FF
+        v = (v * 0x00000101) & 0x0F00F00F
+        v = (v * 0x00000011) & 0xC30C30C3
+        v = (v * 0x00000005) & 0x49249249
+        return v
+
+    return expand_bits(q[..., 0]) * 4 + expand_bits(q[..., 1]) * 2 + expand_bits(q[..., 2])   # bvh.cu:39
+
+
+def morton_order(primpos):
+    """sortedobjid [N,K] (int64): primitive indices in ascending Morton code (mvpraymarch.py:54-55).  Ties keep index
+    order (stable), where the reference's torch.sort leaves them unspecified."""
+    return torch.sort(morton_codes(primpos.detach()), dim=-1, stable=True)[1]
+
+
+def _take(t, order):
+    """t[n, order[n, k], ...] (differentiable)."""
+    if t is None:
+        return None
+    idx = order.view(order.shape + (1,) * (t.dim() - 2)).expand(order.shape + tuple(t.shape[2:]))
+    return torch.gather(t, 1, idx)
+
+
 def mvpraymarch(
     raypos,
     raydir,
@@ -164,13 +197,26 @@ def mvpraymarch(
     Same parameters, same defaults.  `sortprims`, `randomorder`, `maxhitboxes`, `synchitboxes`, `chlast`, `accum`,
     `termthresh`, `griddim`, `blocksize`, `bwdblocksize` and `rayterm` are accepted and, exactly like in the
     reference kernels ("accepted but ignored"), have no effect on the result.
+
+    `usebvh="fixedorder"` (default) marches the primitives of a tile in index order.  `usebvh=True` marches them in
+    Morton order of their centres -- the order the reference's LBVH branch computes (`sortedobjid`, mvpraymarch.py:46-55)
+    but its kernels never apply (they hard-code the implicit heap, utils.h:740-742) -- by
+    gathering the primitive tensors into that order first (one extra pass over the payload; gradients scatter back
+    through the gather).  The order only matters for rays that saturate.
     Returns rayrgba [N,H,W,4]."""
+    if usebvh is False:
+        raise NotImplementedError("mvpraymarch_b200: usebvh=False hands the reference kernels a null BVH "
+                                  "(mvpraymarch.py:132-134); use 'fixedorder' or True")
     if isinstance(primtransf, tuple):
         primpos, primrot, primscale = primtransf
     else:                                                              # packed [N,K,5,3]  (mvpraymarch.py:353-360)
         primpos = primtransf[:, :, 0, :].contiguous()
         primrot = primtransf[:, :, 1:4, :].contiguous()
         primscale = primtransf[:, :, 4, :].contiguous()
+    if usebvh != "fixedorder":
+        order = morton_order(primpos)
+        primpos, primrot, primscale, template, warp = (_take(t, order) for t in (primpos, primrot, primscale, template, warp))
+        usebvh = "fixedorder"
     options = {
         "algo": algo, "usebvh": usebvh, "sortprims": sortprims, "randomorder": randomorder,
         "maxhitboxes": maxhitboxes, "synchitboxes": synchitboxes, "chlast": chlast, "fadescale": fadescale,

@@ -102,7 +102,43 @@ def test_unsupported_modes_raise():
                     s["template"], None, algo=2)
     with pytest.raises(NotImplementedError):
         mvpraymarch(s["raypos"], s["raydir"], s["stepsize"], s["tminmax"], (s["primpos"], s["primrot"], s["primscale"]),
+                    s["template"], None, usebvh=False)
+    with pytest.raises(RuntimeError, match="CUDA"):     # Morton mode is host logic + the same op: no CPU fallback either
+        mvpraymarch(s["raypos"], s["raydir"], s["stepsize"], s["tminmax"], (s["primpos"], s["primrot"], s["primscale"]),
                     s["template"], None, usebvh=True)
+
+
+def test_morton_order_matches_bit_interleave():
+    """usebvh=True order: op.morton_codes (the reference's magic-multiply expand_bits, bvh.cu:20-41) against a plain
+    bit-by-bit interleave of the quantised centres, ties stable."""
+    import numpy as np
+    from ava256_b200.op import _take, morton_codes, morton_order
+    g = torch.Generator().manual_seed(3)
+    p = torch.rand(3, 97, 3, generator=g) * 2 - 1
+    p[1, 5] = p[1, 50]                                   # a tie
+    p[2, :, 2] = 0.25                                    # degenerate axis: (cmax - cmin) clamps to 1e-8 -> code bits 0
+    c = morton_codes(p).numpy()
+    cmax, cmin = p.max(1, keepdim=True)[0], p.min(1, keepdim=True)[0]
+    q = ((p - cmin) / (cmax - cmin).clamp(min=1e-8) * 1024.0).clamp(0.0, 1023.0).to(torch.int64).numpy()
+    ref = np.zeros(q.shape[:2], np.int64)
+    for i in range(10):
+        ref |= ((q[..., 0] >> i) & 1) << (3 * i + 2)
+        ref |= ((q[..., 1] >> i) & 1) << (3 * i + 1)
+        ref |= ((q[..., 2] >> i) & 1) << (3 * i)
+    assert np.array_equal(c, ref) and c.max() < 2 ** 30 and c.min() >= 0
+    o = morton_order(p).numpy()
+    for n in range(3):
+        assert sorted(o[n]) == list(range(97))
+        cs = c[n][o[n]]
+        assert (np.diff(cs) >= 0).all()
+        same = np.diff(cs) == 0
+        assert (np.diff(o[n])[same] > 0).all()           # stable
+    assert list(o[1]).index(5) + 1 == list(o[1]).index(50)
+    t = torch.rand(3, 97, 2, 3, generator=g, requires_grad=True)
+    got = _take(t, torch.from_numpy(o))
+    assert torch.equal(got[2, 7], t[2, o[2, 7]])
+    got.backward(torch.ones_like(got))
+    assert torch.equal(t.grad, torch.ones_like(t))
 
 
 def test_scene_generator_is_deterministic_and_pinhole():

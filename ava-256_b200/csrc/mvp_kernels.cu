@@ -52,6 +52,13 @@ constexpr int kTileH = 4;
 #ifndef MVP_BLK_TX
 #define MVP_BLK_TX 2
 #endif
+#ifndef MVP_FWD_OPAQUE
+#define MVP_FWD_OPAQUE 2   // forward: per-warp shared state in one record behind a pinned base address (0 = separate arrays,
+                           // 1 = pinned list base only).  Measured on B200: 2.77 vs 2.89 ms per 8 views (-4.4 %)
+#endif
+#ifndef MVP_BWD_OPAQUE
+#define MVP_BWD_OPAQUE 0   // 2: same for the backward kernel -- measured SLOWER (4.43 vs 4.23 ms per 8 views), so off
+#endif
 #ifndef MVP_WARPS
 #define MVP_WARPS 4
 #endif
@@ -694,6 +701,17 @@ __device__ __forceinline__ float4 sample_slab_warped(const float4 *__restrict__ 
     return acc;
 }
 
+template <int CAP, bool kGrad>
+struct __align__(16) FwdWarpSmem {   // MVP_FWD_OPAQUE == 2: one record per warp
+    float4 ring[kRing];
+    RowEntry stage[2 * kStage];
+    unsigned long long bar[2];
+    int k[CAP];
+    int iv[CAP];
+    float ra[kRing];
+    int rm[kGrad ? kRing : 1];
+};
+
 // ------------------------------------------------------------------------------------------------------
 // 4. forward.  CAP = shared-memory list capacity per warp.  The CAP < 512 variant handles every tile whose list
 //    fits (almost all) with a small shared-memory footprint (more L1 for the voxel gathers) and flags the rest;
@@ -701,6 +719,19 @@ __device__ __forceinline__ float4 sample_slab_warped(const float4 *__restrict__ 
 // ------------------------------------------------------------------------------------------------------
 template <int T, bool kGrad, int CAP, bool kWarp>
 __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_FWD_MINB * 4) / kWarps : 16 / kWarps) render_forward_kernel(const Params p) {
+#if MVP_FWD_OPAQUE == 2
+    // all per-warp shared state in one record: every address below is (one pinned per-warp base) + immediate
+    __shared__ FwdWarpSmem<CAP, kGrad> s_w[kWarps];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned woff = (unsigned)__cvta_generic_to_shared(&s_w[warp]);
+    asm volatile("" : "+r"(woff));
+    FwdWarpSmem<CAP, kGrad> *const S = reinterpret_cast<FwdWarpSmem<CAP, kGrad> *>(__cvta_shared_to_generic((size_t)woff));
+    int *const sk = S->k, *const siv = S->iv, *const rm = S->rm;
+    RowEntry *const sstage = S->stage;
+    unsigned long long *const sbar = S->bar;
+    float4 *const ring = S->ring;
+    float *const ra = S->ra;
+#else
     __shared__ int s_k[kWarps][CAP];
     __shared__ int s_iv[kWarps][CAP];
     __shared__ __align__(16) RowEntry s_stage[kWarps][2 * kStage];   // TMA-staged chunks of the tile row's bucket
@@ -709,6 +740,12 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
     __shared__ float s_ra[kWarps][kRing];      // sampled alpha * fade
     __shared__ int s_rm[kWarps][kGrad ? kRing : 1];   // sweep step of the queued sample (needed to record the saturating one)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int *const sk = s_k[warp], *const siv = s_iv[warp], *const rm = s_rm[warp];
+    RowEntry *const sstage = s_stage[warp];
+    unsigned long long *const sbar = s_bar[warp];
+    float4 *const ring = s_ring[warp];
+    float *const ra = s_ra[warp];
+#endif
     const int tx = blockIdx.x * kBlkTX + (warp % kBlkTX), ty = blockIdx.y * kBlkTY + (warp / kBlkTX), n = blockIdx.z;
     if (tx >= p.TXn || ty >= p.TYn) return;   // warps are independent: no CTA-wide barrier below (exited warps count as arrived)
     // Programmatic dependent launch: the 512-entry variant (few, long-running tiles) is launched first and lets the
@@ -724,7 +761,7 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
     TileCtx c;
     float t, x, y, z, r1e;
     int j0;
-    const bool fits = build_tile_list<CAP, true>(p, rdt, n, tx, ty, lane, c, s_k[warp], s_iv[warp], s_stage[warp], s_bar[warp], t, x, y, z, r1e, j0);
+    const bool fits = build_tile_list<CAP, true>(p, rdt, n, tx, ty, lane, c, sk, siv, sstage, sbar, t, x, y, z, r1e, j0);
     (void)fits;   // cannot fail: the tile's candidate count was checked against CAP when the accel was built
 
     const int px = tx * kTileW + (lane & 7), py = ty * kTileH + (lane >> 3);
@@ -746,6 +783,27 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
     const size_t slabsz = (size_t)p.TD * p.TH * p.TW;
     const float4 *tpn = reinterpret_cast<const float4 *>(p.tplate) + (size_t)n * p.K * slabsz;
     const int kstart = dfs_kstart(p.K);
+#if MVP_FWD_OPAQUE == 1
+    // Under the register cap the compiler rematerialises these two base addresses (S2R/LDC/IMAD chains, ~13 of the
+    // ~64 instructions of a (step, slab) event) instead of keeping them: make them opaque so they stay in registers.
+    unsigned skw = (unsigned)__cvta_generic_to_shared(sk);
+    asm volatile("" : "+r"(skw) :: "memory");
+    {
+        unsigned long long pa = (unsigned long long)packn;
+        asm volatile("" : "+l"(pa));
+        packn = reinterpret_cast<const float4 *>(pa);
+    }
+    auto list_k = [&](int slot) { int v; asm("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(skw + 4u * (unsigned)slot)); return v; };
+#else
+#if MVP_FWD_OPAQUE == 2
+    {
+        unsigned long long pa = (unsigned long long)packn;
+        asm volatile("" : "+l"(pa));
+        packn = reinterpret_cast<const float4 *>(pa);
+    }
+#endif
+    auto list_k = [&](int slot) { return sk[slot]; };
+#endif
 
     // Sample compaction.  At one (step, slab) event only ~10 of the 32 rays of a tile are inside the slab, so the valid
     // samples are queued (sample coordinates + owner lane + list slot) and the expensive gather/interpolation runs on
@@ -755,15 +813,12 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
     // sampled in vain and then ignored.  (Measured: neutral at 8^3 / K=16384, -15 % forward time at 16^3 / K=4096.)
     int qn = 0;
     unsigned ownlo = 0, ownhi = 0;   // queue positions (0..63) holding this lane's pending samples
-    float4 *ring = s_ring[warp];
-    float *ra = s_ra[warp];
-    int *rm = s_rm[warp];
     auto flush = [&](int cnt) {
         const bool act = lane < cnt;
         const float4 rec = ring[act ? lane : 0];
         float4 sres = make_float4(0.f, 0.f, 0.f, 0.f);
         if (act) {
-            const int kk = s_k[warp][(__float_as_int(rec.w) >> 5) & 1023];
+            const int kk = sk[(__float_as_int(rec.w) >> 5) & 1023];
             if (kWarp) sres = sample_slab_warped(tpn + (size_t)kk * slabsz, p.warp + ((size_t)n * p.K + kk) * ((size_t)p.WD * p.WH * p.WW * 3), rec.x, rec.y, rec.z, p);
             else sres = sample_slab<T>(tpn + (size_t)kk * slabsz, rec.x, rec.y, rec.z, p.TD, p.TH, p.TW, p.fadescale, p.fadeexp);
         }
@@ -785,7 +840,7 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
                     sat = true;
                     if (kGrad) {
                         jsat = rm[b] + c.off;
-                        int rk = s_k[warp][(__float_as_int(rr.w) >> 5) & 1023] - kstart; if (rk < 0) rk += p.K;
+                        int rk = sk[(__float_as_int(rr.w) >> 5) & 1023] - kstart; if (rk < 0) rk += p.K;
                         ranksat = rk;
                         abefore = acc.w;
                     }
@@ -812,8 +867,8 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
     if (nl > 0 && mstart < kBig) {
         // each lane keeps the interval of list slots `lane` and `lane + 32` in registers (lists are rarely longer)
         int lo0 = kBig, hi0 = -kBig, lo1 = kBig, hi1 = -kBig;
-        if (lane < nl) { const int v = s_iv[warp][lane]; lo0 = iv_lo(v); hi0 = iv_hi(v); }
-        if (lane + 32 < nl) { const int v = s_iv[warp][lane + 32]; lo1 = iv_lo(v); hi1 = iv_hi(v); }
+        if (lane < nl) { const int v = siv[lane]; lo0 = iv_lo(v); hi0 = iv_hi(v); }
+        if (lane + 32 < nl) { const int v = siv[lane + 32]; lo1 = iv_lo(v); hi1 = iv_hi(v); }
         for (int m = mstart;; ++m) {
             const bool on = !done && (m >= ms);
             bool anyslab = false;
@@ -823,14 +878,14 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
                 else if (w == 1) a = (lo1 <= m) && (m <= hi1);
                 else {
                     const int slot = w * 32 + lane;
-                    if (slot < nl) { const int v = s_iv[warp][slot]; a = (iv_lo(v) <= m) && (m <= iv_hi(v)); } else a = false;
+                    if (slot < nl) { const int v = siv[slot]; a = (iv_lo(v) <= m) && (m <= iv_hi(v)); } else a = false;
                 }
                 unsigned word = __ballot_sync(0xffffffffu, a);
                 anyslab |= (word != 0);
                 while (word) {
                     const int b = __ffs(word) - 1;
                     word &= word - 1;
-                    const int k = s_k[warp][w * 32 + b];
+                    const int k = list_k(w * 32 + b);
                     const Prim q = load_prim(packn, k);
                     // primtransf.h:119-132
                     const float xm = x - q.px, ym = y - q.py, zm = z - q.pz;
@@ -868,7 +923,7 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
                 if (lo1 > m) nxt = min(nxt, lo1);
                 for (int w = 2; w < nwords; ++w) {
                     const int slot = w * 32 + lane;
-                    if (slot < nl) { const int l = iv_lo(s_iv[warp][slot]); if (l > m) nxt = min(nxt, l); }
+                    if (slot < nl) { const int l = iv_lo(siv[slot]); if (l > m) nxt = min(nxt, l); }
                 }
                 nxt = __reduce_min_sync(0xffffffffu, nxt);
                 if (nxt == kBig) break;          // no slab starts later: nothing left to sample for any lane
@@ -908,8 +963,30 @@ __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d));
 }
 
+template <int CAP>
+struct __align__(16) BwdWarpSmem {   // MVP_BWD_OPAQUE == 2: one record per warp
+    float4 q[kRing];
+    RowEntry stage[2 * kStage];
+    unsigned long long bar[2];
+    int k[CAP];
+    int iv[CAP];
+    float ray[9 * 32];
+};
+
 template <int T, int CAP, bool kWarp>
 __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_BWD_MINB * 4) / kWarps : 12 / kWarps) render_backward_kernel(const Params p) {
+#if MVP_BWD_OPAQUE == 2
+    __shared__ BwdWarpSmem<CAP> s_w[kWarps];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned woff = (unsigned)__cvta_generic_to_shared(&s_w[warp]);
+    asm volatile("" : "+r"(woff));
+    BwdWarpSmem<CAP> *const S = reinterpret_cast<BwdWarpSmem<CAP> *>(__cvta_shared_to_generic((size_t)woff));
+    int *const sk = S->k, *const siv = S->iv;
+    RowEntry *const sstage = S->stage;
+    unsigned long long *const sbar = S->bar;
+    float4 *const sq = S->q;
+    float *const sray = S->ray;
+#else
     __shared__ int s_k[kWarps][CAP];
     __shared__ int s_iv[kWarps][CAP];
     __shared__ float4 s_q[kWarps][kRing];
@@ -917,6 +994,12 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
     __shared__ __align__(16) RowEntry s_stage[kWarps][2 * kStage];   // TMA-staged chunks of the tile row's bucket
     __shared__ __align__(8) unsigned long long s_bar[kWarps][2];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int *const sk = s_k[warp], *const siv = s_iv[warp];
+    RowEntry *const sstage = s_stage[warp];
+    unsigned long long *const sbar = s_bar[warp];
+    float4 *const sq = s_q[warp];
+    float *const sray = s_ray[warp];
+#endif
     const int tx = blockIdx.x * kBlkTX + (warp % kBlkTX), ty = blockIdx.y * kBlkTY + (warp / kBlkTX), n = blockIdx.z;
     if (tx >= p.TXn || ty >= p.TYn) return;
     if (CAP == kMaxHit) asm volatile("griddepcontrol.launch_dependents;");
@@ -930,7 +1013,7 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
     TileCtx c;
     float t0, xb, yb, zb, r1e;   // xb = position at sweep step max(mcur, ms)
     int j0;
-    build_tile_list<CAP, false>(p, rdt, n, tx, ty, lane, c, s_k[warp], s_iv[warp], s_stage[warp], s_bar[warp], t0, xb, yb, zb, r1e, j0);   // measured: the prefetch only pays in forward
+    build_tile_list<CAP, false>(p, rdt, n, tx, ty, lane, c, sk, siv, sstage, sbar, t0, xb, yb, zb, r1e, j0);   // measured: the prefetch only pays in forward
     const int nl = c.nl;
     if (nl == 0) { if (CAP < kMaxHit) asm volatile("griddepcontrol.wait;" ::: "memory"); return; }
 
@@ -947,7 +1030,7 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
         const float4 dL = __ldg(reinterpret_cast<const float4 *>(p.grad_rayrgba) + r);
         const float rs0 = __ldg(p.raysat_in + r * 3 + 0), rs1 = __ldg(p.raysat_in + r * 3 + 1), rs2 = __ldg(p.raysat_in + r * 3 + 2);
         const bool hassat = rs0 > -1.f;
-        float *pr_ = s_ray[warp];
+        float *pr_ = sray;
         pr_[0 * 32 + lane] = dL.x; pr_[1 * 32 + lane] = dL.y; pr_[2 * 32 + lane] = dL.z; pr_[3 * 32 + lane] = dL.w;
         pr_[4 * 32 + lane] = hassat ? rs0 : 0.f; pr_[5 * 32 + lane] = hassat ? rs1 : 0.f; pr_[6 * 32 + lane] = hassat ? rs2 : 0.f;
         pr_[7 * 32 + lane] = hassat ? 1.f : 0.f;
@@ -986,7 +1069,7 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
             const int myslot = w * 32 + lane;
             bool pick = false;
             if (myslot < nl) {
-                const int v = s_iv[warp][myslot];
+                const int v = siv[myslot];
                 const int a0 = max(iv_lo(v), wfirst), b0 = min(iv_hi(v), wlast);
                 pick = (a0 <= b0) && (a0 >= cs) && (a0 < cs + kMaskSteps);
             }
@@ -995,7 +1078,7 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
                 const int bit = __ffs(word) - 1;
                 word &= word - 1;
                 const int slot = w * 32 + bit;
-                const int k = s_k[warp][slot];
+                const int k = sk[slot];
                 int rank = k - kstart; if (rank < 0) rank += p.K;
                 const Prim q = load_prim(packn, k);
                 // Slab-major order needs no cross-lane alignment: every lane walks ITS OWN step interval of this slab
@@ -1037,7 +1120,7 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
                 // whichever lane pops it (per-ray data comes from the owner lane by shuffle; the per-slab gradient sums are
                 // reduced over the warp afterwards, so it does not matter which lane accumulates a sample).
                 int qhead = 0, qn = 0;
-                float4 *ring = s_q[warp];
+                float4 *ring = sq;
                 for (int i = 0; i <= maxlen; ++i) {
                     const bool flush = (i == maxlen);
                     if (!flush) {
@@ -1071,7 +1154,7 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
                         const bool issat = (meta & 256) != 0;
                         // per-ray data of the owner lane
                         if (!act) continue;
-                        const float *pr_ = s_ray[warp] + owner;
+                        const float *pr_ = sray + owner;
                         const float oLx = pr_[0 * 32], oLy = pr_[1 * 32], oLz = pr_[2 * 32], oLw = pr_[3 * 32];
                         const float osr = pr_[4 * 32], osg = pr_[5 * 32], osb = pr_[6 * 32], osa = pr_[7 * 32], oab = pr_[8 * 32];
                         touched = true;

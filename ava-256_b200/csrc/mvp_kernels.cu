@@ -28,8 +28,18 @@
 // Arithmetic mirrors the reference's fp32 operation order where a step function of the result exists
 // (transform + strict validity, slab test, lattice snap, saturation); -use_fast_math is on like the reference.
 
+#ifdef MVP_CPU_EMUL
+// Test-only host build (tests/emul/): the kernels below compiled with g++ on top of a CPU emulation of warps, blocks and
+// shared memory, so the CPU test suite can run this file's logic against the oracle.  Not part of the product library.
+#include "cuda_emul.h"
+#define MVP_GRIDDEP_LAUNCH() ((void)0)
+#define MVP_GRIDDEP_WAIT() ((void)0)
+#else
 #include <cuda_runtime.h>
 #include <math_constants.h>
+#define MVP_GRIDDEP_LAUNCH() asm volatile("griddepcontrol.launch_dependents;")
+#define MVP_GRIDDEP_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+#endif
 #include <stdint.h>
 #include <stdlib.h>
 
@@ -290,7 +300,11 @@ __global__ void __launch_bounds__(kRowThreads) row_lists_kernel(int K, int R, in
                                                                 const unsigned *__restrict__ rx, const unsigned *__restrict__ ry,
                                                                 int *__restrict__ rowcnt, RowEntry *__restrict__ rowlist,
                                                                 unsigned char *__restrict__ tileflag) {
-    extern __shared__ int s_tilecnt[];   // [TXn] candidates (rectangle overlaps) per 8-pixel tile column of this row
+#ifdef MVP_CPU_EMUL
+    MVP_EMUL_DYN_SMEM(int, s_tilecnt);
+#else
+    extern __shared__ int s_tilecnt[];
+#endif   // [TXn] candidates (rectangle overlaps) per 8-pixel tile column of this row
     const int row = blockIdx.x, n = blockIdx.y;
     const int ylo = row * kTileH, yhi = ylo + kTileH - 1;
     const unsigned *rxn = rx + (size_t)n * K, *ryn = ry + (size_t)n * K;
@@ -375,9 +389,13 @@ struct Ray {
 
 // 1/x as the reference gets it under -use_fast_math (MUFU.RCP)
 __device__ __forceinline__ float fast_rcp(float x) {
+#ifdef MVP_CPU_EMUL
+    return 1.f / x;
+#else
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
+#endif
 }
 
 // utils.h:744-755: line vs slab in slab coordinates.  Returns hit; lo/hi valid when hit.
@@ -412,6 +430,19 @@ __device__ __forceinline__ int iv_hi(int v) { const int h = v >> 16; return h ==
 // ---- TMA bulk copy (cp.async.bulk, global -> shared) + mbarrier, used to stage the tile row's bucket ----
 constexpr int kStage = 32;   // bucket entries per staged chunk (256 B), double buffered per warp
 
+#ifdef MVP_CPU_EMUL
+// emulation: the bulk copy is a memcpy by the issuing lane; the mbarrier is a phase counter (try_wait.parity(P) succeeds
+// once the phase of parity P has completed)
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int) { *bar = 0; }
+__device__ __forceinline__ void mbar_fence_init() {}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    memcpy(dst, src, bytes);
+    *bar += 1;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    while ((unsigned)(*(volatile unsigned long long *)bar & 1) == parity) emul::yield();
+}
+#else
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -435,6 +466,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
                      : "memory");
     } while (!ok);
 }
+#endif
 
 struct TileCtx {
     // per-lane
@@ -750,10 +782,10 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
     if (tx >= p.TXn || ty >= p.TYn) return;   // warps are independent: no CTA-wide barrier below (exited warps count as arrived)
     // Programmatic dependent launch: the 512-entry variant (few, long-running tiles) is launched first and lets the
     // fast variant start while it is still running; the fast variant waits for it only at its very end.
-    if (CAP == kMaxHit) asm volatile("griddepcontrol.launch_dependents;");
+    if (CAP == kMaxHit) MVP_GRIDDEP_LAUNCH();
     const bool heavy = p.tileflag[((size_t)n * p.TYn + ty) * p.TXn + tx] != 0;
     if ((CAP == kMaxHit) != heavy) {
-        if (CAP < kMaxHit) asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (CAP < kMaxHit) MVP_GRIDDEP_WAIT();
         return;
     }
 
@@ -948,7 +980,7 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
             p.rayaux[r] = make_int4(jsat, ranksat, __float_as_int(abefore), jlast);
         }
     }
-    if (CAP < kMaxHit) asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (CAP < kMaxHit) MVP_GRIDDEP_WAIT();
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -960,7 +992,11 @@ __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float 
     return;
 #endif
     // no "memory" clobber: the gradient buffer is never read in this kernel, loads must stay free to move
+#ifdef MVP_CPU_EMUL
+    atomicAdd(addr, a); atomicAdd(addr + 1, b); atomicAdd(addr + 2, c); atomicAdd(addr + 3, d);
+#else
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d));
+#endif
 }
 
 template <int CAP>
@@ -1002,10 +1038,10 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
 #endif
     const int tx = blockIdx.x * kBlkTX + (warp % kBlkTX), ty = blockIdx.y * kBlkTY + (warp / kBlkTX), n = blockIdx.z;
     if (tx >= p.TXn || ty >= p.TYn) return;
-    if (CAP == kMaxHit) asm volatile("griddepcontrol.launch_dependents;");
+    if (CAP == kMaxHit) MVP_GRIDDEP_LAUNCH();
     const bool heavy = p.tileflag[((size_t)n * p.TYn + ty) * p.TXn + tx] != 0;
     if ((CAP == kMaxHit) != heavy) {
-        if (CAP < kMaxHit) asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (CAP < kMaxHit) MVP_GRIDDEP_WAIT();
         return;
     }
 
@@ -1015,7 +1051,7 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
     int j0;
     build_tile_list<CAP, false>(p, rdt, n, tx, ty, lane, c, sk, siv, sstage, sbar, t0, xb, yb, zb, r1e, j0);   // measured: the prefetch only pays in forward
     const int nl = c.nl;
-    if (nl == 0) { if (CAP < kMaxHit) asm volatile("griddepcontrol.wait;" ::: "memory"); return; }
+    if (nl == 0) { if (CAP < kMaxHit) MVP_GRIDDEP_WAIT(); return; }
 
     const int px = tx * kTileW + (lane & 7), py = ty * kTileH + (lane >> 3);
     const size_t r = ((size_t)n * p.H + min(py, p.H - 1)) * p.W + min(px, p.W - 1);
@@ -1044,7 +1080,7 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
     const float foff = (float)c.off;
     const int wlast = __reduce_max_sync(0xffffffffu, mlast);
     const int wfirst = __reduce_min_sync(0xffffffffu, ms);
-    if (wlast < wfirst || wfirst >= kBig) { if (CAP < kMaxHit) asm volatile("griddepcontrol.wait;" ::: "memory"); return; }
+    if (wlast < wfirst || wfirst >= kBig) { if (CAP < kMaxHit) MVP_GRIDDEP_WAIT(); return; }
 
     const float4 *packn = p.pack + (size_t)n * p.K * 4;
     const size_t slabsz = (size_t)p.TD * p.TH * p.TW;
@@ -1352,13 +1388,28 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
             }   // while (word)
         }       // for (w)
     }           // for (cs)
-    if (CAP < kMaxHit) asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (CAP < kMaxHit) MVP_GRIDDEP_WAIT();
 }
+
+// plain launch of the 512-entry variant (first in the stream); variadic because the kernel name contains commas
+#ifdef MVP_CPU_EMUL
+#define MVP_LAUNCH_HEAVY(...)                                   \
+    do {                                                        \
+        auto kern_ = __VA_ARGS__;                               \
+        MVP_LAUNCH(kern_, grid, kWarps * 32, 0, st, p);         \
+    } while (0)
+#else
+#define MVP_LAUNCH_HEAVY(...) __VA_ARGS__<<<grid, kWarps * 32, 0, st>>>(p)
+#endif
 
 // Launches `kern` as a programmatic dependent of the previous kernel in the stream (it may start before that kernel has
 // finished; it executes griddepcontrol.wait before exiting, so it never completes first).
 template <typename KernT>
 cudaError_t launch_dependent(KernT kern, dim3 grid, int threads, cudaStream_t st, const Params &p) {
+#ifdef MVP_CPU_EMUL
+    MVP_LAUNCH(kern, grid, threads, 0, st, p);
+    return cudaSuccess;
+#else
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(threads);
@@ -1370,6 +1421,7 @@ cudaError_t launch_dependent(KernT kern, dim3 grid, int threads, cudaStream_t st
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kern, p);
+#endif
 }
 
 int check_shape(const mvp_shape &s) {
@@ -1388,6 +1440,16 @@ int launch_accel(const mvp_shape &s, const float *raypos, const float *raydir, c
     if (e != cudaSuccess) return (int)e;
     const size_t HW = (size_t)s.H * s.W;
     dim3 gfit((unsigned)((HW + kFitThreads * kFitRaysPerThread - 1) / (kFitThreads * kFitRaysPerThread)), s.N);
+#ifdef MVP_CPU_EMUL
+    MVP_LAUNCH(fit_camera_kernel, gfit, kFitThreads, 0, st, s.H, s.W, raypos, raydir, cam, bad);
+    const size_t NK = (size_t)s.N * s.K;
+    MVP_LAUNCH(prim_setup_kernel, (unsigned)((NK + 127) / 128), 128, 0, st, s.N, s.K, s.H, s.W, primpos, primrot, primscale, cam, bad,
+               reinterpret_cast<float4 *>(ws + L.pack), reinterpret_cast<unsigned *>(ws + L.rx), reinterpret_cast<unsigned *>(ws + L.ry));
+    const int TXn = (s.W + kTileW - 1) / kTileW;
+    MVP_LAUNCH(row_lists_kernel, dim3(L.R, s.N), kRowThreads, (size_t)TXn * sizeof(int), st, s.K, L.R, L.rowcap, TXn, kFastCap,
+               reinterpret_cast<unsigned *>(ws + L.rx), reinterpret_cast<unsigned *>(ws + L.ry), reinterpret_cast<int *>(ws + L.rowcnt),
+               reinterpret_cast<RowEntry *>(ws + L.rowlist), reinterpret_cast<unsigned char *>(ws + L.tileflag));
+#else
     fit_camera_kernel<<<gfit, kFitThreads, 0, st>>>(s.H, s.W, raypos, raydir, cam, bad);
     const size_t NK = (size_t)s.N * s.K;
     prim_setup_kernel<<<(unsigned)((NK + 127) / 128), 128, 0, st>>>(
@@ -1398,6 +1460,7 @@ int launch_accel(const mvp_shape &s, const float *raypos, const float *raydir, c
         s.K, L.R, L.rowcap, TXn, kFastCap, reinterpret_cast<unsigned *>(ws + L.rx), reinterpret_cast<unsigned *>(ws + L.ry),
         reinterpret_cast<int *>(ws + L.rowcnt), reinterpret_cast<RowEntry *>(ws + L.rowlist),
         reinterpret_cast<unsigned char *>(ws + L.tileflag));
+#endif
     e = cudaGetLastError();
     return e == cudaSuccess ? MVP_OK : (int)e;
 }
@@ -1485,10 +1548,10 @@ int mvp_raymarch_forward(const mvp_forward_args *a, void *stream) {
 #define MVP_LAUNCH_FWD(TT, WW_)                                                                              \
     do {                                                                                                     \
         if (a->raysat) {                                                                                     \
-            render_forward_kernel<TT, true, kMaxHit, WW_><<<grid, kWarps * 32, 0, st>>>(p);                  \
+            MVP_LAUNCH_HEAVY(render_forward_kernel<TT, true, kMaxHit, WW_>);                                 \
             launch_dependent(render_forward_kernel<TT, true, kFastCap, WW_>, grid, kWarps * 32, st, p);      \
         } else {                                                                                             \
-            render_forward_kernel<TT, false, kMaxHit, WW_><<<grid, kWarps * 32, 0, st>>>(p);                 \
+            MVP_LAUNCH_HEAVY(render_forward_kernel<TT, false, kMaxHit, WW_>);                                \
             launch_dependent(render_forward_kernel<TT, false, kFastCap, WW_>, grid, kWarps * 32, st, p);     \
         }                                                                                                    \
     } while (0)
@@ -1531,7 +1594,7 @@ int mvp_raymarch_backward(const mvp_backward_args *a, void *stream) {
     const int cubic = (a->shape.TD == a->shape.TH && a->shape.TH == a->shape.TW) ? a->shape.TD : 0;
 #define MVP_LAUNCH_BWD(TT, WW_)                                                                  \
     do {                                                                                         \
-        render_backward_kernel<TT, kMaxHit, WW_><<<grid, kWarps * 32, 0, st>>>(p);               \
+        MVP_LAUNCH_HEAVY(render_backward_kernel<TT, kMaxHit, WW_>);                              \
         launch_dependent(render_backward_kernel<TT, kFastCap, WW_>, grid, kWarps * 32, st, p);   \
     } while (0)
     if (a->algo == 1) MVP_LAUNCH_BWD(0, true);

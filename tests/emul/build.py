@@ -18,5 +18,23 @@ def build():
     return LIB
 
 
+KSRC = [os.path.join(HERE, "mvp_emul.cpp"), os.path.join(HERE, "cuda_emul.cpp")]
+KDEP = KSRC + [os.path.join(HERE, "cuda_emul.h"), os.path.join(ROOT, "ava-256_b200", "csrc", "mvp_kernels.cu"),
+               os.path.join(ROOT, "include", "mvpraymarch_b200.h")]
+KLIB = os.path.join(HERE, "libmvp_emul.so")
+
+
+def build_kernels(opt="-O1"):
+    """libmvp_emul.so: the product kernels' source compiled for the host on the CPU emulation of cuda_emul.h."""
+    if os.path.exists(KLIB) and all(os.path.getmtime(KLIB) >= os.path.getmtime(f) for f in KDEP + [__file__]):
+        return KLIB
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    subprocess.check_call(["g++", "-std=c++20", opt, "-g", "-ffp-contract=off", "-shared", "-fPIC", "-pthread", "-Wno-attributes",
+                           "-Wno-unknown-pragmas", "-I" + cuda_inc, "-I" + HERE, "-I" + os.path.join(ROOT, "include")] + KSRC +
+                          ["-o", KLIB])
+    return KLIB
+
+
 if __name__ == "__main__":
     print(build())
+    print(build_kernels())

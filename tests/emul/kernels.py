@@ -1,0 +1,102 @@
+"""TEST INFRASTRUCTURE: numpy front-end of tests/emul/libmvp_emul.so -- the PRODUCT kernels' source
+(ava-256_b200/csrc/mvp_kernels.cu) compiled for the host on the CPU emulation of warps / blocks / shared memory in
+cuda_emul.h.  Same C-ABI as the product library (struct layouts are taken from ava256_b200.lib), host pointers in
+place of device pointers."""
+import ctypes
+
+import numpy as np
+
+from ava256_b200 import lib as _abi
+from tests.emul.build import build_kernels
+
+_LIB = None
+
+
+def load():
+    global _LIB
+    if _LIB is None:
+        L = ctypes.CDLL(build_kernels())
+        L.mvp_workspace_bytes.restype = ctypes.c_size_t
+        L.mvp_workspace_bytes.argtypes = [ctypes.POINTER(_abi.Shape)]
+        L.mvp_raymarch_forward.restype = ctypes.c_int
+        L.mvp_raymarch_forward.argtypes = [ctypes.POINTER(_abi.ForwardArgs), ctypes.c_void_p]
+        L.mvp_raymarch_backward.restype = ctypes.c_int
+        L.mvp_raymarch_backward.argtypes = [ctypes.POINTER(_abi.BackwardArgs), ctypes.c_void_p]
+        L.mvp_abi_version.restype = ctypes.c_int
+        assert L.mvp_abi_version() == _abi.ABI_VERSION
+        _LIB = L
+    return _LIB
+
+
+def set_lane_order(mode):
+    """'forward' | 'reverse' | 'random': order in which the lanes of a block run between collectives."""
+    load().emul_set_lane_order({"forward": 0, "reverse": 1, "random": 2}[mode])
+
+
+def _p(a):
+    return None if a is None else ctypes.c_void_p(a.ctypes.data)
+
+
+def _aligned(nbytes, align=256):
+    raw = np.zeros(nbytes + align, np.uint8)
+    off = (-raw.ctypes.data) % align
+    return raw[off:off + nbytes]
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def forward_backward(raypos, raydir, stepsize, tminmax, primpos, primrot, primscale, template, grad_rayrgba=None, warp=None,
+                     fadescale=8.0, fadeexp=8.0):
+    """Runs the emulated forward (and, when grad_rayrgba is given, backward) kernels.
+    Returns (rayrgba, raysat, grads) with grads = [primpos, primrot, primscale, template(, warp)] or None."""
+    L = load()
+    raypos, raydir, tminmax, primpos, primrot, primscale, template = map(_f32, (raypos, raydir, tminmax, primpos, primrot, primscale, template))
+    warp = None if warp is None else _f32(warp)
+    N, H, W = raypos.shape[:3]
+    K = primpos.shape[1]
+    TD, TH, TW = template.shape[2:5]
+    shape = _abi.Shape(N, H, W, K, TD, TH, TW)
+    wsb = L.mvp_workspace_bytes(ctypes.byref(shape))
+    assert wsb > 0
+    ws = _aligned(wsb)
+    rayrgba = np.full((N, H, W, 4), np.nan, np.float32)
+    want_grad = grad_rayrgba is not None
+    raysat = np.full((N, H, W, 3), np.nan, np.float32) if want_grad else None
+    rayaux = np.zeros((N, H, W, 4), np.int32) if want_grad else None
+    a = _abi.ForwardArgs()
+    a.shape = shape
+    a.stepsize, a.fadescale, a.fadeexp, a.flags = float(stepsize), float(fadescale), float(fadeexp), 0
+    a.raypos, a.raydir, a.tminmax = _p(raypos), _p(raydir), _p(tminmax)
+    a.primpos, a.primrot, a.primscale, a.tplate = _p(primpos), _p(primrot), _p(primscale), _p(template)
+    a.rayrgba, a.raysat, a.rayaux = _p(rayrgba), _p(raysat), _p(rayaux)
+    a.workspace, a.workspace_bytes = _p(ws), wsb
+    a.algo = 1 if warp is not None else 0
+    if warp is not None:
+        a.warp = _p(warp)
+        a.WD, a.WH, a.WW = warp.shape[2:5]
+    rc = L.mvp_raymarch_forward(ctypes.byref(a), None)
+    assert rc == 0, rc
+    if not want_grad:
+        return rayrgba, None, None
+    grad_rayrgba = _f32(grad_rayrgba)
+    grads = [np.zeros_like(x) for x in (primpos, primrot, primscale, template)]
+    gwarp = np.zeros_like(warp) if warp is not None else None
+    b = _abi.BackwardArgs()
+    b.shape = shape
+    b.stepsize, b.fadescale, b.fadeexp, b.flags = float(stepsize), float(fadescale), float(fadeexp), _abi.FLAG_ACCEL_VALID
+    b.raypos, b.raydir, b.tminmax = _p(raypos), _p(raydir), _p(tminmax)
+    b.primpos, b.primrot, b.primscale, b.tplate = _p(primpos), _p(primrot), _p(primscale), _p(template)
+    b.grad_rayrgba, b.raysat, b.rayaux = _p(grad_rayrgba), _p(raysat), _p(rayaux)
+    b.grad_primpos, b.grad_primrot, b.grad_primscale, b.grad_tplate = (_p(g) for g in grads)
+    b.workspace, b.workspace_bytes = _p(ws), wsb
+    b.algo = a.algo
+    if warp is not None:
+        b.warp, b.grad_warp = _p(warp), _p(gwarp)
+        b.WD, b.WH, b.WW = warp.shape[2:5]
+    rc = L.mvp_raymarch_backward(ctypes.byref(b), None)
+    assert rc == 0, rc
+    if gwarp is not None:
+        grads.append(gwarp)
+    return rayrgba, raysat, grads

@@ -66,6 +66,16 @@ constexpr int kTileH = 4;
 #define MVP_FWD_OPAQUE 2   // forward: per-warp shared state in one record behind a pinned base address (0 = separate arrays,
                            // 1 = pinned list base only).  Measured on B200: 2.77 vs 2.89 ms per 8 views (-4.4 %)
 #endif
+#ifndef MVP_LIST_CAP_MIN
+#define MVP_LIST_CAP_MIN 4096
+#endif
+#ifndef MVP_LIST_CAP_PER_TILE
+#define MVP_LIST_CAP_PER_TILE 24   // average saved entries per tile the workspace provides (C3 scene: 8 on average)
+#endif
+#ifndef MVP_LIST_REUSE
+#define MVP_LIST_REUSE 0   // 1: the forward saves each tile's slab list and each ray's first step, the backward loads them
+                           // instead of rebuilding (-13 % backward instructions; not yet measured on the GPU)
+#endif
 #ifndef MVP_BWD_OPAQUE
 #define MVP_BWD_OPAQUE 0   // 2: same for the backward kernel -- measured SLOWER (4.43 vs 4.23 ms per 8 views), so off
 #endif
@@ -105,6 +115,10 @@ struct __align__(8) RowEntry { int k; unsigned xr; };   // xr = x0 | x1 << 16  (
 struct Layout {
     size_t cam, bad, pack, rx, ry, rowcnt, rowlist, tileflag, total;
     int R, rowcap;
+#if MVP_LIST_REUSE
+    size_t tilehdr, listbuf, listcur, rayj0;
+    int listcap;      // saved list entries per view (tiles that do not fit are rebuilt by the backward)
+#endif
 };
 
 __host__ __device__ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -122,6 +136,17 @@ __host__ inline Layout make_layout(const mvp_shape &s) {
     L.rowcnt = off;  off = align256(off + (size_t)s.N * L.R * 4);
     L.rowlist = off; off = align256(off + (size_t)s.N * L.R * L.rowcap * sizeof(RowEntry));
     L.tileflag = off; off = align256(off + (size_t)s.N * ((s.H + kTileH - 1) / kTileH) * ((s.W + kTileW - 1) / kTileW));
+#if MVP_LIST_REUSE
+    {
+        const size_t tiles = (size_t)((s.H + kTileH - 1) / kTileH) * ((s.W + kTileW - 1) / kTileW);
+        const size_t cap = tiles * MVP_LIST_CAP_PER_TILE < MVP_LIST_CAP_MIN ? MVP_LIST_CAP_MIN : tiles * MVP_LIST_CAP_PER_TILE;
+        L.listcap = (int)(cap < (size_t)0x3fffffff ? cap : (size_t)0x3fffffff);
+        L.tilehdr = off; off = align256(off + (size_t)s.N * tiles * sizeof(int2));
+        L.listbuf = off; off = align256(off + (size_t)s.N * L.listcap * sizeof(int2));
+        L.listcur = off; off = align256(off + (size_t)s.N * sizeof(int));
+        L.rayj0 = off;   off = align256(off + (size_t)s.N * s.H * s.W * sizeof(int));
+    }
+#endif
     L.total = off;
     return L;
 }
@@ -491,6 +516,13 @@ struct Params {
     int TXn, TYn;
     unsigned slab_bytes;          // TD*TH*TW*16
     unsigned char *tileflag;
+#if MVP_LIST_REUSE
+    int2 *tilehdr;                // per tile: (offset into the view's listbuf, entries) or (-1, -1) = not saved
+    int2 *listbuf;                // per view `listcap` entries (slab index, packed step interval)
+    int *listcur;                 // per view bump cursor
+    int *rayj0;                   // per ray: first lattice step, or kNoHitJ0
+    int listcap;
+#endif
     // forward outputs
     float *rayrgba, *raysat;
     int4 *rayaux;
@@ -638,6 +670,72 @@ __device__ __forceinline__ bool build_tile_list(const Params &p, float rdt, int 
     j0 = incs;
     return true;
 }
+
+#if MVP_LIST_REUSE
+constexpr int kNoHitJ0 = -0x7fffffff - 1;
+#ifdef MVP_CPU_EMUL
+int g_emul_saved_list_tiles[2];   // [0] tiles whose saved list the backward loaded, [1] tiles it rebuilt
+#endif
+
+// Forward (gradient mode): keep what build_tile_list produced for the backward.
+__device__ __forceinline__ void save_tile_list(const Params &p, int n, int tx, int ty, int lane, const TileCtx &c, const int *s_k,
+                                               const int *s_iv, size_t r, bool hashit, int j0) {
+    const int nl = c.nl;
+    int base = 0;
+    if (lane == 0 && nl > 0) base = atomicAdd(p.listcur + n, nl);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    const bool ok = base + nl <= p.listcap;
+    if (ok) {
+        int2 *dst = p.listbuf + (size_t)n * p.listcap + base;
+        for (int i = lane; i < nl; i += 32) dst[i] = make_int2(s_k[i], s_iv[i]);
+    }
+    if (lane == 0) p.tilehdr[((size_t)n * p.TYn + ty) * p.TXn + tx] = ok ? make_int2(base, nl) : make_int2(-1, -1);
+    if (c.inimg) p.rayj0[r] = hashit ? j0 : kNoHitJ0;
+}
+
+// Backward: restore the outputs of build_tile_list the adjoint uses (ray, off, list, first step and its position) from
+// what the forward saved.  Returns false (warp-uniform) when this tile's list was not saved.
+__device__ __forceinline__ bool load_saved_tile_list(const Params &p, float rdt, int n, int tx, int ty, int lane, TileCtx &c, int *s_k,
+                                                     int *s_iv, float &x, float &y, float &z, int &j0) {
+    const int2 hdr = __ldg(p.tilehdr + ((size_t)n * p.TYn + ty) * p.TXn + tx);
+#ifdef MVP_CPU_EMUL
+    if (lane == 0) atomicAdd(&g_emul_saved_list_tiles[hdr.y < 0 ? 1 : 0], 1);   // test hook: which path did the tile take
+#endif
+    if (hdr.y < 0) return false;
+    const int px = tx * kTileW + (lane & 7), py = ty * kTileH + (lane >> 3);
+    c.inimg = (px < p.W) && (py < p.H);
+    const int cx = min(px, p.W - 1), cy = min(py, p.H - 1);
+    const size_t r = ((size_t)n * p.H + cy) * p.W + cx;
+    c.ray.ox = __ldg(p.raypos + r * 3 + 0); c.ray.oy = __ldg(p.raypos + r * 3 + 1); c.ray.oz = __ldg(p.raypos + r * 3 + 2);
+    c.ray.dx = __ldg(p.raydir + r * 3 + 0); c.ray.dy = __ldg(p.raydir + r * 3 + 1); c.ray.dz = __ldg(p.raydir + r * 3 + 2);
+    const float2 tmm = __ldg(reinterpret_cast<const float2 *>(p.tminmax) + r);
+    c.ray.tmin = tmm.x; c.ray.tmax = tmm.y;
+    const float tsteps = c.ray.tmin * rdt;
+    float tref = c.inimg ? tsteps : CUDART_INF_F;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tref = fminf(tref, __shfl_xor_sync(0xffffffffu, tref, o));
+    c.off = clamp_step(ceilf(tref - tsteps));
+    const int2 *src = p.listbuf + (size_t)n * p.listcap + hdr.x;
+    for (int i = lane; i < hdr.y; i += 32) {
+        const int2 e = __ldg(src + i);
+        s_k[i] = e.x; s_iv[i] = e.y;
+    }
+    __syncwarp();
+    c.nl = hdr.y;
+    j0 = c.inimg ? __ldg(p.rayj0 + r) : kNoHitJ0;
+    const bool hit = j0 != kNoHitJ0;
+    c.rt0 = hit ? 0.f : 1.f; c.rt1 = hit ? 1.f : 0.f;   // the adjoint only asks whether rt0 <= rt1
+    if (!hit) j0 = 0;
+    // position of lattice step j0 (mvpraymarch_subset_kernel.h:63-72 as compiled; same expressions as build_tile_list)
+    const float xs = __fmaf_rn(c.ray.dx, c.ray.tmin, c.ray.ox), ys = __fmaf_rn(c.ray.dy, c.ray.tmin, c.ray.oy),
+                zs = __fmaf_rn(c.ray.dz, c.ray.tmin, c.ray.oz);
+    const float fi = (float)j0;
+    x = __fmaf_rn(__fmul_rn(c.ray.dx, fi), p.dt, xs);
+    y = __fmaf_rn(__fmul_rn(c.ray.dy, fi), p.dt, ys);
+    z = __fmaf_rn(__fmul_rn(c.ray.dz, fi), p.dt, zs);
+    return true;
+}
+#endif
 
 // primsampler.h:44-66 + utils.h:408-502.  T > 0: cubic slab with compile-time strides; T == 0: runtime dims.
 // Only called for valid samples (|y| < 1), for which (a) the reference's +-100 clamp is a no-op and (b) the only
@@ -800,6 +898,9 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
     const size_t r = ((size_t)n * p.H + min(py, p.H - 1)) * p.W + min(px, p.W - 1);
 
     const bool hashit = c.inimg && (c.rt0 <= c.rt1);
+#if MVP_LIST_REUSE
+    if (kGrad) save_tile_list(p, n, tx, ty, lane, c, sk, siv, r, hashit, j0);
+#endif
     bool done = !hashit || (t > r1e);
     const int ms = done ? kBig : (j0 - c.off);   // sweep step at which this lane starts marching
 
@@ -1049,6 +1150,9 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
     TileCtx c;
     float t0, xb, yb, zb, r1e;   // xb = position at sweep step max(mcur, ms)
     int j0;
+#if MVP_LIST_REUSE
+    if (!load_saved_tile_list(p, rdt, n, tx, ty, lane, c, sk, siv, xb, yb, zb, j0))
+#endif
     build_tile_list<CAP, false>(p, rdt, n, tx, ty, lane, c, sk, siv, sstage, sbar, t0, xb, yb, zb, r1e, j0);   // measured: the prefetch only pays in forward
     const int nl = c.nl;
     if (nl == 0) { if (CAP < kMaxHit) MVP_GRIDDEP_WAIT(); return; }
@@ -1438,6 +1542,11 @@ int launch_accel(const mvp_shape &s, const float *raypos, const float *raydir, c
     int *bad = reinterpret_cast<int *>(ws + L.bad);
     cudaError_t e = cudaMemsetAsync(bad, 0, (size_t)s.N * sizeof(int), st);
     if (e != cudaSuccess) return (int)e;
+#if MVP_LIST_REUSE
+    // a new accel structure invalidates whatever lists an earlier forward saved in this workspace
+    e = cudaMemsetAsync(ws + L.tilehdr, 0xff, L.listbuf - L.tilehdr, st);
+    if (e != cudaSuccess) return (int)e;
+#endif
     const size_t HW = (size_t)s.H * s.W;
     dim3 gfit((unsigned)((HW + kFitThreads * kFitRaysPerThread - 1) / (kFitThreads * kFitRaysPerThread)), s.N);
 #ifdef MVP_CPU_EMUL
@@ -1479,6 +1588,13 @@ void fill_params(Params &p, const mvp_shape &s, float stepsize, float fadescale,
     p.TYn = (s.H + kTileH - 1) / kTileH;
     p.tileflag = reinterpret_cast<unsigned char *>(ws + L.tileflag);
     p.slab_bytes = (unsigned)((size_t)s.TD * s.TH * s.TW * 16);
+#if MVP_LIST_REUSE
+    p.tilehdr = reinterpret_cast<int2 *>(ws + L.tilehdr);
+    p.listbuf = reinterpret_cast<int2 *>(ws + L.listbuf);
+    p.listcur = reinterpret_cast<int *>(ws + L.listcur);
+    p.rayj0 = reinterpret_cast<int *>(ws + L.rayj0);
+    p.listcap = L.listcap;
+#endif
 }
 
 }  // namespace
@@ -1544,6 +1660,12 @@ int mvp_raymarch_forward(const mvp_forward_args *a, void *stream) {
     p.warp = a->warp; p.WD = a->WD; p.WH = a->WH; p.WW = a->WW;
     dim3 grid((p.TXn + kBlkTX - 1) / kBlkTX, (p.TYn + kBlkTY - 1) / kBlkTY, a->shape.N);
     if (grid.y > 65535) return MVP_ERR_SHAPE;
+#if MVP_LIST_REUSE
+    if (a->raysat) {
+        cudaError_t e0 = cudaMemsetAsync(p.listcur, 0, (size_t)a->shape.N * sizeof(int), st);
+        if (e0 != cudaSuccess) return (int)e0;
+    }
+#endif
     const int cubic = (a->shape.TD == a->shape.TH && a->shape.TH == a->shape.TW) ? a->shape.TD : 0;
 #define MVP_LAUNCH_FWD(TT, WW_)                                                                              \
     do {                                                                                                     \
@@ -1605,5 +1727,12 @@ int mvp_raymarch_backward(const mvp_backward_args *a, void *stream) {
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? MVP_OK : (int)e;
 }
+
+#if defined(MVP_CPU_EMUL) && MVP_LIST_REUSE
+void mvp_emul_saved_list_tiles(int *loaded, int *rebuilt) {
+    *loaded = g_emul_saved_list_tiles[0]; *rebuilt = g_emul_saved_list_tiles[1];
+    g_emul_saved_list_tiles[0] = g_emul_saved_list_tiles[1] = 0;
+}
+#endif
 
 }  // extern "C"

@@ -24,15 +24,18 @@ KDEP = KSRC + [os.path.join(HERE, "cuda_emul.h"), os.path.join(ROOT, "ava-256_b2
 KLIB = os.path.join(HERE, "libmvp_emul.so")
 
 
-def build_kernels(opt="-O1"):
-    """libmvp_emul.so: the product kernels' source compiled for the host on the CPU emulation of cuda_emul.h."""
-    if os.path.exists(KLIB) and all(os.path.getmtime(KLIB) >= os.path.getmtime(f) for f in KDEP + [__file__]):
-        return KLIB
+def build_kernels(defines=(), opt="-O1"):
+    """libmvp_emul[_<defines>].so: the product kernels' source compiled for the host on the CPU emulation of cuda_emul.h.
+    `defines` selects one of the kernels' build-time variants, e.g. ("MVP_LIST_REUSE=1",)."""
+    tag = "".join("_" + d.replace("=", "").replace("MVP_", "").lower() for d in defines)
+    lib = KLIB[:-3] + tag + ".so"
+    if os.path.exists(lib) and all(os.path.getmtime(lib) >= os.path.getmtime(f) for f in KDEP + [__file__]):
+        return lib
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
     subprocess.check_call(["g++", "-std=c++20", opt, "-g", "-ffp-contract=off", "-shared", "-fPIC", "-pthread", "-Wno-attributes",
-                           "-Wno-unknown-pragmas", "-I" + cuda_inc, "-I" + HERE, "-I" + os.path.join(ROOT, "include")] + KSRC +
-                          ["-o", KLIB])
-    return KLIB
+                           "-Wno-unknown-pragmas", "-I" + cuda_inc, "-I" + HERE, "-I" + os.path.join(ROOT, "include")] +
+                          ["-D" + d for d in defines] + KSRC + ["-o", lib])
+    return lib
 
 
 if __name__ == "__main__":

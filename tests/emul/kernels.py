@@ -9,13 +9,19 @@ import numpy as np
 from ava256_b200 import lib as _abi
 from tests.emul.build import build_kernels
 
-_LIB = None
+_LIBS = {}
+_variant = ()
+
+
+def use_variant(defines=()):
+    """Select the build-time variant of the kernels (a tuple of -D defines) used by subsequent calls."""
+    global _variant
+    _variant = tuple(defines)
 
 
 def load():
-    global _LIB
-    if _LIB is None:
-        L = ctypes.CDLL(build_kernels())
+    if _variant not in _LIBS:
+        L = ctypes.CDLL(build_kernels(_variant))
         L.mvp_workspace_bytes.restype = ctypes.c_size_t
         L.mvp_workspace_bytes.argtypes = [ctypes.POINTER(_abi.Shape)]
         L.mvp_raymarch_forward.restype = ctypes.c_int
@@ -24,8 +30,8 @@ def load():
         L.mvp_raymarch_backward.argtypes = [ctypes.POINTER(_abi.BackwardArgs), ctypes.c_void_p]
         L.mvp_abi_version.restype = ctypes.c_int
         assert L.mvp_abi_version() == _abi.ABI_VERSION
-        _LIB = L
-    return _LIB
+        _LIBS[_variant] = L
+    return _LIBS[_variant]
 
 
 def set_lane_order(mode):

@@ -634,7 +634,9 @@ __device__ __forceinline__ bool build_tile_list(const Params &p, float rdt, int 
             if (__any_sync(0xffffffffu, hit)) {
                 const int wlo = __reduce_min_sync(0xffffffffu, jlo), whi = __reduce_max_sync(0xffffffffu, jhi);
                 if (nl < CAP) {
-                    if (lane == 0) { s_k[nl] = kk; s_iv[nl] = pack_iv(wlo, whi); }
+                    if (lane == 0) {
+                        s_k[nl] = kk; s_iv[nl] = pack_iv(wlo, whi);
+                    }
                     ++nl;
                 } else if (CAP < kMaxHit) {
                     return false;          // warp-uniform
@@ -831,6 +833,16 @@ __device__ __forceinline__ float4 sample_slab_warped(const float4 *__restrict__ 
     return acc;
 }
 
+#if defined(MVP_CPU_EMUL) && defined(MVP_EMUL_STATS)
+// work counters of the emulated forward (tests / design studies only): [0] (step, 32-slot word) ballots, [1] (step, slab)
+// events, [2] events with at least one valid lane, [3] valid lanes (= samples queued), [4] flushes, [5] tiles with a list,
+// [6] events with a lane geometrically inside the slab (whether or not it still marches), [7] such lanes
+long long g_emul_fwd_stats[8];
+#define MVP_STAT(i, v) do { if (lane == 0) stat_[i] += (v); } while (0)
+#else
+#define MVP_STAT(i, v) ((void)0)
+#endif
+
 template <int CAP, bool kGrad>
 struct __align__(16) FwdWarpSmem {   // MVP_FWD_OPAQUE == 2: one record per warp
     float4 ring[kRing];
@@ -911,6 +923,10 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
     bool sat = false;
 
     const int nl = c.nl;
+#if defined(MVP_CPU_EMUL) && defined(MVP_EMUL_STATS)
+    long long stat_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (nl > 0) MVP_STAT(5, 1);
+#endif
     const int nwords = (nl + 31) >> 5;
     const float4 *packn = p.pack + (size_t)n * p.K * 4;
     const size_t slabsz = (size_t)p.TD * p.TH * p.TW;
@@ -947,6 +963,7 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
     int qn = 0;
     unsigned ownlo = 0, ownhi = 0;   // queue positions (0..63) holding this lane's pending samples
     auto flush = [&](int cnt) {
+        MVP_STAT(4, 1);
         const bool act = lane < cnt;
         const float4 rec = ring[act ? lane : 0];
         float4 sres = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1015,9 +1032,11 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
                 }
                 unsigned word = __ballot_sync(0xffffffffu, a);
                 anyslab |= (word != 0);
+                MVP_STAT(0, 1);
                 while (word) {
                     const int b = __ffs(word) - 1;
                     word &= word - 1;
+                    MVP_STAT(1, 1);
                     const int k = list_k(w * 32 + b);
                     const Prim q = load_prim(packn, k);
                     // primtransf.h:119-132
@@ -1028,7 +1047,11 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
                     const bool valid = (fabsf(y0) < 1.f) && (fabsf(y1) < 1.f) && (fabsf(y2) < 1.f);
                     const bool want = valid && on && !sat && (t < r1e);
                     const unsigned vm = __ballot_sync(0xffffffffu, want);
+#if defined(MVP_CPU_EMUL) && defined(MVP_EMUL_STATS)
+                    { const unsigned gm = __ballot_sync(0xffffffffu, valid && c.inimg); MVP_STAT(6, gm != 0); MVP_STAT(7, __popc(gm)); }
+#endif
                     if (vm) {
+                        MVP_STAT(2, 1); MVP_STAT(3, __popc(vm));
                         if (want) {
                             const int pos = qn + __popc(vm & ((1u << lane) - 1u));
                             ring[pos] = make_float4(y0, y1, y2, __int_as_float(lane | ((w * 32 + b) << 5)));
@@ -1081,6 +1104,9 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
             p.rayaux[r] = make_int4(jsat, ranksat, __float_as_int(abefore), jlast);
         }
     }
+#if defined(MVP_CPU_EMUL) && defined(MVP_EMUL_STATS)
+    if (lane == 0) for (int i = 0; i < 8; ++i) if (stat_[i]) std::atomic_ref<long long>(g_emul_fwd_stats[i]).fetch_add(stat_[i]);
+#endif
     if (CAP < kMaxHit) MVP_GRIDDEP_WAIT();
 }
 
@@ -1728,6 +1754,11 @@ int mvp_raymarch_backward(const mvp_backward_args *a, void *stream) {
     return e == cudaSuccess ? MVP_OK : (int)e;
 }
 
+#if defined(MVP_CPU_EMUL) && defined(MVP_EMUL_STATS)
+void mvp_emul_fwd_stats(long long *out) {
+    for (int i = 0; i < 8; ++i) { out[i] = g_emul_fwd_stats[i]; g_emul_fwd_stats[i] = 0; }
+}
+#endif
 #if defined(MVP_CPU_EMUL) && MVP_LIST_REUSE
 void mvp_emul_saved_list_tiles(int *loaded, int *rebuilt) {
     *loaded = g_emul_saved_list_tiles[0]; *rebuilt = g_emul_saved_list_tiles[1];

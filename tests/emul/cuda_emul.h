@@ -241,6 +241,27 @@ inline unsigned __reduce_max_sync(unsigned, unsigned v) {
     for (int i = 0; i < 32; ++i) if ((m >> i) & 1) r = std::max(r, emul::from_bits<unsigned>(o[i]));
     return r;
 }
+inline unsigned __reduce_or_sync(unsigned, unsigned v) {
+    unsigned long long o[32];
+    const unsigned m = emul::warp_gather(emul::to_bits(v), o);
+    unsigned r = 0;
+    for (int i = 0; i < 32; ++i) if ((m >> i) & 1) r |= emul::from_bits<unsigned>(o[i]);
+    return r;
+}
+inline unsigned __reduce_and_sync(unsigned, unsigned v) {
+    unsigned long long o[32];
+    const unsigned m = emul::warp_gather(emul::to_bits(v), o);
+    unsigned r = 0xffffffffu;
+    for (int i = 0; i < 32; ++i) if ((m >> i) & 1) r &= emul::from_bits<unsigned>(o[i]);
+    return r;
+}
+inline int __reduce_add_sync(unsigned, int v) {
+    unsigned long long o[32];
+    const unsigned m = emul::warp_gather(emul::to_bits(v), o);
+    int r = 0;
+    for (int i = 0; i < 32; ++i) if ((m >> i) & 1) r += emul::from_bits<int>(o[i]);
+    return r;
+}
 inline void __syncthreads() { emul::block_barrier(0); }
 inline int __syncthreads_or(int pred) { return emul::block_barrier(pred); }
 

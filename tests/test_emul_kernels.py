@@ -91,6 +91,8 @@ VARIANTS = {
     "list_reuse_overflow": ("MVP_LIST_REUSE=1", "MVP_LIST_CAP_PER_TILE=1", "MVP_LIST_CAP_MIN=16"),  # most tiles do not fit: mixes both paths
     "bwd_record": ("MVP_BWD_OPAQUE=2",),
     "fwd_arrays": ("MVP_FWD_OPAQUE=0",),
+    "list_margin": ("MVP_LIST_MARGIN=1",),                                  # step intervals from the fp-drift bound
+    "list_margin_reuse": ("MVP_LIST_MARGIN=1", "MVP_LIST_REUSE=1"),
 }
 
 
@@ -107,7 +109,7 @@ def test_kernel_variants_match_the_default_build(kernels, name, variant):
         assert np.array_equal(out0, out1) and np.array_equal(sat0, sat1)
         for x, y in zip(g0, g1):
             assert relerr(x, y) <= 1e-5
-    if variant.startswith("list_reuse"):
+    if variant in ("list_reuse", "list_reuse_overflow"):
         import ctypes
         loaded, rebuilt = ctypes.c_int(), ctypes.c_int()
         kernels.load().mvp_emul_saved_list_tiles(ctypes.byref(loaded), ctypes.byref(rebuilt))

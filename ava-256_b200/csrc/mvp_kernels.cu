@@ -68,7 +68,8 @@ constexpr int kTileH = 4;
 #endif
 #ifndef MVP_LIST_MARGIN
 #define MVP_LIST_MARGIN 0   // 1: step intervals of the tile lists from a bound on the fp drift of the marched positions instead of a
-                            // whole step of slack on each side (-20 % forward events on the bench scene; not yet measured on the GPU)
+                            // whole step of slack on each side: -26 % forward events, forward 2.66 vs 2.76 ms per 8 views on B200; off until
+                            // the zero-scale fix (NaN margin) has been re-run on a GPU
 #endif
 #ifndef MVP_LIST_CAP_MIN
 #define MVP_LIST_CAP_MIN 4096
@@ -77,8 +78,8 @@ constexpr int kTileH = 4;
 #define MVP_LIST_CAP_PER_TILE 24   // average saved entries per tile the workspace provides (C3 scene: 8 on average)
 #endif
 #ifndef MVP_LIST_REUSE
-#define MVP_LIST_REUSE 0   // 1: the forward saves each tile's slab list and each ray's first step, the backward loads them
-                           // instead of rebuilding (-13 % backward instructions; not yet measured on the GPU)
+#define MVP_LIST_REUSE 1   // the forward (gradient mode) saves each tile's slab list and each ray's first step, the backward loads
+                           // them instead of rebuilding.  Measured on B200: backward 3.44 vs 4.23 ms per 8 views (-19 %)
 #endif
 #ifndef MVP_BWD_OPAQUE
 #define MVP_BWD_OPAQUE 0   // 2: same for the backward kernel -- measured SLOWER (4.43 vs 4.23 ms per 8 views), so off
@@ -457,7 +458,9 @@ __device__ __forceinline__ bool slab_test_margin(const Prim &q, const Ray &r, fl
     const float n0 = fminf(a0, b0), x0 = fmaxf(a0, b0), n1 = fminf(a1, b1), x1 = fmaxf(a1, b1), n2 = fminf(a2, b2), x2 = fmaxf(a2, b2);
     lo = fmaxf(fmaxf(n0, n1), n2);
     hi = fminf(fminf(x0, x1), x2);
-    const float w0 = epos * fabsf(q.sx * i0), w1 = epos * fabsf(q.sy * i1), w2 = epos * fabsf(q.sz * i2);
+    // s_i = 0 (infinite slab along that axis) gives i_i = inf and s_i * i_i = NaN: fminf drops the NaN, the margin becomes
+    // huge and the (already infinite) axis interval stays infinite
+    const float w0 = epos * fminf(fabsf(q.sx * i0), 1e30f), w1 = epos * fminf(fabsf(q.sy * i1), 1e30f), w2 = epos * fminf(fabsf(q.sz * i2), 1e30f);
     lom = fmaxf(fmaxf(n0 - w0, n1 - w1), n2 - w2);
     him = fminf(fminf(x0 + w0, x1 + w1), x2 + w2);
     return lo <= hi;
@@ -1300,8 +1303,26 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
                 // Slab-major order needs no cross-lane alignment: every lane walks ITS OWN step interval of this slab
                 // (recomputed from the reference's slab test), so all rays that cross the slab are busy together.
                 float lo, hi;
-                const bool hit = slab_test(q, c.ray, lo, hi) && hashit;
                 int la = kBig, lb = -kBig;               // lane's candidate sweep steps [la, lb]
+#if MVP_LIST_MARGIN
+                // same drift-bound intervals as the tile lists (build_tile_list); the bound is recomputed per slab instead
+                // of living in two registers for the whole kernel
+                {
+                    const float nsteps = fmaxf(c.ray.tmax - c.ray.tmin, 0.f) * rdt + 8.f;
+                    const float epos = 1.7320508f * nsteps * 1.1920929e-7f + 1.9073486e-6f;
+                    const float eps0 = fmaxf(0.001953125f, nsteps * 4.7683716e-7f);
+                    float lom, him;
+                    slab_test_margin(q, c.ray, epos, lo, hi, lom, him);
+                    if (hashit && lom <= him) {
+                        la = max(clamp_step(ceilf((lom - c.ray.tmin) * rdt - eps0) - foff), max(ms, cs));
+                        lb = min(clamp_step(floorf((him - c.ray.tmin) * rdt + eps0) - foff), mlast);
+                        if (rank > ranksat) lb = min(lb, msat - 1);      // samples after the saturating one do not exist
+                    }
+                }
+                const bool hit = false;
+#else
+                const bool hit = slab_test(q, c.ray, lo, hi) && hashit;
+#endif
                 if (hit) {
                     // candidate lattice steps floor((lo-tmin)/dt) .. floor((hi-tmin)/dt)+1: the strictly-inside range plus one
                     // step of slack on each side, because lo/hi carry ~1e-6 relative error (rcp.approx) and the forward's

@@ -115,3 +115,24 @@ def build_case(name):
     g = torch.Generator().manual_seed(4242)
     grad = torch.randn(*s["raypos"].shape[:3], 4, generator=g)
     return s, grad
+
+
+EDGE_KINDS = ("zero_scale", "rays_miss_volume", "large_step", "tiny_step")
+
+
+def edge_scene(kind):
+    s = gradcheck_like_scene(N=1, H=12, W=16, k3=2, M=4, seed=11, alpha_gain=30.0)
+    if kind == "zero_scale":
+        # SURVEY.md "input-distribution caveat": a decoder that skipped its warm-up feeds primscale = 0 (infinite slabs)
+        s["primscale"][0, 1] = 0.0
+        s["primscale"][0, 5, 2] = 0.0
+    elif kind == "rays_miss_volume":
+        # tmin > tmax for half of the rays (compute_raydirs gives that for rays missing the unit cube)
+        s["tminmax"][0, :, :8, 0] = 9.0
+        s["tminmax"][0, :, :8, 1] = 8.0
+    elif kind == "large_step":
+        s["stepsize"] = 1.7
+    elif kind == "tiny_step":
+        s["stepsize"] = 6.0 / 400.0
+        s["template"][..., 3] *= 0.05
+    return s

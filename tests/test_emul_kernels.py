@@ -9,7 +9,9 @@ import os
 import numpy as np
 import pytest
 
-from tests.helpers import CASES, build_case, relerr, scene_args_np
+import torch
+
+from tests.helpers import CASES, EDGE_KINDS, build_case, edge_scene, relerr, scene_args_np
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 FWD_TOL, BWD_TOL = 1e-5, 1e-4        # vs the oracle (same IEEE arithmetic; gradients differ by summation order)
@@ -85,9 +87,29 @@ def test_emulated_argument_validation_matches_product(kernels):
     assert L.mvp_workspace_bytes(ctypes.byref(s)) == lib.LIB.mvp_workspace_bytes(ctypes.byref(s)) > 0
 
 
-# build-time variants of the kernels that are not the default yet (waiting for a GPU measurement): same results required
+@pytest.mark.parametrize("variant", [(), ("MVP_LIST_MARGIN=1", "MVP_LIST_REUSE=1"), ("MVP_LIST_MARGIN=0", "MVP_LIST_REUSE=0")])
+@pytest.mark.parametrize("kind", EDGE_KINDS)
+def test_emulated_edge_cases_vs_oracle(kernels, kind, variant):
+    """Degenerate inputs the reference tolerates (zero scale = infinite slab, rays missing the volume, one-step and
+    many-step marches), for the default build and the list variants either way round."""
+    from oracle import oracle
+    s = edge_scene(kind)
+    grad = torch.randn(*s["raypos"].shape[:3], 4, generator=torch.Generator().manual_seed(17))
+    a, kw = scene_args_np(s)
+    kernels.use_variant(variant)
+    out, _, grads = kernels.forward_backward(*a, grad_rayrgba=grad.numpy(), **kw)
+    ref, raysat = oracle.forward(*a, **kw)
+    assert np.isfinite(out).all() and relerr(out, ref) <= FWD_TOL
+    gref = oracle.backward(*a, grad.numpy(), raysat, **kw)
+    for nm, g, r in zip(("primpos", "primrot", "primscale", "template"), grads, gref):
+        assert np.isfinite(g).all(), nm
+        assert relerr(g, r) <= BWD_TOL, nm
+
+
+# build-time variants of the kernels (former defaults, and candidates waiting for a GPU measurement): same results required
 VARIANTS = {
-    "list_reuse": ("MVP_LIST_REUSE=1",),                                   # backward loads the lists the forward saved
+    "list_rebuild": ("MVP_LIST_REUSE=0",),                                 # backward rebuilds the lists (the former default)
+    "list_reuse": ("MVP_LIST_REUSE=1",),                                   # backward loads the lists the forward saved (default)
     "list_reuse_overflow": ("MVP_LIST_REUSE=1", "MVP_LIST_CAP_PER_TILE=1", "MVP_LIST_CAP_MIN=16"),  # most tiles do not fit: mixes both paths
     "bwd_record": ("MVP_BWD_OPAQUE=2",),
     "fwd_arrays": ("MVP_FWD_OPAQUE=0",),

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.helpers import CASES, build_case, relerr, scene_args_np
+from tests.helpers import CASES, build_case, edge_scene, relerr, scene_args_np
 
 pytestmark = pytest.mark.gpu
 
@@ -111,29 +111,10 @@ def test_reference_extension_side_by_side():
         assert relerr(g_, r.cpu().numpy()) <= BWD_TOL, nm
 
 
-def _edge_scene(kind):
-    from tests.helpers import gradcheck_like_scene
-    s = gradcheck_like_scene(N=1, H=12, W=16, k3=2, M=4, seed=11, alpha_gain=30.0)
-    if kind == "zero_scale":
-        # SURVEY.md "input-distribution caveat": a decoder that skipped its warm-up feeds primscale = 0 (infinite slabs)
-        s["primscale"][0, 1] = 0.0
-        s["primscale"][0, 5, 2] = 0.0
-    elif kind == "rays_miss_volume":
-        # tmin > tmax for half of the rays (compute_raydirs gives that for rays missing the unit cube)
-        s["tminmax"][0, :, :8, 0] = 9.0
-        s["tminmax"][0, :, :8, 1] = 8.0
-    elif kind == "large_step":
-        s["stepsize"] = 1.7
-    elif kind == "tiny_step":
-        s["stepsize"] = 6.0 / 400.0
-        s["template"][..., 3] *= 0.05
-    return s
-
-
 @pytest.mark.parametrize("kind", ["zero_scale", "rays_miss_volume", "large_step", "tiny_step"])
 def test_edge_cases_vs_oracle(kind):
     from oracle import oracle
-    s = _edge_scene(kind)
+    s = edge_scene(kind)
     g = torch.Generator().manual_seed(17)
     grad = torch.randn(*s["raypos"].shape[:3], 4, generator=g)
     out, grads = run_ours(s, grad)

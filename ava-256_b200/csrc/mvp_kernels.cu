@@ -66,6 +66,10 @@ constexpr int kTileH = 4;
 #define MVP_FWD_OPAQUE 2   // forward: per-warp shared state in one record behind a pinned base address (0 = separate arrays,
                            // 1 = pinned list base only).  Measured on B200: 2.77 vs 2.89 ms per 8 views (-4.4 %)
 #endif
+#ifndef MVP_XBUCKETS
+#define MVP_XBUCKETS 0   // 1: second bucketing level in x (groups of 8 tile columns): a tile scans ~45 instead of ~350 bucket
+                          // entries (-80 % of the chunk scans, ~7 % of the forward's instructions); not yet measured on the GPU
+#endif
 #ifndef MVP_LIST_MARGIN
 #define MVP_LIST_MARGIN 0   // 1: step intervals of the tile lists from a bound on the fp drift of the marched positions instead of a
                             // whole step of slack on each side: -26 % forward events, forward 2.66 vs 2.76 ms per 8 views on B200; off until
@@ -99,6 +103,10 @@ constexpr int kRing = 64;        // sample queue / ring per warp (forward and ba
 #ifndef MVP_FASTCAP
 #define MVP_FASTCAP 256
 #endif
+#if MVP_XBUCKETS
+constexpr int kGrpTiles = 8;       // tile columns per x-group
+constexpr int kGrpCap = 1024;     // group-bucket entries per tile row; groups that do not fit keep using the row bucket
+#endif
 constexpr int kFastCap = MVP_FASTCAP;   // shared-memory list capacity of the common-case render kernels
 constexpr int kBig = 1 << 30;
 #ifndef MVP_BWD_MINB
@@ -120,6 +128,10 @@ struct __align__(8) RowEntry { int k; unsigned xr; };   // xr = x0 | x1 << 16  (
 struct Layout {
     size_t cam, bad, pack, rx, ry, rowcnt, rowlist, tileflag, total;
     int R, rowcap;
+#if MVP_XBUCKETS
+    size_t grphdr, grplist;
+    int NG;           // x-groups per tile row
+#endif
 #if MVP_LIST_REUSE
     size_t tilehdr, listbuf, listcur, rayj0;
     int listcap;      // saved list entries per view (tiles that do not fit are rebuilt by the backward)
@@ -141,6 +153,11 @@ __host__ inline Layout make_layout(const mvp_shape &s) {
     L.rowcnt = off;  off = align256(off + (size_t)s.N * L.R * 4);
     L.rowlist = off; off = align256(off + (size_t)s.N * L.R * L.rowcap * sizeof(RowEntry));
     L.tileflag = off; off = align256(off + (size_t)s.N * ((s.H + kTileH - 1) / kTileH) * ((s.W + kTileW - 1) / kTileW));
+#if MVP_XBUCKETS
+    L.NG = ((s.W + kTileW - 1) / kTileW + kGrpTiles - 1) / kGrpTiles;
+    L.grphdr = off;  off = align256(off + (size_t)s.N * L.R * L.NG * sizeof(int2));
+    L.grplist = off; off = align256(off + (size_t)s.N * L.R * kGrpCap * sizeof(RowEntry));
+#endif
 #if MVP_LIST_REUSE
     {
         const size_t tiles = (size_t)((s.H + kTileH - 1) / kTileH) * ((s.W + kTileW - 1) / kTileW);
@@ -329,7 +346,11 @@ constexpr int kRowThreads = 256;
 __global__ void __launch_bounds__(kRowThreads) row_lists_kernel(int K, int R, int rowcap, int TXn, int fastcap,
                                                                 const unsigned *__restrict__ rx, const unsigned *__restrict__ ry,
                                                                 int *__restrict__ rowcnt, RowEntry *__restrict__ rowlist,
-                                                                unsigned char *__restrict__ tileflag) {
+                                                                unsigned char *__restrict__ tileflag
+#if MVP_XBUCKETS
+                                                                , int NG, int2 *__restrict__ grphdr, RowEntry *__restrict__ grplist
+#endif
+                                                                ) {
 #ifdef MVP_CPU_EMUL
     MVP_EMUL_DYN_SMEM(int, s_tilecnt);
 #else
@@ -386,6 +407,63 @@ __global__ void __launch_bounds__(kRowThreads) row_lists_kernel(int K, int R, in
     __syncthreads();
     unsigned char *fl = tileflag + ((size_t)n * R + row) * TXn;
     for (int i = threadIdx.x; i < TXn; i += kRowThreads) fl[i] = (s_tilecnt[i] > fastcap) ? 1 : 0;
+#if MVP_XBUCKETS
+    // Second level: for every group of kGrpTiles tile columns, the row's entries (still in rank order) whose pixel range
+    // touches the group, packed one group after the other into the row's group buffer (even offsets: 16-byte aligned for
+    // the TMA staging).  Groups that no longer fit, and rows whose bucket overflowed, are marked (-1, -1): their tiles keep
+    // scanning the row bucket.
+    {
+        const int total = s_base;        // every thread reads it before it is reused below
+        __syncthreads();
+        int2 *hdr = grphdr + ((size_t)n * R + row) * NG;
+        RowEntry *gout = grplist + ((size_t)n * R + row) * kGrpCap;
+        __shared__ int s_goff;
+        if (threadIdx.x == 0) s_goff = 0;
+        __syncthreads();
+        for (int g = 0; g < NG; ++g) {
+            if (total > rowcap) {
+                if (threadIdx.x == 0) hdr[g] = make_int2(-1, -1);
+                continue;
+            }
+            const int gx0 = g * kGrpTiles * kTileW, gx1 = gx0 + kGrpTiles * kTileW - 1;
+            const int goff = s_goff;
+            if (threadIdx.x == 0) s_base = 0;
+            __syncthreads();
+            for (int j0 = 0; j0 < total; j0 += kRowThreads) {
+                const int j = j0 + threadIdx.x;
+                bool in = false;
+                RowEntry e;
+                e.k = 0; e.xr = 0;
+                if (j < total) {
+                    e = out[j];
+                    const int x0 = (int)(e.xr & 0xffffu), x1 = (int)(e.xr >> 16);
+                    in = (x0 <= x1) && (x0 <= gx1) && (x1 >= gx0);
+                }
+                const unsigned b = __ballot_sync(0xffffffffu, in);
+                if (lane == 0) s_wcnt[warp] = __popc(b);
+                __syncthreads();
+                int pre = s_base;
+                for (int w = 0; w < warp; ++w) pre += s_wcnt[w];
+                const int pos = goff + pre + __popc(b & ((1u << lane) - 1u));
+                if (in && pos < kGrpCap) gout[pos] = e;
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    int t = 0;
+                    for (int w = 0; w < kRowThreads / 32; ++w) t += s_wcnt[w];
+                    s_base += t;
+                }
+                __syncthreads();
+            }
+            if (threadIdx.x == 0) {
+                const int cnt = s_base;
+                const bool ok = goff + cnt <= kGrpCap;
+                hdr[g] = ok ? make_int2(goff, cnt) : make_int2(-1, -1);
+                if (ok) s_goff = goff + ((cnt + 1) & ~1);
+            }
+            __syncthreads();
+        }
+    }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -545,6 +623,11 @@ struct Params {
     int TXn, TYn;
     unsigned slab_bytes;          // TD*TH*TW*16
     unsigned char *tileflag;
+#if MVP_XBUCKETS
+    const int2 *grphdr;           // per (view, tile row, x-group): (offset into the row's group buffer, entries) or (-1, -1)
+    const RowEntry *grplist;      // per (view, tile row): kGrpCap entries
+    int NG;
+#endif
 #if MVP_LIST_REUSE
     int2 *tilehdr;                // per tile: (offset into the view's listbuf, entries) or (-1, -1) = not saved
     int2 *listbuf;                // per view `listcap` entries (slab index, packed step interval)
@@ -565,6 +648,10 @@ struct Params {
     float *g_warp;
     int WD, WH, WW;
 };
+
+#if defined(MVP_CPU_EMUL) && defined(MVP_EMUL_STATS)
+long long g_emul_list_chunks;   // 32-entry bucket chunks scanned by build_tile_list (forward + backward)
+#endif
 
 // Builds the warp's slab list (rank order, at most CAP entries in shared memory), each slab's warp step interval and
 // each lane's rtminmax, in one pass over the tile row's bucket.
@@ -608,8 +695,17 @@ __device__ __forceinline__ bool build_tile_list(const Params &p, float rdt, int 
     const float4 *packn = p.pack + (size_t)n * p.K * 4;
     const int cnt = p.rowcnt[(size_t)n * p.R + ty];
     const bool overflow = cnt > p.rowcap;
+#if MVP_XBUCKETS
+    int total = overflow ? p.K : cnt;
+    const RowEntry *rl = p.rowlist + ((size_t)n * p.R + ty) * p.rowcap;
+    if (!overflow) {
+        const int2 gh = __ldg(p.grphdr + ((size_t)n * p.R + ty) * p.NG + tx / kGrpTiles);
+        if (gh.y >= 0) { rl = p.grplist + ((size_t)n * p.R + ty) * kGrpCap + gh.x; total = gh.y; }
+    }
+#else
     const int total = overflow ? p.K : cnt;
     const RowEntry *rl = p.rowlist + ((size_t)n * p.R + ty) * p.rowcap;
+#endif
     const unsigned *rxn = p.rx + (size_t)n * p.K, *ryn = p.ry + (size_t)n * p.K;
     const int tx0 = tx * kTileW, tx1 = tx0 + kTileW - 1, ty0 = ty * kTileH, ty1 = ty0 + kTileH - 1;
     const int kstart = dfs_kstart(p.K);
@@ -628,6 +724,9 @@ __device__ __forceinline__ bool build_tile_list(const Params &p, float rdt, int 
         stage_issue(0);
     }
     for (int base = 0; base < total; base += 32) {
+#if defined(MVP_CPU_EMUL) && defined(MVP_EMUL_STATS)
+        if (lane == 0) std::atomic_ref<long long>(g_emul_list_chunks).fetch_add(1);
+#endif
         const int idx = base + lane;
         int k = 0;
         bool cand = false;
@@ -1654,7 +1753,11 @@ int launch_accel(const mvp_shape &s, const float *raypos, const float *raydir, c
     const int TXn = (s.W + kTileW - 1) / kTileW;
     MVP_LAUNCH(row_lists_kernel, dim3(L.R, s.N), kRowThreads, (size_t)TXn * sizeof(int), st, s.K, L.R, L.rowcap, TXn, kFastCap,
                reinterpret_cast<unsigned *>(ws + L.rx), reinterpret_cast<unsigned *>(ws + L.ry), reinterpret_cast<int *>(ws + L.rowcnt),
-               reinterpret_cast<RowEntry *>(ws + L.rowlist), reinterpret_cast<unsigned char *>(ws + L.tileflag));
+               reinterpret_cast<RowEntry *>(ws + L.rowlist), reinterpret_cast<unsigned char *>(ws + L.tileflag)
+#if MVP_XBUCKETS
+               , L.NG, reinterpret_cast<int2 *>(ws + L.grphdr), reinterpret_cast<RowEntry *>(ws + L.grplist)
+#endif
+               );
 #else
     fit_camera_kernel<<<gfit, kFitThreads, 0, st>>>(s.H, s.W, raypos, raydir, cam, bad);
     const size_t NK = (size_t)s.N * s.K;
@@ -1665,7 +1768,11 @@ int launch_accel(const mvp_shape &s, const float *raypos, const float *raydir, c
     row_lists_kernel<<<dim3(L.R, s.N), kRowThreads, (size_t)TXn * sizeof(int), st>>>(
         s.K, L.R, L.rowcap, TXn, kFastCap, reinterpret_cast<unsigned *>(ws + L.rx), reinterpret_cast<unsigned *>(ws + L.ry),
         reinterpret_cast<int *>(ws + L.rowcnt), reinterpret_cast<RowEntry *>(ws + L.rowlist),
-        reinterpret_cast<unsigned char *>(ws + L.tileflag));
+        reinterpret_cast<unsigned char *>(ws + L.tileflag)
+#if MVP_XBUCKETS
+        , L.NG, reinterpret_cast<int2 *>(ws + L.grphdr), reinterpret_cast<RowEntry *>(ws + L.grplist)
+#endif
+        );
 #endif
     e = cudaGetLastError();
     return e == cudaSuccess ? MVP_OK : (int)e;
@@ -1685,6 +1792,11 @@ void fill_params(Params &p, const mvp_shape &s, float stepsize, float fadescale,
     p.TYn = (s.H + kTileH - 1) / kTileH;
     p.tileflag = reinterpret_cast<unsigned char *>(ws + L.tileflag);
     p.slab_bytes = (unsigned)((size_t)s.TD * s.TH * s.TW * 16);
+#if MVP_XBUCKETS
+    p.grphdr = reinterpret_cast<const int2 *>(ws + L.grphdr);
+    p.grplist = reinterpret_cast<const RowEntry *>(ws + L.grplist);
+    p.NG = L.NG;
+#endif
 #if MVP_LIST_REUSE
     p.tilehdr = reinterpret_cast<int2 *>(ws + L.tilehdr);
     p.listbuf = reinterpret_cast<int2 *>(ws + L.listbuf);
@@ -1829,6 +1941,7 @@ int mvp_raymarch_backward(const mvp_backward_args *a, void *stream) {
 void mvp_emul_fwd_stats(long long *out) {
     for (int i = 0; i < 8; ++i) { out[i] = g_emul_fwd_stats[i]; g_emul_fwd_stats[i] = 0; }
 }
+long long mvp_emul_list_chunks(void) { const long long v = g_emul_list_chunks; g_emul_list_chunks = 0; return v; }
 #endif
 #if defined(MVP_CPU_EMUL) && MVP_LIST_REUSE
 void mvp_emul_saved_list_tiles(int *loaded, int *rebuilt) {

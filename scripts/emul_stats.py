@@ -29,7 +29,9 @@ for tag, defs in VARIANTS:
     dt = time.time() - t0
     st = (ctypes.c_longlong * 8)()
     L.mvp_emul_fwd_stats(st)
-    print("%-9s %6.1fs  " % (tag, dt) + "  ".join("%s=%d" % (n, v) for n, v in zip(NAMES, st)))
+    L.mvp_emul_list_chunks.restype = ctypes.c_longlong
+    chunks = L.mvp_emul_list_chunks()
+    print("%-9s %6.1fs  " % (tag, dt) + "  ".join("%s=%d" % (n, v) for n, v in zip(NAMES, st)) + "  list_chunks=%d" % chunks)
     if ref is None:
         ref = out
     else:

@@ -113,6 +113,8 @@ VARIANTS = {
     "list_reuse_overflow": ("MVP_LIST_REUSE=1", "MVP_LIST_CAP_PER_TILE=1", "MVP_LIST_CAP_MIN=16"),  # most tiles do not fit: mixes both paths
     "bwd_record": ("MVP_BWD_OPAQUE=2",),
     "fwd_arrays": ("MVP_FWD_OPAQUE=0",),
+    "xbuckets": ("MVP_XBUCKETS=1",),                                        # second bucketing level in x
+    "xbuckets_all": ("MVP_XBUCKETS=1", "MVP_LIST_MARGIN=1"),
     "list_margin": ("MVP_LIST_MARGIN=1",),                                  # step intervals from the fp-drift bound
     "list_margin_reuse": ("MVP_LIST_MARGIN=1", "MVP_LIST_REUSE=1"),
 }

@@ -651,6 +651,7 @@ struct Params {
 
 #if defined(MVP_CPU_EMUL) && defined(MVP_EMUL_STATS)
 long long g_emul_list_chunks;   // 32-entry bucket chunks scanned by build_tile_list (forward + backward)
+long long g_emul_bwd_stats[8];  // see render_backward_kernel
 #endif
 
 // Builds the warp's slab list (rank order, at most CAP entries in shared memory), each slab's warp step interval and
@@ -1432,6 +1433,12 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
                 }
                 const int len = lb - la + 1;
                 const int maxlen = __reduce_max_sync(0xffffffffu, len);
+#if defined(MVP_CPU_EMUL) && defined(MVP_EMUL_STATS)
+                // [0] (tile, slab) visits, [1] visits with work, [2] warp steps (sum of maxlen), [3] lane steps inside a lane's
+                // interval, [4] valid lane steps (= samples), [5] batches, [6] position-carry steps
+                if (lane == 0) { std::atomic_ref<long long>(g_emul_bwd_stats[0]).fetch_add(1); if (maxlen > 0) { std::atomic_ref<long long>(g_emul_bwd_stats[1]).fetch_add(1); std::atomic_ref<long long>(g_emul_bwd_stats[2]).fetch_add(maxlen); } }
+                if (maxlen > 0 && len > 0) std::atomic_ref<long long>(g_emul_bwd_stats[3]).fetch_add(len);
+#endif
                 if (maxlen <= 0) continue;
                 const float4 *slab = tpn + (size_t)k * slabsz;
                 float *gslab = gtn + (size_t)k * slabsz * 4;
@@ -1447,6 +1454,9 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
                 {
                     const int adv = (len > 0) ? (la - max(cs, ms)) : 0;
                     const int maxadv = __reduce_max_sync(0xffffffffu, adv);
+#if defined(MVP_CPU_EMUL) && defined(MVP_EMUL_STATS)
+                    if (lane == 0) std::atomic_ref<long long>(g_emul_bwd_stats[6]).fetch_add(maxadv);
+#endif
                     for (int i = 0; i < maxadv; ++i) {
                         if (i < adv) { x = __fmaf_rn(c.ray.dx, p.dt, x); y = __fmaf_rn(c.ray.dy, p.dt, y); z = __fmaf_rn(c.ray.dz, p.dt, z); }
                     }
@@ -1475,10 +1485,16 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
                                 ring[pos] = make_float4(xm, ym, zm, __int_as_float(lane | (issat ? 256 : 0)));
                             }
                             qn += __popc(vm);
+#if defined(MVP_CPU_EMUL) && defined(MVP_EMUL_STATS)
+                            if (lane == 0) std::atomic_ref<long long>(g_emul_bwd_stats[4]).fetch_add(__popc(vm));
+#endif
                             __syncwarp();
                         }
                     }
                     while (qn >= 32 || (flush && qn > 0)) {
+#if defined(MVP_CPU_EMUL) && defined(MVP_EMUL_STATS)
+                        if (lane == 0) std::atomic_ref<long long>(g_emul_bwd_stats[5]).fetch_add(1);
+#endif
                         const int cnt = min(qn, 32);
                         const bool act = lane < cnt;
                         const float4 rec = ring[(qhead + (act ? lane : 0)) & (kRing - 1)];
@@ -1940,6 +1956,9 @@ int mvp_raymarch_backward(const mvp_backward_args *a, void *stream) {
 #if defined(MVP_CPU_EMUL) && defined(MVP_EMUL_STATS)
 void mvp_emul_fwd_stats(long long *out) {
     for (int i = 0; i < 8; ++i) { out[i] = g_emul_fwd_stats[i]; g_emul_fwd_stats[i] = 0; }
+}
+void mvp_emul_bwd_stats(long long *out) {
+    for (int i = 0; i < 8; ++i) { out[i] = g_emul_bwd_stats[i]; g_emul_bwd_stats[i] = 0; }
 }
 long long mvp_emul_list_chunks(void) { const long long v = g_emul_list_chunks; g_emul_list_chunks = 0; return v; }
 #endif

@@ -25,13 +25,17 @@ for tag, defs in VARIANTS:
     kernels.use_variant(defs)
     L = kernels.load()
     t0 = time.time()
-    out, _, _ = kernels.forward_backward(*args)
+    grad = np.random.default_rng(1).standard_normal(args[0].shape[:3] + (4,)).astype(np.float32)
+    out, _, _ = kernels.forward_backward(*args, grad_rayrgba=grad)
     dt = time.time() - t0
     st = (ctypes.c_longlong * 8)()
     L.mvp_emul_fwd_stats(st)
     L.mvp_emul_list_chunks.restype = ctypes.c_longlong
     chunks = L.mvp_emul_list_chunks()
     print("%-9s %6.1fs  " % (tag, dt) + "  ".join("%s=%d" % (n, v) for n, v in zip(NAMES, st)) + "  list_chunks=%d" % chunks)
+    bs = (ctypes.c_longlong * 8)()
+    L.mvp_emul_bwd_stats(bs)
+    print("          backward: " + "  ".join("%s=%d" % (n, v) for n, v in zip(("slab_visits", "visits_with_work", "warp_steps", "lane_steps", "samples", "batches", "carry_steps"), bs)))
     if ref is None:
         ref = out
     else:

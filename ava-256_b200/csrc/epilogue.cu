@@ -17,7 +17,17 @@
 //
 // Compiled WITHOUT -use_fast_math: the bodies use explicit single-rounding intrinsics so the forward results are
 // bit-identical to the eager PyTorch expressions they replace.
+#ifdef MVP_CPU_EMUL   // test-only host build on the CPU emulation (tests/emul/), see mvp_kernels.cu
+#include "cuda_emul.h"
+#define MVP_EPI_LAUNCH(grid, st, ...)              \
+    do {                                           \
+        auto kern_ = MVP_EPI_KERNEL;               \
+        MVP_LAUNCH(kern_, grid, kThreads, 0, st, __VA_ARGS__); \
+    } while (0)
+#else
 #include <cuda_runtime.h>
+#define MVP_EPI_LAUNCH(grid, st, ...) MVP_EPI_KERNEL<<<grid, kThreads, 0, st>>>(__VA_ARGS__)
+#endif
 #include <stdint.h>
 
 #include "epilogue_body.h"
@@ -98,10 +108,18 @@ extern "C" int mvp_composite_forward(int32_t N, int32_t H, int32_t W, const floa
     cudaStream_t st = (cudaStream_t)stream;
     if (vec) {
         dim3 grid((unsigned)((a.HW / 4 + kThreads - 1) / kThreads), N);
-        composite_forward_kernel<4><<<grid, kThreads, 0, st>>>(a);
+        {
+#define MVP_EPI_KERNEL composite_forward_kernel<4>
+        MVP_EPI_LAUNCH(grid, st, a);
+#undef MVP_EPI_KERNEL
+        }
     } else {
         dim3 grid((unsigned)((a.HW + kThreads - 1) / kThreads), N);
-        composite_forward_kernel<1><<<grid, kThreads, 0, st>>>(a);
+        {
+#define MVP_EPI_KERNEL composite_forward_kernel<1>
+        MVP_EPI_LAUNCH(grid, st, a);
+#undef MVP_EPI_KERNEL
+        }
     }
     return finish();
 }
@@ -124,10 +142,18 @@ extern "C" int mvp_composite_backward(int32_t N, int32_t H, int32_t W, const flo
     cudaStream_t st = (cudaStream_t)stream;
     if (vec) {
         dim3 grid((unsigned)((a.HW / 4 + kThreads - 1) / kThreads), N);
-        composite_backward_kernel<4><<<grid, kThreads, 0, st>>>(a, grad_ccw, grad_ccb);
+        {
+#define MVP_EPI_KERNEL composite_backward_kernel<4>
+        MVP_EPI_LAUNCH(grid, st, a, grad_ccw, grad_ccb);
+#undef MVP_EPI_KERNEL
+        }
     } else {
         dim3 grid((unsigned)((a.HW + kThreads - 1) / kThreads), N);
-        composite_backward_kernel<1><<<grid, kThreads, 0, st>>>(a, grad_ccw, grad_ccb);
+        {
+#define MVP_EPI_KERNEL composite_backward_kernel<1>
+        MVP_EPI_LAUNCH(grid, st, a, grad_ccw, grad_ccb);
+#undef MVP_EPI_KERNEL
+        }
     }
     return finish();
 }
@@ -150,14 +176,38 @@ int launch_payload(int32_t N, int32_t hb, int32_t wb, int32_t B, const PayloadAr
     if (total == 0) return MVP_ERR_SHAPE;
     const unsigned grid = (unsigned)((total + kThreads - 1) / kThreads);
     if (vec && B == 8) {
-        if (kBwd) payload_backward_kernel<4, 8><<<grid, kThreads, 0, st>>>(a, total);
-        else payload_forward_kernel<4, 8><<<grid, kThreads, 0, st>>>(a, total);
+        if (kBwd) {
+#define MVP_EPI_KERNEL payload_backward_kernel<4, 8>
+        MVP_EPI_LAUNCH(grid, st, a, total);
+#undef MVP_EPI_KERNEL
+        }
+        else {
+#define MVP_EPI_KERNEL payload_forward_kernel<4, 8>
+        MVP_EPI_LAUNCH(grid, st, a, total);
+#undef MVP_EPI_KERNEL
+        }
     } else if (vec) {
-        if (kBwd) payload_backward_kernel<4, 0><<<grid, kThreads, 0, st>>>(a, total);
-        else payload_forward_kernel<4, 0><<<grid, kThreads, 0, st>>>(a, total);
+        if (kBwd) {
+#define MVP_EPI_KERNEL payload_backward_kernel<4, 0>
+        MVP_EPI_LAUNCH(grid, st, a, total);
+#undef MVP_EPI_KERNEL
+        }
+        else {
+#define MVP_EPI_KERNEL payload_forward_kernel<4, 0>
+        MVP_EPI_LAUNCH(grid, st, a, total);
+#undef MVP_EPI_KERNEL
+        }
     } else {
-        if (kBwd) payload_backward_kernel<1, 0><<<grid, kThreads, 0, st>>>(a, total);
-        else payload_forward_kernel<1, 0><<<grid, kThreads, 0, st>>>(a, total);
+        if (kBwd) {
+#define MVP_EPI_KERNEL payload_backward_kernel<1, 0>
+        MVP_EPI_LAUNCH(grid, st, a, total);
+#undef MVP_EPI_KERNEL
+        }
+        else {
+#define MVP_EPI_KERNEL payload_forward_kernel<1, 0>
+        MVP_EPI_LAUNCH(grid, st, a, total);
+#undef MVP_EPI_KERNEL
+        }
     }
     return finish();
 }

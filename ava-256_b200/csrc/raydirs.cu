@@ -6,7 +6,11 @@
 // Compiled WITHOUT -use_fast_math, like the reference's utils extension (extensions/utils/setup.py has no such flag):
 // IEEE division, rnorm3df for the normalisation.  Pure streaming kernel: 32 B written per ray, no reads to speak of
 // -> HBM-write bound; one thread per ray, x fastest for coalesced 12/12/8-byte stores.
+#ifdef MVP_CPU_EMUL   // test-only host build on the CPU emulation (tests/emul/), see mvp_kernels.cu
+#include "cuda_emul.h"
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 #include "mvpraymarch_b200.h"
@@ -53,9 +57,14 @@ extern "C" int mvp_compute_raydirs(int32_t N, int32_t H, int32_t W, const float 
     if (!viewpos || !viewrot || !focal || !princpt || !raypos || !raydir || !tminmax) return MVP_ERR_NULL;
     if (N < 1 || H < 1 || W < 1 || H > 65535 || N > 65535) return MVP_ERR_SHAPE;
     dim3 grid((W + 255) / 256, H, N);
+#ifdef MVP_CPU_EMUL
+    MVP_LAUNCH(compute_raydirs_kernel, grid, 256, 0, stream, N, H, W, viewpos, viewrot, focal, princpt,
+               reinterpret_cast<const float2 *>(pixelcoords), volradius, raypos, raydir, reinterpret_cast<float2 *>(tminmax));
+#else
     compute_raydirs_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(N, H, W, viewpos, viewrot, focal, princpt,
                                                                   reinterpret_cast<const float2 *>(pixelcoords), volradius, raypos,
                                                                   raydir, reinterpret_cast<float2 *>(tminmax));
+#endif
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? MVP_OK : (int)e;
 }

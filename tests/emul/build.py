@@ -38,6 +38,24 @@ def build_kernels(defines=(), opt="-O1"):
     return lib
 
 
+ALIB = os.path.join(HERE, "libaux_emul.so")
+
+
+def build_aux():
+    """libaux_emul.so: raydirs.cu + epilogue.cu compiled for the host on the CPU emulation."""
+    src = [os.path.join(HERE, "aux_emul.cpp"), os.path.join(HERE, "cuda_emul.cpp")]
+    dep = src + [os.path.join(HERE, "cuda_emul.h"), BODY, os.path.join(ROOT, "ava-256_b200", "csrc", "raydirs.cu"),
+                 os.path.join(ROOT, "ava-256_b200", "csrc", "epilogue.cu"), os.path.join(ROOT, "include", "mvpraymarch_b200.h")]
+    if os.path.exists(ALIB) and all(os.path.getmtime(ALIB) >= os.path.getmtime(f) for f in dep + [__file__]):
+        return ALIB
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-g", "-ffp-contract=off", "-shared", "-fPIC", "-pthread", "-Wno-attributes",
+                           "-Wno-unknown-pragmas", "-I" + cuda_inc, "-I" + HERE, "-I" + os.path.dirname(BODY),
+                           "-I" + os.path.join(ROOT, "include")] + src + ["-o", ALIB])
+    return ALIB
+
+
 if __name__ == "__main__":
     print(build())
     print(build_kernels())
+    print(build_aux())

@@ -143,3 +143,92 @@ def test_kernel_variants_match_the_default_build(kernels, name, variant):
             assert loaded.value + rebuilt.value > 0
             if name == "head_small":
                 assert loaded.value > 0 and rebuilt.value > 0             # tiny workspace: both paths in one launch
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# auxiliary kernels (raydirs.cu, epilogue.cu) on the same emulation: thread -> element mapping, vector paths, block reduction
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def aux():
+    import ctypes
+    from tests.emul.build import build_aux
+    L = ctypes.CDLL(build_aux())
+    P, I, F = ctypes.c_void_p, ctypes.c_int32, ctypes.c_float
+    L.mvp_compute_raydirs.argtypes = [I] * 3 + [P] * 5 + [F] + [P] * 4
+    L.mvp_composite_forward.argtypes = [I] * 3 + [P] * 7
+    L.mvp_composite_backward.argtypes = [I] * 3 + [P] * 10
+    L.mvp_assemble_payload_forward.argtypes = [I] * 4 + [P] * 2 + [F] * 2 + [P] * 2
+    L.mvp_assemble_payload_backward.argtypes = [I] * 4 + [P] * 2 + [F] + [P] * 3
+    return L
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+@pytest.mark.parametrize("with_pixelcoords", [False, True])
+def test_emulated_raydirs_kernel(aux, with_pixelcoords):
+    from ava256_b200 import scene
+    n, H, W = 3, 37, 301                                   # W > 256: two blocks per image row, ragged tail
+    campos, camrot = scene.look_at_cameras(n)
+    campos, camrot = campos.float().contiguous(), camrot.float().contiguous()
+    focal = torch.full((n, 2), scene.FOCAL_FULLRES / (scene.FULLRES_H / H))
+    princpt = torch.tensor([[W / 2.0, H / 2.0]]).expand(n, 2).contiguous()
+    pc = None
+    if with_pixelcoords:
+        py, px = torch.meshgrid(torch.arange(H).float(), torch.arange(W).float(), indexing="ij")
+        pc = torch.stack([px, py], dim=-1)[None].repeat(n, 1, 1, 1).contiguous()
+    rp, rd, tmm = torch.full((n, H, W, 3), float("nan")), torch.full((n, H, W, 3), float("nan")), torch.full((n, H, W, 2), float("nan"))
+    assert aux.mvp_compute_raydirs(n, H, W, _ptr(campos), _ptr(camrot), _ptr(focal), _ptr(princpt), _ptr(pc), scene.VOLRADIUS,
+                                   _ptr(rp), _ptr(rd), _ptr(tmm), None) == 0
+    hp, hd, ht = scene.compute_raydirs_host(campos, camrot, focal, princpt, H, W)
+    assert relerr(rp.numpy(), hp.numpy()) < 1e-6 and relerr(rd.numpy(), hd.numpy()) < 1e-6 and relerr(tmm.numpy(), ht.numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("shape", [(3, 6, 10), (2, 7, 9), (2, 33, 67), (1, 64, 48)])
+@pytest.mark.parametrize("with_cc,with_bg", [(False, False), (True, True)])
+def test_emulated_composite_kernels(aux, shape, with_cc, with_bg):
+    from oracle.epilogue_ref import composite_ref
+    N, H, W = shape
+    g = torch.Generator().manual_seed(H)
+    rayrgba = torch.rand(N, H, W, 4, generator=g)
+    rayrgba[..., :3] *= 255.0
+    ccw = (1.0 + 0.3 * torch.randn(N, 3, generator=g)) if with_cc else None
+    ccb = (5.0 * torch.randn(N, 3, generator=g)) if with_cc else None
+    bg = (255.0 * torch.rand(N, 3, H, W, generator=g)) if with_bg else None
+    g_rgb, g_alpha = torch.randn(N, 3, H, W, generator=g), torch.randn(N, 1, H, W, generator=g)
+    leaves = [None if t is None else t.clone().requires_grad_(True) for t in (rayrgba, ccw, ccb, bg)]
+    ref_rgb, ref_alpha = composite_ref(*leaves)
+    ((ref_rgb * g_rgb).sum() + (ref_alpha * g_alpha).sum()).backward()
+    rgb, alpha = torch.full((N, 3, H, W), float("nan")), torch.full((N, 1, H, W), float("nan"))
+    assert aux.mvp_composite_forward(N, H, W, _ptr(rayrgba), _ptr(ccw), _ptr(ccb), _ptr(bg), _ptr(rgb), _ptr(alpha), None) == 0
+    assert torch.equal(rgb, ref_rgb.detach()) and torch.equal(alpha, ref_alpha.detach())
+    grad_rayrgba = torch.full((N, H, W, 4), float("nan"))
+    grad_ccw = torch.zeros(N, 3) if with_cc else None
+    grad_ccb = torch.zeros(N, 3) if with_cc else None
+    grad_bg = torch.full((N, 3, H, W), float("nan")) if with_bg else None
+    assert aux.mvp_composite_backward(N, H, W, _ptr(rayrgba), _ptr(ccw), _ptr(bg), _ptr(g_rgb), _ptr(g_alpha), _ptr(grad_rayrgba),
+                                      _ptr(grad_ccw), _ptr(grad_ccb), _ptr(grad_bg), None) == 0
+    torch.testing.assert_close(grad_rayrgba, leaves[0].grad, rtol=1e-6, atol=1e-4)
+    if with_cc:
+        torch.testing.assert_close(grad_ccw, leaves[1].grad, rtol=1e-4, atol=1e-1)
+        torch.testing.assert_close(grad_ccb, leaves[2].grad, rtol=1e-4, atol=1e-3)
+    if with_bg:
+        torch.testing.assert_close(grad_bg, leaves[3].grad, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("N,hb,wb,B", [(2, 2, 3, 8), (1, 3, 2, 4), (1, 4, 2, 3), (1, 1, 1, 1), (1, 2, 2, 16), (1, 9, 9, 8)])
+def test_emulated_payload_kernels(aux, N, hb, wb, B):
+    from oracle.epilogue_ref import assemble_payload_ref
+    g = torch.Generator().manual_seed(B)
+    tex = (torch.randn(N, 3 * B, hb * B, wb * B, generator=g) * 4.0 - 2.0).requires_grad_(True)
+    opa = torch.randn(N, B, hb * B, wb * B, generator=g).requires_grad_(True)
+    gt = torch.randn(N, hb * wb, B, B, B, 4, generator=g)
+    ref = assemble_payload_ref(tex, opa, B)
+    (ref * gt).sum().backward()
+    tp = torch.full(tuple(ref.shape), float("nan"))
+    assert aux.mvp_assemble_payload_forward(N, hb, wb, B, _ptr(tex), _ptr(opa), 25.0, 100.0, _ptr(tp), None) == 0
+    assert torch.equal(tp, ref.detach())
+    gtex, gopa = torch.full(tuple(tex.shape), float("nan")), torch.full(tuple(opa.shape), float("nan"))
+    assert aux.mvp_assemble_payload_backward(N, hb, wb, B, _ptr(tp), _ptr(gt), 25.0, _ptr(gtex), _ptr(gopa), None) == 0
+    assert torch.equal(gtex, tex.grad) and torch.equal(gopa, opa.grad)

@@ -24,6 +24,8 @@
 //     issues one atomic per value per (warp, slab); payload gradients go out as 128-bit vector reductions
 //     (red.global.add.v4.f32) instead of 32 scalar atomics per sample.
 //   * The tile row's bucket is staged through shared memory by the TMA engine (cp.async.bulk + mbarrier).
+//   * In gradient mode the forward saves each tile's list and each ray's first step in the workspace; the backward loads
+//     them instead of repeating the bucket scan and the exact slab tests.
 //
 // Arithmetic mirrors the reference's fp32 operation order where a step function of the result exists
 // (transform + strict validity, slab test, lattice snap, saturation); -use_fast_math is on like the reference.

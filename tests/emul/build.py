@@ -27,7 +27,7 @@ KLIB = os.path.join(HERE, "libmvp_emul.so")
 def build_kernels(defines=(), opt="-O1"):
     """libmvp_emul[_<defines>].so: the product kernels' source compiled for the host on the CPU emulation of cuda_emul.h.
     `defines` selects one of the kernels' build-time variants, e.g. ("MVP_LIST_REUSE=1",)."""
-    tag = "".join("_" + d.replace("=", "").replace("MVP_", "").lower() for d in defines)
+    tag = "".join("_" + d.replace("=", "").replace("MVP_", "").lower() for d in defines) + ("" if opt == "-O1" else "_" + opt.strip("-").lower())
     lib = KLIB[:-3] + tag + ".so"
     if os.path.exists(lib) and all(os.path.getmtime(lib) >= os.path.getmtime(f) for f in KDEP + [__file__]):
         return lib

@@ -11,17 +11,20 @@ from tests.emul.build import build_kernels
 
 _LIBS = {}
 _variant = ()
+_opt = "-O1"
 
 
-def use_variant(defines=()):
-    """Select the build-time variant of the kernels (a tuple of -D defines) used by subsequent calls."""
-    global _variant
-    _variant = tuple(defines)
+def use_variant(defines=(), opt="-O1"):
+    """Select the build-time variant of the kernels (a tuple of -D defines) used by subsequent calls; opt="-O0" builds
+    three times faster and is plenty for the small test scenes."""
+    global _variant, _opt
+    _variant, _opt = tuple(defines), opt
 
 
 def load():
-    if _variant not in _LIBS:
-        L = ctypes.CDLL(build_kernels(_variant))
+    key = (_variant, _opt)
+    if key not in _LIBS:
+        L = ctypes.CDLL(build_kernels(_variant, _opt))
         L.mvp_workspace_bytes.restype = ctypes.c_size_t
         L.mvp_workspace_bytes.argtypes = [ctypes.POINTER(_abi.Shape)]
         L.mvp_raymarch_forward.restype = ctypes.c_int
@@ -30,8 +33,8 @@ def load():
         L.mvp_raymarch_backward.argtypes = [ctypes.POINTER(_abi.BackwardArgs), ctypes.c_void_p]
         L.mvp_abi_version.restype = ctypes.c_int
         assert L.mvp_abi_version() == _abi.ABI_VERSION
-        _LIBS[_variant] = L
-    return _LIBS[_variant]
+        _LIBS[key] = L
+    return _LIBS[key]
 
 
 def set_lane_order(mode):

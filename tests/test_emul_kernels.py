@@ -96,7 +96,7 @@ def test_emulated_edge_cases_vs_oracle(kernels, kind, variant):
     s = edge_scene(kind)
     grad = torch.randn(*s["raypos"].shape[:3], 4, generator=torch.Generator().manual_seed(17))
     a, kw = scene_args_np(s)
-    kernels.use_variant(variant)
+    kernels.use_variant(variant, opt="-O0" if variant else "-O1")
     out, _, grads = kernels.forward_backward(*a, grad_rayrgba=grad.numpy(), **kw)
     ref, raysat = oracle.forward(*a, **kw)
     assert np.isfinite(out).all() and relerr(out, ref) <= FWD_TOL
@@ -126,7 +126,7 @@ def test_kernel_variants_match_the_default_build(kernels, name, variant):
     s, grad = build_case(name)
     a, kw = scene_args_np(s)
     out0, sat0, g0 = kernels.forward_backward(*a, grad_rayrgba=grad.numpy(), **kw)
-    kernels.use_variant(VARIANTS[variant])
+    kernels.use_variant(VARIANTS[variant], opt="-O0")
     for order in ("forward", "random"):
         kernels.set_lane_order(order)
         out1, sat1, g1 = kernels.forward_backward(*a, grad_rayrgba=grad.numpy(), **kw)

@@ -1830,6 +1830,19 @@ extern "C" {
 
 int mvp_abi_version(void) { return MVP_ABI_VERSION; }
 
+#define MVP_STR2(x) #x
+#define MVP_STR(x) MVP_STR2(x)
+const char *mvp_build_config(void) {
+    return "FWD_OPAQUE=" MVP_STR(MVP_FWD_OPAQUE) " BWD_OPAQUE=" MVP_STR(MVP_BWD_OPAQUE) " LIST_REUSE=" MVP_STR(MVP_LIST_REUSE)
+           " LIST_MARGIN=" MVP_STR(MVP_LIST_MARGIN) " XBUCKETS=" MVP_STR(MVP_XBUCKETS) " FASTCAP=" MVP_STR(MVP_FASTCAP)
+           " CHUNK=" MVP_STR(MVP_CHUNK) " FWD_MINB=" MVP_STR(MVP_FWD_MINB) " BWD_MINB=" MVP_STR(MVP_BWD_MINB)
+           " WARPS=" MVP_STR(MVP_WARPS) " BLK_TX=" MVP_STR(MVP_BLK_TX)
+#ifdef MVP_CPU_EMUL
+           " CPU_EMUL"
+#endif
+        ;
+}
+
 const char *mvp_error_string(int code) {
     switch (code) {
         case MVP_OK: return "ok";

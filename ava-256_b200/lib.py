@@ -43,9 +43,9 @@ class BackwardArgs(ctypes.Structure):
 
 
 FLAG_ACCEL_VALID = 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 
-EXPORTS = ("mvp_abi_version", "mvp_error_string", "mvp_workspace_bytes", "mvp_build_accel", "mvp_raymarch_forward",
+EXPORTS = ("mvp_abi_version", "mvp_build_config", "mvp_error_string", "mvp_workspace_bytes", "mvp_build_accel", "mvp_raymarch_forward",
            "mvp_raymarch_backward", "mvp_compute_raydirs", "mvp_forward_launch_count", "mvp_backward_launch_count",
            "mvp_composite_forward", "mvp_composite_backward", "mvp_assemble_payload_forward",
            "mvp_assemble_payload_backward")
@@ -65,6 +65,7 @@ def _load():
             raise RuntimeError("mvpraymarch_b200: %s does not export %s" % (path, name))
     lib.mvp_abi_version.restype = ctypes.c_int
     lib.mvp_error_string.restype = ctypes.c_char_p
+    lib.mvp_build_config.restype = ctypes.c_char_p
     lib.mvp_error_string.argtypes = [ctypes.c_int]
     lib.mvp_workspace_bytes.restype = ctypes.c_size_t
     lib.mvp_workspace_bytes.argtypes = [ctypes.POINTER(Shape)]

@@ -367,6 +367,7 @@ def run_ours(args, rank, world):
                                "%d views per rank" % (views, h, w, k, t, nv),
                    "parallelism": "views sharded over %d rank(s), 1 NCCL all-reduce of %.1f MB primitive grads per step" % (world, flat.numel() * 4 / 1e6),
                    "l2": "inputs (%.1f GB template per rank) larger than the 126 MB L2; no explicit flush" % (nv * k * t ** 3 * 16 / 1e9),
+                   "kernel_build": lib.LIB.mvp_build_config().decode(),
                    "scene": {"alpha_mu": ALPHA_MU, "alpha_sigma": ALPHA_SIGMA, "saturated_ray_frac": sat_frac, "covered_ray_frac": cover}},
         "roofline": dominant, "roofline_forward": roof_f, "roofline_backward": roof_b,
         "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,

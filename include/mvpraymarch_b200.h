@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define MVP_ABI_VERSION 3
+#define MVP_ABI_VERSION 4
 
 #define MVP_OK 0
 #define MVP_ERR_NULL (-1)      /* a required pointer is NULL */
@@ -103,6 +103,8 @@ typedef struct mvp_backward_args {
 } mvp_backward_args;
 
 int mvp_abi_version(void);
+/* Build-time knobs of the kernels in this library, e.g. "FWD_OPAQUE=2 LIST_REUSE=1 ..." (for bench / bug reports). */
+const char *mvp_build_config(void);
 const char *mvp_error_string(int code);
 
 /* Bytes of scratch the accel structure + per-call state need for this shape (0 for an invalid shape). */

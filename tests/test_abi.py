@@ -27,7 +27,9 @@ def test_header_symbols_are_exported():
     for n in names:
         assert hasattr(lib.LIB, n), n
     assert sorted(names) == sorted(lib.EXPORTS)
-    assert lib.LIB.mvp_abi_version() == 3
+    assert lib.LIB.mvp_abi_version() == 4
+    cfg = lib.LIB.mvp_build_config().decode()
+    assert "LIST_REUSE=" in cfg and "FWD_OPAQUE=" in cfg and "CPU_EMUL" not in cfg
 
 
 def test_workspace_bytes_and_shape_validation():

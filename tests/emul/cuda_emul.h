@@ -272,8 +272,11 @@ inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 inline float __fdiv_rn(float a, float b) { return a / b; }
-inline int __float2int_rd(float x) { return (int)std::floor(x); }
-inline int __float2int_rn(float x) { return (int)std::nearbyint(x); }
+// cvt.*.s32.f32 saturates and maps NaN to 0
+inline int emul_sat_int(float x) { return x != x ? 0 : x >= 2147483648.f ? 0x7fffffff : x <= -2147483648.f ? (-0x7fffffff - 1) : (int)x; }
+inline int __float2int_rd(float x) { return emul_sat_int(std::floor(x)); }
+inline int __float2int_rn(float x) { return emul_sat_int(std::nearbyint(x)); }
+inline int __float2int_rz(float x) { return emul_sat_int(std::trunc(x)); }
 inline int __float_as_int(float x) { int i; std::memcpy(&i, &x, 4); return i; }
 inline float __int_as_float(int i) { float x; std::memcpy(&x, &i, 4); return x; }
 inline unsigned __float_as_uint(float x) { unsigned i; std::memcpy(&i, &x, 4); return i; }

@@ -85,7 +85,10 @@ typedef struct mvp_forward_args {
 typedef struct mvp_backward_args {
     mvp_shape shape;
     float stepsize, fadescale, fadeexp;
-    uint32_t flags;          /* MVP_FLAG_ACCEL_VALID if `workspace` is the one the forward call filled */
+    uint32_t flags;          /* MVP_FLAG_ACCEL_VALID if `workspace` is the one the forward call filled: besides the accel
+                              * structure it then holds each tile's slab list and each ray's first step as the forward (called
+                              * with raysat != NULL) saved them, and the backward loads them instead of rebuilding; without the
+                              * flag, or for tiles that did not fit, everything is rebuilt from the inputs */
     const float *raypos, *raydir, *tminmax;
     const float *primpos, *primrot, *primscale;
     const float *tplate;

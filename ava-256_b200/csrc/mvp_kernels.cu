@@ -46,6 +46,14 @@
 #include <stdlib.h>
 
 #include "mvpraymarch_b200.h"
+#include <stddef.h>
+
+// C-ABI layout pins (the ctypes mirror in ava-256_b200/lib.py and INTEGRATION.md are checked against the same numbers)
+static_assert(sizeof(mvp_shape) == 28, "mvp_shape layout");
+static_assert(sizeof(mvp_forward_args) == 168 && offsetof(mvp_forward_args, raypos) == 48 && offsetof(mvp_forward_args, workspace_bytes) == 136 &&
+                  offsetof(mvp_forward_args, algo) == 164, "mvp_forward_args layout");
+static_assert(sizeof(mvp_backward_args) == 208 && offsetof(mvp_backward_args, grad_rayrgba) == 104 && offsetof(mvp_backward_args, workspace_bytes) == 168 &&
+                  offsetof(mvp_backward_args, algo) == 204, "mvp_backward_args layout");
 
 // experiment knobs (defaults = measured best)
 #ifndef MVP_BWD_LO_SLACK
@@ -285,23 +293,26 @@ __global__ void __launch_bounds__(kFitThreads) fit_camera_kernel(int H, int W, c
 // 2. per-slab record + pixel rectangle
 //    record (4 x float4): (pos.xyz, s.x) (R row0, s.y) (R row1, s.z) (R row2, 0)
 // ------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) prim_setup_kernel(int N, int K, int H, int W, const float *__restrict__ primpos,
+__global__ void __launch_bounds__(128) prim_setup_kernel(int N, int K, int H, int W, int pview, const float *__restrict__ primpos,
                                                          const float *__restrict__ primrot, const float *__restrict__ primscale,
                                                          const Cam *__restrict__ cam, const int *__restrict__ bad,
                                                          float4 *__restrict__ pack, unsigned *__restrict__ rx, unsigned *__restrict__ ry) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)N * K) return;
     const int n = (int)(i / (size_t)K);
-    const float *pp = primpos + i * 3, *pr = primrot + i * 9, *ps = primscale + i * 3;
+    const size_t ip = pview ? i : i - (size_t)n * K;     // index of the slab in the primitive tensors / record array
+    const float *pp = primpos + ip * 3, *pr = primrot + ip * 9, *ps = primscale + ip * 3;
     float p0 = pp[0], p1 = pp[1], p2 = pp[2];
     float r[9];
 #pragma unroll
     for (int j = 0; j < 9; ++j) r[j] = pr[j];
     float s0 = ps[0], s1 = ps[1], s2 = ps[2];
-    pack[i * 4 + 0] = make_float4(p0, p1, p2, s0);
-    pack[i * 4 + 1] = make_float4(r[0], r[1], r[2], s1);
-    pack[i * 4 + 2] = make_float4(r[3], r[4], r[5], s2);
-    pack[i * 4 + 3] = make_float4(r[6], r[7], r[8], 0.f);
+    if (pview || n == 0) {
+        pack[ip * 4 + 0] = make_float4(p0, p1, p2, s0);
+        pack[ip * 4 + 1] = make_float4(r[0], r[1], r[2], s1);
+        pack[ip * 4 + 2] = make_float4(r[3], r[4], r[5], s2);
+        pack[ip * 4 + 3] = make_float4(r[6], r[7], r[8], 0.f);
+    }
 
     // rectangle: full screen unless the view is a verified pinhole and all 8 corners are on one side of it
     int x0 = 0, x1 = W - 1, y0 = 0, y1 = H - 1;
@@ -614,6 +625,7 @@ struct TileCtx {
 
 struct Params {
     int N, H, W, K, TD, TH, TW;
+    int pview;                    // 1: primitive tensors are per view [N,K,...]; 0: one set [1,K,...] shared by all views
     float dt, fadescale, fadeexp;
     const float *raypos, *raydir, *tminmax;
     const float *tplate;
@@ -635,7 +647,8 @@ struct Params {
     int2 *listbuf;                // per view `listcap` entries (slab index, packed step interval)
     int *listcur;                 // per view bump cursor
     int *rayj0;                   // per ray: first lattice step, or kNoHitJ0
-    int listcap;
+    int listcap;                  // entries of storage per view (stride of listbuf)
+    int listlimit;                // entries the forward may use (= listcap; smaller only under MVP_FLAG_TEST_TINY_LISTS)
 #endif
     // forward outputs
     float *rayrgba, *raysat;
@@ -695,7 +708,7 @@ __device__ __forceinline__ bool build_tile_list(const Params &p, float rdt, int 
     const float eps0 = fmaxf(0.001953125f, nsteps * 4.7683716e-7f);
 #endif
 
-    const float4 *packn = p.pack + (size_t)n * p.K * 4;
+    const float4 *packn = p.pack + (size_t)(n * p.pview) * p.K * 4;
     const int cnt = p.rowcnt[(size_t)n * p.R + ty];
     const bool overflow = cnt > p.rowcap;
 #if MVP_XBUCKETS
@@ -806,7 +819,7 @@ __device__ __forceinline__ bool build_tile_list(const Params &p, float rdt, int 
     // TMA bulk prefetch (cp.async.bulk.prefetch.L2): pull the payload slabs this tile is about to sample into L2 while
     // the lattice set-up runs; one lane per slab, fire and forget.
     if (kPrefetch && p.slab_bytes >= 16) {
-        const char *tp = reinterpret_cast<const char *>(p.tplate) + (size_t)n * p.K * p.slab_bytes;
+        const char *tp = reinterpret_cast<const char *>(p.tplate) + (size_t)(n * p.pview) * p.K * p.slab_bytes;
         for (int i = lane; i < nl; i += 32) {
             const char *a = tp + (size_t)s_k[i] * p.slab_bytes;
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(p.slab_bytes) : "memory");
@@ -841,7 +854,7 @@ __device__ __forceinline__ void save_tile_list(const Params &p, int n, int tx, i
     int base = 0;
     if (lane == 0 && nl > 0) base = atomicAdd(p.listcur + n, nl);
     base = __shfl_sync(0xffffffffu, base, 0);
-    const bool ok = base + nl <= p.listcap;
+    const bool ok = base + nl <= p.listlimit;
     if (ok) {
         int2 *dst = p.listbuf + (size_t)n * p.listcap + base;
         for (int i = lane; i < nl; i += 32) dst[i] = make_int2(s_k[i], s_iv[i]);
@@ -1083,9 +1096,9 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
     if (nl > 0) MVP_STAT(5, 1);
 #endif
     const int nwords = (nl + 31) >> 5;
-    const float4 *packn = p.pack + (size_t)n * p.K * 4;
+    const float4 *packn = p.pack + (size_t)(n * p.pview) * p.K * 4;
     const size_t slabsz = (size_t)p.TD * p.TH * p.TW;
-    const float4 *tpn = reinterpret_cast<const float4 *>(p.tplate) + (size_t)n * p.K * slabsz;
+    const float4 *tpn = reinterpret_cast<const float4 *>(p.tplate) + (size_t)(n * p.pview) * p.K * slabsz;
     const int kstart = dfs_kstart(p.K);
 #if MVP_FWD_OPAQUE == 1
     // Under the register cap the compiler rematerialises these two base addresses (S2R/LDC/IMAD chains, ~13 of the
@@ -1124,7 +1137,7 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
         float4 sres = make_float4(0.f, 0.f, 0.f, 0.f);
         if (act) {
             const int kk = sk[(__float_as_int(rec.w) >> 5) & 1023];
-            if (kWarp) sres = sample_slab_warped(tpn + (size_t)kk * slabsz, p.warp + ((size_t)n * p.K + kk) * ((size_t)p.WD * p.WH * p.WW * 3), rec.x, rec.y, rec.z, p);
+            if (kWarp) sres = sample_slab_warped(tpn + (size_t)kk * slabsz, p.warp + ((size_t)(n * p.pview) * p.K + kk) * ((size_t)p.WD * p.WH * p.WW * 3), rec.x, rec.y, rec.z, p);
             else sres = sample_slab<T>(tpn + (size_t)kk * slabsz, rec.x, rec.y, rec.z, p.TD, p.TH, p.TW, p.fadescale, p.fadeexp);
         }
         __syncwarp();
@@ -1367,11 +1380,11 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
     const int wfirst = __reduce_min_sync(0xffffffffu, ms);
     if (wlast < wfirst || wfirst >= kBig) { if (CAP < kMaxHit) MVP_GRIDDEP_WAIT(); return; }
 
-    const float4 *packn = p.pack + (size_t)n * p.K * 4;
+    const float4 *packn = p.pack + (size_t)(n * p.pview) * p.K * 4;
     const size_t slabsz = (size_t)p.TD * p.TH * p.TW;
-    const float4 *tpn = reinterpret_cast<const float4 *>(p.tplate) + (size_t)n * p.K * slabsz;
-    float *gtn = p.g_tplate + (size_t)n * p.K * slabsz * 4;
-    float *gpn = p.g_primpos + (size_t)n * p.K * 3, *grn = p.g_primrot + (size_t)n * p.K * 9, *gsn = p.g_primscale + (size_t)n * p.K * 3;
+    const float4 *tpn = reinterpret_cast<const float4 *>(p.tplate) + (size_t)(n * p.pview) * p.K * slabsz;
+    float *gtn = p.g_tplate + (size_t)(n * p.pview) * p.K * slabsz * 4;
+    float *gpn = p.g_primpos + (size_t)(n * p.pview) * p.K * 3, *grn = p.g_primrot + (size_t)(n * p.pview) * p.K * 9, *gsn = p.g_primscale + (size_t)(n * p.pview) * p.K * 3;
     const int td = T > 0 ? T : p.TD, th = T > 0 ? T : p.TH, tw = T > 0 ? T : p.TW;
     const float gmx = (float)(tw - 1) * 0.5f, gmy = (float)(th - 1) * 0.5f, gmz = (float)(td - 1) * 0.5f;
     const int sx = tw > 1 ? 1 : 0, sy = th > 1 ? tw : 0, sz = td > 1 ? th * tw : 0;
@@ -1585,8 +1598,8 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
                         } else {
                         // ---- algo 1 (PrimSamplerTW<true>): payload sampled at the warp-field-displaced position ----
                         const size_t wsl = (size_t)p.WD * p.WH * p.WW * 3;
-                        const float *wk = p.warp + ((size_t)n * p.K + k) * wsl;
-                        float *gwk = p.g_warp + ((size_t)n * p.K + k) * wsl;
+                        const float *wk = p.warp + ((size_t)(n * p.pview) * p.K + k) * wsl;
+                        float *gwk = p.g_warp + ((size_t)(n * p.pview) * p.K + k) * wsl;
                         const float e1 = p.fadeexp - 1.f;
                         const float pw0 = __powf(fabsf(y0), e1), pw1 = __powf(fabsf(y1), e1), pw2 = __powf(fabsf(y2), e1);
                         const float fade = __expf(-p.fadescale * (pw0 * fabsf(y0) + pw1 * fabsf(y1) + pw2 * fabsf(y2)));
@@ -1750,7 +1763,7 @@ int check_shape(const mvp_shape &s) {
     return MVP_OK;
 }
 
-int launch_accel(const mvp_shape &s, const float *raypos, const float *raydir, const float *primpos, const float *primrot,
+int launch_accel(const mvp_shape &s, int pview, const float *raypos, const float *raydir, const float *primpos, const float *primrot,
                  const float *primscale, char *ws, const Layout &L, cudaStream_t st) {
     Cam *cam = reinterpret_cast<Cam *>(ws + L.cam);
     int *bad = reinterpret_cast<int *>(ws + L.bad);
@@ -1766,7 +1779,7 @@ int launch_accel(const mvp_shape &s, const float *raypos, const float *raydir, c
 #ifdef MVP_CPU_EMUL
     MVP_LAUNCH(fit_camera_kernel, gfit, kFitThreads, 0, st, s.H, s.W, raypos, raydir, cam, bad);
     const size_t NK = (size_t)s.N * s.K;
-    MVP_LAUNCH(prim_setup_kernel, (unsigned)((NK + 127) / 128), 128, 0, st, s.N, s.K, s.H, s.W, primpos, primrot, primscale, cam, bad,
+    MVP_LAUNCH(prim_setup_kernel, (unsigned)((NK + 127) / 128), 128, 0, st, s.N, s.K, s.H, s.W, pview, primpos, primrot, primscale, cam, bad,
                reinterpret_cast<float4 *>(ws + L.pack), reinterpret_cast<unsigned *>(ws + L.rx), reinterpret_cast<unsigned *>(ws + L.ry));
     const int TXn = (s.W + kTileW - 1) / kTileW;
     MVP_LAUNCH(row_lists_kernel, dim3(L.R, s.N), kRowThreads, (size_t)TXn * sizeof(int), st, s.K, L.R, L.rowcap, TXn, kFastCap,
@@ -1780,7 +1793,7 @@ int launch_accel(const mvp_shape &s, const float *raypos, const float *raydir, c
     fit_camera_kernel<<<gfit, kFitThreads, 0, st>>>(s.H, s.W, raypos, raydir, cam, bad);
     const size_t NK = (size_t)s.N * s.K;
     prim_setup_kernel<<<(unsigned)((NK + 127) / 128), 128, 0, st>>>(
-        s.N, s.K, s.H, s.W, primpos, primrot, primscale, cam, bad, reinterpret_cast<float4 *>(ws + L.pack),
+        s.N, s.K, s.H, s.W, pview, primpos, primrot, primscale, cam, bad, reinterpret_cast<float4 *>(ws + L.pack),
         reinterpret_cast<unsigned *>(ws + L.rx), reinterpret_cast<unsigned *>(ws + L.ry));
     const int TXn = (s.W + kTileW - 1) / kTileW;
     row_lists_kernel<<<dim3(L.R, s.N), kRowThreads, (size_t)TXn * sizeof(int), st>>>(
@@ -1821,6 +1834,7 @@ void fill_params(Params &p, const mvp_shape &s, float stepsize, float fadescale,
     p.listcur = reinterpret_cast<int *>(ws + L.listcur);
     p.rayj0 = reinterpret_cast<int *>(ws + L.rayj0);
     p.listcap = L.listcap;
+    p.listlimit = L.listcap;
 #endif
 }
 
@@ -1851,7 +1865,8 @@ const char *mvp_error_string(int code) {
         case MVP_ERR_STEPSIZE: return "stepsize must be finite and > 0";
         case MVP_ERR_WORKSPACE: return "workspace too small or not 256-byte aligned";
         case MVP_ERR_ALGO: return "unsupported algo";
-        case MVP_ERR_ALIGN: return "channels-last buffer is not 16-byte aligned";
+        case MVP_ERR_ALIGN: return "misaligned buffer (tplate/rayrgba/grad_rayrgba/grad_tplate/rayaux: 16 bytes, tminmax: 8, others: 4)";
+        case MVP_ERR_STRUCT: return "args->struct_size does not match this library's argument struct (ABI mismatch)";
         default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
     }
 }
@@ -1861,21 +1876,40 @@ size_t mvp_workspace_bytes(const mvp_shape *shape) {
     return make_layout(*shape).total;
 }
 
-int mvp_build_accel(const mvp_shape *shape, const float *raypos, const float *raydir, const float *primpos,
+int mvp_build_accel(const mvp_shape *shape, uint32_t flags, const float *raypos, const float *raydir, const float *primpos,
                     const float *primrot, const float *primscale, void *workspace, size_t workspace_bytes, void *stream) {
     if (!shape || !raypos || !raydir || !primpos || !primrot || !primscale || !workspace) return MVP_ERR_NULL;
     int rc = check_shape(*shape);
     if (rc != MVP_OK) return rc;
     const Layout L = make_layout(*shape);
     if (workspace_bytes < L.total || ((uintptr_t)workspace & 255)) return MVP_ERR_WORKSPACE;
-    return launch_accel(*shape, raypos, raydir, primpos, primrot, primscale, (char *)workspace, L, (cudaStream_t)stream);
+    return launch_accel(*shape, (flags & MVP_FLAG_SHARED_PRIMS) ? 0 : 1, raypos, raydir, primpos, primrot, primscale, (char *)workspace, L,
+                        (cudaStream_t)stream);
+}
+
+int mvp_debug_saved_tiles(const mvp_shape *shape, const void *host_workspace_copy, int *saved, int *not_saved) {
+    if (!shape || !host_workspace_copy || !saved || !not_saved || check_shape(*shape) != MVP_OK) return MVP_ERR_NULL;
+    *saved = *not_saved = 0;
+#if MVP_LIST_REUSE
+    const Layout L = make_layout(*shape);
+    const size_t tiles = (size_t)shape->N * ((shape->H + kTileH - 1) / kTileH) * ((shape->W + kTileW - 1) / kTileW);
+    const int2 *hdr = reinterpret_cast<const int2 *>((const char *)host_workspace_copy + L.tilehdr);
+    for (size_t i = 0; i < tiles; ++i) {
+        if (hdr[i].y > 0) ++*saved;
+        else if (hdr[i].y < 0) ++*not_saved;
+    }
+#endif
+    return MVP_OK;
 }
 
 int mvp_forward_launch_count(uint32_t flags) { return (flags & MVP_FLAG_ACCEL_VALID) ? 2 : 5; }
 int mvp_backward_launch_count(uint32_t flags) { return (flags & MVP_FLAG_ACCEL_VALID) ? 2 : 5; }
 
+static inline bool misaligned(const void *p, uintptr_t a) { return p && ((uintptr_t)p & (a - 1)); }
+
 int mvp_raymarch_forward(const mvp_forward_args *a, void *stream) {
     if (!a) return MVP_ERR_NULL;
+    if (a->struct_size != sizeof(mvp_forward_args)) return MVP_ERR_STRUCT;
     if (!a->raypos || !a->raydir || !a->tminmax || !a->primpos || !a->primrot || !a->primscale || !a->tplate || !a->rayrgba ||
         !a->workspace)
         return MVP_ERR_NULL;
@@ -1887,14 +1921,24 @@ int mvp_raymarch_forward(const mvp_forward_args *a, void *stream) {
     if (!(a->stepsize > 0.f) || !(a->stepsize < 3.0e38f)) return MVP_ERR_STEPSIZE;
     const Layout L = make_layout(a->shape);
     if (a->workspace_bytes < L.total || ((uintptr_t)a->workspace & 255)) return MVP_ERR_WORKSPACE;
+    // vector accesses: float4 (tplate, rayrgba), int4 (rayaux), float2 (tminmax); everything else is read as scalars
+    if (misaligned(a->tplate, 16) || misaligned(a->rayrgba, 16) || misaligned(a->rayaux, 16) || misaligned(a->tminmax, 8) ||
+        misaligned(a->raypos, 4) || misaligned(a->raydir, 4) || misaligned(a->primpos, 4) || misaligned(a->primrot, 4) ||
+        misaligned(a->primscale, 4) || misaligned(a->raysat, 4) || misaligned(a->warp, 4))
+        return MVP_ERR_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
     char *ws = (char *)a->workspace;
+    const int pview = (a->flags & MVP_FLAG_SHARED_PRIMS) ? 0 : 1;
     if (!(a->flags & MVP_FLAG_ACCEL_VALID)) {
-        rc = launch_accel(a->shape, a->raypos, a->raydir, a->primpos, a->primrot, a->primscale, ws, L, st);
+        rc = launch_accel(a->shape, pview, a->raypos, a->raydir, a->primpos, a->primrot, a->primscale, ws, L, st);
         if (rc != MVP_OK) return rc;
     }
     Params p{};
     fill_params(p, a->shape, a->stepsize, a->fadescale, a->fadeexp, ws, L);
+    p.pview = pview;
+#if MVP_LIST_REUSE
+    if (a->flags & MVP_FLAG_TEST_TINY_LISTS) p.listlimit = p.listcap < 16 ? p.listcap : 16;
+#endif
     p.raypos = a->raypos; p.raydir = a->raydir; p.tminmax = a->tminmax; p.tplate = a->tplate;
     p.rayrgba = a->rayrgba; p.raysat = a->raysat; p.rayaux = reinterpret_cast<int4 *>(a->rayaux);
     p.warp = a->warp; p.WD = a->WD; p.WH = a->WH; p.WW = a->WW;
@@ -1928,6 +1972,7 @@ int mvp_raymarch_forward(const mvp_forward_args *a, void *stream) {
 
 int mvp_raymarch_backward(const mvp_backward_args *a, void *stream) {
     if (!a) return MVP_ERR_NULL;
+    if (a->struct_size != sizeof(mvp_backward_args)) return MVP_ERR_STRUCT;
     if (!a->raypos || !a->raydir || !a->tminmax || !a->primpos || !a->primrot || !a->primscale || !a->tplate ||
         !a->grad_rayrgba || !a->raysat || !a->rayaux || !a->grad_primpos || !a->grad_primrot || !a->grad_primscale ||
         !a->grad_tplate || !a->workspace)
@@ -1939,14 +1984,30 @@ int mvp_raymarch_backward(const mvp_backward_args *a, void *stream) {
     if (!(a->stepsize > 0.f) || !(a->stepsize < 3.0e38f)) return MVP_ERR_STEPSIZE;
     const Layout L = make_layout(a->shape);
     if (a->workspace_bytes < L.total || ((uintptr_t)a->workspace & 255)) return MVP_ERR_WORKSPACE;
+    if (misaligned(a->tplate, 16) || misaligned(a->grad_tplate, 16) || misaligned(a->grad_rayrgba, 16) || misaligned(a->rayaux, 16) ||
+        misaligned(a->tminmax, 8) || misaligned(a->raypos, 4) || misaligned(a->raydir, 4) || misaligned(a->primpos, 4) ||
+        misaligned(a->primrot, 4) || misaligned(a->primscale, 4) || misaligned(a->raysat, 4) || misaligned(a->grad_primpos, 4) ||
+        misaligned(a->grad_primrot, 4) || misaligned(a->grad_primscale, 4) || misaligned(a->warp, 4) || misaligned(a->grad_warp, 4))
+        return MVP_ERR_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
     char *ws = (char *)a->workspace;
+    const int pview = (a->flags & MVP_FLAG_SHARED_PRIMS) ? 0 : 1;
     if (!(a->flags & MVP_FLAG_ACCEL_VALID)) {
-        rc = launch_accel(a->shape, a->raypos, a->raydir, a->primpos, a->primrot, a->primscale, ws, L, st);
+        rc = launch_accel(a->shape, pview, a->raypos, a->raydir, a->primpos, a->primrot, a->primscale, ws, L, st);
         if (rc != MVP_OK) return rc;
+    }
+    if (a->flags & MVP_FLAG_ZERO_GRADS) {
+        const size_t nk = (size_t)(pview ? a->shape.N : 1) * a->shape.K;
+        cudaError_t z = cudaMemsetAsync(a->grad_primpos, 0, nk * 3 * sizeof(float), st);
+        if (z == cudaSuccess) z = cudaMemsetAsync(a->grad_primrot, 0, nk * 9 * sizeof(float), st);
+        if (z == cudaSuccess) z = cudaMemsetAsync(a->grad_primscale, 0, nk * 3 * sizeof(float), st);
+        if (z == cudaSuccess) z = cudaMemsetAsync(a->grad_tplate, 0, nk * a->shape.TD * a->shape.TH * a->shape.TW * 4 * sizeof(float), st);
+        if (z == cudaSuccess && a->algo == 1) z = cudaMemsetAsync(a->grad_warp, 0, nk * a->WD * a->WH * a->WW * 3 * sizeof(float), st);
+        if (z != cudaSuccess) return (int)z;
     }
     Params p{};
     fill_params(p, a->shape, a->stepsize, a->fadescale, a->fadeexp, ws, L);
+    p.pview = pview;
     p.raypos = a->raypos; p.raydir = a->raydir; p.tminmax = a->tminmax; p.tplate = a->tplate;
     p.grad_rayrgba = a->grad_rayrgba; p.raysat_in = a->raysat; p.rayaux_in = reinterpret_cast<const int4 *>(a->rayaux);
     p.g_primpos = a->grad_primpos; p.g_primrot = a->grad_primrot; p.g_primscale = a->grad_primscale; p.g_tplate = a->grad_tplate;

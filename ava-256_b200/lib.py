@@ -13,7 +13,9 @@ class Shape(ctypes.Structure):
 
 
 class ForwardArgs(ctypes.Structure):
+    """struct mvp_forward_args; the constructor fills struct_size."""
     _fields_ = [
+        ("struct_size", ctypes.c_uint32),
         ("shape", Shape),
         ("stepsize", ctypes.c_float), ("fadescale", ctypes.c_float), ("fadeexp", ctypes.c_float),
         ("flags", ctypes.c_uint32),
@@ -27,7 +29,9 @@ class ForwardArgs(ctypes.Structure):
 
 
 class BackwardArgs(ctypes.Structure):
+    """struct mvp_backward_args; the constructor fills struct_size."""
     _fields_ = [
+        ("struct_size", ctypes.c_uint32),
         ("shape", Shape),
         ("stepsize", ctypes.c_float), ("fadescale", ctypes.c_float), ("fadeexp", ctypes.c_float),
         ("flags", ctypes.c_uint32),
@@ -42,23 +46,42 @@ class BackwardArgs(ctypes.Structure):
     ]
 
 
+def _sized_init(cls):
+    def __init__(self, *a, **kw):
+        ctypes.Structure.__init__(self, *a, **kw)
+        self.struct_size = ctypes.sizeof(cls)
+    cls.__init__ = __init__
+
+
+_sized_init(ForwardArgs)
+_sized_init(BackwardArgs)
+
 FLAG_ACCEL_VALID = 1
-ABI_VERSION = 4
+FLAG_ZERO_GRADS = 2
+FLAG_SHARED_PRIMS = 4
+FLAG_TEST_TINY_LISTS = 0x100
+ABI_VERSION = 5
+# layout pins, equal to the static_asserts in csrc/mvp_kernels.cu (tests/test_abi.py compares)
+SIZEOF = {"Shape": 28, "ForwardArgs": 168, "BackwardArgs": 208}
 
 EXPORTS = ("mvp_abi_version", "mvp_build_config", "mvp_error_string", "mvp_workspace_bytes", "mvp_build_accel", "mvp_raymarch_forward",
            "mvp_raymarch_backward", "mvp_compute_raydirs", "mvp_forward_launch_count", "mvp_backward_launch_count",
            "mvp_composite_forward", "mvp_composite_backward", "mvp_assemble_payload_forward",
-           "mvp_assemble_payload_backward")
+           "mvp_assemble_payload_backward", "mvp_debug_saved_tiles")
 
 
 def _load():
     path = _build.LIB
     if _build.needs_build():
         try:
-            _build.build()
-        except Exception as e:  # nvcc missing on the GPU box is fine as long as a prebuilt .so travelled with the repo
-            if not os.path.exists(path):
-                raise RuntimeError("mvpraymarch_b200: CUDA library missing and could not be built: %r" % (e,))
+            _build.build()         # serialised across processes by a file lock, installed atomically (build.py)
+        except Exception as e:
+            # A prebuilt .so that travelled with the repo is acceptable only where it cannot be rebuilt (no nvcc on the
+            # box); a failed compile of newer sources must not silently fall back to a stale library.
+            if not os.path.exists(path) or _build.have_nvcc():
+                raise RuntimeError("mvpraymarch_b200: CUDA library is missing or stale and could not be built: %r" % (e,))
+            import warnings
+            warnings.warn("mvpraymarch_b200: sources are newer than %s but nvcc is not available; loading the prebuilt library" % path)
     lib = ctypes.CDLL(path)
     for name in EXPORTS:
         if not hasattr(lib, name):
@@ -70,7 +93,7 @@ def _load():
     lib.mvp_workspace_bytes.restype = ctypes.c_size_t
     lib.mvp_workspace_bytes.argtypes = [ctypes.POINTER(Shape)]
     lib.mvp_build_accel.restype = ctypes.c_int
-    lib.mvp_build_accel.argtypes = [ctypes.POINTER(Shape)] + [c_f] * 6 + [ctypes.c_size_t, c_f]
+    lib.mvp_build_accel.argtypes = [ctypes.POINTER(Shape), ctypes.c_uint32] + [c_f] * 6 + [ctypes.c_size_t, c_f]
     lib.mvp_raymarch_forward.restype = ctypes.c_int
     lib.mvp_raymarch_forward.argtypes = [ctypes.POINTER(ForwardArgs), c_f]
     lib.mvp_raymarch_backward.restype = ctypes.c_int
@@ -90,7 +113,9 @@ def _load():
     lib.mvp_backward_launch_count.restype = ctypes.c_int
     lib.mvp_backward_launch_count.argtypes = [ctypes.c_uint32]
     if lib.mvp_abi_version() != ABI_VERSION:
-        raise RuntimeError("mvpraymarch_b200: ABI version mismatch")
+        raise RuntimeError("mvpraymarch_b200: ABI version mismatch (library %d, binding %d)" % (lib.mvp_abi_version(), ABI_VERSION))
+    for cls in (Shape, ForwardArgs, BackwardArgs):
+        assert ctypes.sizeof(cls) == SIZEOF[cls.__name__], cls.__name__
     return lib
 
 

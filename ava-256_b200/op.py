@@ -22,6 +22,14 @@ def _ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
+def _aligned(t, nbytes):
+    """The kernels read channels-last buffers with 128-bit accesses (C-ABI: MVP_ERR_ALIGN).  A contiguous view into a
+    larger buffer can start anywhere; such a tensor is copied once to a fresh (256-byte aligned) allocation."""
+    if t is not None and t.data_ptr() % nbytes:
+        return t.clone()
+    return t
+
+
 def _check_f32_cuda(name, t):
     if not t.is_cuda:
         raise RuntimeError("%s must be a CUDA tensor" % name)          # mvpraymarch.cpp:102
@@ -69,6 +77,19 @@ class MVPRaymarch(Function):
         K = primpos.size(1)
         TD, TH, TW = template.shape[2:5]
         dev = raypos.device
+        # The reference never checks that the leading dimensions agree (a mismatch reads out of bounds there).  Here:
+        # rays and tminmax must agree; the primitive tensors must agree with each other and have a batch of N, or of 1
+        # = one set of primitives shared by all N views (extension, SURVEY.md section 8e "optional fast path":
+        # nothing is replicated in HBM and the gradients of all views accumulate into the one set).
+        assert raydir.shape[:3] == (N, H, W) and tminmax.shape[:3] == (N, H, W), "raypos / raydir / tminmax disagree on [N,H,W]"
+        NP = primpos.size(0)
+        assert NP in (N, 1), "primitive batch (%d) must equal the number of views (%d) or be 1 (shared)" % (NP, N)
+        assert primrot.shape[:2] == (NP, K) and primscale.shape[:2] == (NP, K) and template.shape[:2] == (NP, K), \
+            "primpos / primrot / primscale / template disagree on [N,K]"
+        if warp is not None:
+            assert warp.shape[:2] == (NP, K), "warp disagrees with the primitives on [N,K]"
+        shared = NP == 1 and N > 1
+        template, tminmax = _aligned(template, 16), _aligned(tminmax, 8)
         with torch.cuda.device(dev):
             wsbytes = _lib.workspace_bytes(N, H, W, K, TD, TH, TW)
             workspace = torch.empty(wsbytes, dtype=torch.uint8, device=dev)
@@ -81,7 +102,7 @@ class MVPRaymarch(Function):
             a = _lib.ForwardArgs()
             a.shape = _lib.Shape(N, H, W, K, TD, TH, TW)
             a.stepsize, a.fadescale, a.fadeexp = float(stepsize), float(options["fadescale"]), float(options["fadeexp"])
-            a.flags = 0
+            a.flags = _lib.FLAG_SHARED_PRIMS if shared else 0
             a.raypos, a.raydir, a.tminmax = _ptr(raypos), _ptr(raydir), _ptr(tminmax)
             a.primpos, a.primrot, a.primscale = _ptr(primpos), _ptr(primrot), _ptr(primscale)
             a.tplate = _ptr(template)
@@ -98,6 +119,7 @@ class MVPRaymarch(Function):
             ctx.save_for_backward(raypos, raydir, tminmax, primpos, primrot, primscale, template, raysat, rayaux, workspace, warp)
             ctx.options = options
             ctx.stepsize = float(stepsize)
+            ctx.shared = shared
         return rayrgba
 
     @staticmethod
@@ -109,17 +131,20 @@ class MVPRaymarch(Function):
         TD, TH, TW = template.shape[2:5]
         dev = raypos.device
         with torch.cuda.device(dev):
-            grad_rayrgba = grad_rayrgba.contiguous()                   # mvpraymarch.py:264
-            grad_primpos = torch.zeros_like(primpos)                   # mvpraymarch.py:240-246
-            grad_primrot = torch.zeros_like(primrot)
-            grad_primscale = torch.zeros_like(primscale)
-            grad_template = torch.zeros_like(template)
-            grad_warp = torch.zeros_like(warp) if warp is not None else None     # mvpraymarch.py:246
+            grad_rayrgba = _aligned(grad_rayrgba.contiguous(), 16)     # mvpraymarch.py:264
+            # mvpraymarch.py:240-246 zeros_like's these; here the library zero-fills them on the stream (MVP_FLAG_ZERO_GRADS)
+            grad_primpos = torch.empty_like(primpos)
+            grad_primrot = torch.empty_like(primrot)
+            grad_primscale = torch.empty_like(primscale)
+            grad_template = torch.empty_like(template)
             usewarp = options["algo"] == 1
+            grad_warp = None
+            if warp is not None:                                       # mvpraymarch.py:246 (zero when algo 0 ignores it)
+                grad_warp = torch.empty_like(warp) if usewarp else torch.zeros_like(warp)
             a = _lib.BackwardArgs()
             a.shape = _lib.Shape(N, H, W, K, TD, TH, TW)
             a.stepsize, a.fadescale, a.fadeexp = ctx.stepsize, float(options["fadescale"]), float(options["fadeexp"])
-            a.flags = _lib.FLAG_ACCEL_VALID
+            a.flags = _lib.FLAG_ACCEL_VALID | _lib.FLAG_ZERO_GRADS | (_lib.FLAG_SHARED_PRIMS if ctx.shared else 0)
             a.raypos, a.raydir, a.tminmax = _ptr(raypos), _ptr(raydir), _ptr(tminmax)
             a.primpos, a.primrot, a.primscale = _ptr(primpos), _ptr(primrot), _ptr(primscale)
             a.tplate = _ptr(template)

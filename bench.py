@@ -103,15 +103,14 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------
 # reference arm: the reference's own CPU autograd path (mvpraymarch.py:567-633 restated in oracle/torch_ref.py)
 # ----------------------------------------------------------------------------------------------------------------
-def cpu_autograd_sample(side=96, k=64, t=8, steps=1, warmup=0):
+def cpu_autograd_sample(hh=96, ww=64, k=64, t=8, steps=1, warmup=0):
     """Bounded sample of the same kind of workload (head scene, dome camera) on the host cores.
     Returns (MP/s fwd+bwd, seconds per step, description)."""
     from ava256_b200 import scene
     from oracle import torch_ref
     # the loop is ~10^4 small ATen ops: beyond ~16 threads the fork/join cost dominates and it gets slower
     torch.set_num_threads(min(os.cpu_count() or 1, 16))
-    s = scene.make_scene(1, side, side * 2 // 3, k, t, alpha_mu=ALPHA_MU, alpha_sigma=ALPHA_SIGMA)
-    hh, ww = s["raypos"].shape[1:3]
+    s = scene.make_scene(1, hh, ww, k, t, alpha_mu=ALPHA_MU, alpha_sigma=ALPHA_SIGMA)
     stepsize = 2.0 / 16.0          # SURVEY 8d: keeps the autograd graph at ~16 steps
     g = torch.randn(1, hh, ww, 4, generator=torch.Generator().manual_seed(1))
     times = []
@@ -126,7 +125,18 @@ def cpu_autograd_sample(side=96, k=64, t=8, steps=1, warmup=0):
     return hh * ww / sec / 1e6, sec, desc
 
 
+def workload_config(views, h, w, k, t):
+    """`config` of the JSON line: names the workload only, so that both arms (ours, --impl reference) print the same dict."""
+    return {"workload": "C3: %d views %dx%d, K=%d, %d^3 RGBA, dt=1/256, one subject (template materialised per view), "
+                        "fwd+bwd of the mvpraymarch op" % (views, h, w, k, t),
+            "views": views, "height": h, "width": w, "prims": k, "voxels": t,
+            "l2": "inputs (%.1f GB template) larger than the 126 MB L2; no explicit flush" % (views * k * t ** 3 * 16 / 1e9)}
+
+
 def run_reference(args, rank):
+    """The reference's own CPU implementation of the path (its PyTorch autograd loop) on the host cores.  Every step is a
+    BOUNDED SAMPLE of the workload -- a reduced C1 (1 view 96x64, K=64, 8^3, 16 steps per ray): true C1 (128x128, K=256) takes
+    ~40 s per step and runs once in the default arm's `cpu_baseline` leg instead."""
     if rank != 0:
         return
     mps, sec, desc = cpu_autograd_sample(steps=args.steps, warmup=args.warmup)
@@ -135,13 +145,104 @@ def run_reference(args, rank):
         "impl": "reference", "metric": "rendered MP/s (fwd+bwd)", "value": mps, "unit": "MP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C3: %d views %dx%d, K=%d, %d^3 RGBA (reference arm: bounded CPU sample of it)" % (VIEWS, H, W, K, T),
-                   "parallelism": "cpu threads"},
-        "cpu_baseline": {"value": mps, "unit": "MP/s", "cores": cores, "kind": "port", "sample": desc},
+        "config": workload_config(args.views, args.height, args.width, args.prims, args.voxels),
+        "sample": "reduced C1: " + desc,
+        "cpu_baseline": {"value": mps, "unit": "MP/s", "cores": cores, "kind": "port", "sample": "reduced C1: " + desc},
         "e2e": {"value": mps, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# checker legs of our arm (rank 0, N=1): the UNMODIFIED reference CUDA extension (oracle/_ref, prebuilt) on the same scene
+# ----------------------------------------------------------------------------------------------------------------
+def ref_cuda_leg(s, stepsize, grad_out, out, grads, chunk=16, reps=5, warm=2):
+    """Times the reference kernels (compiled for sm_100 from the reference's sources by oracle/build_ref.py) on the tensors
+    the timed region just used, and compares view 0.  The reference launches on legacy stream 0 (= torch's default stream)
+    and cudaMalloc/cudaFree's inside compute_aabb (bvh.cu:261-293), so every call is bracketed by device-wide syncs;
+    views go in chunks (its int32 strides overflow at N*K*T^3*4 >= 2^31, primsampler.h:31-36).  Returns
+    (ref_cuda_baseline dict, parity_check dict) or (None, None) when the extension did not travel to this box."""
+    from tests import refext
+    if not refext.available():
+        return None, None
+    m = refext.module()
+    names = ("primpos", "primrot", "primscale", "template")
+    nv = s["raypos"].shape[0]
+    hh, ww = s["raypos"].shape[1:3]
+    k = s["primpos"].shape[1]
+    dev = s["raypos"].device
+    slab = s["template"][0, 0].numel()
+    chunk = max(1, min(chunk, nv, (2 ** 31 - 1) // (k * slab)))
+    bounds = [(i, min(i + chunk, nv)) for i in range(0, nv, chunk)]
+    tree = refext._tree(chunk, k, dev)
+    aabb = torch.empty((chunk, 2 * k - 1, 2, 3), device=dev)
+    rgba = torch.empty((chunk, hh, ww, 4), device=dev)
+    rsat = torch.empty((chunk, hh, ww, 3), device=dev)
+    gbuf = [torch.empty_like(s[n][:chunk]) for n in names]
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    def one_pass(keep_first=False):
+        tf = tb = 0.0
+        first = None
+        for (a0, a1) in bounds:
+            c = a1 - a0
+            v = {n: s[n][a0:a1] for n in ("raypos", "raydir", "tminmax") + names}
+            so, nc, na = tree[0][:c], tree[1][:c], tree[2][:c]
+            rsat[:c].fill_(-1.0)                                   # mvpraymarch.py:147-148 (not timed: torch glue)
+            for g_ in gbuf:
+                g_[:c].zero_()                                     # mvpraymarch.py:240-246 (not timed)
+            torch.cuda.synchronize()
+            e0, e1, e2 = ev(), ev(), ev()
+            e0.record()
+            m.compute_aabb(v["primpos"], v["primrot"], v["primscale"], so, nc, na, aabb[:c], 0)
+            m.raymarch_forward(v["raypos"], v["raydir"], stepsize, v["tminmax"], so, nc, aabb[:c], v["primpos"], v["primrot"],
+                               v["primscale"], v["template"], None, rgba[:c], rsat[:c], None, 0, False, 512, True, True, 8.0, 8.0,
+                               0, 0.0, 3, 8, 16)
+            e1.record()
+            m.raymarch_backward(v["raypos"], v["raydir"], stepsize, v["tminmax"], so, nc, aabb[:c], v["primpos"], gbuf[0][:c],
+                                v["primrot"], gbuf[1][:c], v["primscale"], gbuf[2][:c], v["template"], gbuf[3][:c], None, None,
+                                rgba[:c], grad_out[a0:a1], rsat[:c], None, 0, False, 512, True, True, 8.0, 8.0, 0, 0.0, 3, 8, 16)
+            e2.record()
+            torch.cuda.synchronize()
+            tf += e0.elapsed_time(e1)
+            tb += e1.elapsed_time(e2)
+            if keep_first and first is None:
+                first = (rgba[0].clone(), rsat[0].clone(), [g_[0].clone() for g_ in gbuf])
+        return tf, tb, first
+
+    first = None
+    for i in range(warm):
+        _, _, f_ = one_pass(keep_first=(i == 0))
+        first = first or f_
+    tfs, tbs = [], []
+    for _ in range(reps):
+        tf, tb, _ = one_pass()
+        tfs.append(tf)
+        tbs.append(tb)
+    tfs.sort()
+    tbs.sort()
+    fwd, bwd = tfs[len(tfs) // 2] / nv, tbs[len(tbs) // 2] / nv
+    base = {"what": "unmodified reference CUDA extension (oracle/_ref, -arch=sm_100 -use_fast_math), same scene and tensors, "
+                    "%d views in chunks of %d, compute_aabb + raymarch_forward / raymarch_backward kernels only "
+                    "(its torch allocations and zero-fills not timed), median of %d passes after %d warm-ups" % (nv, chunk, reps, warm),
+            "fwd_ms_per_view": fwd, "bwd_ms_per_view": bwd, "mps": hh * ww / ((fwd + bwd) * 1e-3) / 1e6,
+            "fwd_ms_per_view_minmax": [tfs[0] / nv, tfs[-1] / nv], "bwd_ms_per_view_minmax": [tbs[0] / nv, tbs[-1] / nv]}
+
+    def rel(a, b):
+        return float((a - b).abs().max()) / max(float(b.abs().max()), 1e-30)
+
+    r_rgba, r_sat, r_g = first
+    check = {"against": "reference CUDA extension (oracle/_ref), view 0 of the timed tensors",
+             "fwd": rel(out[0], r_rgba),
+             "satmask_mismatch_frac": float(((r_sat[..., 0] > -1.0) != (out[0][..., 3] >= 1.0)).float().mean()),
+             "saturated_frac": float((r_sat[..., 0] > -1.0).float().mean()),
+             "grads": {n: rel(g_[0], r_) for n, g_, r_ in zip(names, grads, r_g)},
+             "gates": {"fwd": 1e-4, "satmask_mismatch_frac": 1e-4, "grads": 1e-3}}
+    check["ok"] = bool(check["fwd"] <= 1e-4 and check["satmask_mismatch_frac"] <= 1e-4 and all(v <= 1e-3 for v in check["grads"].values()))
+    return base, check
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -165,6 +266,7 @@ def run_ours(args, rank, world):
     grad_out = torch.randn(nv, h, w, 4, device=dev, generator=gen)
     leaves = [s[n].requires_grad_(True) for n in ("primpos", "primrot", "primscale", "template")]
     flat = torch.zeros(k * t ** 3 * 4 + k * 15, device=dev)     # all-reduced primitive gradients of the subject
+    flat_numel = flat.numel()
 
     def barrier():
         if world > 1:
@@ -249,6 +351,15 @@ def run_ours(args, rank, world):
     bwd_ms = time_kernel(lambda: lib.check(lib.LIB.mvp_raymarch_backward(ctypes.byref(ba), stream)), reps)
     del gs, ws
     log("kernel-only: fwd %.2f ms, bwd %.2f ms per launch (%d views)" % (fwd_ms, bwd_ms, nv))
+
+    # ---- checker legs (rank 0, single GPU): reference CUDA kernels on the same tensors: timing + parity of view 0 ----
+    ref_cuda = parity = None
+    if world == 1 and not args.no_check:
+        ref_cuda, parity = ref_cuda_leg(s, stepsize, grad_out, out.detach(), [x.grad for x in leaves])
+        if ref_cuda is not None:
+            log("reference CUDA kernels: fwd %.3f / bwd %.3f ms per view; parity ok=%s" % (ref_cuda["fwd_ms_per_view"], ref_cuda["bwd_ms_per_view"], parity["ok"]))
+        else:
+            log("reference CUDA extension (oracle/_ref) not on this box: no ref_cuda_baseline / parity_check")
 
     # ---- end-to-end through the public op with HOST buffers (pinned): H2D of the step's inputs, D2H of the results ----
     # The host hands over, every step: the rays of all views, one subject's primitives/payload and the image
@@ -343,34 +454,36 @@ def run_ours(args, rank, world):
     roof_b = {"kernel": "render_backward_kernel", "bound": "hbm", "achieved": bwd_gbs, "peak": peak, "unit": "GB/s",
               "frac": bwd_gbs / peak, "traffic": None, "ms_per_launch": bwd_ms, "algorithmic_bytes_per_launch": bb,
               "peak_source": peak_src}
-    # traffic (dram bytes per launch) comes from the committed ncu capture of the same kernels, if present
+    # traffic (dram bytes per launch): NOT measured in this run (ncu cannot run inside a timed bench); it is the per-view
+    # figure of the committed `ncu --set full` capture named in profiles/traffic.json, valid only for the kernel build it
+    # names -- reported with its source, or null when the capture is of another build / shape.
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):
         with open(tr) as f:
             tj = json.load(f)
+        same_build = tj.get("kernel_build") == lib.LIB.mvp_build_config().decode()
         for r_ in (roof_f, roof_b):
             per_view = tj.get(r_["kernel"], {}).get("dram_bytes_per_view")
-            if per_view and (h, w, k, t) == tuple(tj.get("shape", ())):
+            if per_view and (h, w, k, t) == tuple(tj.get("shape", ())) and same_build:
                 r_["traffic"] = per_view * nv
-    cpu_mps, cpu_sec, cpu_desc = (None, None, None)
+                r_["traffic_source"] = "committed ncu capture %s (per view x %d views), not this run" % (tj.get("source", "profiles/traffic.json"), nv)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cpu_mps, cpu_sec, cpu_desc = cpu_autograd_sample(steps=1, warmup=0)
-        cpu = {"value": cpu_mps, "unit": "MP/s", "cores": torch.get_num_threads(), "kind": "port", "sample": cpu_desc,
+        # SURVEY 8d / BASELINE.json config 1: true C1 (1 x 128x128, K=256, 8^3, ~16 steps per ray), once
+        cpu_mps, cpu_sec, cpu_desc = cpu_autograd_sample(128, 128, 256, 8, steps=1, warmup=0)
+        cpu = {"value": cpu_mps, "unit": "MP/s", "cores": torch.get_num_threads(), "kind": "port", "sample": "C1: " + cpu_desc + ", 1 step",
                "seconds_per_sample_step": cpu_sec}
     dominant = roof_b if bwd_ms >= fwd_ms else roof_f
     line = {
         "metric": "rendered MP/s (fwd+bwd)", "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C3: %d views %dx%d, K=%d, %d^3 RGBA, dt=1/256, one subject (template materialised per view); "
-                               "%d views per rank" % (views, h, w, k, t, nv),
-                   "parallelism": "views sharded over %d rank(s), 1 NCCL all-reduce of %.1f MB primitive grads per step" % (world, flat.numel() * 4 / 1e6),
-                   "l2": "inputs (%.1f GB template per rank) larger than the 126 MB L2; no explicit flush" % (nv * k * t ** 3 * 16 / 1e9),
-                   "kernel_build": lib.LIB.mvp_build_config().decode(),
-                   "scene": {"alpha_mu": ALPHA_MU, "alpha_sigma": ALPHA_SIGMA, "saturated_ray_frac": sat_frac, "covered_ray_frac": cover}},
+        "config": workload_config(views, h, w, k, t),
+        "parallelism": "views sharded over %d rank(s) (%d per rank), 1 NCCL all-reduce of %.1f MB primitive grads per step" % (world, nv, flat_numel * 4 / 1e6),
+        "kernel_build": lib.LIB.mvp_build_config().decode(),
+        "scene": {"alpha_mu": ALPHA_MU, "alpha_sigma": ALPHA_SIGMA, "saturated_ray_frac": sat_frac, "covered_ray_frac": cover},
         "roofline": dominant, "roofline_forward": roof_f, "roofline_backward": roof_b,
-        "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+        "cpu_baseline": cpu, "ref_cuda_baseline": ref_cuda, "parity_check": parity, "e2e": e2e, "clocks": clocks,
         "gpu_launches": args.steps * (lib.LIB.mvp_forward_launch_count(0) + lib.LIB.mvp_backward_launch_count(lib.FLAG_ACCEL_VALID)),
         "kernel_ms": {"forward_all_views_per_rank": fwd_ms, "backward_all_views_per_rank": bwd_ms},
     }
@@ -391,6 +504,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-chunk", type=int, default=8, help="views per pipelined chunk in the e2e measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-check", action="store_true", help="skip the reference-CUDA legs (ref_cuda_baseline, parity_check)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     rank = int(os.environ.get("RANK", 0))

@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define MVP_ABI_VERSION 4
+#define MVP_ABI_VERSION 5
 
 #define MVP_OK 0
 #define MVP_ERR_NULL (-1)      /* a required pointer is NULL */
@@ -54,7 +54,9 @@ extern "C" {
 #define MVP_ERR_STEPSIZE (-3)  /* stepsize must be finite and > 0 */
 #define MVP_ERR_WORKSPACE (-4) /* workspace too small or misaligned (256 B) */
 #define MVP_ERR_ALGO (-5)      /* algo must be 0 (no warp field) or 1 (warp field, primsampler.h:53-58) */
-#define MVP_ERR_ALIGN (-6)     /* a channels-last (float4-accessed) buffer is not 16-byte aligned */
+#define MVP_ERR_ALIGN (-6)     /* a vector-accessed buffer is misaligned: tplate, rayrgba, grad_rayrgba, grad_tplate, rayaux
+                                * need 16 bytes, tminmax 8, everything else 4 */
+#define MVP_ERR_STRUCT (-7)    /* args->struct_size != sizeof(the struct this library was built with) */
 
 typedef struct mvp_shape {
     int32_t N, H, W, K, TD, TH, TW;
@@ -62,8 +64,17 @@ typedef struct mvp_shape {
 
 /* flags */
 #define MVP_FLAG_ACCEL_VALID 1u /* workspace already holds the accel structure of these primitives+rays */
+#define MVP_FLAG_ZERO_GRADS 2u  /* backward only: the library zero-fills the gradient buffers on `stream` before it
+                                 * accumulates into them (replaces the caller's zeros_like of mvpraymarch.py:240-246) */
+#define MVP_FLAG_SHARED_PRIMS 4u /* primpos/primrot/primscale/tplate/warp (and their gradients) have a batch dimension of
+                                 * ONE that all N views share: [1,K,...] instead of [N,K,...] (SURVEY.md section 8e
+                                 * "optional fast path"); gradients of all views accumulate into the one set.  Must be the
+                                 * same in mvp_build_accel / forward / backward calls that share a workspace. */
+#define MVP_FLAG_TEST_TINY_LISTS 0x100u /* test hook: forward keeps at most 16 saved tile-list entries per view, so almost
+                                 * every tile takes the backward's rebuild path */
 
 typedef struct mvp_forward_args {
+    uint32_t struct_size;    /* = sizeof(mvp_forward_args); a truncated or stale caller-side struct is rejected */
     mvp_shape shape;
     float stepsize, fadescale, fadeexp;
     uint32_t flags;
@@ -83,6 +94,7 @@ typedef struct mvp_forward_args {
 } mvp_forward_args;
 
 typedef struct mvp_backward_args {
+    uint32_t struct_size;    /* = sizeof(mvp_backward_args) */
     mvp_shape shape;
     float stepsize, fadescale, fadeexp;
     uint32_t flags;          /* MVP_FLAG_ACCEL_VALID if `workspace` is the one the forward call filled: besides the accel
@@ -95,8 +107,8 @@ typedef struct mvp_backward_args {
     const float *grad_rayrgba; /* [N,H,W,4] */
     const float *raysat;       /* from forward */
     const int32_t *rayaux;     /* from forward */
-    float *grad_primpos, *grad_primrot, *grad_primscale; /* out, accumulated into: caller zero-fills */
-    float *grad_tplate;        /* out, accumulated into: caller zero-fills */
+    float *grad_primpos, *grad_primrot, *grad_primscale; /* out, accumulated into: caller zero-fills (or MVP_FLAG_ZERO_GRADS) */
+    float *grad_tplate;        /* out, accumulated into: caller zero-fills (or MVP_FLAG_ZERO_GRADS) */
     void *workspace;
     size_t workspace_bytes;
     const float *warp;         /* algo 1 only */
@@ -114,7 +126,7 @@ const char *mvp_error_string(int code);
 size_t mvp_workspace_bytes(const mvp_shape *shape);
 
 /* Build the acceleration structure (camera fit, primitive records, screen rectangles, tile-row lists). */
-int mvp_build_accel(const mvp_shape *shape, const float *raypos, const float *raydir,
+int mvp_build_accel(const mvp_shape *shape, uint32_t flags, const float *raypos, const float *raydir,
                     const float *primpos, const float *primrot, const float *primscale,
                     void *workspace, size_t workspace_bytes, void *stream);
 
@@ -151,6 +163,11 @@ int mvp_assemble_payload_forward(int32_t N, int32_t hb, int32_t wb, int32_t B, c
 /* Adjoint: grad_tex / grad_opacity (same shapes as tex / opacity) are written; `tplate` is the forward output (relu mask). */
 int mvp_assemble_payload_backward(int32_t N, int32_t hb, int32_t wb, int32_t B, const float *tplate, const float *grad_tplate,
                                   float rgb_scale, float *grad_tex, float *grad_opacity, void *stream);
+
+/* Test / diagnostics helper (host only, no device work): given a HOST copy of a workspace that a gradient-mode forward
+ * has filled, counts the tiles whose slab list the forward saved for the backward (`saved`, lists with >= 1 entry) and the
+ * tiles it had to mark not-saved because the list storage was full (`not_saved`; the backward rebuilds those). */
+int mvp_debug_saved_tiles(const mvp_shape *shape, const void *host_workspace_copy, int *saved, int *not_saved);
 
 /* Number of kernels the last forward / backward call of this shape launches (for bench.py's gpu_launches). */
 int mvp_forward_launch_count(uint32_t flags);

@@ -57,7 +57,7 @@ def _f32(a):
 
 
 def forward_backward(raypos, raydir, stepsize, tminmax, primpos, primrot, primscale, template, grad_rayrgba=None, warp=None,
-                     fadescale=8.0, fadeexp=8.0):
+                     fadescale=8.0, fadeexp=8.0, fwd_flags=0, bwd_flags=0):
     """Runs the emulated forward (and, when grad_rayrgba is given, backward) kernels.
     Returns (rayrgba, raysat, grads) with grads = [primpos, primrot, primscale, template(, warp)] or None."""
     L = load()
@@ -76,7 +76,7 @@ def forward_backward(raypos, raydir, stepsize, tminmax, primpos, primrot, primsc
     rayaux = np.zeros((N, H, W, 4), np.int32) if want_grad else None
     a = _abi.ForwardArgs()
     a.shape = shape
-    a.stepsize, a.fadescale, a.fadeexp, a.flags = float(stepsize), float(fadescale), float(fadeexp), 0
+    a.stepsize, a.fadescale, a.fadeexp, a.flags = float(stepsize), float(fadescale), float(fadeexp), fwd_flags
     a.raypos, a.raydir, a.tminmax = _p(raypos), _p(raydir), _p(tminmax)
     a.primpos, a.primrot, a.primscale, a.tplate = _p(primpos), _p(primrot), _p(primscale), _p(template)
     a.rayrgba, a.raysat, a.rayaux = _p(rayrgba), _p(raysat), _p(rayaux)
@@ -90,11 +90,12 @@ def forward_backward(raypos, raydir, stepsize, tminmax, primpos, primrot, primsc
     if not want_grad:
         return rayrgba, None, None
     grad_rayrgba = _f32(grad_rayrgba)
-    grads = [np.zeros_like(x) for x in (primpos, primrot, primscale, template)]
-    gwarp = np.zeros_like(warp) if warp is not None else None
+    fill = np.nan if (bwd_flags & _abi.FLAG_ZERO_GRADS) else 0.0           # ZERO_GRADS: the library must overwrite the NaNs
+    grads = [np.full_like(x, fill) for x in (primpos, primrot, primscale, template)]
+    gwarp = np.full_like(warp, fill) if warp is not None else None
     b = _abi.BackwardArgs()
     b.shape = shape
-    b.stepsize, b.fadescale, b.fadeexp, b.flags = float(stepsize), float(fadescale), float(fadeexp), _abi.FLAG_ACCEL_VALID
+    b.stepsize, b.fadescale, b.fadeexp, b.flags = float(stepsize), float(fadescale), float(fadeexp), _abi.FLAG_ACCEL_VALID | bwd_flags
     b.raypos, b.raydir, b.tminmax = _p(raypos), _p(raydir), _p(tminmax)
     b.primpos, b.primrot, b.primscale, b.tplate = _p(primpos), _p(primrot), _p(primscale), _p(template)
     b.grad_rayrgba, b.raysat, b.rayaux = _p(grad_rayrgba), _p(raysat), _p(rayaux)

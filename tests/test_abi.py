@@ -27,9 +27,45 @@ def test_header_symbols_are_exported():
     for n in names:
         assert hasattr(lib.LIB, n), n
     assert sorted(names) == sorted(lib.EXPORTS)
-    assert lib.LIB.mvp_abi_version() == 4
+    assert lib.LIB.mvp_abi_version() == 5
     cfg = lib.LIB.mvp_build_config().decode()
     assert "LIST_REUSE=" in cfg and "FWD_OPAQUE=" in cfg and "CPU_EMUL" not in cfg
+
+
+def test_c_program_through_the_header_alone(tmp_path):
+    """A plain C program (tests/cabi/abi_probe.c) compiled against include/mvpraymarch_b200.h only: dlopen, every symbol
+    it needs, struct sizes, the workspace query and the argument-error paths, with no Python in between.  The sizes it
+    prints must be the ones the ctypes mirror (ava-256_b200/lib.py) and INTEGRATION.md use."""
+    import subprocess
+    from ava256_b200 import lib
+    from ava256_b200 import build as _build
+    exe = str(tmp_path / "abi_probe")
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cabi", "abi_probe.c"), "-o", exe, "-ldl"])
+    out = subprocess.run([exe, _build.LIB], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    facts = dict(line.split(" ", 1) for line in out.stdout.strip().splitlines())
+    assert facts["ok"] == "1" and int(facts["abi"]) == lib.ABI_VERSION
+    assert int(facts["sizeof_shape"]) == ctypes.sizeof(lib.Shape) == lib.SIZEOF["Shape"]
+    assert int(facts["sizeof_forward_args"]) == ctypes.sizeof(lib.ForwardArgs) == lib.SIZEOF["ForwardArgs"]
+    assert int(facts["sizeof_backward_args"]) == ctypes.sizeof(lib.BackwardArgs) == lib.SIZEOF["BackwardArgs"]
+    assert int(facts["workspace_bytes_c3"]) == lib.workspace_bytes(80, 1024, 667, 16384, 8, 8, 8)
+    # the stub printed in INTEGRATION.md states the same struct size
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    assert "ctypes.sizeof(ForwardArgs) == %d" % lib.SIZEOF["ForwardArgs"] in doc
+    for field in ("struct_size", "workspace_bytes", '"warp"', '"WD"', '"WH"', '"WW"', '"algo"'):
+        assert field in doc, field
+
+
+def test_truncated_argument_struct_is_rejected():
+    from ava256_b200 import lib
+    a = lib.ForwardArgs()
+    assert a.struct_size == ctypes.sizeof(lib.ForwardArgs)
+    a.struct_size -= 24                                                         # what an ABI-v4 caller would pass
+    assert lib.LIB.mvp_raymarch_forward(ctypes.byref(a), None) == -7          # MVP_ERR_STRUCT
+    b = lib.BackwardArgs()
+    b.struct_size = 0
+    assert lib.LIB.mvp_raymarch_backward(ctypes.byref(b), None) == -7
 
 
 def test_workspace_bytes_and_shape_validation():

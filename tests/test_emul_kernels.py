@@ -145,6 +145,54 @@ def test_kernel_variants_match_the_default_build(kernels, name, variant):
                 assert loaded.value > 0 and rebuilt.value > 0             # tiny workspace: both paths in one launch
 
 
+def test_emulated_runtime_flags(kernels):
+    """C-ABI flags of the product library on the emulation: MVP_FLAG_TEST_TINY_LISTS (almost every tile takes the backward's
+    rebuild path), MVP_FLAG_ZERO_GRADS (the library zero-fills NaN-initialised gradient buffers)."""
+    import ctypes
+    from ava256_b200 import lib
+    s, grad = build_case("head_small")
+    a, kw = scene_args_np(s)
+    out0, sat0, g0 = kernels.forward_backward(*a, grad_rayrgba=grad.numpy(), **kw)
+    loaded, rebuilt = ctypes.c_int(), ctypes.c_int()
+    kernels.load().mvp_emul_saved_list_tiles(ctypes.byref(loaded), ctypes.byref(rebuilt))
+    assert loaded.value > 0 and rebuilt.value == 0
+    out1, sat1, g1 = kernels.forward_backward(*a, grad_rayrgba=grad.numpy(), fwd_flags=lib.FLAG_TEST_TINY_LISTS,
+                                              bwd_flags=lib.FLAG_ZERO_GRADS, **kw)
+    kernels.load().mvp_emul_saved_list_tiles(ctypes.byref(loaded), ctypes.byref(rebuilt))
+    assert rebuilt.value > loaded.value > 0
+    assert np.array_equal(out0, out1) and np.array_equal(sat0, sat1)
+    for x, y in zip(g0, g1):
+        assert np.isfinite(y).all() and relerr(x, y) <= 1e-5
+
+
+@pytest.mark.parametrize("name", ["head_small", "warp_head"])
+def test_emulated_shared_primitives(kernels, name):
+    """MVP_FLAG_SHARED_PRIMS: one [1,K,...] set of primitives rendered by all views == materialised per-view copies, with
+    the gradients of all views accumulated into the one set."""
+    from ava256_b200 import lib
+    s, grad = build_case(name)
+    N = 3
+    from ava256_b200 import scene
+    H, W = s["raypos"].shape[1:3]
+    rp, rd, tmm = scene.make_rays(N, H, W, view_offset=2)
+    one = {k: s[k][:1].numpy() for k in ("primpos", "primrot", "primscale", "template")}
+    rep = {k: np.repeat(v, N, axis=0) for k, v in one.items()}
+    warp1 = s["warp"][:1].numpy() if "warp" in s else None
+    g = torch.randn(N, H, W, 4, generator=torch.Generator().manual_seed(2)).numpy()
+    kw = dict(fadescale=s["fadescale"], fadeexp=s["fadeexp"])
+    out_m, sat_m, g_m = kernels.forward_backward(rp.numpy(), rd.numpy(), s["stepsize"], tmm.numpy(), rep["primpos"], rep["primrot"],
+                                                 rep["primscale"], rep["template"], grad_rayrgba=g,
+                                                 warp=None if warp1 is None else np.repeat(warp1, N, axis=0), **kw)
+    out_s, sat_s, g_s = kernels.forward_backward(rp.numpy(), rd.numpy(), s["stepsize"], tmm.numpy(), one["primpos"], one["primrot"],
+                                                 one["primscale"], one["template"], grad_rayrgba=g, warp=warp1,
+                                                 fwd_flags=lib.FLAG_SHARED_PRIMS, bwd_flags=lib.FLAG_SHARED_PRIMS | lib.FLAG_ZERO_GRADS, **kw)
+    assert float(out_m[..., 3].max()) > 0.05
+    assert np.array_equal(out_m, out_s) and np.array_equal(sat_m, sat_s)
+    for x, y in zip(g_m, g_s):
+        assert y.shape[0] == 1
+        assert relerr(y, x.sum(axis=0, keepdims=True)) <= 1e-5
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # auxiliary kernels (raydirs.cu, epilogue.cu) on the same emulation: thread -> element mapping, vector paths, block reduction
 # ------------------------------------------------------------------------------------------------------------------

@@ -72,18 +72,14 @@ constexpr int kTileH = 4;
 #ifndef MVP_BLK_TX
 #define MVP_BLK_TX 2
 #endif
-#ifndef MVP_FWD_OPAQUE
-#define MVP_FWD_OPAQUE 2   // forward: per-warp shared state in one record behind a pinned base address (0 = separate arrays,
-                           // 1 = pinned list base only).  Measured on B200: 2.77 vs 2.89 ms per 8 views (-4.4 %)
-#endif
 #ifndef MVP_XBUCKETS
-#define MVP_XBUCKETS 0   // 1: second bucketing level in x (groups of 8 tile columns): a tile scans ~45 instead of ~350 bucket
-                          // entries (-80 % of the chunk scans, ~7 % of the forward's instructions); not yet measured on the GPU
+#define MVP_XBUCKETS 1   // 1: second bucketing level in x (groups of 8 tile columns): a tile scans ~45 instead of ~350 bucket
+                          // entries (-80 % of the chunk scans).  Measured on B200 (round 2): forward 2.68 vs 2.80 ms per 8 views
 #endif
 #ifndef MVP_LIST_MARGIN
-#define MVP_LIST_MARGIN 0   // 1: step intervals of the tile lists from a bound on the fp drift of the marched positions instead of a
-                            // whole step of slack on each side: -26 % forward events, forward 2.66 vs 2.76 ms per 8 views on B200; off until
-                            // the zero-scale fix (NaN margin) has been re-run on a GPU
+#define MVP_LIST_MARGIN 1   // 1: step intervals of the tile lists from a bound on the fp drift of the marched positions instead of a
+                            // whole step of slack on each side: -26 % forward events.  Measured on B200 (round 2, with the zero-scale fix, all
+                            // GPU tests green): forward 2.70 vs 2.80, backward 3.47 vs 3.69 ms per 8 views; both knobs: 2.59 / 3.46
 #endif
 #ifndef MVP_LIST_CAP_MIN
 #define MVP_LIST_CAP_MIN 4096
@@ -94,9 +90,6 @@ constexpr int kTileH = 4;
 #ifndef MVP_LIST_REUSE
 #define MVP_LIST_REUSE 1   // the forward (gradient mode) saves each tile's slab list and each ray's first step, the backward loads
                            // them instead of rebuilding.  Measured on B200: backward 3.44 vs 4.23 ms per 8 views (-19 %)
-#endif
-#ifndef MVP_BWD_OPAQUE
-#define MVP_BWD_OPAQUE 0   // 2: same for the backward kernel -- measured SLOWER (4.43 vs 4.23 ms per 8 views), so off
 #endif
 #ifndef MVP_WARPS
 #define MVP_WARPS 4
@@ -112,6 +105,15 @@ constexpr int kRing = 64;        // sample queue / ring per warp (forward and ba
 #endif
 #ifndef MVP_FASTCAP
 #define MVP_FASTCAP 256
+#endif
+#ifndef MVP_FWD_ASYNC
+#define MVP_FWD_ASYNC 0   // 1: the forward's batch gathers go through cp.async (LDGSTS) into a per-warp staging area and are consumed one
+                          // batch later, so their L1/L2-miss latency overlaps the marching of the next batch instead of stalling the warp
+#endif
+#ifndef MVP_PF_CELL
+#define MVP_PF_CELL 0   // software prefetch of a queued sample's voxel cell at ENQUEUE time, so that the batch's corner gathers hit
+                        // (the gathers' L1/L2 misses are the top stall of both render kernels): 1 = L1 prefetch of the cell's 4
+                        // x-rows, 2 = of all 8 corners, 3 / 4 = the same into L2 only
 #endif
 #if MVP_XBUCKETS
 constexpr int kGrpTiles = 8;       // tile columns per x-group
@@ -136,7 +138,7 @@ struct Cam {          // 64 B per view
 struct __align__(8) RowEntry { int k; unsigned xr; };   // xr = x0 | x1 << 16  (pixels, inclusive)
 
 struct Layout {
-    size_t cam, bad, pack, rx, ry, rowcnt, rowlist, tileflag, total;
+    size_t cam, bad, pack, rx, ry, rowcnt, rowlist, tileflag, heavycnt, heavylist, total;
     int R, rowcap;
 #if MVP_XBUCKETS
     size_t grphdr, grplist;
@@ -163,6 +165,8 @@ __host__ inline Layout make_layout(const mvp_shape &s) {
     L.rowcnt = off;  off = align256(off + (size_t)s.N * L.R * 4);
     L.rowlist = off; off = align256(off + (size_t)s.N * L.R * L.rowcap * sizeof(RowEntry));
     L.tileflag = off; off = align256(off + (size_t)s.N * ((s.H + kTileH - 1) / kTileH) * ((s.W + kTileW - 1) / kTileW));
+    L.heavycnt = off; off = align256(off + sizeof(int));
+    L.heavylist = off; off = align256(off + (size_t)s.N * ((s.H + kTileH - 1) / kTileH) * ((s.W + kTileW - 1) / kTileW) * sizeof(int));
 #if MVP_XBUCKETS
     L.NG = ((s.W + kTileW - 1) / kTileW + kGrpTiles - 1) / kGrpTiles;
     L.grphdr = off;  off = align256(off + (size_t)s.N * L.R * L.NG * sizeof(int2));
@@ -359,7 +363,8 @@ constexpr int kRowThreads = 256;
 __global__ void __launch_bounds__(kRowThreads) row_lists_kernel(int K, int R, int rowcap, int TXn, int fastcap,
                                                                 const unsigned *__restrict__ rx, const unsigned *__restrict__ ry,
                                                                 int *__restrict__ rowcnt, RowEntry *__restrict__ rowlist,
-                                                                unsigned char *__restrict__ tileflag
+                                                                unsigned char *__restrict__ tileflag, int *__restrict__ heavycnt,
+                                                                int *__restrict__ heavylist
 #if MVP_XBUCKETS
                                                                 , int NG, int2 *__restrict__ grphdr, RowEntry *__restrict__ grplist
 #endif
@@ -419,7 +424,11 @@ __global__ void __launch_bounds__(kRowThreads) row_lists_kernel(int K, int R, in
     // everything else is rendered by the 512-entry variant.
     __syncthreads();
     unsigned char *fl = tileflag + ((size_t)n * R + row) * TXn;
-    for (int i = threadIdx.x; i < TXn; i += kRowThreads) fl[i] = (s_tilecnt[i] > fastcap) ? 1 : 0;
+    for (int i = threadIdx.x; i < TXn; i += kRowThreads) {
+        const bool heavy = s_tilecnt[i] > fastcap;
+        fl[i] = heavy ? 1 : 0;
+        if (heavy) heavylist[atomicAdd(heavycnt, 1)] = (n * R + row) * TXn + i;   // rendered by the persistent 512-entry kernels
+    }
 #if MVP_XBUCKETS
     // Second level: for every group of kGrpTiles tile columns, the row's entries (still in rank order) whose pixel range
     // touches the group, packed one group after the other into the row's group buffer (even offsets: 16-byte aligned for
@@ -637,6 +646,8 @@ struct Params {
     int TXn, TYn;
     unsigned slab_bytes;          // TD*TH*TW*16
     unsigned char *tileflag;
+    const int *heavycnt;          // number of heavy tiles (candidates > fast list capacity) of this launch ...
+    const int *heavylist;         // ... and their ids ((n * TYn + ty) * TXn + tx), in no particular order
 #if MVP_XBUCKETS
     const int2 *grphdr;           // per (view, tile row, x-group): (offset into the row's group buffer, entries) or (-1, -1)
     const RowEntry *grplist;      // per (view, tile row): kGrpCap entries
@@ -948,6 +959,33 @@ __device__ __forceinline__ float4 sample_slab(const float4 *__restrict__ slab, f
     return acc;
 }
 
+#if MVP_PF_CELL
+// Prefetch the voxel cell a valid sample at slab coordinate (y0, y1, y2) will gather (same cell arithmetic as sample_slab).
+template <int T>
+__device__ __forceinline__ void prefetch_cell(const float4 *__restrict__ slab, float y0, float y1, float y2, int TD, int TH, int TW) {
+#ifndef MVP_CPU_EMUL
+    const int td = T > 0 ? T : TD, th = T > 0 ? T : TH, tw = T > 0 ? T : TW;
+    const int ix = __float2int_rd(((y0 + 1.f) * 0.5f) * (float)(tw - 1)), iy = __float2int_rd(((y1 + 1.f) * 0.5f) * (float)(th - 1)),
+              iz = __float2int_rd(((y2 + 1.f) * 0.5f) * (float)(td - 1));
+    int cx, cy, cz;
+    if (T >= 2) { cx = min(ix, T - 2); cy = min(iy, T - 2); cz = min(iz, T - 2); }
+    else { cx = max(min(ix, tw - 2), 0); cy = max(min(iy, th - 2), 0); cz = max(min(iz, td - 2), 0); }
+    const int sx = tw > 1 ? 1 : 0, sy = th > 1 ? tw : 0, sz = td > 1 ? th * tw : 0;
+    const float4 *pc = slab + ((cz * th + cy) * tw + cx);
+#if MVP_PF_CELL <= 2
+#define MVP_PF_(a) asm volatile("prefetch.global.L1 [%0];" ::"l"(a))
+#else
+#define MVP_PF_(a) asm volatile("prefetch.global.L2 [%0];" ::"l"(a))
+#endif
+    MVP_PF_(pc); MVP_PF_(pc + sy); MVP_PF_(pc + sz); MVP_PF_(pc + sz + sy);
+#if MVP_PF_CELL == 2 || MVP_PF_CELL == 4
+    MVP_PF_(pc + sx); MVP_PF_(pc + sy + sx); MVP_PF_(pc + sz + sx); MVP_PF_(pc + sz + sy + sx);
+#endif
+#undef MVP_PF_
+#endif
+}
+#endif
+
 // ---- generic trilinear cell for an ARBITRARY position (utils.h:408-502: +-100 clamp, corners outside the grid
 //      contribute nothing); used by the warp-field path (algo 1), where the warped position may leave the slab ----
 struct CellG {
@@ -1011,16 +1049,45 @@ long long g_emul_fwd_stats[8];
 #define MVP_STAT(i, v) ((void)0)
 #endif
 
+#if MVP_FWD_ASYNC
+constexpr int kQOff = 32;            // ring[0, 32): the batch in flight; ring[32, 96): the sample queue
+constexpr int kFwdRing = 96;
+#else
+constexpr int kQOff = 0;
+constexpr int kFwdRing = kRing;
+#endif
 template <int CAP, bool kGrad>
-struct __align__(16) FwdWarpSmem {   // MVP_FWD_OPAQUE == 2: one record per warp
-    float4 ring[kRing];
+struct __align__(16) FwdWarpSmem {   // per-warp shared state of the forward kernel
+    float4 ring[kFwdRing];
+#if MVP_FWD_ASYNC
+    float4 gat[8 * 32];               // staged corner texels of the batch in flight: [corner][lane]
+#endif
     RowEntry stage[2 * kStage];
     unsigned long long bar[2];
     int k[CAP];
     int iv[CAP];
     float ra[kRing];
-    int rm[kGrad ? kRing : 1];
+    int rm[kGrad ? kFwdRing : 1];
 };
+
+// cp.async (LDGSTS): 16-byte global -> shared copies that complete in the background (per-thread groups)
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src) {
+#ifdef MVP_CPU_EMUL
+    memcpy(dst_smem, src, 16);
+#else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_commit() {
+#ifndef MVP_CPU_EMUL
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+#ifndef MVP_CPU_EMUL
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+}
 
 // ------------------------------------------------------------------------------------------------------
 // 4. forward.  CAP = shared-memory list capacity per warp.  The CAP < 512 variant handles every tile whose list
@@ -1028,44 +1095,13 @@ struct __align__(16) FwdWarpSmem {   // MVP_FWD_OPAQUE == 2: one record per warp
 //    the CAP == 512 variant then renders only the flagged tiles.
 // ------------------------------------------------------------------------------------------------------
 template <int T, bool kGrad, int CAP, bool kWarp>
-__global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_FWD_MINB * 4) / kWarps : 16 / kWarps) render_forward_kernel(const Params p) {
-#if MVP_FWD_OPAQUE == 2
-    // all per-warp shared state in one record: every address below is (one pinned per-warp base) + immediate
-    __shared__ FwdWarpSmem<CAP, kGrad> s_w[kWarps];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned woff = (unsigned)__cvta_generic_to_shared(&s_w[warp]);
-    asm volatile("" : "+r"(woff));
-    FwdWarpSmem<CAP, kGrad> *const S = reinterpret_cast<FwdWarpSmem<CAP, kGrad> *>(__cvta_shared_to_generic((size_t)woff));
+__device__ __forceinline__ void forward_tile(const Params &p, const int n, const int tx, const int ty, const int lane, FwdWarpSmem<CAP, kGrad> *const S) {
+    // all per-warp shared state lives in one record: every address below is (one pinned per-warp base) + immediate
     int *const sk = S->k, *const siv = S->iv, *const rm = S->rm;
     RowEntry *const sstage = S->stage;
     unsigned long long *const sbar = S->bar;
     float4 *const ring = S->ring;
     float *const ra = S->ra;
-#else
-    __shared__ int s_k[kWarps][CAP];
-    __shared__ int s_iv[kWarps][CAP];
-    __shared__ __align__(16) RowEntry s_stage[kWarps][2 * kStage];   // TMA-staged chunks of the tile row's bucket
-    __shared__ __align__(8) unsigned long long s_bar[kWarps][2];
-    __shared__ float4 s_ring[kWarps][kRing];   // sample queue: (y0, y1, y2, owner | slot << 5) -> (r, g, b, same) once sampled
-    __shared__ float s_ra[kWarps][kRing];      // sampled alpha * fade
-    __shared__ int s_rm[kWarps][kGrad ? kRing : 1];   // sweep step of the queued sample (needed to record the saturating one)
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int *const sk = s_k[warp], *const siv = s_iv[warp], *const rm = s_rm[warp];
-    RowEntry *const sstage = s_stage[warp];
-    unsigned long long *const sbar = s_bar[warp];
-    float4 *const ring = s_ring[warp];
-    float *const ra = s_ra[warp];
-#endif
-    const int tx = blockIdx.x * kBlkTX + (warp % kBlkTX), ty = blockIdx.y * kBlkTY + (warp / kBlkTX), n = blockIdx.z;
-    if (tx >= p.TXn || ty >= p.TYn) return;   // warps are independent: no CTA-wide barrier below (exited warps count as arrived)
-    // Programmatic dependent launch: the 512-entry variant (few, long-running tiles) is launched first and lets the
-    // fast variant start while it is still running; the fast variant waits for it only at its very end.
-    if (CAP == kMaxHit) MVP_GRIDDEP_LAUNCH();
-    const bool heavy = p.tileflag[((size_t)n * p.TYn + ty) * p.TXn + tx] != 0;
-    if ((CAP == kMaxHit) != heavy) {
-        if (CAP < kMaxHit) MVP_GRIDDEP_WAIT();
-        return;
-    }
 
     const float rdt = fast_rcp(p.dt);   // MUFU.RCP(stepsize), as the reference (SASS 0x16c0)
     TileCtx c;
@@ -1100,27 +1136,13 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
     const size_t slabsz = (size_t)p.TD * p.TH * p.TW;
     const float4 *tpn = reinterpret_cast<const float4 *>(p.tplate) + (size_t)(n * p.pview) * p.K * slabsz;
     const int kstart = dfs_kstart(p.K);
-#if MVP_FWD_OPAQUE == 1
-    // Under the register cap the compiler rematerialises these two base addresses (S2R/LDC/IMAD chains, ~13 of the
-    // ~64 instructions of a (step, slab) event) instead of keeping them: make them opaque so they stay in registers.
-    unsigned skw = (unsigned)__cvta_generic_to_shared(sk);
-    asm volatile("" : "+r"(skw) :: "memory");
     {
+        // pinned: under the register cap the compiler would otherwise re-materialise this base address per event
         unsigned long long pa = (unsigned long long)packn;
         asm volatile("" : "+l"(pa));
         packn = reinterpret_cast<const float4 *>(pa);
     }
-    auto list_k = [&](int slot) { int v; asm("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(skw + 4u * (unsigned)slot)); return v; };
-#else
-#if MVP_FWD_OPAQUE == 2
-    {
-        unsigned long long pa = (unsigned long long)packn;
-        asm volatile("" : "+l"(pa));
-        packn = reinterpret_cast<const float4 *>(pa);
-    }
-#endif
     auto list_k = [&](int slot) { return sk[slot]; };
-#endif
 
     // Sample compaction.  At one (step, slab) event only ~10 of the 32 rays of a tile are inside the slab, so the valid
     // samples are queued (sample coordinates + owner lane + list slot) and the expensive gather/interpolation runs on
@@ -1130,27 +1152,14 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
     // sampled in vain and then ignored.  (Measured: neutral at 8^3 / K=16384, -15 % forward time at 16^3 / K=4096.)
     int qn = 0;
     unsigned ownlo = 0, ownhi = 0;   // queue positions (0..63) holding this lane's pending samples
-    auto flush = [&](int cnt) {
-        MVP_STAT(4, 1);
-        const bool act = lane < cnt;
-        const float4 rec = ring[act ? lane : 0];
-        float4 sres = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (act) {
-            const int kk = sk[(__float_as_int(rec.w) >> 5) & 1023];
-            if (kWarp) sres = sample_slab_warped(tpn + (size_t)kk * slabsz, p.warp + ((size_t)(n * p.pview) * p.K + kk) * ((size_t)p.WD * p.WH * p.WW * 3), rec.x, rec.y, rec.z, p);
-            else sres = sample_slab<T>(tpn + (size_t)kk * slabsz, rec.x, rec.y, rec.z, p.TD, p.TH, p.TW, p.fadescale, p.fadeexp);
-        }
-        __syncwarp();
-        if (act) { ring[lane] = make_float4(sres.x, sres.y, sres.z, rec.w); ra[lane] = sres.w; }
-        __syncwarp();
-        unsigned mine = ownlo & (cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u));
+    // primaccum.h:63-79 for this ray's samples among the first sampled entries of the ring (bit b of `mine` = ring[b])
+    auto composite = [&](unsigned mine) {
         while (mine) {
             const int b = __ffs(mine) - 1;
             mine &= mine - 1;
             if (!sat) {
                 const float4 rr = ring[b];
                 const float aw = ra[b];
-                // primaccum.h:63-79
                 const float newa = __fmaf_rn(aw, p.dt, acc.w);
                 const float contrib = __fadd_rn(fminf(newa, 1.f), -acc.w);
                 if (newa >= 1.f) {
@@ -1167,6 +1176,113 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
                 acc.z = __fmaf_rn(contrib, rr.z, acc.z); acc.w = __fadd_rn(acc.w, contrib);
             }
         }
+    };
+#if MVP_FWD_ASYNC
+    // Two-stage batches.  issue(): the first `cnt` queued samples become the batch in flight -- every lane computes the voxel
+    // cell and fade of one sample and starts 8 cp.async corner copies into its column of the staging area; complete(), one
+    // batch later: the copies have landed long ago, the lane interpolates from shared memory and every ray composites its
+    // samples of that batch in queue order.  A ray therefore learns that it saturated one batch later than in the synchronous
+    // scheme; what it queued in between is sampled in vain and ignored, exactly as before.
+    constexpr bool kAsync = (T == 8 || T == 16) && !kWarp;   // cell index packed in 3 x 4 bits of the entry's meta word
+    float4 *const gat = S->gat;
+    int pend = 0;
+    unsigned ownp = 0;
+    auto complete = [&]() {
+        if (pend == 0) return;   // warp-uniform
+        if (kAsync) {
+            cp_async_wait_all();
+            if (lane < pend) {
+                const float4 e = ring[lane];
+                const float fade = ra[lane];
+                const int meta = __float_as_int(e.w);
+                const int cx = (meta >> 15) & 15, cy = (meta >> 19) & 15, cz = (meta >> 23) & 15;
+                const float bx0 = e.x - (float)cx, bx1 = (float)(cx + 1) - e.x;
+                const float by0 = e.y - (float)cy, by1 = (float)(cy + 1) - e.y;
+                const float bz0 = e.z - (float)cz, bz1 = (float)(cz + 1) - e.z;
+                const float4 v000 = gat[0 * 32 + lane], v001 = gat[1 * 32 + lane], v010 = gat[2 * 32 + lane], v011 = gat[3 * 32 + lane];
+                const float4 v100 = gat[4 * 32 + lane], v101 = gat[5 * 32 + lane], v110 = gat[6 * 32 + lane], v111 = gat[7 * 32 + lane];
+                // same weights and accumulation order as sample_slab
+                const float w00 = bx1 * by1, w01 = bx0 * by1, w10 = bx1 * by0, w11 = bx0 * by0;
+                float4 a4;
+                float w;
+                w = w00 * bz1; a4.x = w * v000.x; a4.y = w * v000.y; a4.z = w * v000.z; a4.w = w * v000.w;
+                w = w01 * bz1; a4.x = __fmaf_rn(w, v001.x, a4.x); a4.y = __fmaf_rn(w, v001.y, a4.y); a4.z = __fmaf_rn(w, v001.z, a4.z); a4.w = __fmaf_rn(w, v001.w, a4.w);
+                w = w10 * bz1; a4.x = __fmaf_rn(w, v010.x, a4.x); a4.y = __fmaf_rn(w, v010.y, a4.y); a4.z = __fmaf_rn(w, v010.z, a4.z); a4.w = __fmaf_rn(w, v010.w, a4.w);
+                w = w11 * bz1; a4.x = __fmaf_rn(w, v011.x, a4.x); a4.y = __fmaf_rn(w, v011.y, a4.y); a4.z = __fmaf_rn(w, v011.z, a4.z); a4.w = __fmaf_rn(w, v011.w, a4.w);
+                w = w00 * bz0; a4.x = __fmaf_rn(w, v100.x, a4.x); a4.y = __fmaf_rn(w, v100.y, a4.y); a4.z = __fmaf_rn(w, v100.z, a4.z); a4.w = __fmaf_rn(w, v100.w, a4.w);
+                w = w01 * bz0; a4.x = __fmaf_rn(w, v101.x, a4.x); a4.y = __fmaf_rn(w, v101.y, a4.y); a4.z = __fmaf_rn(w, v101.z, a4.z); a4.w = __fmaf_rn(w, v101.w, a4.w);
+                w = w10 * bz0; a4.x = __fmaf_rn(w, v110.x, a4.x); a4.y = __fmaf_rn(w, v110.y, a4.y); a4.z = __fmaf_rn(w, v110.z, a4.z); a4.w = __fmaf_rn(w, v110.w, a4.w);
+                w = w11 * bz0; a4.x = __fmaf_rn(w, v111.x, a4.x); a4.y = __fmaf_rn(w, v111.y, a4.y); a4.z = __fmaf_rn(w, v111.z, a4.z); a4.w = __fmaf_rn(w, v111.w, a4.w);
+                ring[lane] = make_float4(a4.x, a4.y, a4.z, e.w);    // a lane only rewrites its own entry
+                ra[lane] = a4.w * fade;
+            }
+        }
+        __syncwarp();
+        composite(ownp);
+        __syncwarp();   // every lane is done with ring[0, 32) before the next issue() refills it
+        pend = 0;
+        if (sat) done = true;
+    };
+    auto issue = [&](int cnt) {
+        MVP_STAT(4, 1);
+        const bool act = lane < cnt;
+        const int n2 = qn - cnt;
+        float4 rec = make_float4(0.f, 0.f, 0.f, 0.f), mv = rec;
+        int recm = 0, mvm = 0;
+        if (act) { rec = ring[kQOff + lane]; if (kGrad) recm = rm[kQOff + lane]; }
+        if (lane < n2) { mv = ring[kQOff + cnt + lane]; if (kGrad) mvm = rm[kQOff + cnt + lane]; }
+        __syncwarp();
+        if (act) {
+            const int meta = __float_as_int(rec.w);
+            const int kk = sk[(meta >> 5) & 1023];
+            const float4 *slab = tpn + (size_t)kk * slabsz;
+            if (kAsync) {
+                constexpr int TT = T > 0 ? T : 2;
+                const float fade = __expf(-p.fadescale * (__powf(fabsf(rec.x), p.fadeexp) + __powf(fabsf(rec.y), p.fadeexp) + __powf(fabsf(rec.z), p.fadeexp)));
+                const float fx = ((rec.x + 1.f) * 0.5f) * (float)(TT - 1);
+                const float fy = ((rec.y + 1.f) * 0.5f) * (float)(TT - 1);
+                const float fz = ((rec.z + 1.f) * 0.5f) * (float)(TT - 1);
+                const int cx = min(__float2int_rd(fx), TT - 2), cy = min(__float2int_rd(fy), TT - 2), cz = min(__float2int_rd(fz), TT - 2);
+                const float4 *pc = slab + ((cz * TT + cy) * TT + cx);
+                float4 *g = gat + lane;
+                cp_async16(g + 0 * 32, pc); cp_async16(g + 1 * 32, pc + 1); cp_async16(g + 2 * 32, pc + TT); cp_async16(g + 3 * 32, pc + TT + 1);
+                cp_async16(g + 4 * 32, pc + TT * TT); cp_async16(g + 5 * 32, pc + TT * TT + 1);
+                cp_async16(g + 6 * 32, pc + TT * TT + TT); cp_async16(g + 7 * 32, pc + TT * TT + TT + 1);
+                ring[lane] = make_float4(fx, fy, fz, __int_as_float(meta | (cx << 15) | (cy << 19) | (cz << 23)));
+                ra[lane] = fade;
+            } else {
+                float4 sres;
+                if (kWarp) sres = sample_slab_warped(slab, p.warp + ((size_t)(n * p.pview) * p.K + kk) * ((size_t)p.WD * p.WH * p.WW * 3), rec.x, rec.y, rec.z, p);
+                else sres = sample_slab<T>(slab, rec.x, rec.y, rec.z, p.TD, p.TH, p.TW, p.fadescale, p.fadeexp);
+                ring[lane] = make_float4(sres.x, sres.y, sres.z, rec.w);
+                ra[lane] = sres.w;
+            }
+            if (kGrad) rm[lane] = recm;
+        }
+        if (lane < n2) { ring[kQOff + lane] = mv; if (kGrad) rm[kQOff + lane] = mvm; }
+        if (kAsync) cp_async_commit();
+        __syncwarp();
+        ownp = ownlo & (cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u));
+        ownlo = ownhi; ownhi = 0;
+        pend = cnt;
+        qn = n2;
+    };
+    auto flush = [&](int cnt) { complete(); issue(cnt); };
+#else
+    auto flush = [&](int cnt) {
+        MVP_STAT(4, 1);
+        const bool act = lane < cnt;
+        const float4 rec = ring[act ? lane : 0];
+        float4 sres = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (act) {
+            const int kk = sk[(__float_as_int(rec.w) >> 5) & 1023];
+            if (kWarp) sres = sample_slab_warped(tpn + (size_t)kk * slabsz, p.warp + ((size_t)(n * p.pview) * p.K + kk) * ((size_t)p.WD * p.WH * p.WW * 3), rec.x, rec.y, rec.z, p);
+            else sres = sample_slab<T>(tpn + (size_t)kk * slabsz, rec.x, rec.y, rec.z, p.TD, p.TH, p.TW, p.fadescale, p.fadeexp);
+        }
+        __syncwarp();
+        if (act) { ring[lane] = make_float4(sres.x, sres.y, sres.z, rec.w); ra[lane] = sres.w; }
+        __syncwarp();
+        composite(ownlo & (cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u)));
         __syncwarp();
         // move what is left of the queue to the front
         const int n2 = qn - cnt;
@@ -1180,6 +1296,7 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
         qn = n2;
         if (sat) done = true;
     };
+#endif
 
     const int mstart = __reduce_min_sync(0xffffffffu, ms);
     if (nl > 0 && mstart < kBig) {
@@ -1222,8 +1339,11 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
                         MVP_STAT(2, 1); MVP_STAT(3, __popc(vm));
                         if (want) {
                             const int pos = qn + __popc(vm & ((1u << lane) - 1u));
-                            ring[pos] = make_float4(y0, y1, y2, __int_as_float(lane | ((w * 32 + b) << 5)));
-                            if (kGrad) rm[pos] = m;
+                            ring[kQOff + pos] = make_float4(y0, y1, y2, __int_as_float(lane | ((w * 32 + b) << 5)));
+                            if (kGrad) rm[kQOff + pos] = m;
+#if MVP_PF_CELL
+                            if (!kWarp) prefetch_cell<T>(tpn + (size_t)k * slabsz, y0, y1, y2, p.TD, p.TH, p.TW);
+#endif
                             if (pos < 32) ownlo |= 1u << pos; else ownhi |= 1u << (pos - 32);
                         }
                         qn += __popc(vm);
@@ -1265,6 +1385,9 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
         }
     }
     if (qn > 0) flush(qn);
+#if MVP_FWD_ASYNC
+    complete();
+#endif
     if (c.inimg) {
         reinterpret_cast<float4 *>(p.rayrgba)[r] = acc;
         if (kGrad) {
@@ -1275,7 +1398,46 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
 #if defined(MVP_CPU_EMUL) && defined(MVP_EMUL_STATS)
     if (lane == 0) for (int i = 0; i < 8; ++i) if (stat_[i]) std::atomic_ref<long long>(g_emul_fwd_stats[i]).fetch_add(stat_[i]);
 #endif
-    if (CAP < kMaxHit) MVP_GRIDDEP_WAIT();
+}
+
+// Tiles whose candidate count exceeds the fast kernels' shared-memory list ("heavy" tiles; none in the benchmark scene) are
+// listed by row_lists_kernel; the CAP == 512 kernels are small persistent grids that walk that list, so a launch with
+// nothing to do costs a few microseconds instead of a full grid of empty CTAs.
+constexpr int kHeavyGrid = 296;
+
+template <int CAP, bool kGrad>
+__device__ __forceinline__ FwdWarpSmem<CAP, kGrad> *pinned_warp_record(FwdWarpSmem<CAP, kGrad> *rec) {
+#ifdef MVP_CPU_EMUL
+    return rec;
+#else
+    unsigned woff = (unsigned)__cvta_generic_to_shared(rec);
+    asm volatile("" : "+r"(woff));
+    return reinterpret_cast<FwdWarpSmem<CAP, kGrad> *>(__cvta_shared_to_generic((size_t)woff));
+#endif
+}
+
+template <int T, bool kGrad, int CAP, bool kWarp>
+__global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_FWD_MINB * 4) / kWarps : 16 / kWarps) render_forward_kernel(const Params p) {
+    __shared__ FwdWarpSmem<CAP, kGrad> s_w[kWarps];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    FwdWarpSmem<CAP, kGrad> *const S = pinned_warp_record<CAP, kGrad>(&s_w[warp]);
+    if (CAP == kMaxHit) {
+        // Programmatic dependent launch: this kernel is launched first and lets the fast variant start at once; the fast
+        // variant waits for it only at its very end.  Warps are independent: no CTA-wide barrier anywhere.
+        MVP_GRIDDEP_LAUNCH();
+        const int cnt = *p.heavycnt;
+        for (int i = blockIdx.x * kWarps + warp; i < cnt; i += gridDim.x * kWarps) {
+            const int id = p.heavylist[i];
+            const int tx = id % p.TXn, ty = (id / p.TXn) % p.TYn, n = id / (p.TXn * p.TYn);
+            forward_tile<T, kGrad, CAP, kWarp>(p, n, tx, ty, lane, S);
+            __syncwarp();
+        }
+    } else {
+        const int tx = blockIdx.x * kBlkTX + (warp % kBlkTX), ty = blockIdx.y * kBlkTY + (warp / kBlkTX), n = blockIdx.z;
+        if (tx >= p.TXn || ty >= p.TYn) return;   // exited warps count as arrived
+        if (p.tileflag[((size_t)n * p.TYn + ty) * p.TXn + tx] == 0) forward_tile<T, kGrad, CAP, kWarp>(p, n, tx, ty, lane, S);
+        MVP_GRIDDEP_WAIT();
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -1295,7 +1457,7 @@ __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float 
 }
 
 template <int CAP>
-struct __align__(16) BwdWarpSmem {   // MVP_BWD_OPAQUE == 2: one record per warp
+struct __align__(16) BwdWarpSmem {   // per-warp shared state of the backward kernel
     float4 q[kRing];
     RowEntry stage[2 * kStage];
     unsigned long long bar[2];
@@ -1305,40 +1467,12 @@ struct __align__(16) BwdWarpSmem {   // MVP_BWD_OPAQUE == 2: one record per warp
 };
 
 template <int T, int CAP, bool kWarp>
-__global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_BWD_MINB * 4) / kWarps : 12 / kWarps) render_backward_kernel(const Params p) {
-#if MVP_BWD_OPAQUE == 2
-    __shared__ BwdWarpSmem<CAP> s_w[kWarps];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned woff = (unsigned)__cvta_generic_to_shared(&s_w[warp]);
-    asm volatile("" : "+r"(woff));
-    BwdWarpSmem<CAP> *const S = reinterpret_cast<BwdWarpSmem<CAP> *>(__cvta_shared_to_generic((size_t)woff));
+__device__ __forceinline__ void backward_tile(const Params &p, const int n, const int tx, const int ty, const int lane, BwdWarpSmem<CAP> *const S) {
     int *const sk = S->k, *const siv = S->iv;
     RowEntry *const sstage = S->stage;
     unsigned long long *const sbar = S->bar;
     float4 *const sq = S->q;
-    float *const sray = S->ray;
-#else
-    __shared__ int s_k[kWarps][CAP];
-    __shared__ int s_iv[kWarps][CAP];
-    __shared__ float4 s_q[kWarps][kRing];
-    __shared__ float s_ray[kWarps][9 * 32];   // per-ray adjoint constants: dL.xyzw, saturation colour + flag, alpha before saturation
-    __shared__ __align__(16) RowEntry s_stage[kWarps][2 * kStage];   // TMA-staged chunks of the tile row's bucket
-    __shared__ __align__(8) unsigned long long s_bar[kWarps][2];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int *const sk = s_k[warp], *const siv = s_iv[warp];
-    RowEntry *const sstage = s_stage[warp];
-    unsigned long long *const sbar = s_bar[warp];
-    float4 *const sq = s_q[warp];
-    float *const sray = s_ray[warp];
-#endif
-    const int tx = blockIdx.x * kBlkTX + (warp % kBlkTX), ty = blockIdx.y * kBlkTY + (warp / kBlkTX), n = blockIdx.z;
-    if (tx >= p.TXn || ty >= p.TYn) return;
-    if (CAP == kMaxHit) MVP_GRIDDEP_LAUNCH();
-    const bool heavy = p.tileflag[((size_t)n * p.TYn + ty) * p.TXn + tx] != 0;
-    if ((CAP == kMaxHit) != heavy) {
-        if (CAP < kMaxHit) MVP_GRIDDEP_WAIT();
-        return;
-    }
+    float *const sray = S->ray;   // per-ray adjoint constants: dL.xyzw, saturation colour + flag, alpha before saturation
 
     const float rdt = fast_rcp(p.dt);
     TileCtx c;
@@ -1349,7 +1483,7 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
 #endif
     build_tile_list<CAP, false>(p, rdt, n, tx, ty, lane, c, sk, siv, sstage, sbar, t0, xb, yb, zb, r1e, j0);   // measured: the prefetch only pays in forward
     const int nl = c.nl;
-    if (nl == 0) { if (CAP < kMaxHit) MVP_GRIDDEP_WAIT(); return; }
+    if (nl == 0) return;
 
     const int px = tx * kTileW + (lane & 7), py = ty * kTileH + (lane >> 3);
     const size_t r = ((size_t)n * p.H + min(py, p.H - 1)) * p.W + min(px, p.W - 1);
@@ -1378,7 +1512,7 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
     const float foff = (float)c.off;
     const int wlast = __reduce_max_sync(0xffffffffu, mlast);
     const int wfirst = __reduce_min_sync(0xffffffffu, ms);
-    if (wlast < wfirst || wfirst >= kBig) { if (CAP < kMaxHit) MVP_GRIDDEP_WAIT(); return; }
+    if (wlast < wfirst || wfirst >= kBig) return;
 
     const float4 *packn = p.pack + (size_t)(n * p.pview) * p.K * 4;
     const size_t slabsz = (size_t)p.TD * p.TH * p.TW;
@@ -1498,6 +1632,9 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
                                 const int pos = (qhead + qn + __popc(vm & ((1u << lane) - 1u))) & (kRing - 1);
                                 const bool issat = ((la + i) == msat) && (rank == ranksat);
                                 ring[pos] = make_float4(xm, ym, zm, __int_as_float(lane | (issat ? 256 : 0)));
+#if MVP_PF_CELL
+                                if (!kWarp) prefetch_cell<T>(slab, y0, y1, y2, p.TD, p.TH, p.TW);
+#endif
                             }
                             qn += __popc(vm);
 #if defined(MVP_CPU_EMUL) && defined(MVP_EMUL_STATS)
@@ -1719,18 +1856,39 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
             }   // while (word)
         }       // for (w)
     }           // for (cs)
-    if (CAP < kMaxHit) MVP_GRIDDEP_WAIT();
 }
 
-// plain launch of the 512-entry variant (first in the stream); variadic because the kernel name contains commas
+template <int T, int CAP, bool kWarp>
+__global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_BWD_MINB * 4) / kWarps : 12 / kWarps) render_backward_kernel(const Params p) {
+    __shared__ BwdWarpSmem<CAP> s_w[kWarps];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    BwdWarpSmem<CAP> *const S = &s_w[warp];
+    if (CAP == kMaxHit) {
+        MVP_GRIDDEP_LAUNCH();
+        const int cnt = *p.heavycnt;
+        for (int i = blockIdx.x * kWarps + warp; i < cnt; i += gridDim.x * kWarps) {
+            const int id = p.heavylist[i];
+            const int tx = id % p.TXn, ty = (id / p.TXn) % p.TYn, n = id / (p.TXn * p.TYn);
+            backward_tile<T, CAP, kWarp>(p, n, tx, ty, lane, S);
+            __syncwarp();
+        }
+    } else {
+        const int tx = blockIdx.x * kBlkTX + (warp % kBlkTX), ty = blockIdx.y * kBlkTY + (warp / kBlkTX), n = blockIdx.z;
+        if (tx >= p.TXn || ty >= p.TYn) return;
+        if (p.tileflag[((size_t)n * p.TYn + ty) * p.TXn + tx] == 0) backward_tile<T, CAP, kWarp>(p, n, tx, ty, lane, S);
+        MVP_GRIDDEP_WAIT();
+    }
+}
+
+// plain launch of the 512-entry variant (first in the stream, small persistent grid); variadic because the kernel name contains commas
 #ifdef MVP_CPU_EMUL
 #define MVP_LAUNCH_HEAVY(...)                                   \
     do {                                                        \
         auto kern_ = __VA_ARGS__;                               \
-        MVP_LAUNCH(kern_, grid, kWarps * 32, 0, st, p);         \
+        MVP_LAUNCH(kern_, dim3(kHeavyGrid), kWarps * 32, 0, st, p); \
     } while (0)
 #else
-#define MVP_LAUNCH_HEAVY(...) __VA_ARGS__<<<grid, kWarps * 32, 0, st>>>(p)
+#define MVP_LAUNCH_HEAVY(...) __VA_ARGS__<<<kHeavyGrid, kWarps * 32, 0, st>>>(p)
 #endif
 
 // Launches `kern` as a programmatic dependent of the previous kernel in the stream (it may start before that kernel has
@@ -1760,6 +1918,7 @@ int check_shape(const mvp_shape &s) {
     if (s.H >= 32768 || s.W >= 32768) return MVP_ERR_SHAPE;
     if (s.N > 65535) return MVP_ERR_SHAPE;
     if ((size_t)s.TD * s.TH * s.TW >= ((size_t)1 << 27)) return MVP_ERR_SHAPE;
+    if ((size_t)s.N * ((s.H + kTileH - 1) / kTileH) * ((s.W + kTileW - 1) / kTileW) >= ((size_t)1 << 31)) return MVP_ERR_SHAPE;   // tile ids are ints
     return MVP_OK;
 }
 
@@ -1768,6 +1927,8 @@ int launch_accel(const mvp_shape &s, int pview, const float *raypos, const float
     Cam *cam = reinterpret_cast<Cam *>(ws + L.cam);
     int *bad = reinterpret_cast<int *>(ws + L.bad);
     cudaError_t e = cudaMemsetAsync(bad, 0, (size_t)s.N * sizeof(int), st);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemsetAsync(ws + L.heavycnt, 0, sizeof(int), st);
     if (e != cudaSuccess) return (int)e;
 #if MVP_LIST_REUSE
     // a new accel structure invalidates whatever lists an earlier forward saved in this workspace
@@ -1784,7 +1945,8 @@ int launch_accel(const mvp_shape &s, int pview, const float *raypos, const float
     const int TXn = (s.W + kTileW - 1) / kTileW;
     MVP_LAUNCH(row_lists_kernel, dim3(L.R, s.N), kRowThreads, (size_t)TXn * sizeof(int), st, s.K, L.R, L.rowcap, TXn, kFastCap,
                reinterpret_cast<unsigned *>(ws + L.rx), reinterpret_cast<unsigned *>(ws + L.ry), reinterpret_cast<int *>(ws + L.rowcnt),
-               reinterpret_cast<RowEntry *>(ws + L.rowlist), reinterpret_cast<unsigned char *>(ws + L.tileflag)
+               reinterpret_cast<RowEntry *>(ws + L.rowlist), reinterpret_cast<unsigned char *>(ws + L.tileflag),
+               reinterpret_cast<int *>(ws + L.heavycnt), reinterpret_cast<int *>(ws + L.heavylist)
 #if MVP_XBUCKETS
                , L.NG, reinterpret_cast<int2 *>(ws + L.grphdr), reinterpret_cast<RowEntry *>(ws + L.grplist)
 #endif
@@ -1799,7 +1961,7 @@ int launch_accel(const mvp_shape &s, int pview, const float *raypos, const float
     row_lists_kernel<<<dim3(L.R, s.N), kRowThreads, (size_t)TXn * sizeof(int), st>>>(
         s.K, L.R, L.rowcap, TXn, kFastCap, reinterpret_cast<unsigned *>(ws + L.rx), reinterpret_cast<unsigned *>(ws + L.ry),
         reinterpret_cast<int *>(ws + L.rowcnt), reinterpret_cast<RowEntry *>(ws + L.rowlist),
-        reinterpret_cast<unsigned char *>(ws + L.tileflag)
+        reinterpret_cast<unsigned char *>(ws + L.tileflag), reinterpret_cast<int *>(ws + L.heavycnt), reinterpret_cast<int *>(ws + L.heavylist)
 #if MVP_XBUCKETS
         , L.NG, reinterpret_cast<int2 *>(ws + L.grphdr), reinterpret_cast<RowEntry *>(ws + L.grplist)
 #endif
@@ -1822,6 +1984,8 @@ void fill_params(Params &p, const mvp_shape &s, float stepsize, float fadescale,
     p.TXn = (s.W + kTileW - 1) / kTileW;
     p.TYn = (s.H + kTileH - 1) / kTileH;
     p.tileflag = reinterpret_cast<unsigned char *>(ws + L.tileflag);
+    p.heavycnt = reinterpret_cast<const int *>(ws + L.heavycnt);
+    p.heavylist = reinterpret_cast<const int *>(ws + L.heavylist);
     p.slab_bytes = (unsigned)((size_t)s.TD * s.TH * s.TW * 16);
 #if MVP_XBUCKETS
     p.grphdr = reinterpret_cast<const int2 *>(ws + L.grphdr);
@@ -1847,8 +2011,8 @@ int mvp_abi_version(void) { return MVP_ABI_VERSION; }
 #define MVP_STR2(x) #x
 #define MVP_STR(x) MVP_STR2(x)
 const char *mvp_build_config(void) {
-    return "FWD_OPAQUE=" MVP_STR(MVP_FWD_OPAQUE) " BWD_OPAQUE=" MVP_STR(MVP_BWD_OPAQUE) " LIST_REUSE=" MVP_STR(MVP_LIST_REUSE)
-           " LIST_MARGIN=" MVP_STR(MVP_LIST_MARGIN) " XBUCKETS=" MVP_STR(MVP_XBUCKETS) " FASTCAP=" MVP_STR(MVP_FASTCAP)
+    return "LIST_REUSE=" MVP_STR(MVP_LIST_REUSE)
+           " LIST_MARGIN=" MVP_STR(MVP_LIST_MARGIN) " XBUCKETS=" MVP_STR(MVP_XBUCKETS) " FASTCAP=" MVP_STR(MVP_FASTCAP) " PF_CELL=" MVP_STR(MVP_PF_CELL) " FWD_ASYNC=" MVP_STR(MVP_FWD_ASYNC)
            " CHUNK=" MVP_STR(MVP_CHUNK) " FWD_MINB=" MVP_STR(MVP_FWD_MINB) " BWD_MINB=" MVP_STR(MVP_BWD_MINB)
            " WARPS=" MVP_STR(MVP_WARPS) " BLK_TX=" MVP_STR(MVP_BLK_TX)
 #ifdef MVP_CPU_EMUL

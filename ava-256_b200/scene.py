@@ -19,19 +19,24 @@ FULLRES_H = 4096
 ELLIPSOID_MM = (95.0, 178.0, 112.0)   # asset mesh half-extent (x, y, z)
 
 
-def fibonacci_dirs(n, offset=0):
-    """n well-spread unit vectors (Fibonacci lattice), restricted to the frontal 60% of the sphere like the rig."""
-    i = torch.arange(offset, offset + n, dtype=torch.float64) + 0.5
-    total = max(80, n + offset)
+def fibonacci_dirs(n, offset=0, ids=None):
+    """n well-spread unit vectors (Fibonacci lattice), restricted to the frontal 60% of the sphere like the rig.
+    `ids` (optional) selects arbitrary lattice points of the 80-camera dome instead of the block [offset, offset + n)."""
+    if ids is not None:
+        i = torch.as_tensor(list(ids), dtype=torch.float64) + 0.5
+        total = max(80, int(max(ids)) + 1)
+    else:
+        i = torch.arange(offset, offset + n, dtype=torch.float64) + 0.5
+        total = max(80, n + offset)
     z = 1.0 - 1.2 * i / total          # z in (1, -0.2]: front and sides, like a capture dome
     r = torch.sqrt(torch.clamp(1.0 - z * z, min=0.0))
     phi = i * math.pi * (3.0 - math.sqrt(5.0))
     return torch.stack([r * torch.cos(phi), r * torch.sin(phi), z], dim=-1)
 
 
-def look_at_cameras(n, offset=0):
+def look_at_cameras(n, offset=0, ids=None):
     """Returns (campos [n,3] in mm, camrot [n,3,3] rows = camera x,y,z axes in world coords)."""
-    d = fibonacci_dirs(n, offset)
+    d = fibonacci_dirs(n, offset, ids)
     campos = d * CAM_DIST_MM
     zc = -d                                                    # camera looks at the origin
     up = torch.tensor([0.0, 1.0, 0.0], dtype=torch.float64).expand_as(zc)
@@ -65,9 +70,9 @@ def compute_raydirs_host(campos, camrot, focal, princpt, H, W, volradius=VOLRADI
     return rp.contiguous(), rd.contiguous(), tminmax.contiguous()
 
 
-def make_rays(n_views, H, W, view_offset=0, dtype=torch.float32):
+def make_rays(n_views, H, W, view_offset=0, dtype=torch.float32, view_ids=None):
     """Rays of `n_views` dome cameras looking at the head: raypos, raydir [n,H,W,3], tminmax [n,H,W,2]."""
-    campos, camrot = look_at_cameras(n_views, view_offset)
+    campos, camrot = look_at_cameras(n_views, view_offset, view_ids)
     ds = FULLRES_H / H
     focal = torch.full((n_views, 2), FOCAL_FULLRES / ds, dtype=torch.float64)
     princpt = torch.tensor([[W / 2.0, H / 2.0]], dtype=torch.float64).expand(n_views, 2)
@@ -126,14 +131,14 @@ def make_payload(K, T, seed=1112, alpha_mu=6.0, alpha_sigma=6.0, dtype=torch.flo
 
 
 def make_scene(n_views, H, W, K, T, seed=1112, view_offset=0, device="cpu", alpha_mu=6.0, alpha_sigma=6.0,
-               share_primitives=True):
+               share_primitives=True, view_ids=None):
     """Full op inputs for `n_views` views of one subject, laid out as the reference op takes them.
 
     Returns dict(raypos, raydir, tminmax, primpos [N,K,3], primrot [N,K,3,3], primscale [N,K,3],
     template [N,K,T,T,T,4], stepsize).  With share_primitives the per-view tensors are materialised copies of
     one subject's primitives (SURVEY 8d "template materialised per view").
     """
-    rp, rd, tmm = make_rays(n_views, H, W, view_offset)
+    rp, rd, tmm = make_rays(n_views, H, W, view_offset, view_ids=view_ids)
     pos, rot, scale = make_primitives(K, seed)
     dev = torch.device(device)
     tpl = make_payload(K, T, seed, alpha_mu, alpha_sigma, device="cpu" if dev.type == "cpu" else device)

@@ -259,13 +259,18 @@ def run_ours(args, rank, world):
     views, h, w, k, t = args.views, args.height, args.width, args.prims, args.voxels
     assert views % world == 0, "views must divide over ranks"
     nv = views // world                      # contiguous block of views per rank
-    s = scene.make_scene(nv, h, w, k, t, seed=1112, view_offset=rank * nv, device=dev, alpha_mu=ALPHA_MU, alpha_sigma=ALPHA_SIGMA)
+    # views are interleaved over the ranks (rank, rank + world, ...): equal coverage per rank (parallel.rank_views)
+    vids = parallel.rank_views(views, rank, world, interleave=not args.contiguous_views)
+    s = scene.make_scene(nv, h, w, k, t, seed=1112, view_ids=vids, device=dev, alpha_mu=ALPHA_MU, alpha_sigma=ALPHA_SIGMA)
     stepsize = s["stepsize"]
     log("scene ready: %d views/rank %dx%d K=%d T=%d" % (nv, h, w, k, t))
     gen = torch.Generator(device=dev).manual_seed(1112 + rank)
     grad_out = torch.randn(nv, h, w, 4, device=dev, generator=gen)
     leaves = [s[n].requires_grad_(True) for n in ("primpos", "primrot", "primscale", "template")]
-    flat = torch.zeros(k * t ** 3 * 4 + k * 15, device=dev)     # all-reduced primitive gradients of the subject
+    # all-reduced primitive gradients of the subject: double-buffered, the NCCL all-reduce of step i runs under the
+    # forward of step i+1 (parallel.GradReducer); every all-reduce is waited for inside the timed region
+    red = parallel.GradReducer(k, t, t, t, dev)
+    flat = red.bufs[0]
     flat_numel = flat.numel()
 
     def barrier():
@@ -279,11 +284,12 @@ def run_ours(args, rank, world):
         out = mvpraymarch(s["raypos"], s["raydir"], stepsize, s["tminmax"], (leaves[0], leaves[1], leaves[2]), leaves[3], None)
         out.backward(grad_out)
         # views of a step share the subject's primitives: local sum over the rank's views, one all-reduce
-        parallel.reduce_primitive_grads(leaves[3].grad, leaves[0].grad, leaves[1].grad, leaves[2].grad, flat=flat)
+        red.reduce(leaves[3].grad, leaves[0].grad, leaves[1].grad, leaves[2].grad)
         return out
 
     for i in range(args.warmup):
         out = step()
+        red.finish()
         torch.cuda.synchronize()
         log("warmup step %d done" % i)
     barrier()
@@ -295,15 +301,34 @@ def run_ours(args, rank, world):
     e0.record()
     for _ in range(args.steps):
         out = step()
+    red.finish()                 # the compute stream waits for the last all-reduce: it is inside the timed region
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    # the collective alone (not overlapped), for the record
+    allreduce_ms = None
+    if world > 1:
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ea.record()
+        for _ in range(5):
+            dist.all_reduce(red.bufs[1])
+        eb.record()
+        barrier()
+        ta = torch.tensor([ea.elapsed_time(eb) / 5], device=dev)
+        dist.all_reduce(ta, op=dist.ReduceOp.MAX)
+        allreduce_ms = float(ta.item())
     log("timed region: %.1f ms for %d steps" % (ms, args.steps))
     clocks = sampler.stop() if rank == 0 else None
     tms = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms_step = float(tms.item()) / args.steps
+    rank_ms = [ms / args.steps]
+    if world > 1:                   # per-rank step times: imbalance between the ranks' view sets is visible in the record
+        allms = [torch.zeros(1, device=dev) for _ in range(world)]
+        dist.all_gather(allms, torch.tensor([ms / args.steps], device=dev))
+        rank_ms = [float(x.item()) for x in allms]
     value = views * h * w / (ms_step * 1e-3) / 1e6
     sat_frac = float((out[..., 3] >= 0.999).float().mean())
     cover = float((out[..., 3] > 0).float().mean())
@@ -375,39 +400,51 @@ def run_ours(args, rank, world):
         host_flat = torch.empty(flat.numel()).pin_memory()
         h2d = sum(x.numel() * 4 for x in host_in.values()) + sum(x.numel() * 4 for x in host_prim.values()) + host_grad.numel() * 4
         d2h = host_out.numel() * 4 + host_flat.numel() * 4
-        dev_in = {n: s[n] for n in host_in}            # device staging buffers (reused, overwritten every step)
-        dev_grad = grad_out
+        # device staging: two full sets (rays, image gradient, the subject's primitives, the reduced-gradient buffer), so the
+        # uploads of step i+1 run while step i computes and the downloads of step i run under step i+1
+        dev_in = [{n: s[n] for n in host_in}, {n: torch.empty_like(s[n]) for n in host_in}]
+        dev_grad = [grad_out, torch.empty_like(grad_out)]
+        names = ("primpos", "primrot", "primscale", "template")
         del leaves, tl
         torch.cuda.empty_cache()
+        dev_prim = [{n: torch.empty(host_prim[n].shape, device=dev) for n in names} for _ in range(2)]
+        flats = red.bufs
         chunk = max(1, min(nv, args.e2e_chunk))
         bounds = [(i, min(i + chunk, nv)) for i in range(0, nv, chunk)]
         s_in, s_out, s_cmp = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.current_stream()
-        names = ("primpos", "primrot", "primscale", "template")
+        cmp_done, flat_out_done = [None, None], [None, None]
 
-        def e2e_step():
+        def e2e_step(i):
+            b_ = i & 1
             ev_in = []
             with torch.cuda.stream(s_in):
-                s_in.wait_stream(s_cmp)
-                pr = {n: x.to(dev, non_blocking=True) for n, x in host_prim.items()}
+                if cmp_done[b_] is not None:
+                    s_in.wait_event(cmp_done[b_])                  # step i-2 has finished reading this buffer set
+                for n in names:
+                    dev_prim[b_][n].copy_(host_prim[n], non_blocking=True)
                 for (a0, a1) in bounds:
-                    for n in dev_in:
-                        dev_in[n][a0:a1].copy_(host_in[n][a0:a1], non_blocking=True)
-                    dev_grad[a0:a1].copy_(host_grad[a0:a1], non_blocking=True)
+                    for n in host_in:
+                        dev_in[b_][n][a0:a1].copy_(host_in[n][a0:a1], non_blocking=True)
+                    dev_grad[b_][a0:a1].copy_(host_grad[a0:a1], non_blocking=True)
                     e = torch.cuda.Event()
                     e.record(s_in)
                     ev_in.append(e)
-            flat.zero_()
+            flat_ = flats[b_]
+            if flat_out_done[b_] is not None:
+                s_cmp.wait_event(flat_out_done[b_])                # its previous download is over
+            flat_.zero_()
+            di, pr = dev_in[b_], dev_prim[b_]
             for ci, (a0, a1) in enumerate(bounds):
                 s_cmp.wait_event(ev_in[ci])
                 nvc = a1 - a0
                 lv = [pr[n][None].expand(nvc, *pr[n].shape).contiguous().requires_grad_(True) for n in names]
-                o_ = mvpraymarch(dev_in["raypos"][a0:a1], dev_in["raydir"][a0:a1], stepsize, dev_in["tminmax"][a0:a1],
+                o_ = mvpraymarch(di["raypos"][a0:a1], di["raydir"][a0:a1], stepsize, di["tminmax"][a0:a1],
                                  (lv[0], lv[1], lv[2]), lv[3], None)
-                o_.backward(dev_grad[a0:a1])
+                o_.backward(dev_grad[b_][a0:a1])
                 off = 0
                 for x in (lv[3], lv[0], lv[1], lv[2]):
                     n_ = x[0].numel()
-                    flat[off:off + n_] += x.grad.view(nvc, n_).sum(dim=0)
+                    flat_[off:off + n_] += x.grad.view(nvc, n_).sum(dim=0)
                     off += n_
                 od = o_.detach()
                 e = torch.cuda.Event()
@@ -417,19 +454,33 @@ def run_ours(args, rank, world):
                     host_out[a0:a1].copy_(od, non_blocking=True)
                     od.record_stream(s_out)
             if world > 1:
-                dist.all_reduce(flat)
-            host_flat.copy_(flat, non_blocking=True)
+                dist.all_reduce(flat_)
+            e = torch.cuda.Event()
+            e.record(s_cmp)
+            cmp_done[b_] = e
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(e)
+                host_flat.copy_(flat_, non_blocking=True)
+                e2 = torch.cuda.Event()
+                e2.record(s_out)
+                flat_out_done[b_] = e2
+
+        def e2e_drain():
+            s_cmp.wait_stream(s_in)
             s_cmp.wait_stream(s_out)
 
         log("e2e buffers pinned")
-        e2e_step()
+        e2e_step(0)
+        e2e_step(1)
+        e2e_drain()
         barrier()
-        log("e2e warm-up step done")
+        log("e2e warm-up steps done")
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        nrep = max(1, min(args.steps, 3))
+        nrep = max(2, args.steps)
         a.record()
-        for _ in range(nrep):
-            e2e_step()
+        for i in range(nrep):
+            e2e_step(i)
+        e2e_drain()                      # every upload, kernel and download of the nrep steps is inside the timed region
         b.record()
         barrier()
         te = torch.tensor([a.elapsed_time(b) / nrep], device=dev)
@@ -437,10 +488,11 @@ def run_ours(args, rank, world):
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": views * h * w / (float(te.item()) * 1e-3) / 1e6, "unit": "MP/s",
                "h2d_bytes_per_step": int(h2d * world), "d2h_bytes_per_step": int(d2h * world),
-               "ms_per_step": float(te.item()),
-               "what": "pinned host rays + one subject's primitives + grad_out -> device, per-view expand, op fwd+bwd, "
-                       "view-sum (+all-reduce), rayrgba + reduced gradients -> pinned host; views streamed in chunks of %d "
-                       "(H2D / compute / D2H overlapped on three streams)" % chunk}
+               "ms_per_step": float(te.item()), "steps": nrep,
+               "what": "every step: pinned host rays + one subject's primitives + grad_out -> device, per-view expand, op fwd+bwd, "
+                       "view-sum (+all-reduce), rayrgba + reduced gradients -> pinned host; views streamed in chunks of %d, device "
+                       "staging double-buffered so H2D of step i+1 / compute of step i / D2H of step i-1 overlap (three streams); "
+                       "%d steps timed back to back, all copies inside the timed region" % (chunk, nrep)}
 
     log("e2e done")
     if rank != 0:
@@ -479,13 +531,14 @@ def run_ours(args, rank, world):
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": workload_config(views, h, w, k, t),
-        "parallelism": "views sharded over %d rank(s) (%d per rank), 1 NCCL all-reduce of %.1f MB primitive grads per step" % (world, nv, flat_numel * 4 / 1e6),
+        "parallelism": "views sharded over %d rank(s) (%d per rank), interleaved, 1 NCCL all-reduce of %.1f MB primitive grads per step, overlapped with the next step's forward" % (world, nv, flat_numel * 4 / 1e6),
         "kernel_build": lib.LIB.mvp_build_config().decode(),
         "scene": {"alpha_mu": ALPHA_MU, "alpha_sigma": ALPHA_SIGMA, "saturated_ray_frac": sat_frac, "covered_ray_frac": cover},
         "roofline": dominant, "roofline_forward": roof_f, "roofline_backward": roof_b,
         "cpu_baseline": cpu, "ref_cuda_baseline": ref_cuda, "parity_check": parity, "e2e": e2e, "clocks": clocks,
         "gpu_launches": args.steps * (lib.LIB.mvp_forward_launch_count(0) + lib.LIB.mvp_backward_launch_count(lib.FLAG_ACCEL_VALID)),
         "kernel_ms": {"forward_all_views_per_rank": fwd_ms, "backward_all_views_per_rank": bwd_ms},
+        "rank_ms_per_step": rank_ms, "allreduce_ms": allreduce_ms,
     }
     print(json.dumps(line), flush=True)
 
@@ -502,6 +555,7 @@ def main():
     ap.add_argument("--prims", type=int, default=K)
     ap.add_argument("--voxels", type=int, default=T)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--contiguous-views", action="store_true", help="contiguous view blocks per rank instead of interleaved")
     ap.add_argument("--e2e-chunk", type=int, default=8, help="views per pipelined chunk in the e2e measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true", help="skip the reference-CUDA legs (ref_cuda_baseline, parity_check)")

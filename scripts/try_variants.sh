@@ -10,6 +10,6 @@ for spec in "$@"; do
     cp .variants/$v.so ava-256_b200/libmvpraymarch_b200.so
     echo "== $v" >> $log
     case $what in *T*) ALPHA_MU=17 ALPHA_SIGMA=6 timeout 60 python scripts/time_modes.py 2>&1 | tail -1 >> $log;; esac
-    case $what in *P*) timeout 90 python -m pytest tests -m gpu -q -x 2>&1 | tail -2 >> $log;; esac
+    case $what in *P*) timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -2 >> $log;; esac
 done
 cat $log

@@ -29,7 +29,7 @@ def test_header_symbols_are_exported():
     assert sorted(names) == sorted(lib.EXPORTS)
     assert lib.LIB.mvp_abi_version() == 5
     cfg = lib.LIB.mvp_build_config().decode()
-    assert "LIST_REUSE=" in cfg and "FWD_OPAQUE=" in cfg and "CPU_EMUL" not in cfg
+    assert "LIST_REUSE=" in cfg and "FASTCAP=" in cfg and "CPU_EMUL" not in cfg
 
 
 def test_c_program_through_the_header_alone(tmp_path):

@@ -111,12 +111,13 @@ VARIANTS = {
     "list_rebuild": ("MVP_LIST_REUSE=0",),                                 # backward rebuilds the lists (the former default)
     "list_reuse": ("MVP_LIST_REUSE=1",),                                   # backward loads the lists the forward saved (default)
     "list_reuse_overflow": ("MVP_LIST_REUSE=1", "MVP_LIST_CAP_PER_TILE=1", "MVP_LIST_CAP_MIN=16"),  # most tiles do not fit: mixes both paths
-    "bwd_record": ("MVP_BWD_OPAQUE=2",),
-    "fwd_arrays": ("MVP_FWD_OPAQUE=0",),
     "xbuckets": ("MVP_XBUCKETS=1",),                                        # second bucketing level in x
     "xbuckets_all": ("MVP_XBUCKETS=1", "MVP_LIST_MARGIN=1"),
     "list_margin": ("MVP_LIST_MARGIN=1",),                                  # step intervals from the fp-drift bound
     "list_margin_reuse": ("MVP_LIST_MARGIN=1", "MVP_LIST_REUSE=1"),
+    "no_xbuckets_no_margin": ("MVP_XBUCKETS=0", "MVP_LIST_MARGIN=0"),      # the round-1 defaults
+    "fwd_async": ("MVP_FWD_ASYNC=1", "MVP_FASTCAP=128"),                   # cp.async-staged gathers, consumed one batch later
+    "fwd_sync": ("MVP_FWD_ASYNC=0",),
 }
 
 

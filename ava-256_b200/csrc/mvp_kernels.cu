@@ -34,13 +34,9 @@
 // Test-only host build (tests/emul/): the kernels below compiled with g++ on top of a CPU emulation of warps, blocks and
 // shared memory, so the CPU test suite can run this file's logic against the oracle.  Not part of the product library.
 #include "cuda_emul.h"
-#define MVP_GRIDDEP_LAUNCH() ((void)0)
-#define MVP_GRIDDEP_WAIT() ((void)0)
 #else
 #include <cuda_runtime.h>
 #include <math_constants.h>
-#define MVP_GRIDDEP_LAUNCH() asm volatile("griddepcontrol.launch_dependents;")
-#define MVP_GRIDDEP_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
 #endif
 #include <stdint.h>
 #include <stdlib.h>
@@ -106,6 +102,11 @@ constexpr int kRing = 64;        // sample queue / ring per warp (forward and ba
 #ifndef MVP_FASTCAP
 #define MVP_FASTCAP 256
 #endif
+#ifndef MVP_BWD_SMEMREC
+#define MVP_BWD_SMEMREC 1   // backward: the current slab's 64-byte record lives in shared memory; the step loop re-reads it after every
+                            // batch adjoint and the adjoint reads what it needs from there, so the record's 15 registers are not
+                            // live across the adjoint (the kernel's register peak)
+#endif
 #ifndef MVP_FWD_ASYNC
 #define MVP_FWD_ASYNC 0   // 1: the forward's batch gathers go through cp.async (LDGSTS) into a per-warp staging area and are consumed one
                           // batch later, so their L1/L2-miss latency overlaps the marching of the next batch instead of stalling the warp
@@ -138,7 +139,7 @@ struct Cam {          // 64 B per view
 struct __align__(8) RowEntry { int k; unsigned xr; };   // xr = x0 | x1 << 16  (pixels, inclusive)
 
 struct Layout {
-    size_t cam, bad, pack, rx, ry, rowcnt, rowlist, tileflag, heavycnt, heavylist, total;
+    size_t cam, bad, pack, rx, ry, rowcnt, rowlist, heavycnt, heavylist, total;
     int R, rowcap;
 #if MVP_XBUCKETS
     size_t grphdr, grplist;
@@ -164,7 +165,6 @@ __host__ inline Layout make_layout(const mvp_shape &s) {
     L.ry = off;      off = align256(off + (size_t)s.N * s.K * 4);
     L.rowcnt = off;  off = align256(off + (size_t)s.N * L.R * 4);
     L.rowlist = off; off = align256(off + (size_t)s.N * L.R * L.rowcap * sizeof(RowEntry));
-    L.tileflag = off; off = align256(off + (size_t)s.N * ((s.H + kTileH - 1) / kTileH) * ((s.W + kTileW - 1) / kTileW));
     L.heavycnt = off; off = align256(off + sizeof(int));
     L.heavylist = off; off = align256(off + (size_t)s.N * ((s.H + kTileH - 1) / kTileH) * ((s.W + kTileW - 1) / kTileW) * sizeof(int));
 #if MVP_XBUCKETS
@@ -358,101 +358,64 @@ __global__ void __launch_bounds__(128) prim_setup_kernel(int N, int K, int H, in
 // ------------------------------------------------------------------------------------------------------
 // 3. tile-row buckets in DFS-rank order (deterministic ordered compaction; one CTA per (row, view))
 // ------------------------------------------------------------------------------------------------------
-constexpr int kRowThreads = 256;
+constexpr int kRowThreads = 256;          // 8 warps = 8 tile rows per CTA
 
-__global__ void __launch_bounds__(kRowThreads) row_lists_kernel(int K, int R, int rowcap, int TXn, int fastcap,
+// One WARP per (tile row, view): it walks the view's slabs in DFS-rank order, 32 at a time, and appends those whose rectangle
+// touches the row -- an ordered compaction that needs nothing but a ballot per step (no block-wide barrier: the round-1 kernel
+// spent its time in three __syncthreads per 256 slabs).  The 8 warps of a CTA read the same rectangle arrays (L1 hits).
+__global__ void __launch_bounds__(kRowThreads) row_lists_kernel(int K, int R, int rowcap, int TXn,
                                                                 const unsigned *__restrict__ rx, const unsigned *__restrict__ ry,
-                                                                int *__restrict__ rowcnt, RowEntry *__restrict__ rowlist,
-                                                                unsigned char *__restrict__ tileflag, int *__restrict__ heavycnt,
-                                                                int *__restrict__ heavylist
+                                                                int *__restrict__ rowcnt, RowEntry *__restrict__ rowlist
 #if MVP_XBUCKETS
                                                                 , int NG, int2 *__restrict__ grphdr, RowEntry *__restrict__ grplist
 #endif
                                                                 ) {
-#ifdef MVP_CPU_EMUL
-    MVP_EMUL_DYN_SMEM(int, s_tilecnt);
-#else
-    extern __shared__ int s_tilecnt[];
-#endif   // [TXn] candidates (rectangle overlaps) per 8-pixel tile column of this row
-    const int row = blockIdx.x, n = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row = blockIdx.x * (kRowThreads / 32) + warp, n = blockIdx.y;
+    if (row >= R) return;                      // warps are independent
     const int ylo = row * kTileH, yhi = ylo + kTileH - 1;
     const unsigned *rxn = rx + (size_t)n * K, *ryn = ry + (size_t)n * K;
     RowEntry *out = rowlist + ((size_t)n * R + row) * rowcap;
     const int kstart = dfs_kstart(K);
-    __shared__ int s_wcnt[kRowThreads / 32];
-    __shared__ int s_base;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_base = 0;
-    for (int i = threadIdx.x; i < TXn; i += kRowThreads) s_tilecnt[i] = 0;
-    __syncthreads();
-    for (int j0 = 0; j0 < K; j0 += kRowThreads) {
-        const int j = j0 + threadIdx.x;
+    const unsigned below = (1u << lane) - 1u;
+    int total = 0;
+    for (int j0 = 0; j0 < K; j0 += 32) {
+        const int j = j0 + lane;
         bool in = false;
         int k = 0;
         unsigned xr = 0;
         if (j < K) {
             k = j + kstart; if (k >= K) k -= K;
-            unsigned yr = __ldg(ryn + k);
-            int y0 = (int)(yr & 0xffffu), y1 = (int)(yr >> 16);
+            const unsigned yr = __ldg(ryn + k);
+            const int y0 = (int)(yr & 0xffffu), y1 = (int)(yr >> 16);
             in = (y0 <= y1) && (y0 <= yhi) && (y1 >= ylo);
             if (in) xr = __ldg(rxn + k);
         }
-        unsigned b = __ballot_sync(0xffffffffu, in);
-        if (lane == 0) s_wcnt[warp] = __popc(b);
-        __syncthreads();
-        int pre = s_base;
-        for (int w = 0; w < warp; ++w) pre += s_wcnt[w];
-        int pos = pre + __popc(b & ((1u << lane) - 1u));
+        const unsigned b = __ballot_sync(0xffffffffu, in);
+        const int pos = total + __popc(b & below);
         if (in && pos < rowcap) { RowEntry e; e.k = k; e.xr = xr; out[pos] = e; }
-        if (in) {
-            const int x0 = (int)(xr & 0xffffu), x1 = (int)(xr >> 16);
-            if (x0 <= x1) {
-                const int t1 = min(x1 / kTileW, TXn - 1);
-                for (int tcol = x0 / kTileW; tcol <= t1; ++tcol) atomicAdd(&s_tilecnt[tcol], 1);
-            }
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int t = 0;
-            for (int w = 0; w < kRowThreads / 32; ++w) t += s_wcnt[w];
-            s_base += t;
-        }
-        __syncthreads();
+        total += __popc(b);
     }
-    if (threadIdx.x == 0) rowcnt[(size_t)n * R + row] = s_base;   // may exceed rowcap: consumers then scan all slabs
-    // A tile whose candidate count fits the fast kernel's shared-memory list can never overflow it (list <= candidates);
-    // everything else is rendered by the 512-entry variant.
-    __syncthreads();
-    unsigned char *fl = tileflag + ((size_t)n * R + row) * TXn;
-    for (int i = threadIdx.x; i < TXn; i += kRowThreads) {
-        const bool heavy = s_tilecnt[i] > fastcap;
-        fl[i] = heavy ? 1 : 0;
-        if (heavy) heavylist[atomicAdd(heavycnt, 1)] = (n * R + row) * TXn + i;   // rendered by the persistent 512-entry kernels
-    }
+    if (lane == 0) rowcnt[(size_t)n * R + row] = total;   // may exceed rowcap: consumers then scan all slabs
 #if MVP_XBUCKETS
     // Second level: for every group of kGrpTiles tile columns, the row's entries (still in rank order) whose pixel range
     // touches the group, packed one group after the other into the row's group buffer (even offsets: 16-byte aligned for
     // the TMA staging).  Groups that no longer fit, and rows whose bucket overflowed, are marked (-1, -1): their tiles keep
     // scanning the row bucket.
     {
-        const int total = s_base;        // every thread reads it before it is reused below
-        __syncthreads();
+        __syncwarp();                          // this warp's bucket writes are visible to all its lanes
         int2 *hdr = grphdr + ((size_t)n * R + row) * NG;
         RowEntry *gout = grplist + ((size_t)n * R + row) * kGrpCap;
-        __shared__ int s_goff;
-        if (threadIdx.x == 0) s_goff = 0;
-        __syncthreads();
+        int goff = 0;
         for (int g = 0; g < NG; ++g) {
             if (total > rowcap) {
-                if (threadIdx.x == 0) hdr[g] = make_int2(-1, -1);
+                if (lane == 0) hdr[g] = make_int2(-1, -1);
                 continue;
             }
             const int gx0 = g * kGrpTiles * kTileW, gx1 = gx0 + kGrpTiles * kTileW - 1;
-            const int goff = s_goff;
-            if (threadIdx.x == 0) s_base = 0;
-            __syncthreads();
-            for (int j0 = 0; j0 < total; j0 += kRowThreads) {
-                const int j = j0 + threadIdx.x;
+            int cnt = 0;
+            for (int j0 = 0; j0 < total; j0 += 32) {
+                const int j = j0 + lane;
                 bool in = false;
                 RowEntry e;
                 e.k = 0; e.xr = 0;
@@ -462,27 +425,13 @@ __global__ void __launch_bounds__(kRowThreads) row_lists_kernel(int K, int R, in
                     in = (x0 <= x1) && (x0 <= gx1) && (x1 >= gx0);
                 }
                 const unsigned b = __ballot_sync(0xffffffffu, in);
-                if (lane == 0) s_wcnt[warp] = __popc(b);
-                __syncthreads();
-                int pre = s_base;
-                for (int w = 0; w < warp; ++w) pre += s_wcnt[w];
-                const int pos = goff + pre + __popc(b & ((1u << lane) - 1u));
+                const int pos = goff + cnt + __popc(b & below);
                 if (in && pos < kGrpCap) gout[pos] = e;
-                __syncthreads();
-                if (threadIdx.x == 0) {
-                    int t = 0;
-                    for (int w = 0; w < kRowThreads / 32; ++w) t += s_wcnt[w];
-                    s_base += t;
-                }
-                __syncthreads();
+                cnt += __popc(b);
             }
-            if (threadIdx.x == 0) {
-                const int cnt = s_base;
-                const bool ok = goff + cnt <= kGrpCap;
-                hdr[g] = ok ? make_int2(goff, cnt) : make_int2(-1, -1);
-                if (ok) s_goff = goff + ((cnt + 1) & ~1);
-            }
-            __syncthreads();
+            const bool ok = goff + cnt <= kGrpCap;
+            if (lane == 0) hdr[g] = ok ? make_int2(goff, cnt) : make_int2(-1, -1);
+            if (ok) goff += (cnt + 1) & ~1;
         }
     }
 #endif
@@ -589,6 +538,7 @@ constexpr int kStage = 32;   // bucket entries per staged chunk (256 B), double 
 // once the phase of parity P has completed)
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, int) { *bar = 0; }
 __device__ __forceinline__ void mbar_fence_init() {}
+__device__ __forceinline__ void mbar_inval(unsigned long long *) {}
 __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
     memcpy(dst, src, bytes);
     *bar += 1;
@@ -605,6 +555,11 @@ __device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
 // fence.mbarrier_init.release.cluster: a cluster-scope fence compiles to CCTL.IVALL, which invalidates the SM's whole
 // L1D -- fatal for a kernel that lives off L1 hits and starts a new tile per warp all the time.
 __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// An mbarrier must be invalidated before its memory is initialised again (a persistent warp builds one list per tile;
+// mbarrier.init on a live barrier is undefined -- on B200 it ends in "unspecified launch failure").
+__device__ __forceinline__ void mbar_inval(unsigned long long *bar) {
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
@@ -645,9 +600,8 @@ struct Params {
     int R, rowcap;
     int TXn, TYn;
     unsigned slab_bytes;          // TD*TH*TW*16
-    unsigned char *tileflag;
-    const int *heavycnt;          // number of heavy tiles (candidates > fast list capacity) of this launch ...
-    const int *heavylist;         // ... and their ids ((n * TYn + ty) * TXn + tx), in no particular order
+    int *heavycnt;                // tiles whose slab list overflowed the fast kernel's shared-memory list in THIS call ...
+    int *heavylist;               // ... and their ids ((n * TYn + ty) * TXn + tx), in no particular order; the 512-entry kernel renders them
 #if MVP_XBUCKETS
     const int2 *grphdr;           // per (view, tile row, x-group): (offset into the row's group buffer, entries) or (-1, -1)
     const RowEntry *grplist;      // per (view, tile row): kGrpCap entries
@@ -689,7 +643,7 @@ long long g_emul_bwd_stats[8];  // see render_backward_kernel
 // depth beats both "every lane starts at its own first hit" (the reference's lock-step loop) and a plane fitted to
 // the first-hit depths (0.57 vs 0.70 ms per 1024x667 view) because neighbouring slabs sit at randomly different
 // depths while the sweep planes stay coherent.
-// Returns false when the list would exceed CAP (< 512); cannot happen for tiles classified "fast" at accel build.
+// Returns false when the list would exceed CAP (< 512): the caller hands the tile to the 512-entry kernel.
 template <int CAP, bool kPrefetch>
 __device__ __forceinline__ bool build_tile_list(const Params &p, float rdt, int n, int tx, int ty, int lane, TileCtx &c,
                                                 int *s_k, int *s_iv, RowEntry *s_stage, unsigned long long *s_bar, float &t,
@@ -818,13 +772,20 @@ __device__ __forceinline__ bool build_tile_list(const Params &p, float rdt, int 
                     }
                     ++nl;
                 } else if (CAP < kMaxHit) {
-                    return false;          // warp-uniform
+                    // the list does not fit this kernel's shared-memory capacity (warp-uniform): the 512-entry kernel takes the
+                    // tile.  A bulk copy of the next bucket chunk may still be in flight into this warp's staging buffer.
+                    if (!overflow && base + kStage < total) mbar_wait(s_bar + ((ch + 1) & 1), (unsigned)(((ch + 1) >> 1) & 1));
+                    __syncwarp();
+                    if (!overflow && lane == 0) { mbar_inval(s_bar); mbar_inval(s_bar + 1); }
+                    __syncwarp();
+                    return false;
                 }
             }
         }
         __syncwarp();   // every lane has consumed this chunk before its buffer is refilled
     }
     __syncwarp();
+    if (!overflow && total > 0 && lane == 0) { mbar_inval(s_bar); mbar_inval(s_bar + 1); }   // all staged chunks have been waited for
     c.nl = nl;
 #if MVP_PREFETCH
     // TMA bulk prefetch (cp.async.bulk.prefetch.L2): pull the payload slabs this tile is about to sample into L2 while
@@ -875,14 +836,17 @@ __device__ __forceinline__ void save_tile_list(const Params &p, int n, int tx, i
 }
 
 // Backward: restore the outputs of build_tile_list the adjoint uses (ray, off, list, first step and its position) from
-// what the forward saved.  Returns false (warp-uniform) when this tile's list was not saved.
-__device__ __forceinline__ bool load_saved_tile_list(const Params &p, float rdt, int n, int tx, int ty, int lane, TileCtx &c, int *s_k,
+// what the forward saved.  Returns (warp-uniform) 1 = loaded, 0 = this tile's list was not saved (rebuild it), 2 = it was
+// saved but is longer than this kernel's shared-memory list (the 512-entry kernel takes the tile).
+template <int CAP>
+__device__ __forceinline__ int load_saved_tile_list(const Params &p, float rdt, int n, int tx, int ty, int lane, TileCtx &c, int *s_k,
                                                      int *s_iv, float &x, float &y, float &z, int &j0) {
     const int2 hdr = __ldg(p.tilehdr + ((size_t)n * p.TYn + ty) * p.TXn + tx);
 #ifdef MVP_CPU_EMUL
     if (lane == 0) atomicAdd(&g_emul_saved_list_tiles[hdr.y < 0 ? 1 : 0], 1);   // test hook: which path did the tile take
 #endif
-    if (hdr.y < 0) return false;
+    if (hdr.y < 0) return 0;
+    if (hdr.y > CAP) return 2;
     const int px = tx * kTileW + (lane & 7), py = ty * kTileH + (lane >> 3);
     c.inimg = (px < p.W) && (py < p.H);
     const int cx = min(px, p.W - 1), cy = min(py, p.H - 1);
@@ -914,7 +878,7 @@ __device__ __forceinline__ bool load_saved_tile_list(const Params &p, float rdt,
     x = __fmaf_rn(__fmul_rn(c.ray.dx, fi), p.dt, xs);
     y = __fmaf_rn(__fmul_rn(c.ray.dy, fi), p.dt, ys);
     z = __fmaf_rn(__fmul_rn(c.ray.dz, fi), p.dt, zs);
-    return true;
+    return 1;
 }
 #endif
 
@@ -1095,7 +1059,7 @@ __device__ __forceinline__ void cp_async_wait_all() {
 //    the CAP == 512 variant then renders only the flagged tiles.
 // ------------------------------------------------------------------------------------------------------
 template <int T, bool kGrad, int CAP, bool kWarp>
-__device__ __forceinline__ void forward_tile(const Params &p, const int n, const int tx, const int ty, const int lane, FwdWarpSmem<CAP, kGrad> *const S) {
+__device__ __forceinline__ bool forward_tile(const Params &p, const int n, const int tx, const int ty, const int lane, FwdWarpSmem<CAP, kGrad> *const S) {
     // all per-warp shared state lives in one record: every address below is (one pinned per-warp base) + immediate
     int *const sk = S->k, *const siv = S->iv, *const rm = S->rm;
     RowEntry *const sstage = S->stage;
@@ -1107,8 +1071,7 @@ __device__ __forceinline__ void forward_tile(const Params &p, const int n, const
     TileCtx c;
     float t, x, y, z, r1e;
     int j0;
-    const bool fits = build_tile_list<CAP, true>(p, rdt, n, tx, ty, lane, c, sk, siv, sstage, sbar, t, x, y, z, r1e, j0);
-    (void)fits;   // cannot fail: the tile's candidate count was checked against CAP when the accel was built
+    if (!build_tile_list<CAP, true>(p, rdt, n, tx, ty, lane, c, sk, siv, sstage, sbar, t, x, y, z, r1e, j0)) return false;
 
     const int px = tx * kTileW + (lane & 7), py = ty * kTileH + (lane >> 3);
     const size_t r = ((size_t)n * p.H + min(py, p.H - 1)) * p.W + min(px, p.W - 1);
@@ -1398,12 +1361,14 @@ __device__ __forceinline__ void forward_tile(const Params &p, const int n, const
 #if defined(MVP_CPU_EMUL) && defined(MVP_EMUL_STATS)
     if (lane == 0) for (int i = 0; i < 8; ++i) if (stat_[i]) std::atomic_ref<long long>(g_emul_fwd_stats[i]).fetch_add(stat_[i]);
 #endif
+    return true;
 }
 
-// Tiles whose candidate count exceeds the fast kernels' shared-memory list ("heavy" tiles; none in the benchmark scene) are
-// listed by row_lists_kernel; the CAP == 512 kernels are small persistent grids that walk that list, so a launch with
-// nothing to do costs a few microseconds instead of a full grid of empty CTAs.
-constexpr int kHeavyGrid = 296;
+// Tiles whose slab list overflows the fast kernels' shared-memory list ("heavy" tiles: silhouette tiles of very dense
+// scenes; none in the benchmark scene) are appended to a list by the fast kernel and rendered afterwards by the CAP == 512
+// kernel, a small persistent grid that walks that list -- so the 512-entry launch costs a few microseconds when there is
+// nothing to do, and the fast kernel's shared-memory footprint is set by the common case, not by the reference's cap.
+constexpr int kHeavyGrid = 592;   // 4 CTAs per SM
 
 template <int CAP, bool kGrad>
 __device__ __forceinline__ FwdWarpSmem<CAP, kGrad> *pinned_warp_record(FwdWarpSmem<CAP, kGrad> *rec) {
@@ -1421,10 +1386,8 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
     __shared__ FwdWarpSmem<CAP, kGrad> s_w[kWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     FwdWarpSmem<CAP, kGrad> *const S = pinned_warp_record<CAP, kGrad>(&s_w[warp]);
+    // warps are independent: no CTA-wide barrier anywhere
     if (CAP == kMaxHit) {
-        // Programmatic dependent launch: this kernel is launched first and lets the fast variant start at once; the fast
-        // variant waits for it only at its very end.  Warps are independent: no CTA-wide barrier anywhere.
-        MVP_GRIDDEP_LAUNCH();
         const int cnt = *p.heavycnt;
         for (int i = blockIdx.x * kWarps + warp; i < cnt; i += gridDim.x * kWarps) {
             const int id = p.heavylist[i];
@@ -1434,9 +1397,9 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
         }
     } else {
         const int tx = blockIdx.x * kBlkTX + (warp % kBlkTX), ty = blockIdx.y * kBlkTY + (warp / kBlkTX), n = blockIdx.z;
-        if (tx >= p.TXn || ty >= p.TYn) return;   // exited warps count as arrived
-        if (p.tileflag[((size_t)n * p.TYn + ty) * p.TXn + tx] == 0) forward_tile<T, kGrad, CAP, kWarp>(p, n, tx, ty, lane, S);
-        MVP_GRIDDEP_WAIT();
+        if (tx >= p.TXn || ty >= p.TYn) return;
+        if (!forward_tile<T, kGrad, CAP, kWarp>(p, n, tx, ty, lane, S) && lane == 0)
+            p.heavylist[atomicAdd(p.heavycnt, 1)] = (n * p.TYn + ty) * p.TXn + tx;
     }
 }
 
@@ -1456,6 +1419,30 @@ __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float 
 #endif
 }
 
+// dL/d(index) of one sample (utils.h:591-642) in full generality, i.e. including an axis whose cell was clamped (the sample sits
+// exactly on the slab's far face: probability ~2^-24 per axis, the upper voxel is then the reference's LOWER corner and the only
+// one it sees).  Taken by those samples only; it runs after the main corner pass, when few values of the batch adjoint are live, so its
+// 12 accumulators do not add to the register peak.
+__device__ __forceinline__ float3 index_grad_general(const float4 *pc, int sx, int sy, int sz, float bx0, float bx1, float by0, float by1,
+                                                  float bz0, float bz1, float oLx, float oLy, float oLz, float A, float B, int clamp_mask) {
+    const float wx_[2] = {bx1, bx0}, wy_[2] = {by1, by0}, wz_[2] = {bz1, bz0};
+    float gpU[3] = {0.f, 0.f, 0.f}, gpL[3] = {0.f, 0.f, 0.f}, gaU[3] = {0.f, 0.f, 0.f}, gaL[3] = {0.f, 0.f, 0.f};
+    for (int cn = 0; cn < 8; ++cn) {
+        const int bx = cn & 1, byy = (cn >> 1) & 1, bz = (cn >> 2) & 1;
+        const float4 v = __ldg(pc + ((bx ? sx : 0) + (byy ? sy : 0) + (bz ? sz : 0)));
+        const float pr = v.x * oLx + v.y * oLy + v.z * oLz;
+        const float wyz = wy_[byy] * wz_[bz], wxz = wx_[bx] * wz_[bz], wxy = wx_[bx] * wy_[byy];
+        if (bx) { gpU[0] += pr * wyz; gaU[0] += v.w * wyz; } else { gpL[0] += pr * wyz; gaL[0] += v.w * wyz; }
+        if (byy) { gpU[1] += pr * wxz; gaU[1] += v.w * wxz; } else { gpL[1] += pr * wxz; gaL[1] += v.w * wxz; }
+        if (bz) { gpU[2] += pr * wxy; gaU[2] += v.w * wxy; } else { gpL[2] += pr * wxy; gaL[2] += v.w * wxy; }
+    }
+    float3 g;
+    g.x = (clamp_mask & 1) ? -(A * gpU[0] + B * gaU[0]) : (A * (gpU[0] - gpL[0]) + B * (gaU[0] - gaL[0]));
+    g.y = (clamp_mask & 2) ? -(A * gpU[1] + B * gaU[1]) : (A * (gpU[1] - gpL[1]) + B * (gaU[1] - gaL[1]));
+    g.z = (clamp_mask & 4) ? -(A * gpU[2] + B * gaU[2]) : (A * (gpU[2] - gpL[2]) + B * (gaU[2] - gaL[2]));
+    return g;
+}
+
 template <int CAP>
 struct __align__(16) BwdWarpSmem {   // per-warp shared state of the backward kernel
     float4 q[kRing];
@@ -1464,10 +1451,32 @@ struct __align__(16) BwdWarpSmem {   // per-warp shared state of the backward ke
     int k[CAP];
     int iv[CAP];
     float ray[9 * 32];
+    float4 rec[4];          // record of the slab being processed (MVP_BWD_SMEMREC)
 };
 
+// The slab record from shared memory through loads the compiler can neither hoist nor keep alive: the caller decides where the
+// 15 values are live.
+__device__ __forceinline__ Prim load_rec_shared(const float4 *rec) {
+    float4 a, b, c, d;
+#ifdef MVP_CPU_EMUL
+    a = rec[0]; b = rec[1]; c = rec[2]; d = rec[3];
+#else
+    const unsigned addr = smem_u32(rec);
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(addr));
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+16];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(addr));
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+32];" : "=f"(c.x), "=f"(c.y), "=f"(c.z), "=f"(c.w) : "r"(addr));
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+48];" : "=f"(d.x), "=f"(d.y), "=f"(d.z), "=f"(d.w) : "r"(addr));
+#endif
+    Prim q;
+    q.px = a.x; q.py = a.y; q.pz = a.z; q.sx = a.w;
+    q.r00 = b.x; q.r01 = b.y; q.r02 = b.z; q.sy = b.w;
+    q.r10 = c.x; q.r11 = c.y; q.r12 = c.z; q.sz = c.w;
+    q.r20 = d.x; q.r21 = d.y; q.r22 = d.z;
+    return q;
+}
+
 template <int T, int CAP, bool kWarp>
-__device__ __forceinline__ void backward_tile(const Params &p, const int n, const int tx, const int ty, const int lane, BwdWarpSmem<CAP> *const S) {
+__device__ __forceinline__ bool backward_tile(const Params &p, const int n, const int tx, const int ty, const int lane, BwdWarpSmem<CAP> *const S) {
     int *const sk = S->k, *const siv = S->iv;
     RowEntry *const sstage = S->stage;
     unsigned long long *const sbar = S->bar;
@@ -1478,12 +1487,14 @@ __device__ __forceinline__ void backward_tile(const Params &p, const int n, cons
     TileCtx c;
     float t0, xb, yb, zb, r1e;   // xb = position at sweep step max(mcur, ms)
     int j0;
+    int have = 0;           // 0: rebuild the list, 1: loaded what the forward saved, 2: the saved list does not fit this kernel
 #if MVP_LIST_REUSE
-    if (!load_saved_tile_list(p, rdt, n, tx, ty, lane, c, sk, siv, xb, yb, zb, j0))
+    have = load_saved_tile_list<CAP>(p, rdt, n, tx, ty, lane, c, sk, siv, xb, yb, zb, j0);
+    if (have == 2) return false;
 #endif
-    build_tile_list<CAP, false>(p, rdt, n, tx, ty, lane, c, sk, siv, sstage, sbar, t0, xb, yb, zb, r1e, j0);   // measured: the prefetch only pays in forward
+    if (have == 0 && !build_tile_list<CAP, false>(p, rdt, n, tx, ty, lane, c, sk, siv, sstage, sbar, t0, xb, yb, zb, r1e, j0)) return false;
     const int nl = c.nl;
-    if (nl == 0) return;
+    if (nl == 0) return true;
 
     const int px = tx * kTileW + (lane & 7), py = ty * kTileH + (lane >> 3);
     const size_t r = ((size_t)n * p.H + min(py, p.H - 1)) * p.W + min(px, p.W - 1);
@@ -1512,13 +1523,13 @@ __device__ __forceinline__ void backward_tile(const Params &p, const int n, cons
     const float foff = (float)c.off;
     const int wlast = __reduce_max_sync(0xffffffffu, mlast);
     const int wfirst = __reduce_min_sync(0xffffffffu, ms);
-    if (wlast < wfirst || wfirst >= kBig) return;
+    if (wlast < wfirst || wfirst >= kBig) return true;
 
     const float4 *packn = p.pack + (size_t)(n * p.pview) * p.K * 4;
     const size_t slabsz = (size_t)p.TD * p.TH * p.TW;
-    const float4 *tpn = reinterpret_cast<const float4 *>(p.tplate) + (size_t)(n * p.pview) * p.K * slabsz;
-    float *gtn = p.g_tplate + (size_t)(n * p.pview) * p.K * slabsz * 4;
-    float *gpn = p.g_primpos + (size_t)(n * p.pview) * p.K * 3, *grn = p.g_primrot + (size_t)(n * p.pview) * p.K * 9, *gsn = p.g_primscale + (size_t)(n * p.pview) * p.K * 3;
+    // bases of the primitive tensors are re-derived from the parameter block where they are used (cheap constant-bank
+    // arithmetic) instead of living in a dozen registers for the whole tile
+    const size_t pvK = (size_t)(n * p.pview) * p.K;
     const int td = T > 0 ? T : p.TD, th = T > 0 ? T : p.TH, tw = T > 0 ? T : p.TW;
     const float gmx = (float)(tw - 1) * 0.5f, gmy = (float)(th - 1) * 0.5f, gmz = (float)(td - 1) * 0.5f;
     const int sx = tw > 1 ? 1 : 0, sy = th > 1 ? tw : 0, sz = td > 1 ? th * tw : 0;
@@ -1548,11 +1559,21 @@ __device__ __forceinline__ void backward_tile(const Params &p, const int n, cons
                 const int slot = w * 32 + bit;
                 const int k = sk[slot];
                 int rank = k - kstart; if (rank < 0) rank += p.K;
+#if MVP_BWD_SMEMREC
+                __syncwarp();                                  // the previous slab's last readers of the record are done
+                if (lane < 4) S->rec[lane] = __ldg(packn + (size_t)k * 4 + lane);
+                __syncwarp();
+#else
                 const Prim q = load_prim(packn, k);
+#endif
                 // Slab-major order needs no cross-lane alignment: every lane walks ITS OWN step interval of this slab
                 // (recomputed from the reference's slab test), so all rays that cross the slab are busy together.
                 float lo, hi;
                 int la = kBig, lb = -kBig;               // lane's candidate sweep steps [la, lb]
+#if MVP_BWD_SMEMREC
+                {
+                const Prim q = load_rec_shared(S->rec);
+#endif
 #if MVP_LIST_MARGIN
                 // same drift-bound intervals as the tile lists (build_tile_list); the bound is recomputed per slab instead
                 // of living in two registers for the whole kernel
@@ -1580,6 +1601,9 @@ __device__ __forceinline__ void backward_tile(const Params &p, const int n, cons
                     lb = min(clamp_step(floorf((hi - c.ray.tmin) * rdt) + MVP_BWD_HI_SLACK - foff), mlast);
                     if (rank > ranksat) lb = min(lb, msat - 1);      // samples after the saturating one do not exist
                 }
+#if MVP_BWD_SMEMREC
+                }
+#endif
                 const int len = lb - la + 1;
                 const int maxlen = __reduce_max_sync(0xffffffffu, len);
 #if defined(MVP_CPU_EMUL) && defined(MVP_EMUL_STATS)
@@ -1589,8 +1613,8 @@ __device__ __forceinline__ void backward_tile(const Params &p, const int n, cons
                 if (maxlen > 0 && len > 0) std::atomic_ref<long long>(g_emul_bwd_stats[3]).fetch_add(len);
 #endif
                 if (maxlen <= 0) continue;
-                const float4 *slab = tpn + (size_t)k * slabsz;
-                float *gslab = gtn + (size_t)k * slabsz * 4;
+                const float4 *slab = reinterpret_cast<const float4 *>(p.tplate) + (pvK + k) * slabsz;
+                float *gslab = p.g_tplate + (pvK + k) * slabsz * 4;
                 // transform-gradient accumulators of THIS lane for this slab: Gx[i][j] = sum xm_i * dL/dy_j and
                 // Gy[j] = sum dL/dy_j; grad_rot/scale/pos are linear in them (derived once per slab, before the reduction)
                 float gx[9], gsum[3];
@@ -1616,9 +1640,18 @@ __device__ __forceinline__ void backward_tile(const Params &p, const int n, cons
                 // reduced over the warp afterwards, so it does not matter which lane accumulates a sample).
                 int qhead = 0, qn = 0;
                 float4 *ring = sq;
+#if MVP_BWD_SMEMREC
+                // The step phase (record in registers) runs until a batch is due or the interval is exhausted; the batch adjoint
+                // takes what it needs of the record from shared memory; then the step phase reloads it.
+                for (int i = 0;;) {
+                    {
+                    const Prim q = load_rec_shared(S->rec);
+                    for (; i < maxlen && qn < 32; ++i) {
+#else
                 for (int i = 0; i <= maxlen; ++i) {
                     const bool flush = (i == maxlen);
                     if (!flush) {
+#endif
                         const bool live = i < len;
                         const float xm = x - q.px, ym = y - q.py, zm = z - q.pz;
                         x = __fmaf_rn(c.ray.dx, p.dt, x); y = __fmaf_rn(c.ray.dy, p.dt, y); z = __fmaf_rn(c.ray.dz, p.dt, z);
@@ -1643,7 +1676,15 @@ __device__ __forceinline__ void backward_tile(const Params &p, const int n, cons
                             __syncwarp();
                         }
                     }
+#if MVP_BWD_SMEMREC
+                    }
+                    const bool flush = (i == maxlen);
+                    if (flush && qn == 0) break;
+                    {
+                        const Prim q = load_rec_shared(S->rec);
+#else
                     while (qn >= 32 || (flush && qn > 0)) {
+#endif
 #if defined(MVP_CPU_EMUL) && defined(MVP_EMUL_STATS)
                         if (lane == 0) std::atomic_ref<long long>(g_emul_bwd_stats[5]).fetch_add(1);
 #endif
@@ -1691,22 +1732,20 @@ __device__ __forceinline__ void backward_tile(const Params &p, const int n, cons
                         // accumulate the index-gradient sums for both parts now and combine afterwards.
                         const float wx_[2] = {bx1, bx0}, wy_[2] = {by1, by0}, wz_[2] = {bz1, bz0};
                         float4 sv = make_float4(0.f, 0.f, 0.f, 0.f);
-                        float gpU[3] = {0.f, 0.f, 0.f}, gpL[3] = {0.f, 0.f, 0.f};   // rgb part: upper / lower corner sums per axis
-                        float gaU[3] = {0.f, 0.f, 0.f}, gaL[3] = {0.f, 0.f, 0.f};   // alpha part
-                        float wgt[8];
+                        float gp[3] = {0.f, 0.f, 0.f}, ga[3] = {0.f, 0.f, 0.f};   // signed (upper - lower) corner sums per axis: rgb / alpha part
 #pragma unroll
                         for (int cn = 0; cn < 8; ++cn) {
                             const int bx = cn & 1, byy = (cn >> 1) & 1, bz = (cn >> 2) & 1;
                             const float4 v = __ldg(pc + ((bx ? sx : 0) + (byy ? sy : 0) + (bz ? sz : 0)));
                             const float w_ = (wx_[bx] * wy_[byy]) * wz_[bz];
-                            wgt[cn] = w_;
                             sv.x = __fmaf_rn(w_, v.x, sv.x); sv.y = __fmaf_rn(w_, v.y, sv.y);
                             sv.z = __fmaf_rn(w_, v.z, sv.z); sv.w = __fmaf_rn(w_, v.w, sv.w);
                             const float pr = v.x * oLx + v.y * oLy + v.z * oLz;
                             const float wyz = wy_[byy] * wz_[bz], wxz = wx_[bx] * wz_[bz], wxy = wx_[bx] * wy_[byy];
-                            if (bx) { gpU[0] += pr * wyz; gaU[0] += v.w * wyz; } else { gpL[0] += pr * wyz; gaL[0] += v.w * wyz; }
-                            if (byy) { gpU[1] += pr * wxz; gaU[1] += v.w * wxz; } else { gpL[1] += pr * wxz; gaL[1] += v.w * wxz; }
-                            if (bz) { gpU[2] += pr * wxy; gaU[2] += v.w * wxy; } else { gpL[2] += pr * wxy; gaL[2] += v.w * wxy; }
+                            // d(weight)/d(index) is +1 on the upper corner of an axis, -1 on the lower one
+                            gp[0] += (bx ? pr : -pr) * wyz; ga[0] += (bx ? v.w : -v.w) * wyz;
+                            gp[1] += (byy ? pr : -pr) * wxz; ga[1] += (byy ? v.w : -v.w) * wxz;
+                            gp[2] += (bz ? pr : -pr) * wxy; ga[2] += (bz ? v.w : -v.w) * wxy;
                         }
                         sv.w *= fade;
                         // ---- primaccum.h:81-98 with the saturating sample known from forward ----
@@ -1724,13 +1763,17 @@ __device__ __forceinline__ void backward_tile(const Params &p, const int n, cons
 #pragma unroll
                         for (int cn = 0; cn < 8; ++cn) {
                             const int o = ((cn & 1) ? sx : 0) + ((cn & 2) ? sy : 0) + ((cn & 4) ? sz : 0);
-                            red_add_v4(gc + (size_t)o * 4, wgt[cn] * d0, wgt[cn] * d1, wgt[cn] * d2, wgt[cn] * B);
+                            const float w_ = (wx_[cn & 1] * wy_[(cn >> 1) & 1]) * wz_[(cn >> 2) & 1];   // same product as above
+                            red_add_v4(gc + (size_t)o * 4, w_ * d0, w_ * d1, w_ * d2, w_ * B);
                         }
                         // dL/d(index): d(weight)/d(index) is +1 on the upper corner, -1 on the lower one; on a clamped axis
                         // the reference sees the upper voxel as ITS lower corner (sign -1) and no other corner.
-                        const float gix = ex ? -(A * gpU[0] + B * gaU[0]) : (A * (gpU[0] - gpL[0]) + B * (gaU[0] - gaL[0]));
-                        const float giy = ey ? -(A * gpU[1] + B * gaU[1]) : (A * (gpU[1] - gpL[1]) + B * (gaU[1] - gaL[1]));
-                        const float giz = ez ? -(A * gpU[2] + B * gaU[2]) : (A * (gpU[2] - gpL[2]) + B * (gaU[2] - gaL[2]));
+                        float gix = A * gp[0] + B * ga[0], giy = A * gp[1] + B * ga[1], giz = A * gp[2] + B * ga[2];
+                        if (ex || ey || ez) {     // a sample exactly on a far face of the slab: see index_grad_general
+                            const float3 gg = index_grad_general(pc, sx, sy, sz, bx0, bx1, by0, by1, bz0, bz1, oLx, oLy, oLz, A, B,
+                                                                 (ex ? 1 : 0) | (ey ? 2 : 0) | (ez ? 4 : 0));
+                            gix = gg.x; giy = gg.y; giz = gg.z;
+                        }
                         gy0 += gmx * gix; gy1 += gmy * giy; gy2 += gmz * giz;
                         } else {
                         // ---- algo 1 (PrimSamplerTW<true>): payload sampled at the warp-field-displaced position ----
@@ -1805,6 +1848,9 @@ __device__ __forceinline__ void backward_tile(const Params &p, const int n, cons
                 }
                 if (!__any_sync(0xffffffffu, touched)) continue;
                 // grad_scale_j = sum_i R[i][j] Gx[i][j];  grad_rot[i][j] = s_j Gx[i][j];  grad_pos = -R (s * Gy)
+#if MVP_BWD_SMEMREC
+                const Prim q = load_rec_shared(S->rec);
+#endif
                 float g[16];
                 g[0] = q.r00 * gx[0] + q.r10 * gx[3] + q.r20 * gx[6];
                 g[1] = q.r01 * gx[1] + q.r11 * gx[4] + q.r21 * gx[7];
@@ -1850,12 +1896,14 @@ __device__ __forceinline__ void backward_tile(const Params &p, const int n, cons
                 g[0] += __shfl_xor_sync(0xffffffffu, g[0], 1);
                 const int vi = lane >> 1;
                 if (!(lane & 1) && vi < 15) {
-                    float *dst = vi < 3 ? (gsn + (size_t)k * 3 + vi) : (vi < 12 ? (grn + (size_t)k * 9 + (vi - 3)) : (gpn + (size_t)k * 3 + (vi - 12)));
+                    float *dst = vi < 3 ? (p.g_primscale + (pvK + k) * 3 + vi)
+                                        : (vi < 12 ? (p.g_primrot + (pvK + k) * 9 + (vi - 3)) : (p.g_primpos + (pvK + k) * 3 + (vi - 12)));
                     atomicAdd(dst, g[0]);
                 }
             }   // while (word)
         }       // for (w)
     }           // for (cs)
+    return true;
 }
 
 template <int T, int CAP, bool kWarp>
@@ -1864,7 +1912,6 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     BwdWarpSmem<CAP> *const S = &s_w[warp];
     if (CAP == kMaxHit) {
-        MVP_GRIDDEP_LAUNCH();
         const int cnt = *p.heavycnt;
         for (int i = blockIdx.x * kWarps + warp; i < cnt; i += gridDim.x * kWarps) {
             const int id = p.heavylist[i];
@@ -1875,43 +1922,29 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
     } else {
         const int tx = blockIdx.x * kBlkTX + (warp % kBlkTX), ty = blockIdx.y * kBlkTY + (warp / kBlkTX), n = blockIdx.z;
         if (tx >= p.TXn || ty >= p.TYn) return;
-        if (p.tileflag[((size_t)n * p.TYn + ty) * p.TXn + tx] == 0) backward_tile<T, CAP, kWarp>(p, n, tx, ty, lane, S);
-        MVP_GRIDDEP_WAIT();
+        if (!backward_tile<T, CAP, kWarp>(p, n, tx, ty, lane, S) && lane == 0)
+            p.heavylist[atomicAdd(p.heavycnt, 1)] = (n * p.TYn + ty) * p.TXn + tx;
     }
 }
 
-// plain launch of the 512-entry variant (first in the stream, small persistent grid); variadic because the kernel name contains commas
+// Launch pair: the fast kernel over the whole tile grid, then the small persistent 512-entry kernel over the tiles the fast
+// one handed over (plain stream order: it reads the heavy-tile counter the fast kernel filled).  Variadic macros because the
+// kernel names contain commas.
 #ifdef MVP_CPU_EMUL
+#define MVP_LAUNCH_FAST(...)                                    \
+    do {                                                        \
+        auto kern_ = __VA_ARGS__;                               \
+        MVP_LAUNCH(kern_, grid, kWarps * 32, 0, st, p);         \
+    } while (0)
 #define MVP_LAUNCH_HEAVY(...)                                   \
     do {                                                        \
         auto kern_ = __VA_ARGS__;                               \
         MVP_LAUNCH(kern_, dim3(kHeavyGrid), kWarps * 32, 0, st, p); \
     } while (0)
 #else
+#define MVP_LAUNCH_FAST(...) __VA_ARGS__<<<grid, kWarps * 32, 0, st>>>(p)
 #define MVP_LAUNCH_HEAVY(...) __VA_ARGS__<<<kHeavyGrid, kWarps * 32, 0, st>>>(p)
 #endif
-
-// Launches `kern` as a programmatic dependent of the previous kernel in the stream (it may start before that kernel has
-// finished; it executes griddepcontrol.wait before exiting, so it never completes first).
-template <typename KernT>
-cudaError_t launch_dependent(KernT kern, dim3 grid, int threads, cudaStream_t st, const Params &p) {
-#ifdef MVP_CPU_EMUL
-    MVP_LAUNCH(kern, grid, threads, 0, st, p);
-    return cudaSuccess;
-#else
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = grid;
-    cfg.blockDim = dim3(threads);
-    cfg.dynamicSmemBytes = 0;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, p);
-#endif
-}
 
 int check_shape(const mvp_shape &s) {
     if (s.N < 1 || s.H < 1 || s.W < 1 || s.K < 1 || s.TD < 1 || s.TH < 1 || s.TW < 1) return MVP_ERR_SHAPE;
@@ -1928,8 +1961,6 @@ int launch_accel(const mvp_shape &s, int pview, const float *raypos, const float
     int *bad = reinterpret_cast<int *>(ws + L.bad);
     cudaError_t e = cudaMemsetAsync(bad, 0, (size_t)s.N * sizeof(int), st);
     if (e != cudaSuccess) return (int)e;
-    e = cudaMemsetAsync(ws + L.heavycnt, 0, sizeof(int), st);
-    if (e != cudaSuccess) return (int)e;
 #if MVP_LIST_REUSE
     // a new accel structure invalidates whatever lists an earlier forward saved in this workspace
     e = cudaMemsetAsync(ws + L.tilehdr, 0xff, L.listbuf - L.tilehdr, st);
@@ -1943,10 +1974,9 @@ int launch_accel(const mvp_shape &s, int pview, const float *raypos, const float
     MVP_LAUNCH(prim_setup_kernel, (unsigned)((NK + 127) / 128), 128, 0, st, s.N, s.K, s.H, s.W, pview, primpos, primrot, primscale, cam, bad,
                reinterpret_cast<float4 *>(ws + L.pack), reinterpret_cast<unsigned *>(ws + L.rx), reinterpret_cast<unsigned *>(ws + L.ry));
     const int TXn = (s.W + kTileW - 1) / kTileW;
-    MVP_LAUNCH(row_lists_kernel, dim3(L.R, s.N), kRowThreads, (size_t)TXn * sizeof(int), st, s.K, L.R, L.rowcap, TXn, kFastCap,
+    MVP_LAUNCH(row_lists_kernel, dim3((L.R + kRowThreads / 32 - 1) / (kRowThreads / 32), s.N), kRowThreads, 0, st, s.K, L.R, L.rowcap, TXn,
                reinterpret_cast<unsigned *>(ws + L.rx), reinterpret_cast<unsigned *>(ws + L.ry), reinterpret_cast<int *>(ws + L.rowcnt),
-               reinterpret_cast<RowEntry *>(ws + L.rowlist), reinterpret_cast<unsigned char *>(ws + L.tileflag),
-               reinterpret_cast<int *>(ws + L.heavycnt), reinterpret_cast<int *>(ws + L.heavylist)
+               reinterpret_cast<RowEntry *>(ws + L.rowlist)
 #if MVP_XBUCKETS
                , L.NG, reinterpret_cast<int2 *>(ws + L.grphdr), reinterpret_cast<RowEntry *>(ws + L.grplist)
 #endif
@@ -1958,10 +1988,9 @@ int launch_accel(const mvp_shape &s, int pview, const float *raypos, const float
         s.N, s.K, s.H, s.W, pview, primpos, primrot, primscale, cam, bad, reinterpret_cast<float4 *>(ws + L.pack),
         reinterpret_cast<unsigned *>(ws + L.rx), reinterpret_cast<unsigned *>(ws + L.ry));
     const int TXn = (s.W + kTileW - 1) / kTileW;
-    row_lists_kernel<<<dim3(L.R, s.N), kRowThreads, (size_t)TXn * sizeof(int), st>>>(
-        s.K, L.R, L.rowcap, TXn, kFastCap, reinterpret_cast<unsigned *>(ws + L.rx), reinterpret_cast<unsigned *>(ws + L.ry),
-        reinterpret_cast<int *>(ws + L.rowcnt), reinterpret_cast<RowEntry *>(ws + L.rowlist),
-        reinterpret_cast<unsigned char *>(ws + L.tileflag), reinterpret_cast<int *>(ws + L.heavycnt), reinterpret_cast<int *>(ws + L.heavylist)
+    row_lists_kernel<<<dim3((L.R + kRowThreads / 32 - 1) / (kRowThreads / 32), s.N), kRowThreads, 0, st>>>(
+        s.K, L.R, L.rowcap, TXn, reinterpret_cast<unsigned *>(ws + L.rx), reinterpret_cast<unsigned *>(ws + L.ry),
+        reinterpret_cast<int *>(ws + L.rowcnt), reinterpret_cast<RowEntry *>(ws + L.rowlist)
 #if MVP_XBUCKETS
         , L.NG, reinterpret_cast<int2 *>(ws + L.grphdr), reinterpret_cast<RowEntry *>(ws + L.grplist)
 #endif
@@ -1983,9 +2012,8 @@ void fill_params(Params &p, const mvp_shape &s, float stepsize, float fadescale,
     p.R = L.R; p.rowcap = L.rowcap;
     p.TXn = (s.W + kTileW - 1) / kTileW;
     p.TYn = (s.H + kTileH - 1) / kTileH;
-    p.tileflag = reinterpret_cast<unsigned char *>(ws + L.tileflag);
-    p.heavycnt = reinterpret_cast<const int *>(ws + L.heavycnt);
-    p.heavylist = reinterpret_cast<const int *>(ws + L.heavylist);
+    p.heavycnt = reinterpret_cast<int *>(ws + L.heavycnt);
+    p.heavylist = reinterpret_cast<int *>(ws + L.heavylist);
     p.slab_bytes = (unsigned)((size_t)s.TD * s.TH * s.TW * 16);
 #if MVP_XBUCKETS
     p.grphdr = reinterpret_cast<const int2 *>(ws + L.grphdr);
@@ -2012,7 +2040,7 @@ int mvp_abi_version(void) { return MVP_ABI_VERSION; }
 #define MVP_STR(x) MVP_STR2(x)
 const char *mvp_build_config(void) {
     return "LIST_REUSE=" MVP_STR(MVP_LIST_REUSE)
-           " LIST_MARGIN=" MVP_STR(MVP_LIST_MARGIN) " XBUCKETS=" MVP_STR(MVP_XBUCKETS) " FASTCAP=" MVP_STR(MVP_FASTCAP) " PF_CELL=" MVP_STR(MVP_PF_CELL) " FWD_ASYNC=" MVP_STR(MVP_FWD_ASYNC)
+           " LIST_MARGIN=" MVP_STR(MVP_LIST_MARGIN) " XBUCKETS=" MVP_STR(MVP_XBUCKETS) " FASTCAP=" MVP_STR(MVP_FASTCAP) " PF_CELL=" MVP_STR(MVP_PF_CELL) " FWD_ASYNC=" MVP_STR(MVP_FWD_ASYNC) " BWD_SMEMREC=" MVP_STR(MVP_BWD_SMEMREC)
            " CHUNK=" MVP_STR(MVP_CHUNK) " FWD_MINB=" MVP_STR(MVP_FWD_MINB) " BWD_MINB=" MVP_STR(MVP_BWD_MINB)
            " WARPS=" MVP_STR(MVP_WARPS) " BLK_TX=" MVP_STR(MVP_BLK_TX)
 #ifdef MVP_CPU_EMUL
@@ -2108,6 +2136,10 @@ int mvp_raymarch_forward(const mvp_forward_args *a, void *stream) {
     p.warp = a->warp; p.WD = a->WD; p.WH = a->WH; p.WW = a->WW;
     dim3 grid((p.TXn + kBlkTX - 1) / kBlkTX, (p.TYn + kBlkTY - 1) / kBlkTY, a->shape.N);
     if (grid.y > 65535) return MVP_ERR_SHAPE;
+    {
+        cudaError_t e0 = cudaMemsetAsync(p.heavycnt, 0, sizeof(int), st);
+        if (e0 != cudaSuccess) return (int)e0;
+    }
 #if MVP_LIST_REUSE
     if (a->raysat) {
         cudaError_t e0 = cudaMemsetAsync(p.listcur, 0, (size_t)a->shape.N * sizeof(int), st);
@@ -2118,11 +2150,11 @@ int mvp_raymarch_forward(const mvp_forward_args *a, void *stream) {
 #define MVP_LAUNCH_FWD(TT, WW_)                                                                              \
     do {                                                                                                     \
         if (a->raysat) {                                                                                     \
+            MVP_LAUNCH_FAST(render_forward_kernel<TT, true, kFastCap, WW_>);                                 \
             MVP_LAUNCH_HEAVY(render_forward_kernel<TT, true, kMaxHit, WW_>);                                 \
-            launch_dependent(render_forward_kernel<TT, true, kFastCap, WW_>, grid, kWarps * 32, st, p);      \
         } else {                                                                                             \
+            MVP_LAUNCH_FAST(render_forward_kernel<TT, false, kFastCap, WW_>);                                \
             MVP_LAUNCH_HEAVY(render_forward_kernel<TT, false, kMaxHit, WW_>);                                \
-            launch_dependent(render_forward_kernel<TT, false, kFastCap, WW_>, grid, kWarps * 32, st, p);     \
         }                                                                                                    \
     } while (0)
     if (a->algo == 1) MVP_LAUNCH_FWD(0, true);
@@ -2178,11 +2210,15 @@ int mvp_raymarch_backward(const mvp_backward_args *a, void *stream) {
     p.warp = a->warp; p.g_warp = a->grad_warp; p.WD = a->WD; p.WH = a->WH; p.WW = a->WW;
     dim3 grid((p.TXn + kBlkTX - 1) / kBlkTX, (p.TYn + kBlkTY - 1) / kBlkTY, a->shape.N);
     if (grid.y > 65535) return MVP_ERR_SHAPE;
+    {
+        cudaError_t e0 = cudaMemsetAsync(p.heavycnt, 0, sizeof(int), st);
+        if (e0 != cudaSuccess) return (int)e0;
+    }
     const int cubic = (a->shape.TD == a->shape.TH && a->shape.TH == a->shape.TW) ? a->shape.TD : 0;
 #define MVP_LAUNCH_BWD(TT, WW_)                                                                  \
     do {                                                                                         \
+        MVP_LAUNCH_FAST(render_backward_kernel<TT, kFastCap, WW_>);                              \
         MVP_LAUNCH_HEAVY(render_backward_kernel<TT, kMaxHit, WW_>);                              \
-        launch_dependent(render_backward_kernel<TT, kFastCap, WW_>, grid, kWarps * 32, st, p);   \
     } while (0)
     if (a->algo == 1) MVP_LAUNCH_BWD(0, true);
     else if (cubic == 8) MVP_LAUNCH_BWD(8, false);

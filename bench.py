@@ -157,7 +157,7 @@ def run_reference(args, rank):
 # ----------------------------------------------------------------------------------------------------------------
 # checker legs of our arm (rank 0, N=1): the UNMODIFIED reference CUDA extension (oracle/_ref, prebuilt) on the same scene
 # ----------------------------------------------------------------------------------------------------------------
-def ref_cuda_leg(s, stepsize, grad_out, out, grads, chunk=16, reps=5, warm=2):
+def ref_cuda_leg(s, stepsize, grad_out, out, grads, chunk=16, reps=7, warm=2):
     """Times the reference kernels (compiled for sm_100 from the reference's sources by oracle/build_ref.py) on the tensors
     the timed region just used, and compares view 0.  The reference launches on legacy stream 0 (= torch's default stream)
     and cudaMalloc/cudaFree's inside compute_aabb (bvh.cu:261-293), so every call is bracketed by device-wide syncs;
@@ -185,7 +185,7 @@ def ref_cuda_leg(s, stepsize, grad_out, out, grads, chunk=16, reps=5, warm=2):
         return torch.cuda.Event(enable_timing=True)
 
     def one_pass(keep_first=False):
-        tf = tb = 0.0
+        ta = tf = tb = 0.0
         first = None
         for (a0, a1) in bounds:
             c = a1 - a0
@@ -195,9 +195,10 @@ def ref_cuda_leg(s, stepsize, grad_out, out, grads, chunk=16, reps=5, warm=2):
             for g_ in gbuf:
                 g_[:c].zero_()                                     # mvpraymarch.py:240-246 (not timed)
             torch.cuda.synchronize()
-            e0, e1, e2 = ev(), ev(), ev()
-            e0.record()
+            ea, e0, e1, e2 = ev(), ev(), ev(), ev()
+            ea.record()
             m.compute_aabb(v["primpos"], v["primrot"], v["primscale"], so, nc, na, aabb[:c], 0)
+            e0.record()
             m.raymarch_forward(v["raypos"], v["raydir"], stepsize, v["tminmax"], so, nc, aabb[:c], v["primpos"], v["primrot"],
                                v["primscale"], v["template"], None, rgba[:c], rsat[:c], None, 0, False, 512, True, True, 8.0, 8.0,
                                0, 0.0, 3, 8, 16)
@@ -207,29 +208,35 @@ def ref_cuda_leg(s, stepsize, grad_out, out, grads, chunk=16, reps=5, warm=2):
                                 rgba[:c], grad_out[a0:a1], rsat[:c], None, 0, False, 512, True, True, 8.0, 8.0, 0, 0.0, 3, 8, 16)
             e2.record()
             torch.cuda.synchronize()
+            ta += ea.elapsed_time(e0)
             tf += e0.elapsed_time(e1)
             tb += e1.elapsed_time(e2)
             if keep_first and first is None:
                 first = (rgba[0].clone(), rsat[0].clone(), [g_[0].clone() for g_ in gbuf])
-        return tf, tb, first
+        return ta, tf, tb, first
 
     first = None
     for i in range(warm):
-        _, _, f_ = one_pass(keep_first=(i == 0))
+        _, _, _, f_ = one_pass(keep_first=(i == 0))
         first = first or f_
-    tfs, tbs = [], []
+    tas, tfs, tbs = [], [], []
     for _ in range(reps):
-        tf, tb, _ = one_pass()
+        ta, tf, tb, _ = one_pass()
+        tas.append(ta)
         tfs.append(tf)
         tbs.append(tb)
+    tas.sort()
     tfs.sort()
     tbs.sort()
-    fwd, bwd = tfs[len(tfs) // 2] / nv, tbs[len(tbs) // 2] / nv
+    aab, fwd, bwd = tas[len(tas) // 2] / nv, tfs[len(tfs) // 2] / nv, tbs[len(tbs) // 2] / nv
     base = {"what": "unmodified reference CUDA extension (oracle/_ref, -arch=sm_100 -use_fast_math), same scene and tensors, "
-                    "%d views in chunks of %d, compute_aabb + raymarch_forward / raymarch_backward kernels only "
-                    "(its torch allocations and zero-fills not timed), median of %d passes after %d warm-ups" % (nv, chunk, reps, warm),
-            "fwd_ms_per_view": fwd, "bwd_ms_per_view": bwd, "mps": hh * ww / ((fwd + bwd) * 1e-3) / 1e6,
-            "fwd_ms_per_view_minmax": [tfs[0] / nv, tfs[-1] / nv], "bwd_ms_per_view_minmax": [tbs[0] / nv, tbs[-1] / nv]}
+                    "%d views in chunks of %d; raymarch_forward and raymarch_backward kernels timed alone with CUDA events, "
+                    "compute_aabb (with its cudaMalloc / cudaFree, bvh.cu:261-293) separately; its torch allocations and zero-fills "
+                    "not timed; median of %d passes after %d warm-ups" % (nv, chunk, reps, warm),
+            "fwd_ms_per_view": fwd, "bwd_ms_per_view": bwd, "aabb_ms_per_view": aab,
+            "mps": hh * ww / ((fwd + bwd) * 1e-3) / 1e6, "mps_with_aabb": hh * ww / ((aab + fwd + bwd) * 1e-3) / 1e6,
+            "fwd_ms_per_view_minmax": [tfs[0] / nv, tfs[-1] / nv], "bwd_ms_per_view_minmax": [tbs[0] / nv, tbs[-1] / nv],
+            "aabb_ms_per_view_minmax": [tas[0] / nv, tas[-1] / nv]}
 
     def rel(a, b):
         return float((a - b).abs().max()) / max(float(b.abs().max()), 1e-30)
@@ -376,6 +383,43 @@ def run_ours(args, rank, world):
     bwd_ms = time_kernel(lambda: lib.check(lib.LIB.mvp_raymarch_backward(ctypes.byref(ba), stream)), reps)
     del gs, ws
     log("kernel-only: fwd %.2f ms, bwd %.2f ms per launch (%d views)" % (fwd_ms, bwd_ms, nv))
+
+    # ---- second configuration (not the headline, SURVEY 8e "optional fast path"): the subject's primitives passed ONCE,
+    # [1,K,...], shared by all views of the rank -- nothing is replicated in HBM, no 10.7 GB zero-fill, no view-sum; the
+    # gradients of all views accumulate into the one set, which is what the all-reduce needs anyway ----
+    shared_cfg = None
+    if not args.no_shared_leg:
+        sh = [x.detach()[:1].clone().requires_grad_(True) for x in leaves]
+
+        def shared_step():
+            for x in sh:
+                x.grad = None
+            o_ = mvpraymarch(s["raypos"], s["raydir"], stepsize, s["tminmax"], (sh[0], sh[1], sh[2]), sh[3], None)
+            o_.backward(grad_out)
+            if world > 1:
+                fl = torch.cat([sh[3].grad.reshape(-1), sh[0].grad.reshape(-1), sh[1].grad.reshape(-1), sh[2].grad.reshape(-1)])
+                dist.all_reduce(fl)
+            return o_
+
+        o_sh = shared_step()
+        same = bool(torch.equal(o_sh.detach(), out.detach()))
+        barrier()
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nsh = max(2, min(args.steps, 10))
+        ea.record()
+        for _ in range(nsh):
+            shared_step()
+        eb.record()
+        barrier()
+        tsh = torch.tensor([ea.elapsed_time(eb) / nsh], device=dev)
+        if world > 1:
+            dist.all_reduce(tsh, op=dist.ReduceOp.MAX)
+        shared_cfg = {"what": "same views, the subject's primitives passed once as [1,K,...] (MVP_FLAG_SHARED_PRIMS): no per-view "
+                              "copies, gradients of all views accumulate into one set; NOT the headline configuration",
+                      "ms_per_step": float(tsh.item()), "value": views * h * w / (float(tsh.item()) * 1e-3) / 1e6, "unit": "MP/s",
+                      "images_identical_to_headline_config": same}
+        del sh, o_sh
+        log("shared-primitive configuration: %.2f ms per step" % shared_cfg["ms_per_step"])
 
     # ---- checker legs (rank 0, single GPU): reference CUDA kernels on the same tensors: timing + parity of view 0 ----
     ref_cuda = parity = None
@@ -536,6 +580,7 @@ def run_ours(args, rank, world):
         "scene": {"alpha_mu": ALPHA_MU, "alpha_sigma": ALPHA_SIGMA, "saturated_ray_frac": sat_frac, "covered_ray_frac": cover},
         "roofline": dominant, "roofline_forward": roof_f, "roofline_backward": roof_b,
         "cpu_baseline": cpu, "ref_cuda_baseline": ref_cuda, "parity_check": parity, "e2e": e2e, "clocks": clocks,
+        "shared_primitives_config": shared_cfg,
         "gpu_launches": args.steps * (lib.LIB.mvp_forward_launch_count(0) + lib.LIB.mvp_backward_launch_count(lib.FLAG_ACCEL_VALID)),
         "kernel_ms": {"forward_all_views_per_rank": fwd_ms, "backward_all_views_per_rank": bwd_ms},
         "rank_ms_per_step": rank_ms, "allreduce_ms": allreduce_ms,
@@ -558,6 +603,7 @@ def main():
     ap.add_argument("--contiguous-views", action="store_true", help="contiguous view blocks per rank instead of interleaved")
     ap.add_argument("--e2e-chunk", type=int, default=8, help="views per pipelined chunk in the e2e measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-shared-leg", action="store_true", help="skip the shared-primitive ([1,K,...]) configuration")
     ap.add_argument("--no-check", action="store_true", help="skip the reference-CUDA legs (ref_cuda_baseline, parity_check)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

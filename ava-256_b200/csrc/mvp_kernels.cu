@@ -23,9 +23,16 @@
 //     own step interval), keeps factored transform gradients in registers, reduces them with a 16-value butterfly and
 //     issues one atomic per value per (warp, slab); payload gradients go out as 128-bit vector reductions
 //     (red.global.add.v4.f32) instead of 32 scalar atomics per sample.
-//   * The tile row's bucket is staged through shared memory by the TMA engine (cp.async.bulk + mbarrier).
+//   * The tile row's bucket (second level: the row's entries that touch a group of 8 tile columns) is staged through shared
+//     memory by the TMA engine (cp.async.bulk + mbarrier); list entries carry step intervals derived from a bound on the
+//     fp drift of the marched positions.
 //   * In gradient mode the forward saves each tile's list and each ray's first step in the workspace; the backward loads
 //     them instead of repeating the bucket scan and the exact slab tests.
+//   * Two kernels per pass: the fast one (256-entry shared-memory lists) renders every tile whose list fits -- all of them in
+//     the benchmark scene -- and appends the others to an overflow list; a small persistent 512-entry kernel (the reference's
+//     cap, utils.h:779-781) then renders those.
+//   * Backward register diet: the slab record and, optionally, the per-lane state that is only touched between batches live in
+//     shared memory, so the batch adjoint (the kernel's register peak) sees few live values.
 //
 // Arithmetic mirrors the reference's fp32 operation order where a step function of the result exists
 // (transform + strict validity, slab test, lattice snap, saturation); -use_fast_math is on like the reference.
@@ -107,6 +114,16 @@ constexpr int kRing = 64;        // sample queue / ring per warp (forward and ba
                             // batch adjoint and the adjoint reads what it needs from there, so the record's 15 registers are not
                             // live across the adjoint (the kernel's register peak)
 #endif
+#ifndef MVP_CTA_ORDER
+#define MVP_CTA_ORDER 1   // 1: the render kernels' CTAs run in descending order of a cost estimate (candidate slabs of the CTA's tile rows),
+                          // over all views of the launch: the expensive silhouette tiles -- a single warp can be busy for ~1 ms with
+                          // one of them -- start first and the cheap background tiles fill in behind, instead of a launch ending with
+                          // a few long-running warps.  Matters for small launches (10 views per rank at 8 GPUs); 0: plain grid order
+#endif
+#ifndef MVP_BWD_LANESMEM
+#define MVP_BWD_LANESMEM 0   // backward: per-lane state that is only touched between batches (ray origin / t-range, sweep limits, chunk
+                             // base position, the 12 transform-gradient accumulators) lives in shared memory instead of registers
+#endif
 #ifndef MVP_FWD_ASYNC
 #define MVP_FWD_ASYNC 0   // 1: the forward's batch gathers go through cp.async (LDGSTS) into a per-warp staging area and are consumed one
                           // batch later, so their L1/L2-miss latency overlaps the marching of the next batch instead of stalling the warp
@@ -122,6 +139,7 @@ constexpr int kGrpCap = 1024;     // group-bucket entries per tile row; groups t
 #endif
 constexpr int kFastCap = MVP_FASTCAP;   // shared-memory list capacity of the common-case render kernels
 constexpr int kBig = 1 << 30;
+constexpr int kCostClasses = 64;   // cost classes of the CTA ordering (counting sort)
 #ifndef MVP_BWD_MINB
 #define MVP_BWD_MINB 4   // resident CTAs per SM the backward kernel is compiled for (register cap 65536 / (128 * MINB))
 #endif
@@ -139,7 +157,7 @@ struct Cam {          // 64 B per view
 struct __align__(8) RowEntry { int k; unsigned xr; };   // xr = x0 | x1 << 16  (pixels, inclusive)
 
 struct Layout {
-    size_t cam, bad, pack, rx, ry, rowcnt, rowlist, heavycnt, heavylist, total;
+    size_t cam, bad, pack, rx, ry, rowcnt, rowlist, heavycnt, heavylist, ctaorder, ctahist, total;
     int R, rowcap;
 #if MVP_XBUCKETS
     size_t grphdr, grplist;
@@ -165,6 +183,11 @@ __host__ inline Layout make_layout(const mvp_shape &s) {
     L.ry = off;      off = align256(off + (size_t)s.N * s.K * 4);
     L.rowcnt = off;  off = align256(off + (size_t)s.N * L.R * 4);
     L.rowlist = off; off = align256(off + (size_t)s.N * L.R * L.rowcap * sizeof(RowEntry));
+    {
+        const size_t ctas = (size_t)s.N * (((s.H + kTileH - 1) / kTileH + kBlkTY - 1) / kBlkTY) * (((s.W + kTileW - 1) / kTileW + kBlkTX - 1) / kBlkTX);
+        L.ctaorder = off; off = align256(off + ctas * sizeof(int));
+        L.ctahist = off;  off = align256(off + 2 * kCostClasses * sizeof(int));
+    }
     L.heavycnt = off; off = align256(off + sizeof(int));
     L.heavylist = off; off = align256(off + (size_t)s.N * ((s.H + kTileH - 1) / kTileH) * ((s.W + kTileW - 1) / kTileW) * sizeof(int));
 #if MVP_XBUCKETS
@@ -438,6 +461,59 @@ __global__ void __launch_bounds__(kRowThreads) row_lists_kernel(int K, int R, in
 }
 
 // ------------------------------------------------------------------------------------------------------
+// 3b. CTA order: counting sort of the launch's CTAs (2x2 tiles) by descending cost class.  Cost estimate = the number of
+//     candidate slabs of the CTA's tile rows in its x-group (row bucket sizes), i.e. how long its lists can get.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int cta_cost_class(int n, int by, int bx, int R, int TXn, const int *__restrict__ rowcnt, int rowcap
+#if MVP_XBUCKETS
+                                              , int NG, const int2 *__restrict__ grphdr
+#endif
+                                              ) {
+    int cost = 0;
+    for (int r = by * kBlkTY; r < min((by + 1) * kBlkTY, R); ++r) {
+        int c = rowcnt[(size_t)n * R + r];
+#if MVP_XBUCKETS
+        if (c <= rowcap) {
+            const int g = (bx * kBlkTX) / kGrpTiles;
+            const int2 gh = grphdr[((size_t)n * R + r) * NG + g];
+            if (gh.y >= 0) c = gh.y;
+        }
+#endif
+        cost += c;
+    }
+    return min(kCostClasses - 1, cost >> 3);
+}
+
+// pass 0: histogram of the classes (hist[0 .. kCostClasses));  pass 1: scatter (cursor = hist[kCostClasses ..), zeroed)
+__global__ void __launch_bounds__(256) order_ctas_kernel(int pass, int N, int CXn, int CYn, int R, int TXn, const int *__restrict__ rowcnt,
+                                                         int rowcap,
+#if MVP_XBUCKETS
+                                                         int NG, const int2 *__restrict__ grphdr,
+#endif
+                                                         int *__restrict__ hist, int *__restrict__ order) {
+    __shared__ int s_base[kCostClasses];
+    if (pass == 1) {
+        // descending cost: class kCostClasses-1 first
+        if (threadIdx.x == 0) {
+            int acc = 0;
+            for (int c = kCostClasses - 1; c >= 0; --c) { s_base[c] = acc; acc += hist[c]; }
+        }
+        __syncthreads();
+    }
+    const size_t total = (size_t)N * CXn * CYn;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int bx = (int)(i % CXn), by = (int)((i / CXn) % CYn), n = (int)(i / ((size_t)CXn * CYn));
+    const int c = cta_cost_class(n, by, bx, R, TXn, rowcnt, rowcap
+#if MVP_XBUCKETS
+                                 , NG, grphdr
+#endif
+    );
+    if (pass == 0) atomicAdd(hist + c, 1);
+    else order[s_base[c] + atomicAdd(hist + kCostClasses + c, 1)] = (int)i;
+}
+
+// ------------------------------------------------------------------------------------------------------
 // device helpers shared by forward and backward
 // ------------------------------------------------------------------------------------------------------
 struct Prim {
@@ -600,6 +676,8 @@ struct Params {
     int R, rowcap;
     int TXn, TYn;
     unsigned slab_bytes;          // TD*TH*TW*16
+    int CXn, CYn;                 // CTAs (kBlkTX x kBlkTY tiles) per view in x / y
+    const int *ctaorder;          // CTA ids ((n * CYn + by) * CXn + bx) in descending order of estimated cost (MVP_CTA_ORDER)
     int *heavycnt;                // tiles whose slab list overflowed the fast kernel's shared-memory list in THIS call ...
     int *heavylist;               // ... and their ids ((n * TYn + ty) * TXn + tx), in no particular order; the 512-entry kernel renders them
 #if MVP_XBUCKETS
@@ -1396,7 +1474,14 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
             __syncwarp();
         }
     } else {
+#if MVP_CTA_ORDER
+        // 1-D grid; CTA b renders the b-th most expensive 2x2-tile block of the launch (order_ctas_kernel)
+        const int cid = p.ctaorder[blockIdx.x];
+        const int bx = cid % p.CXn, by = (cid / p.CXn) % p.CYn, n = cid / (p.CXn * p.CYn);
+        const int tx = bx * kBlkTX + (warp % kBlkTX), ty = by * kBlkTY + (warp / kBlkTX);
+#else
         const int tx = blockIdx.x * kBlkTX + (warp % kBlkTX), ty = blockIdx.y * kBlkTY + (warp / kBlkTX), n = blockIdx.z;
+#endif
         if (tx >= p.TXn || ty >= p.TYn) return;
         if (!forward_tile<T, kGrad, CAP, kWarp>(p, n, tx, ty, lane, S) && lane == 0)
             p.heavylist[atomicAdd(p.heavycnt, 1)] = (n * p.TYn + ty) * p.TXn + tx;
@@ -1452,6 +1537,9 @@ struct __align__(16) BwdWarpSmem {   // per-warp shared state of the backward ke
     int iv[CAP];
     float ray[9 * 32];
     float4 rec[4];          // record of the slab being processed (MVP_BWD_SMEMREC)
+#if MVP_BWD_LANESMEM
+    float ls[24 * 32];      // [field][lane]: see backward_tile
+#endif
 };
 
 // The slab record from shared memory through loads the compiler can neither hoist nor keep alive: the caller decides where the
@@ -1535,14 +1623,54 @@ __device__ __forceinline__ bool backward_tile(const Params &p, const int n, cons
     const int sx = tw > 1 ? 1 : 0, sy = th > 1 ? tw : 0, sz = td > 1 ? th * tw : 0;
     const int kstart = dfs_kstart(p.K);
 
+#if MVP_BWD_LANESMEM
+    // per-lane state that is only read between batches: parked in shared memory ([field][lane], conflict-free), read back
+    // through volatile accesses so that the compiler cannot keep it in registers across the batch adjoint
+    volatile float *const ls = S->ls + lane;
+    ls[0 * 32] = c.ray.ox; ls[1 * 32] = c.ray.oy; ls[2 * 32] = c.ray.oz; ls[3 * 32] = c.ray.tmin; ls[4 * 32] = c.ray.tmax;
+    ls[5 * 32] = __int_as_float(ms); ls[6 * 32] = __int_as_float(mlast); ls[7 * 32] = __int_as_float(msat); ls[8 * 32] = __int_as_float(ranksat);
+    ls[9 * 32] = xb; ls[10 * 32] = yb; ls[11 * 32] = zb;
+#define L_OX ls[0 * 32]
+#define L_OY ls[1 * 32]
+#define L_OZ ls[2 * 32]
+#define L_TMIN ls[3 * 32]
+#define L_TMAX ls[4 * 32]
+#define L_MS __float_as_int(ls[5 * 32])
+#define L_MLAST __float_as_int(ls[6 * 32])
+#define L_MSAT __float_as_int(ls[7 * 32])
+#define L_RANKSAT __float_as_int(ls[8 * 32])
+#define L_XB ls[9 * 32]
+#define L_YB ls[10 * 32]
+#define L_ZB ls[11 * 32]
+#define L_GX(i) ls[(12 + (i)) * 32]
+#else
+#define L_OX c.ray.ox
+#define L_OY c.ray.oy
+#define L_OZ c.ray.oz
+#define L_TMIN c.ray.tmin
+#define L_TMAX c.ray.tmax
+#define L_MS ms
+#define L_MLAST mlast
+#define L_MSAT msat
+#define L_RANKSAT ranksat
+#define L_XB xb
+#define L_YB yb
+#define L_ZB zb
+#endif
+    const float rdx = c.ray.dx, rdy = c.ray.dy, rdz = c.ray.dz;   // the only ray values the step loops need
     // Slabs are processed in the order of their first sweep step, 16-step chunk by chunk, so that each lane's
     // position can be carried forward with the SAME fma sequence the forward kernel executed (bit-identical sample
     // positions: the trilinear position gradient is discontinuous across voxel cells, so this matters).
     int mcur = wfirst;
     const int nwords = (nl + 31) >> 5;
     for (int cs = wfirst; cs <= wlast; cs += kMaskSteps) {
-        for (; mcur < cs; ++mcur) {
-            if (mcur >= ms) { xb = __fmaf_rn(c.ray.dx, p.dt, xb); yb = __fmaf_rn(c.ray.dy, p.dt, yb); zb = __fmaf_rn(c.ray.dz, p.dt, zb); }
+        if (mcur < cs) {
+            float xb_ = L_XB, yb_ = L_YB, zb_ = L_ZB;
+            const int ms_ = L_MS;
+            for (; mcur < cs; ++mcur) {
+                if (mcur >= ms_) { xb_ = __fmaf_rn(rdx, p.dt, xb_); yb_ = __fmaf_rn(rdy, p.dt, yb_); zb_ = __fmaf_rn(rdz, p.dt, zb_); }
+            }
+            L_XB = xb_; L_YB = yb_; L_ZB = zb_;
         }
         for (int w = 0; w < nwords; ++w) {
             const int myslot = w * 32 + lane;
@@ -1578,28 +1706,32 @@ __device__ __forceinline__ bool backward_tile(const Params &p, const int n, cons
                 // same drift-bound intervals as the tile lists (build_tile_list); the bound is recomputed per slab instead
                 // of living in two registers for the whole kernel
                 {
-                    const float nsteps = fmaxf(c.ray.tmax - c.ray.tmin, 0.f) * rdt + 8.f;
+                    Ray ry;
+                    ry.ox = L_OX; ry.oy = L_OY; ry.oz = L_OZ; ry.dx = rdx; ry.dy = rdy; ry.dz = rdz; ry.tmin = L_TMIN; ry.tmax = L_TMAX;
+                    const float nsteps = fmaxf(ry.tmax - ry.tmin, 0.f) * rdt + 8.f;
                     const float epos = 1.7320508f * nsteps * 1.1920929e-7f + 1.9073486e-6f;
                     const float eps0 = fmaxf(0.001953125f, nsteps * 4.7683716e-7f);
                     float lom, him;
-                    slab_test_margin(q, c.ray, epos, lo, hi, lom, him);
+                    slab_test_margin(q, ry, epos, lo, hi, lom, him);
                     if (hashit && lom <= him) {
-                        la = max(clamp_step(ceilf((lom - c.ray.tmin) * rdt - eps0) - foff), max(ms, cs));
-                        lb = min(clamp_step(floorf((him - c.ray.tmin) * rdt + eps0) - foff), mlast);
-                        if (rank > ranksat) lb = min(lb, msat - 1);      // samples after the saturating one do not exist
+                        la = max(clamp_step(ceilf((lom - ry.tmin) * rdt - eps0) - foff), max(L_MS, cs));
+                        lb = min(clamp_step(floorf((him - ry.tmin) * rdt + eps0) - foff), L_MLAST);
+                        if (rank > L_RANKSAT) lb = min(lb, L_MSAT - 1);      // samples after the saturating one do not exist
                     }
                 }
                 const bool hit = false;
 #else
-                const bool hit = slab_test(q, c.ray, lo, hi) && hashit;
+                Ray ry;
+                ry.ox = L_OX; ry.oy = L_OY; ry.oz = L_OZ; ry.dx = rdx; ry.dy = rdy; ry.dz = rdz; ry.tmin = L_TMIN; ry.tmax = L_TMAX;
+                const bool hit = slab_test(q, ry, lo, hi) && hashit;
 #endif
                 if (hit) {
                     // candidate lattice steps floor((lo-tmin)/dt) .. floor((hi-tmin)/dt)+1: the strictly-inside range plus one
                     // step of slack on each side, because lo/hi carry ~1e-6 relative error (rcp.approx) and the forward's
                     // validity test, not this interval, decides which samples exist.
-                    la = max(clamp_step(floorf((lo - c.ray.tmin) * rdt) + MVP_BWD_LO_SLACK - foff), max(ms, cs));
-                    lb = min(clamp_step(floorf((hi - c.ray.tmin) * rdt) + MVP_BWD_HI_SLACK - foff), mlast);
-                    if (rank > ranksat) lb = min(lb, msat - 1);      // samples after the saturating one do not exist
+                    la = max(clamp_step(floorf((lo - L_TMIN) * rdt) + MVP_BWD_LO_SLACK - foff), max(L_MS, cs));
+                    lb = min(clamp_step(floorf((hi - L_TMIN) * rdt) + MVP_BWD_HI_SLACK - foff), L_MLAST);
+                    if (rank > L_RANKSAT) lb = min(lb, L_MSAT - 1);      // samples after the saturating one do not exist
                 }
 #if MVP_BWD_SMEMREC
                 }
@@ -1617,21 +1749,28 @@ __device__ __forceinline__ bool backward_tile(const Params &p, const int n, cons
                 float *gslab = p.g_tplate + (pvK + k) * slabsz * 4;
                 // transform-gradient accumulators of THIS lane for this slab: Gx[i][j] = sum xm_i * dL/dy_j and
                 // Gy[j] = sum dL/dy_j; grad_rot/scale/pos are linear in them (derived once per slab, before the reduction)
+#if MVP_BWD_LANESMEM
+#pragma unroll
+                for (int i = 0; i < 12; ++i) L_GX(i) = 0.f;
+#else
                 float gx[9], gsum[3];
 #pragma unroll
                 for (int i = 0; i < 9; ++i) gx[i] = 0.f;
                 gsum[0] = gsum[1] = gsum[2] = 0.f;
+#endif
                 bool touched = false;
+                // the step at which this lane's walk of this slab meets the ray's saturating sample (-1: never)
+                const int isat_i = (rank == L_RANKSAT) ? (L_MSAT - la) : -1;
                 // carry the lane's position from the chunk base (step max(cs, ms)) to its first candidate step
-                float x = xb, y = yb, z = zb;
+                float x = L_XB, y = L_YB, z = L_ZB;
                 {
-                    const int adv = (len > 0) ? (la - max(cs, ms)) : 0;
+                    const int adv = (len > 0) ? (la - max(cs, L_MS)) : 0;
                     const int maxadv = __reduce_max_sync(0xffffffffu, adv);
 #if defined(MVP_CPU_EMUL) && defined(MVP_EMUL_STATS)
                     if (lane == 0) std::atomic_ref<long long>(g_emul_bwd_stats[6]).fetch_add(maxadv);
 #endif
                     for (int i = 0; i < maxadv; ++i) {
-                        if (i < adv) { x = __fmaf_rn(c.ray.dx, p.dt, x); y = __fmaf_rn(c.ray.dy, p.dt, y); z = __fmaf_rn(c.ray.dz, p.dt, z); }
+                        if (i < adv) { x = __fmaf_rn(rdx, p.dt, x); y = __fmaf_rn(rdy, p.dt, y); z = __fmaf_rn(rdz, p.dt, z); }
                     }
                 }
                 // Sample compaction: lanes enumerate their own valid steps (cheap transform + test) and push the sample
@@ -1654,7 +1793,7 @@ __device__ __forceinline__ bool backward_tile(const Params &p, const int n, cons
 #endif
                         const bool live = i < len;
                         const float xm = x - q.px, ym = y - q.py, zm = z - q.pz;
-                        x = __fmaf_rn(c.ray.dx, p.dt, x); y = __fmaf_rn(c.ray.dy, p.dt, y); z = __fmaf_rn(c.ray.dz, p.dt, z);
+                        x = __fmaf_rn(rdx, p.dt, x); y = __fmaf_rn(rdy, p.dt, y); z = __fmaf_rn(rdz, p.dt, z);
                         const float y0 = __fmul_rn(q.sx, rowdot(q.r00, xm, q.r10, ym, q.r20, zm));
                         const float y1 = __fmul_rn(q.sy, rowdot(q.r01, xm, q.r11, ym, q.r21, zm));
                         const float y2 = __fmul_rn(q.sz, rowdot(q.r02, xm, q.r12, ym, q.r22, zm));
@@ -1663,7 +1802,7 @@ __device__ __forceinline__ bool backward_tile(const Params &p, const int n, cons
                         if (vm) {
                             if (valid) {
                                 const int pos = (qhead + qn + __popc(vm & ((1u << lane) - 1u))) & (kRing - 1);
-                                const bool issat = ((la + i) == msat) && (rank == ranksat);
+                                const bool issat = (i == isat_i);
                                 ring[pos] = make_float4(xm, ym, zm, __int_as_float(lane | (issat ? 256 : 0)));
 #if MVP_PF_CELL
                                 if (!kWarp) prefetch_cell<T>(slab, y0, y1, y2, p.TD, p.TH, p.TW);
@@ -1840,16 +1979,29 @@ __device__ __forceinline__ bool backward_tile(const Params &p, const int n, cons
                         gy0 += ((float)(p.WW - 1) * 0.5f) * h0; gy1 += ((float)(p.WH - 1) * 0.5f) * h1; gy2 += ((float)(p.WD - 1) * 0.5f) * h2;
                         }
                         // ---- primtransf.h:155-179, accumulated in factored form ----
+#if MVP_BWD_LANESMEM
+                        L_GX(0) = L_GX(0) + xm * gy0; L_GX(1) = L_GX(1) + xm * gy1; L_GX(2) = L_GX(2) + xm * gy2;
+                        L_GX(3) = L_GX(3) + ym * gy0; L_GX(4) = L_GX(4) + ym * gy1; L_GX(5) = L_GX(5) + ym * gy2;
+                        L_GX(6) = L_GX(6) + zm * gy0; L_GX(7) = L_GX(7) + zm * gy1; L_GX(8) = L_GX(8) + zm * gy2;
+                        L_GX(9) = L_GX(9) + gy0; L_GX(10) = L_GX(10) + gy1; L_GX(11) = L_GX(11) + gy2;
+#else
                         gx[0] += xm * gy0; gx[1] += xm * gy1; gx[2] += xm * gy2;
                         gx[3] += ym * gy0; gx[4] += ym * gy1; gx[5] += ym * gy2;
                         gx[6] += zm * gy0; gx[7] += zm * gy1; gx[8] += zm * gy2;
                         gsum[0] += gy0; gsum[1] += gy1; gsum[2] += gy2;
+#endif
                     }
                 }
                 if (!__any_sync(0xffffffffu, touched)) continue;
                 // grad_scale_j = sum_i R[i][j] Gx[i][j];  grad_rot[i][j] = s_j Gx[i][j];  grad_pos = -R (s * Gy)
 #if MVP_BWD_SMEMREC
                 const Prim q = load_rec_shared(S->rec);
+#endif
+#if MVP_BWD_LANESMEM
+                float gx[9], gsum[3];
+#pragma unroll
+                for (int i = 0; i < 9; ++i) gx[i] = L_GX(i);
+                gsum[0] = L_GX(9); gsum[1] = L_GX(10); gsum[2] = L_GX(11);
 #endif
                 float g[16];
                 g[0] = q.r00 * gx[0] + q.r10 * gx[3] + q.r20 * gx[6];
@@ -1920,7 +2072,14 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
             __syncwarp();
         }
     } else {
+#if MVP_CTA_ORDER
+        // 1-D grid; CTA b renders the b-th most expensive 2x2-tile block of the launch (order_ctas_kernel)
+        const int cid = p.ctaorder[blockIdx.x];
+        const int bx = cid % p.CXn, by = (cid / p.CXn) % p.CYn, n = cid / (p.CXn * p.CYn);
+        const int tx = bx * kBlkTX + (warp % kBlkTX), ty = by * kBlkTY + (warp / kBlkTX);
+#else
         const int tx = blockIdx.x * kBlkTX + (warp % kBlkTX), ty = blockIdx.y * kBlkTY + (warp / kBlkTX), n = blockIdx.z;
+#endif
         if (tx >= p.TXn || ty >= p.TYn) return;
         if (!backward_tile<T, CAP, kWarp>(p, n, tx, ty, lane, S) && lane == 0)
             p.heavylist[atomicAdd(p.heavycnt, 1)] = (n * p.TYn + ty) * p.TXn + tx;
@@ -1996,6 +2155,32 @@ int launch_accel(const mvp_shape &s, int pview, const float *raypos, const float
 #endif
         );
 #endif
+#if MVP_CTA_ORDER
+    {
+        const int TYn = L.R, CXn = (TXn + kBlkTX - 1) / kBlkTX, CYn = (TYn + kBlkTY - 1) / kBlkTY;
+        const size_t ctas = (size_t)s.N * CXn * CYn;
+        int *hist = reinterpret_cast<int *>(ws + L.ctahist);
+        e = cudaMemsetAsync(hist, 0, 2 * kCostClasses * sizeof(int), st);
+        if (e != cudaSuccess) return (int)e;
+        for (int pass = 0; pass < 2; ++pass) {
+#ifdef MVP_CPU_EMUL
+            MVP_LAUNCH(order_ctas_kernel, (unsigned)((ctas + 255) / 256), 256, 0, st, pass, s.N, CXn, CYn, L.R, TXn,
+                       reinterpret_cast<const int *>(ws + L.rowcnt), L.rowcap,
+#if MVP_XBUCKETS
+                       L.NG, reinterpret_cast<const int2 *>(ws + L.grphdr),
+#endif
+                       hist, reinterpret_cast<int *>(ws + L.ctaorder));
+#else
+            order_ctas_kernel<<<(unsigned)((ctas + 255) / 256), 256, 0, st>>>(pass, s.N, CXn, CYn, L.R, TXn,
+                                                                              reinterpret_cast<const int *>(ws + L.rowcnt), L.rowcap,
+#if MVP_XBUCKETS
+                                                                              L.NG, reinterpret_cast<const int2 *>(ws + L.grphdr),
+#endif
+                                                                              hist, reinterpret_cast<int *>(ws + L.ctaorder));
+#endif
+        }
+    }
+#endif
     e = cudaGetLastError();
     return e == cudaSuccess ? MVP_OK : (int)e;
 }
@@ -2012,6 +2197,9 @@ void fill_params(Params &p, const mvp_shape &s, float stepsize, float fadescale,
     p.R = L.R; p.rowcap = L.rowcap;
     p.TXn = (s.W + kTileW - 1) / kTileW;
     p.TYn = (s.H + kTileH - 1) / kTileH;
+    p.CXn = (p.TXn + kBlkTX - 1) / kBlkTX;
+    p.CYn = (p.TYn + kBlkTY - 1) / kBlkTY;
+    p.ctaorder = reinterpret_cast<const int *>(ws + L.ctaorder);
     p.heavycnt = reinterpret_cast<int *>(ws + L.heavycnt);
     p.heavylist = reinterpret_cast<int *>(ws + L.heavylist);
     p.slab_bytes = (unsigned)((size_t)s.TD * s.TH * s.TW * 16);
@@ -2040,7 +2228,7 @@ int mvp_abi_version(void) { return MVP_ABI_VERSION; }
 #define MVP_STR(x) MVP_STR2(x)
 const char *mvp_build_config(void) {
     return "LIST_REUSE=" MVP_STR(MVP_LIST_REUSE)
-           " LIST_MARGIN=" MVP_STR(MVP_LIST_MARGIN) " XBUCKETS=" MVP_STR(MVP_XBUCKETS) " FASTCAP=" MVP_STR(MVP_FASTCAP) " PF_CELL=" MVP_STR(MVP_PF_CELL) " FWD_ASYNC=" MVP_STR(MVP_FWD_ASYNC) " BWD_SMEMREC=" MVP_STR(MVP_BWD_SMEMREC)
+           " LIST_MARGIN=" MVP_STR(MVP_LIST_MARGIN) " XBUCKETS=" MVP_STR(MVP_XBUCKETS) " FASTCAP=" MVP_STR(MVP_FASTCAP) " PF_CELL=" MVP_STR(MVP_PF_CELL) " FWD_ASYNC=" MVP_STR(MVP_FWD_ASYNC) " BWD_SMEMREC=" MVP_STR(MVP_BWD_SMEMREC) " BWD_LANESMEM=" MVP_STR(MVP_BWD_LANESMEM) " CTA_ORDER=" MVP_STR(MVP_CTA_ORDER)
            " CHUNK=" MVP_STR(MVP_CHUNK) " FWD_MINB=" MVP_STR(MVP_FWD_MINB) " BWD_MINB=" MVP_STR(MVP_BWD_MINB)
            " WARPS=" MVP_STR(MVP_WARPS) " BLK_TX=" MVP_STR(MVP_BLK_TX)
 #ifdef MVP_CPU_EMUL
@@ -2094,8 +2282,8 @@ int mvp_debug_saved_tiles(const mvp_shape *shape, const void *host_workspace_cop
     return MVP_OK;
 }
 
-int mvp_forward_launch_count(uint32_t flags) { return (flags & MVP_FLAG_ACCEL_VALID) ? 2 : 5; }
-int mvp_backward_launch_count(uint32_t flags) { return (flags & MVP_FLAG_ACCEL_VALID) ? 2 : 5; }
+int mvp_forward_launch_count(uint32_t flags) { return (flags & MVP_FLAG_ACCEL_VALID) ? 2 : 5 + 2 * MVP_CTA_ORDER; }
+int mvp_backward_launch_count(uint32_t flags) { return (flags & MVP_FLAG_ACCEL_VALID) ? 2 : 5 + 2 * MVP_CTA_ORDER; }
 
 static inline bool misaligned(const void *p, uintptr_t a) { return p && ((uintptr_t)p & (a - 1)); }
 
@@ -2134,8 +2322,12 @@ int mvp_raymarch_forward(const mvp_forward_args *a, void *stream) {
     p.raypos = a->raypos; p.raydir = a->raydir; p.tminmax = a->tminmax; p.tplate = a->tplate;
     p.rayrgba = a->rayrgba; p.raysat = a->raysat; p.rayaux = reinterpret_cast<int4 *>(a->rayaux);
     p.warp = a->warp; p.WD = a->WD; p.WH = a->WH; p.WW = a->WW;
-    dim3 grid((p.TXn + kBlkTX - 1) / kBlkTX, (p.TYn + kBlkTY - 1) / kBlkTY, a->shape.N);
+#if MVP_CTA_ORDER
+    dim3 grid((unsigned)((size_t)p.CXn * p.CYn * a->shape.N));
+#else
+    dim3 grid(p.CXn, p.CYn, a->shape.N);
     if (grid.y > 65535) return MVP_ERR_SHAPE;
+#endif
     {
         cudaError_t e0 = cudaMemsetAsync(p.heavycnt, 0, sizeof(int), st);
         if (e0 != cudaSuccess) return (int)e0;
@@ -2208,8 +2400,12 @@ int mvp_raymarch_backward(const mvp_backward_args *a, void *stream) {
     p.grad_rayrgba = a->grad_rayrgba; p.raysat_in = a->raysat; p.rayaux_in = reinterpret_cast<const int4 *>(a->rayaux);
     p.g_primpos = a->grad_primpos; p.g_primrot = a->grad_primrot; p.g_primscale = a->grad_primscale; p.g_tplate = a->grad_tplate;
     p.warp = a->warp; p.g_warp = a->grad_warp; p.WD = a->WD; p.WH = a->WH; p.WW = a->WW;
-    dim3 grid((p.TXn + kBlkTX - 1) / kBlkTX, (p.TYn + kBlkTY - 1) / kBlkTY, a->shape.N);
+#if MVP_CTA_ORDER
+    dim3 grid((unsigned)((size_t)p.CXn * p.CYn * a->shape.N));
+#else
+    dim3 grid(p.CXn, p.CYn, a->shape.N);
     if (grid.y > 65535) return MVP_ERR_SHAPE;
+#endif
     {
         cudaError_t e0 = cudaMemsetAsync(p.heavycnt, 0, sizeof(int), st);
         if (e0 != cudaSuccess) return (int)e0;

@@ -117,7 +117,9 @@ VARIANTS = {
     "list_margin_reuse": ("MVP_LIST_MARGIN=1", "MVP_LIST_REUSE=1"),
     "no_xbuckets_no_margin": ("MVP_XBUCKETS=0", "MVP_LIST_MARGIN=0"),      # the round-1 defaults
     "fastcap_small": ("MVP_FASTCAP=8",),                                   # most tiles overflow the fast list -> handed to the 512-entry kernel
-    "bwd_regrecord": ("MVP_BWD_SMEMREC=0",),                               # slab record in registers across the adjoint (round-1 form)
+    "bwd_regrecord": ("MVP_BWD_SMEMREC=0",),
+    "grid_order": ("MVP_CTA_ORDER=0",),                                    # plain grid order instead of the cost-sorted CTA order
+    "bwd_lanesmem": ("MVP_BWD_LANESMEM=1",),                               # per-lane between-batch state in shared memory                               # slab record in registers across the adjoint (round-1 form)
     "fwd_async": ("MVP_FWD_ASYNC=1", "MVP_FASTCAP=128"),                   # cp.async-staged gathers, consumed one batch later
     "fwd_sync": ("MVP_FWD_ASYNC=0",),
 }

@@ -114,6 +114,19 @@ constexpr int kRing = 64;        // sample queue / ring per warp (forward and ba
                             // batch adjoint and the adjoint reads what it needs from there, so the record's 15 registers are not
                             // live across the adjoint (the kernel's register peak)
 #endif
+#ifndef MVP_TILE_CLOCKS
+#define MVP_TILE_CLOCKS 0   // diagnostics build only: the forward kernel records (start, duration) in SM clock cycles and the SM id per tile
+#endif
+#ifndef MVP_CTA_ORDER_MIN
+#define MVP_CTA_ORDER_MIN 0    // > 0: only CTAs of cost class >= this are moved to the front, the others keep the grid order among
+                               // themselves.  Measured (30 / 40 / 50): no better than the full sort for either kernel
+#endif
+#ifndef MVP_CTA_ORDER_MAXVIEWS
+#define MVP_CTA_ORDER_MAXVIEWS 16   // the cost order (and the estimate behind it) is used only for launches of at most this many views.
+                                    // Measured on B200, sorted vs grid order: forward -10..-14 % and backward -2.6 % at 10 views per launch
+                                    // (one rank of an 8-GPU run); at 40 and 80 views the differences (-3 % .. +2 %) are within the
+                                    // box-to-box noise: long launches have no tail to speak of
+#endif
 #ifndef MVP_CTA_ORDER
 #define MVP_CTA_ORDER 1   // 1: the render kernels' CTAs run in descending order of a cost estimate (candidate slabs of the CTA's tile rows),
                           // over all views of the launch: the expensive silhouette tiles -- a single warp can be busy for ~1 ms with
@@ -157,7 +170,7 @@ struct Cam {          // 64 B per view
 struct __align__(8) RowEntry { int k; unsigned xr; };   // xr = x0 | x1 << 16  (pixels, inclusive)
 
 struct Layout {
-    size_t cam, bad, pack, rx, ry, rowcnt, rowlist, heavycnt, heavylist, ctaorder, ctahist, total;
+    size_t cam, bad, pack, rx, ry, rowcnt, rowlist, heavycnt, heavylist, ctaorder, ctahist, tilecnt, tileclk, total;
     int R, rowcap;
 #if MVP_XBUCKETS
     size_t grphdr, grplist;
@@ -187,7 +200,13 @@ __host__ inline Layout make_layout(const mvp_shape &s) {
         const size_t ctas = (size_t)s.N * (((s.H + kTileH - 1) / kTileH + kBlkTY - 1) / kBlkTY) * (((s.W + kTileW - 1) / kTileW + kBlkTX - 1) / kBlkTX);
         L.ctaorder = off; off = align256(off + ctas * sizeof(int));
         L.ctahist = off;  off = align256(off + 2 * kCostClasses * sizeof(int));
+        L.tilecnt = off;  off = align256(off + (size_t)s.N * ((s.H + kTileH - 1) / kTileH) * ((s.W + kTileW - 1) / kTileW) * sizeof(unsigned short));
     }
+#if MVP_TILE_CLOCKS
+    L.tileclk = off; off = align256(off + (size_t)s.N * ((s.H + kTileH - 1) / kTileH) * ((s.W + kTileW - 1) / kTileW) * 4 * sizeof(long long));
+#else
+    L.tileclk = 0;
+#endif
     L.heavycnt = off; off = align256(off + sizeof(int));
     L.heavylist = off; off = align256(off + (size_t)s.N * ((s.H + kTileH - 1) / kTileH) * ((s.W + kTileW - 1) / kTileW) * sizeof(int));
 #if MVP_XBUCKETS
@@ -390,7 +409,8 @@ __global__ void __launch_bounds__(kRowThreads) row_lists_kernel(int K, int R, in
                                                                 const unsigned *__restrict__ rx, const unsigned *__restrict__ ry,
                                                                 int *__restrict__ rowcnt, RowEntry *__restrict__ rowlist
 #if MVP_XBUCKETS
-                                                                , int NG, int2 *__restrict__ grphdr, RowEntry *__restrict__ grplist
+                                                                , int NG, int2 *__restrict__ grphdr, RowEntry *__restrict__ grplist,
+                                                                unsigned short *__restrict__ tilecnt   // NULL: no cost estimate wanted
 #endif
                                                                 ) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -430,31 +450,43 @@ __global__ void __launch_bounds__(kRowThreads) row_lists_kernel(int K, int R, in
         int2 *hdr = grphdr + ((size_t)n * R + row) * NG;
         RowEntry *gout = grplist + ((size_t)n * R + row) * kGrpCap;
         int goff = 0;
+        unsigned short *tc = tilecnt ? tilecnt + ((size_t)n * R + row) * TXn : nullptr;   // candidate slabs per tile: the cost estimate of order_ctas_kernel
         for (int g = 0; g < NG; ++g) {
             if (total > rowcap) {
                 if (lane == 0) hdr[g] = make_int2(-1, -1);
+                if (tilecnt && lane < kGrpTiles && g * kGrpTiles + lane < TXn) tc[g * kGrpTiles + lane] = 0xffff;
                 continue;
             }
             const int gx0 = g * kGrpTiles * kTileW, gx1 = gx0 + kGrpTiles * kTileW - 1;
-            int cnt = 0;
+            int cnt = 0, mine = 0;
             for (int j0 = 0; j0 < total; j0 += 32) {
                 const int j = j0 + lane;
                 bool in = false;
                 RowEntry e;
                 e.k = 0; e.xr = 0;
+                int x0 = 1, x1 = 0;
                 if (j < total) {
                     e = out[j];
-                    const int x0 = (int)(e.xr & 0xffffu), x1 = (int)(e.xr >> 16);
+                    x0 = (int)(e.xr & 0xffffu); x1 = (int)(e.xr >> 16);
                     in = (x0 <= x1) && (x0 <= gx1) && (x1 >= gx0);
                 }
                 const unsigned b = __ballot_sync(0xffffffffu, in);
                 const int pos = goff + cnt + __popc(b & below);
                 if (in && pos < kGrpCap) gout[pos] = e;
                 cnt += __popc(b);
+                if (tilecnt) {
+#pragma unroll
+                    for (int t = 0; t < kGrpTiles; ++t) {
+                        const int tx0 = gx0 + t * kTileW;
+                        const unsigned bt = __ballot_sync(0xffffffffu, in && (x0 <= tx0 + kTileW - 1) && (x1 >= tx0));
+                        if (lane == t) mine += __popc(bt);
+                    }
+                }
             }
             const bool ok = goff + cnt <= kGrpCap;
             if (lane == 0) hdr[g] = ok ? make_int2(goff, cnt) : make_int2(-1, -1);
             if (ok) goff += (cnt + 1) & ~1;
+            if (tilecnt && lane < kGrpTiles && g * kGrpTiles + lane < TXn) tc[g * kGrpTiles + lane] = (unsigned short)min(mine, 0xffff);
         }
     }
 #endif
@@ -462,35 +494,21 @@ __global__ void __launch_bounds__(kRowThreads) row_lists_kernel(int K, int R, in
 
 // ------------------------------------------------------------------------------------------------------
 // 3b. CTA order: counting sort of the launch's CTAs (2x2 tiles) by descending cost class.  Cost estimate = the number of
-//     candidate slabs of the CTA's tile rows in its x-group (row bucket sizes), i.e. how long its lists can get.
+//     candidate slabs of the CTA's four tiles (counted by row_lists_kernel), which correlates 0.72-0.76 with the measured
+//     duration of a tile on B200 (scripts/tile_clocks.py).
 // ------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int cta_cost_class(int n, int by, int bx, int R, int TXn, const int *__restrict__ rowcnt, int rowcap
-#if MVP_XBUCKETS
-                                              , int NG, const int2 *__restrict__ grphdr
-#endif
-                                              ) {
+__device__ __forceinline__ int cta_cost_class(int n, int by, int bx, int R, int TXn, const unsigned short *__restrict__ tilecnt) {
     int cost = 0;
-    for (int r = by * kBlkTY; r < min((by + 1) * kBlkTY, R); ++r) {
-        int c = rowcnt[(size_t)n * R + r];
-#if MVP_XBUCKETS
-        if (c <= rowcap) {
-            const int g = (bx * kBlkTX) / kGrpTiles;
-            const int2 gh = grphdr[((size_t)n * R + r) * NG + g];
-            if (gh.y >= 0) c = gh.y;
-        }
-#endif
-        cost += c;
-    }
-    return min(kCostClasses - 1, cost >> 3);
+    for (int r = by * kBlkTY; r < min((by + 1) * kBlkTY, R); ++r)
+        for (int t = bx * kBlkTX; t < min((bx + 1) * kBlkTX, TXn); ++t) cost += tilecnt[((size_t)n * R + r) * TXn + t];
+    const int c = min(kCostClasses - 1, cost >> 3);
+    return c >= MVP_CTA_ORDER_MIN ? c : 0;
 }
 
 // pass 0: histogram of the classes (hist[0 .. kCostClasses));  pass 1: scatter (cursor = hist[kCostClasses ..), zeroed)
-__global__ void __launch_bounds__(256) order_ctas_kernel(int pass, int N, int CXn, int CYn, int R, int TXn, const int *__restrict__ rowcnt,
-                                                         int rowcap,
-#if MVP_XBUCKETS
-                                                         int NG, const int2 *__restrict__ grphdr,
-#endif
-                                                         int *__restrict__ hist, int *__restrict__ order) {
+__global__ void __launch_bounds__(256) order_ctas_kernel(int pass, int N, int CXn, int CYn, int R, int TXn,
+                                                         const unsigned short *__restrict__ tilecnt, int *__restrict__ hist,
+                                                         int *__restrict__ order) {
     __shared__ int s_base[kCostClasses];
     if (pass == 1) {
         // descending cost: class kCostClasses-1 first
@@ -504,11 +522,7 @@ __global__ void __launch_bounds__(256) order_ctas_kernel(int pass, int N, int CX
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int bx = (int)(i % CXn), by = (int)((i / CXn) % CYn), n = (int)(i / ((size_t)CXn * CYn));
-    const int c = cta_cost_class(n, by, bx, R, TXn, rowcnt, rowcap
-#if MVP_XBUCKETS
-                                 , NG, grphdr
-#endif
-    );
+    const int c = cta_cost_class(n, by, bx, R, TXn, tilecnt);
     if (pass == 0) atomicAdd(hist + c, 1);
     else order[s_base[c] + atomicAdd(hist + kCostClasses + c, 1)] = (int)i;
 }
@@ -676,7 +690,9 @@ struct Params {
     int R, rowcap;
     int TXn, TYn;
     unsigned slab_bytes;          // TD*TH*TW*16
+    long long *tileclk;           // MVP_TILE_CLOCKS diagnostics
     int CXn, CYn;                 // CTAs (kBlkTX x kBlkTY tiles) per view in x / y
+    int use_order;                // this launch follows ctaorder (else plain grid order)
     const int *ctaorder;          // CTA ids ((n * CYn + by) * CXn + bx) in descending order of estimated cost (MVP_CTA_ORDER)
     int *heavycnt;                // tiles whose slab list overflowed the fast kernel's shared-memory list in THIS call ...
     int *heavylist;               // ... and their ids ((n * TYn + ty) * TXn + tx), in no particular order; the 512-entry kernel renders them
@@ -1475,16 +1491,31 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
         }
     } else {
 #if MVP_CTA_ORDER
-        // 1-D grid; CTA b renders the b-th most expensive 2x2-tile block of the launch (order_ctas_kernel)
-        const int cid = p.ctaorder[blockIdx.x];
+        // 1-D grid; CTA b renders the b-th most expensive 2x2-tile block of the launch (order_ctas_kernel), or block b
+        const int cid = p.use_order ? p.ctaorder[blockIdx.x] : (int)blockIdx.x;
         const int bx = cid % p.CXn, by = (cid / p.CXn) % p.CYn, n = cid / (p.CXn * p.CYn);
         const int tx = bx * kBlkTX + (warp % kBlkTX), ty = by * kBlkTY + (warp / kBlkTX);
 #else
         const int tx = blockIdx.x * kBlkTX + (warp % kBlkTX), ty = blockIdx.y * kBlkTY + (warp / kBlkTX), n = blockIdx.z;
 #endif
         if (tx >= p.TXn || ty >= p.TYn) return;
+#if MVP_TILE_CLOCKS
+        const long long t0_ = clock64();
+        long long g0_;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0_));
+#endif
         if (!forward_tile<T, kGrad, CAP, kWarp>(p, n, tx, ty, lane, S) && lane == 0)
             p.heavylist[atomicAdd(p.heavycnt, 1)] = (n * p.TYn + ty) * p.TXn + tx;
+#if MVP_TILE_CLOCKS
+        if (lane == 0) {
+            long long g1_;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1_));
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            long long *o = p.tileclk + (((size_t)n * p.TYn + ty) * p.TXn + tx) * 4;
+            o[0] = g0_; o[1] = g1_; o[2] = clock64() - t0_; o[3] = (long long)smid | ((long long)blockIdx.x << 32);
+        }
+#endif
     }
 }
 
@@ -2073,8 +2104,8 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
         }
     } else {
 #if MVP_CTA_ORDER
-        // 1-D grid; CTA b renders the b-th most expensive 2x2-tile block of the launch (order_ctas_kernel)
-        const int cid = p.ctaorder[blockIdx.x];
+        // 1-D grid; CTA b renders the b-th most expensive 2x2-tile block of the launch (order_ctas_kernel), or block b
+        const int cid = p.use_order ? p.ctaorder[blockIdx.x] : (int)blockIdx.x;
         const int bx = cid % p.CXn, by = (cid / p.CXn) % p.CYn, n = cid / (p.CXn * p.CYn);
         const int tx = bx * kBlkTX + (warp % kBlkTX), ty = by * kBlkTY + (warp / kBlkTX);
 #else
@@ -2125,6 +2156,8 @@ int launch_accel(const mvp_shape &s, int pview, const float *raypos, const float
     e = cudaMemsetAsync(ws + L.tilehdr, 0xff, L.listbuf - L.tilehdr, st);
     if (e != cudaSuccess) return (int)e;
 #endif
+    const bool want_order = MVP_CTA_ORDER && s.N <= MVP_CTA_ORDER_MAXVIEWS;
+    (void)want_order;
     const size_t HW = (size_t)s.H * s.W;
     dim3 gfit((unsigned)((HW + kFitThreads * kFitRaysPerThread - 1) / (kFitThreads * kFitRaysPerThread)), s.N);
 #ifdef MVP_CPU_EMUL
@@ -2137,7 +2170,8 @@ int launch_accel(const mvp_shape &s, int pview, const float *raypos, const float
                reinterpret_cast<unsigned *>(ws + L.rx), reinterpret_cast<unsigned *>(ws + L.ry), reinterpret_cast<int *>(ws + L.rowcnt),
                reinterpret_cast<RowEntry *>(ws + L.rowlist)
 #if MVP_XBUCKETS
-               , L.NG, reinterpret_cast<int2 *>(ws + L.grphdr), reinterpret_cast<RowEntry *>(ws + L.grplist)
+               , L.NG, reinterpret_cast<int2 *>(ws + L.grphdr), reinterpret_cast<RowEntry *>(ws + L.grplist),
+               want_order ? reinterpret_cast<unsigned short *>(ws + L.tilecnt) : nullptr
 #endif
                );
 #else
@@ -2151,32 +2185,30 @@ int launch_accel(const mvp_shape &s, int pview, const float *raypos, const float
         s.K, L.R, L.rowcap, TXn, reinterpret_cast<unsigned *>(ws + L.rx), reinterpret_cast<unsigned *>(ws + L.ry),
         reinterpret_cast<int *>(ws + L.rowcnt), reinterpret_cast<RowEntry *>(ws + L.rowlist)
 #if MVP_XBUCKETS
-        , L.NG, reinterpret_cast<int2 *>(ws + L.grphdr), reinterpret_cast<RowEntry *>(ws + L.grplist)
+        , L.NG, reinterpret_cast<int2 *>(ws + L.grphdr), reinterpret_cast<RowEntry *>(ws + L.grplist),
+        want_order ? reinterpret_cast<unsigned short *>(ws + L.tilecnt) : nullptr
 #endif
         );
 #endif
 #if MVP_CTA_ORDER
-    {
+    if (want_order) {
         const int TYn = L.R, CXn = (TXn + kBlkTX - 1) / kBlkTX, CYn = (TYn + kBlkTY - 1) / kBlkTY;
         const size_t ctas = (size_t)s.N * CXn * CYn;
         int *hist = reinterpret_cast<int *>(ws + L.ctahist);
         e = cudaMemsetAsync(hist, 0, 2 * kCostClasses * sizeof(int), st);
         if (e != cudaSuccess) return (int)e;
+#if !MVP_XBUCKETS
+        e = cudaMemsetAsync(ws + L.tilecnt, 0, (size_t)s.N * L.R * TXn * sizeof(unsigned short), st);   // no cost estimate: grid order
+        if (e != cudaSuccess) return (int)e;
+#endif
         for (int pass = 0; pass < 2; ++pass) {
 #ifdef MVP_CPU_EMUL
             MVP_LAUNCH(order_ctas_kernel, (unsigned)((ctas + 255) / 256), 256, 0, st, pass, s.N, CXn, CYn, L.R, TXn,
-                       reinterpret_cast<const int *>(ws + L.rowcnt), L.rowcap,
-#if MVP_XBUCKETS
-                       L.NG, reinterpret_cast<const int2 *>(ws + L.grphdr),
-#endif
-                       hist, reinterpret_cast<int *>(ws + L.ctaorder));
+                       reinterpret_cast<const unsigned short *>(ws + L.tilecnt), hist, reinterpret_cast<int *>(ws + L.ctaorder));
 #else
             order_ctas_kernel<<<(unsigned)((ctas + 255) / 256), 256, 0, st>>>(pass, s.N, CXn, CYn, L.R, TXn,
-                                                                              reinterpret_cast<const int *>(ws + L.rowcnt), L.rowcap,
-#if MVP_XBUCKETS
-                                                                              L.NG, reinterpret_cast<const int2 *>(ws + L.grphdr),
-#endif
-                                                                              hist, reinterpret_cast<int *>(ws + L.ctaorder));
+                                                                              reinterpret_cast<const unsigned short *>(ws + L.tilecnt), hist,
+                                                                              reinterpret_cast<int *>(ws + L.ctaorder));
 #endif
         }
     }
@@ -2197,6 +2229,7 @@ void fill_params(Params &p, const mvp_shape &s, float stepsize, float fadescale,
     p.R = L.R; p.rowcap = L.rowcap;
     p.TXn = (s.W + kTileW - 1) / kTileW;
     p.TYn = (s.H + kTileH - 1) / kTileH;
+    p.tileclk = reinterpret_cast<long long *>(ws + L.tileclk);
     p.CXn = (p.TXn + kBlkTX - 1) / kBlkTX;
     p.CYn = (p.TYn + kBlkTY - 1) / kBlkTY;
     p.ctaorder = reinterpret_cast<const int *>(ws + L.ctaorder);
@@ -2228,7 +2261,7 @@ int mvp_abi_version(void) { return MVP_ABI_VERSION; }
 #define MVP_STR(x) MVP_STR2(x)
 const char *mvp_build_config(void) {
     return "LIST_REUSE=" MVP_STR(MVP_LIST_REUSE)
-           " LIST_MARGIN=" MVP_STR(MVP_LIST_MARGIN) " XBUCKETS=" MVP_STR(MVP_XBUCKETS) " FASTCAP=" MVP_STR(MVP_FASTCAP) " PF_CELL=" MVP_STR(MVP_PF_CELL) " FWD_ASYNC=" MVP_STR(MVP_FWD_ASYNC) " BWD_SMEMREC=" MVP_STR(MVP_BWD_SMEMREC) " BWD_LANESMEM=" MVP_STR(MVP_BWD_LANESMEM) " CTA_ORDER=" MVP_STR(MVP_CTA_ORDER)
+           " LIST_MARGIN=" MVP_STR(MVP_LIST_MARGIN) " XBUCKETS=" MVP_STR(MVP_XBUCKETS) " FASTCAP=" MVP_STR(MVP_FASTCAP) " PF_CELL=" MVP_STR(MVP_PF_CELL) " FWD_ASYNC=" MVP_STR(MVP_FWD_ASYNC) " BWD_SMEMREC=" MVP_STR(MVP_BWD_SMEMREC) " BWD_LANESMEM=" MVP_STR(MVP_BWD_LANESMEM) " CTA_ORDER=" MVP_STR(MVP_CTA_ORDER) " CTA_ORDER_MIN=" MVP_STR(MVP_CTA_ORDER_MIN)
            " CHUNK=" MVP_STR(MVP_CHUNK) " FWD_MINB=" MVP_STR(MVP_FWD_MINB) " BWD_MINB=" MVP_STR(MVP_BWD_MINB)
            " WARPS=" MVP_STR(MVP_WARPS) " BLK_TX=" MVP_STR(MVP_BLK_TX)
 #ifdef MVP_CPU_EMUL
@@ -2282,8 +2315,13 @@ int mvp_debug_saved_tiles(const mvp_shape *shape, const void *host_workspace_cop
     return MVP_OK;
 }
 
-int mvp_forward_launch_count(uint32_t flags) { return (flags & MVP_FLAG_ACCEL_VALID) ? 2 : 5 + 2 * MVP_CTA_ORDER; }
-int mvp_backward_launch_count(uint32_t flags) { return (flags & MVP_FLAG_ACCEL_VALID) ? 2 : 5 + 2 * MVP_CTA_ORDER; }
+size_t mvp_debug_tileclk_offset(const mvp_shape *shape) {
+    if (!shape || check_shape(*shape) != MVP_OK) return 0;
+    return make_layout(*shape).tileclk;
+}
+
+int mvp_forward_launch_count(uint32_t flags) { return (flags & MVP_FLAG_ACCEL_VALID) ? 2 : 5; }   // + 2 ordering kernels for small launches
+int mvp_backward_launch_count(uint32_t flags) { return (flags & MVP_FLAG_ACCEL_VALID) ? 2 : 5; }
 
 static inline bool misaligned(const void *p, uintptr_t a) { return p && ((uintptr_t)p & (a - 1)); }
 
@@ -2319,6 +2357,7 @@ int mvp_raymarch_forward(const mvp_forward_args *a, void *stream) {
 #if MVP_LIST_REUSE
     if (a->flags & MVP_FLAG_TEST_TINY_LISTS) p.listlimit = p.listcap < 16 ? p.listcap : 16;
 #endif
+    p.use_order = a->shape.N <= MVP_CTA_ORDER_MAXVIEWS;
     p.raypos = a->raypos; p.raydir = a->raydir; p.tminmax = a->tminmax; p.tplate = a->tplate;
     p.rayrgba = a->rayrgba; p.raysat = a->raysat; p.rayaux = reinterpret_cast<int4 *>(a->rayaux);
     p.warp = a->warp; p.WD = a->WD; p.WH = a->WH; p.WW = a->WW;
@@ -2397,6 +2436,7 @@ int mvp_raymarch_backward(const mvp_backward_args *a, void *stream) {
     fill_params(p, a->shape, a->stepsize, a->fadescale, a->fadeexp, ws, L);
     p.pview = pview;
     p.raypos = a->raypos; p.raydir = a->raydir; p.tminmax = a->tminmax; p.tplate = a->tplate;
+    p.use_order = a->shape.N <= MVP_CTA_ORDER_MAXVIEWS;
     p.grad_rayrgba = a->grad_rayrgba; p.raysat_in = a->raysat; p.rayaux_in = reinterpret_cast<const int4 *>(a->rayaux);
     p.g_primpos = a->grad_primpos; p.g_primrot = a->grad_primrot; p.g_primscale = a->grad_primscale; p.g_tplate = a->grad_tplate;
     p.warp = a->warp; p.g_warp = a->grad_warp; p.WD = a->WD; p.WH = a->WH; p.WW = a->WW;

@@ -17,7 +17,7 @@ LIB = os.path.join(HERE, "libmvpraymarch_b200.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-O3", "-std=c++17", "-lineinfo",
+    "-O3", "-std=c++17", "-lineinfo", "-diag-suppress=177",
     "-Xcompiler", "-fPIC",
     "-I" + os.path.join(ROOT, "include"),
 ]

@@ -170,7 +170,7 @@ struct Cam {          // 64 B per view
 struct __align__(8) RowEntry { int k; unsigned xr; };   // xr = x0 | x1 << 16  (pixels, inclusive)
 
 struct Layout {
-    size_t cam, bad, pack, rx, ry, rowcnt, rowlist, heavycnt, heavylist, ctaorder, ctahist, tilecnt, tileclk, total;
+    size_t cam, bad, pack, rx, ry, rowcnt, rowlist, heavycnt, heavylist, ctaorder, ctahist, tilecnt, blky, tileclk, total;
     int R, rowcap;
 #if MVP_XBUCKETS
     size_t grphdr, grplist;
@@ -194,6 +194,7 @@ __host__ inline Layout make_layout(const mvp_shape &s) {
     L.pack = off;    off = align256(off + (size_t)s.N * s.K * 64);
     L.rx = off;      off = align256(off + (size_t)s.N * s.K * 4);
     L.ry = off;      off = align256(off + (size_t)s.N * s.K * 4);
+    L.blky = off;    off = align256(off + (size_t)s.N * ((s.K + 31) / 32) * 4);
     L.rowcnt = off;  off = align256(off + (size_t)s.N * L.R * 4);
     L.rowlist = off; off = align256(off + (size_t)s.N * L.R * L.rowcap * sizeof(RowEntry));
     {
@@ -400,6 +401,27 @@ __global__ void __launch_bounds__(128) prim_setup_kernel(int N, int K, int H, in
 // ------------------------------------------------------------------------------------------------------
 // 3. tile-row buckets in DFS-rank order (deterministic ordered compaction; one CTA per (row, view))
 // ------------------------------------------------------------------------------------------------------
+// y range (pixels) of every block of 32 slabs consecutive in DFS rank: the bucket kernels test a block before its slabs, so a
+// tile row only touches the ~10-20 % of the blocks that can reach it (slabs follow the UV grid: consecutive ranks are neighbours).
+__global__ void __launch_bounds__(256) block_ranges_kernel(int K, const unsigned *__restrict__ ry, unsigned *__restrict__ blky) {
+    const int lane = threadIdx.x & 31;
+    const int NB = (K + 31) / 32;
+    const int blk = blockIdx.x * 8 + (threadIdx.x >> 5), n = blockIdx.y;
+    if (blk >= NB) return;
+    const int kstart = dfs_kstart(K);
+    const int j = blk * 32 + lane;
+    int y0 = 0xffff, y1 = -1;
+    if (j < K) {
+        int k = j + kstart; if (k >= K) k -= K;
+        const unsigned yr = __ldg(ry + (size_t)n * K + k);
+        const int a = (int)(yr & 0xffffu), b = (int)(yr >> 16);
+        if (a <= b) { y0 = a; y1 = b; }
+    }
+    y0 = __reduce_min_sync(0xffffffffu, y0);
+    y1 = __reduce_max_sync(0xffffffffu, y1);
+    if (lane == 0) blky[(size_t)n * NB + blk] = (y1 < 0) ? 1u : ((unsigned)y0 | ((unsigned)y1 << 16));   // 1 | 0 << 16: empty
+}
+
 constexpr int kRowThreads = 256;          // 8 warps = 8 tile rows per CTA
 
 // One WARP per (tile row, view): it walks the view's slabs in DFS-rank order, 32 at a time, and appends those whose rectangle
@@ -407,6 +429,7 @@ constexpr int kRowThreads = 256;          // 8 warps = 8 tile rows per CTA
 // spent its time in three __syncthreads per 256 slabs).  The 8 warps of a CTA read the same rectangle arrays (L1 hits).
 __global__ void __launch_bounds__(kRowThreads) row_lists_kernel(int K, int R, int rowcap, int TXn,
                                                                 const unsigned *__restrict__ rx, const unsigned *__restrict__ ry,
+                                                                const unsigned *__restrict__ blky,
                                                                 int *__restrict__ rowcnt, RowEntry *__restrict__ rowlist
 #if MVP_XBUCKETS
                                                                 , int NG, int2 *__restrict__ grphdr, RowEntry *__restrict__ grplist,
@@ -422,22 +445,35 @@ __global__ void __launch_bounds__(kRowThreads) row_lists_kernel(int K, int R, in
     const int kstart = dfs_kstart(K);
     const unsigned below = (1u << lane) - 1u;
     int total = 0;
-    for (int j0 = 0; j0 < K; j0 += 32) {
-        const int j = j0 + lane;
-        bool in = false;
-        int k = 0;
-        unsigned xr = 0;
-        if (j < K) {
-            k = j + kstart; if (k >= K) k -= K;
-            const unsigned yr = __ldg(ryn + k);
-            const int y0 = (int)(yr & 0xffffu), y1 = (int)(yr >> 16);
-            in = (y0 <= y1) && (y0 <= yhi) && (y1 >= ylo);
-            if (in) xr = __ldg(rxn + k);
+    const int NB = (K + 31) / 32;
+    const unsigned *byn = blky + (size_t)n * NB;
+    for (int bb0 = 0; bb0 < NB; bb0 += 32) {
+        // 32 blocks at a time: which of them can reach this row at all?
+        bool reach = false;
+        if (bb0 + lane < NB) {
+            const unsigned br = __ldg(byn + bb0 + lane);
+            const int b0 = (int)(br & 0xffffu), b1 = (int)(br >> 16);
+            reach = (b0 <= b1) && (b0 <= yhi) && (b1 >= ylo);
         }
-        const unsigned b = __ballot_sync(0xffffffffu, in);
-        const int pos = total + __popc(b & below);
-        if (in && pos < rowcap) { RowEntry e; e.k = k; e.xr = xr; out[pos] = e; }
-        total += __popc(b);
+        unsigned bm = __ballot_sync(0xffffffffu, reach);
+        while (bm) {
+            const int j = (bb0 + __ffs(bm) - 1) * 32 + lane;
+            bm &= bm - 1;
+            bool in = false;
+            int k = 0;
+            unsigned xr = 0;
+            if (j < K) {
+                k = j + kstart; if (k >= K) k -= K;
+                const unsigned yr = __ldg(ryn + k);
+                const int y0 = (int)(yr & 0xffffu), y1 = (int)(yr >> 16);
+                in = (y0 <= y1) && (y0 <= yhi) && (y1 >= ylo);
+                if (in) xr = __ldg(rxn + k);
+            }
+            const unsigned b = __ballot_sync(0xffffffffu, in);
+            const int pos = total + __popc(b & below);
+            if (in && pos < rowcap) { RowEntry e; e.k = k; e.xr = xr; out[pos] = e; }
+            total += __popc(b);
+        }
     }
     if (lane == 0) rowcnt[(size_t)n * R + row] = total;   // may exceed rowcap: consumers then scan all slabs
 #if MVP_XBUCKETS
@@ -492,6 +528,156 @@ __global__ void __launch_bounds__(kRowThreads) row_lists_kernel(int K, int R, in
 #endif
 }
 
+// Same buckets, built by one CTA (8 warps) per (tile row, view): every warp owns a contiguous eighth of the rank-ordered slab
+// sequence (count pass, prefix over the 8 warps, write pass) and a share of the x-groups.  A warp-per-row walk is a chain of
+// ~630 dependent iterations -- 330 us however few views a launch has -- so this form is used for small launches (one rank of
+// an 8-GPU run), where it is 5x shorter; large launches are throughput-bound and keep the single-pass kernel above.
+__global__ void __launch_bounds__(kRowThreads) row_lists_cta_kernel(int K, int R, int rowcap, int TXn,
+                                                                    const unsigned *__restrict__ rx, const unsigned *__restrict__ ry,
+                                                                    const unsigned *__restrict__ blky,
+                                                                    int *__restrict__ rowcnt, RowEntry *__restrict__ rowlist
+#if MVP_XBUCKETS
+                                                                    , int NG, int2 *__restrict__ grphdr, RowEntry *__restrict__ grplist,
+                                                                    unsigned short *__restrict__ tilecnt
+#endif
+                                                                    ) {
+    constexpr int NW = kRowThreads / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row = blockIdx.x, n = blockIdx.y;
+    const int ylo = row * kTileH, yhi = ylo + kTileH - 1;
+    const unsigned *rxn = rx + (size_t)n * K, *ryn = ry + (size_t)n * K;
+    RowEntry *out = rowlist + ((size_t)n * R + row) * rowcap;
+    const int kstart = dfs_kstart(K);
+    const unsigned below = (1u << lane) - 1u;
+    __shared__ int s_cnt[NW];
+    // the warp's segment of the rank-ordered sequence, in blocks of 32 slabs; only blocks whose y range reaches the row are read
+    const int NB = (K + 31) / 32;
+    const unsigned *byn = blky + (size_t)n * NB;
+    const int bper = (NB + NW - 1) / NW;
+    const int b_lo = warp * bper, b_hi = min(NB, b_lo + bper);
+    auto test = [&](int j, int &k, bool &in) {
+        in = false;
+        k = 0;
+        if (j < K) {
+            k = j + kstart; if (k >= K) k -= K;
+            const unsigned yr = __ldg(ryn + k);
+            const int y0 = (int)(yr & 0xffffu), y1 = (int)(yr >> 16);
+            in = (y0 <= y1) && (y0 <= yhi) && (y1 >= ylo);
+        }
+    };
+    auto reach_mask = [&](int bb0) {
+        bool reach = false;
+        if (bb0 + lane < b_hi) {
+            const unsigned br = __ldg(byn + bb0 + lane);
+            const int b0 = (int)(br & 0xffffu), b1 = (int)(br >> 16);
+            reach = (b0 <= b1) && (b0 <= yhi) && (b1 >= ylo);
+        }
+        return __ballot_sync(0xffffffffu, reach);
+    };
+    int mine = 0;
+    for (int bb0 = b_lo; bb0 < b_hi; bb0 += 32) {
+        unsigned bm = reach_mask(bb0);
+        while (bm) {
+            int k; bool in;
+            test((bb0 + __ffs(bm) - 1) * 32 + lane, k, in);
+            bm &= bm - 1;
+            mine += __popc(__ballot_sync(0xffffffffu, in));
+        }
+    }
+    if (lane == 0) s_cnt[warp] = mine;
+    __syncthreads();
+    int base = 0, total = 0;
+    for (int w = 0; w < NW; ++w) { if (w < warp) base += s_cnt[w]; total += s_cnt[w]; }
+    for (int bb0 = b_lo; bb0 < b_hi; bb0 += 32) {
+        unsigned bm = reach_mask(bb0);
+        while (bm) {
+            int k; bool in;
+            test((bb0 + __ffs(bm) - 1) * 32 + lane, k, in);
+            bm &= bm - 1;
+            const unsigned b = __ballot_sync(0xffffffffu, in);
+            const int pos = base + __popc(b & below);
+            if (in && pos < rowcap) { RowEntry e; e.k = k; e.xr = __ldg(rxn + k); out[pos] = e; }
+            base += __popc(b);
+        }
+    }
+    if (threadIdx.x == 0) rowcnt[(size_t)n * R + row] = total;
+#if MVP_XBUCKETS
+    {
+        __shared__ int s_gcnt[64];               // entries per x-group (NG <= 64 groups are parallelised; more: see below)
+        __shared__ int s_goff[64];
+        __threadfence_block();
+        __syncthreads();                          // the row bucket is complete and visible to the whole CTA
+        int2 *hdr = grphdr + ((size_t)n * R + row) * NG;
+        RowEntry *gout = grplist + ((size_t)n * R + row) * kGrpCap;
+        unsigned short *tc = tilecnt ? tilecnt + ((size_t)n * R + row) * TXn : nullptr;
+        if (total > rowcap || NG > 64) {
+            // overflowed row (its tiles scan all slabs), or an image wider than 64 groups (4096 pixels): no second level
+            for (int g = threadIdx.x; g < NG; g += kRowThreads) hdr[g] = make_int2(-1, -1);
+            if (tc) for (int t = threadIdx.x; t < TXn; t += kRowThreads) tc[t] = 0xffff;
+            return;
+        }
+        // count pass: warp w takes groups w, w + NW, ...
+        for (int g = warp; g < NG; g += NW) {
+            const int gx0 = g * kGrpTiles * kTileW, gx1 = gx0 + kGrpTiles * kTileW - 1;
+            int cnt = 0, tmine = 0;
+            for (int j0 = 0; j0 < total; j0 += 32) {
+                const int j = j0 + lane;
+                bool in = false;
+                int x0 = 1, x1 = 0;
+                if (j < total) {
+                    const RowEntry e = out[j];
+                    x0 = (int)(e.xr & 0xffffu); x1 = (int)(e.xr >> 16);
+                    in = (x0 <= x1) && (x0 <= gx1) && (x1 >= gx0);
+                }
+                cnt += __popc(__ballot_sync(0xffffffffu, in));
+                if (tc) {
+#pragma unroll
+                    for (int t = 0; t < kGrpTiles; ++t) {
+                        const int tx0 = gx0 + t * kTileW;
+                        const unsigned bt = __ballot_sync(0xffffffffu, in && (x0 <= tx0 + kTileW - 1) && (x1 >= tx0));
+                        if (lane == t) tmine += __popc(bt);
+                    }
+                }
+            }
+            if (lane == 0) s_gcnt[g] = cnt;
+            if (tc && lane < kGrpTiles && g * kGrpTiles + lane < TXn) tc[g * kGrpTiles + lane] = (unsigned short)min(tmine, 0xffff);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int goff = 0;
+            for (int g = 0; g < NG; ++g) {
+                const bool ok = goff + s_gcnt[g] <= kGrpCap;
+                s_goff[g] = ok ? goff : -1;
+                hdr[g] = ok ? make_int2(goff, s_gcnt[g]) : make_int2(-1, -1);
+                if (ok) goff += (s_gcnt[g] + 1) & ~1;
+            }
+        }
+        __syncthreads();
+        // write pass
+        for (int g = warp; g < NG; g += NW) {
+            const int goff = s_goff[g];
+            if (goff < 0) continue;
+            const int gx0 = g * kGrpTiles * kTileW, gx1 = gx0 + kGrpTiles * kTileW - 1;
+            int cnt = 0;
+            for (int j0 = 0; j0 < total; j0 += 32) {
+                const int j = j0 + lane;
+                bool in = false;
+                RowEntry e;
+                e.k = 0; e.xr = 0;
+                if (j < total) {
+                    e = out[j];
+                    const int x0 = (int)(e.xr & 0xffffu), x1 = (int)(e.xr >> 16);
+                    in = (x0 <= x1) && (x0 <= gx1) && (x1 >= gx0);
+                }
+                const unsigned b = __ballot_sync(0xffffffffu, in);
+                if (in) gout[goff + cnt + __popc(b & below)] = e;
+                cnt += __popc(b);
+            }
+        }
+    }
+#endif
+}
+
 // ------------------------------------------------------------------------------------------------------
 // 3b. CTA order: counting sort of the launch's CTAs (2x2 tiles) by descending cost class.  Cost estimate = the number of
 //     candidate slabs of the CTA's four tiles (counted by row_lists_kernel), which correlates 0.72-0.76 with the measured
@@ -505,26 +691,38 @@ __device__ __forceinline__ int cta_cost_class(int n, int by, int bx, int R, int 
     return c >= MVP_CTA_ORDER_MIN ? c : 0;
 }
 
-// pass 0: histogram of the classes (hist[0 .. kCostClasses));  pass 1: scatter (cursor = hist[kCostClasses ..), zeroed)
+// pass 0: histogram of the classes (hist[0 .. kCostClasses));  pass 1: scatter (cursor = hist[kCostClasses ..), zeroed).
+// Both passes count in shared memory first and touch the global counters once per (block, class): the launch's CTAs fall into
+// a handful of classes, so per-thread global atomics would serialise on a few addresses.
 __global__ void __launch_bounds__(256) order_ctas_kernel(int pass, int N, int CXn, int CYn, int R, int TXn,
                                                          const unsigned short *__restrict__ tilecnt, int *__restrict__ hist,
                                                          int *__restrict__ order) {
+    __shared__ int s_cnt[kCostClasses];
     __shared__ int s_base[kCostClasses];
-    if (pass == 1) {
-        // descending cost: class kCostClasses-1 first
-        if (threadIdx.x == 0) {
-            int acc = 0;
-            for (int c = kCostClasses - 1; c >= 0; --c) { s_base[c] = acc; acc += hist[c]; }
-        }
-        __syncthreads();
-    }
+    for (int c = threadIdx.x; c < kCostClasses; c += blockDim.x) s_cnt[c] = 0;
+    __syncthreads();
     const size_t total = (size_t)N * CXn * CYn;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int bx = (int)(i % CXn), by = (int)((i / CXn) % CYn), n = (int)(i / ((size_t)CXn * CYn));
-    const int c = cta_cost_class(n, by, bx, R, TXn, tilecnt);
-    if (pass == 0) atomicAdd(hist + c, 1);
-    else order[s_base[c] + atomicAdd(hist + kCostClasses + c, 1)] = (int)i;
+    int c = 0, local = 0;
+    if (i < total) {
+        const int bx = (int)(i % CXn), by = (int)((i / CXn) % CYn), n = (int)(i / ((size_t)CXn * CYn));
+        c = cta_cost_class(n, by, bx, R, TXn, tilecnt);
+        local = atomicAdd(&s_cnt[c], 1);          // rank of this CTA among the block's CTAs of its class
+    }
+    __syncthreads();
+    if (pass == 0) {
+        for (int k = threadIdx.x; k < kCostClasses; k += blockDim.x)
+            if (s_cnt[k]) atomicAdd(hist + k, s_cnt[k]);
+        return;
+    }
+    // descending cost: class kCostClasses-1 first; the block reserves one range per class
+    for (int k = threadIdx.x; k < kCostClasses; k += blockDim.x) {
+        int before = 0;
+        for (int q = kCostClasses - 1; q > k; --q) before += hist[q];
+        s_base[k] = s_cnt[k] ? before + atomicAdd(hist + kCostClasses + k, s_cnt[k]) : 0;
+    }
+    __syncthreads();
+    if (i < total) order[s_base[c] + local] = (int)i;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -2158,6 +2356,7 @@ int launch_accel(const mvp_shape &s, int pview, const float *raypos, const float
 #endif
     const bool want_order = MVP_CTA_ORDER && s.N <= MVP_CTA_ORDER_MAXVIEWS;
     (void)want_order;
+    const bool small_launch = s.N <= MVP_CTA_ORDER_MAXVIEWS;   // latency-bound accel build: the parallel bucket kernel
     const size_t HW = (size_t)s.H * s.W;
     dim3 gfit((unsigned)((HW + kFitThreads * kFitRaysPerThread - 1) / (kFitThreads * kFitRaysPerThread)), s.N);
 #ifdef MVP_CPU_EMUL
@@ -2166,14 +2365,28 @@ int launch_accel(const mvp_shape &s, int pview, const float *raypos, const float
     MVP_LAUNCH(prim_setup_kernel, (unsigned)((NK + 127) / 128), 128, 0, st, s.N, s.K, s.H, s.W, pview, primpos, primrot, primscale, cam, bad,
                reinterpret_cast<float4 *>(ws + L.pack), reinterpret_cast<unsigned *>(ws + L.rx), reinterpret_cast<unsigned *>(ws + L.ry));
     const int TXn = (s.W + kTileW - 1) / kTileW;
-    MVP_LAUNCH(row_lists_kernel, dim3((L.R + kRowThreads / 32 - 1) / (kRowThreads / 32), s.N), kRowThreads, 0, st, s.K, L.R, L.rowcap, TXn,
-               reinterpret_cast<unsigned *>(ws + L.rx), reinterpret_cast<unsigned *>(ws + L.ry), reinterpret_cast<int *>(ws + L.rowcnt),
-               reinterpret_cast<RowEntry *>(ws + L.rowlist)
+    MVP_LAUNCH(block_ranges_kernel, dim3(((s.K + 31) / 32 + 7) / 8, s.N), 256, 0, st, s.K, reinterpret_cast<const unsigned *>(ws + L.ry),
+               reinterpret_cast<unsigned *>(ws + L.blky));
+    if (small_launch)
+        MVP_LAUNCH(row_lists_cta_kernel, dim3(L.R, s.N), kRowThreads, 0, st, s.K, L.R, L.rowcap, TXn,
+                   reinterpret_cast<unsigned *>(ws + L.rx), reinterpret_cast<unsigned *>(ws + L.ry),
+                   reinterpret_cast<const unsigned *>(ws + L.blky), reinterpret_cast<int *>(ws + L.rowcnt),
+                   reinterpret_cast<RowEntry *>(ws + L.rowlist)
 #if MVP_XBUCKETS
-               , L.NG, reinterpret_cast<int2 *>(ws + L.grphdr), reinterpret_cast<RowEntry *>(ws + L.grplist),
-               want_order ? reinterpret_cast<unsigned short *>(ws + L.tilecnt) : nullptr
+                   , L.NG, reinterpret_cast<int2 *>(ws + L.grphdr), reinterpret_cast<RowEntry *>(ws + L.grplist),
+                   want_order ? reinterpret_cast<unsigned short *>(ws + L.tilecnt) : nullptr
 #endif
-               );
+                   );
+    else
+        MVP_LAUNCH(row_lists_kernel, dim3((L.R + kRowThreads / 32 - 1) / (kRowThreads / 32), s.N), kRowThreads, 0, st, s.K, L.R, L.rowcap, TXn,
+                   reinterpret_cast<unsigned *>(ws + L.rx), reinterpret_cast<unsigned *>(ws + L.ry),
+                   reinterpret_cast<const unsigned *>(ws + L.blky), reinterpret_cast<int *>(ws + L.rowcnt),
+                   reinterpret_cast<RowEntry *>(ws + L.rowlist)
+#if MVP_XBUCKETS
+                   , L.NG, reinterpret_cast<int2 *>(ws + L.grphdr), reinterpret_cast<RowEntry *>(ws + L.grplist),
+                   want_order ? reinterpret_cast<unsigned short *>(ws + L.tilecnt) : nullptr
+#endif
+                   );
 #else
     fit_camera_kernel<<<gfit, kFitThreads, 0, st>>>(s.H, s.W, raypos, raydir, cam, bad);
     const size_t NK = (size_t)s.N * s.K;
@@ -2181,14 +2394,26 @@ int launch_accel(const mvp_shape &s, int pview, const float *raypos, const float
         s.N, s.K, s.H, s.W, pview, primpos, primrot, primscale, cam, bad, reinterpret_cast<float4 *>(ws + L.pack),
         reinterpret_cast<unsigned *>(ws + L.rx), reinterpret_cast<unsigned *>(ws + L.ry));
     const int TXn = (s.W + kTileW - 1) / kTileW;
-    row_lists_kernel<<<dim3((L.R + kRowThreads / 32 - 1) / (kRowThreads / 32), s.N), kRowThreads, 0, st>>>(
-        s.K, L.R, L.rowcap, TXn, reinterpret_cast<unsigned *>(ws + L.rx), reinterpret_cast<unsigned *>(ws + L.ry),
-        reinterpret_cast<int *>(ws + L.rowcnt), reinterpret_cast<RowEntry *>(ws + L.rowlist)
+    block_ranges_kernel<<<dim3(((s.K + 31) / 32 + 7) / 8, s.N), 256, 0, st>>>(s.K, reinterpret_cast<const unsigned *>(ws + L.ry),
+                                                                               reinterpret_cast<unsigned *>(ws + L.blky));
+    if (small_launch)
+        row_lists_cta_kernel<<<dim3(L.R, s.N), kRowThreads, 0, st>>>(
+            s.K, L.R, L.rowcap, TXn, reinterpret_cast<unsigned *>(ws + L.rx), reinterpret_cast<unsigned *>(ws + L.ry),
+            reinterpret_cast<const unsigned *>(ws + L.blky), reinterpret_cast<int *>(ws + L.rowcnt), reinterpret_cast<RowEntry *>(ws + L.rowlist)
 #if MVP_XBUCKETS
-        , L.NG, reinterpret_cast<int2 *>(ws + L.grphdr), reinterpret_cast<RowEntry *>(ws + L.grplist),
-        want_order ? reinterpret_cast<unsigned short *>(ws + L.tilecnt) : nullptr
+            , L.NG, reinterpret_cast<int2 *>(ws + L.grphdr), reinterpret_cast<RowEntry *>(ws + L.grplist),
+            want_order ? reinterpret_cast<unsigned short *>(ws + L.tilecnt) : nullptr
 #endif
-        );
+            );
+    else
+        row_lists_kernel<<<dim3((L.R + kRowThreads / 32 - 1) / (kRowThreads / 32), s.N), kRowThreads, 0, st>>>(
+            s.K, L.R, L.rowcap, TXn, reinterpret_cast<unsigned *>(ws + L.rx), reinterpret_cast<unsigned *>(ws + L.ry),
+            reinterpret_cast<const unsigned *>(ws + L.blky), reinterpret_cast<int *>(ws + L.rowcnt), reinterpret_cast<RowEntry *>(ws + L.rowlist)
+#if MVP_XBUCKETS
+            , L.NG, reinterpret_cast<int2 *>(ws + L.grphdr), reinterpret_cast<RowEntry *>(ws + L.grplist),
+            want_order ? reinterpret_cast<unsigned short *>(ws + L.tilecnt) : nullptr
+#endif
+            );
 #endif
 #if MVP_CTA_ORDER
     if (want_order) {
@@ -2320,8 +2545,8 @@ size_t mvp_debug_tileclk_offset(const mvp_shape *shape) {
     return make_layout(*shape).tileclk;
 }
 
-int mvp_forward_launch_count(uint32_t flags) { return (flags & MVP_FLAG_ACCEL_VALID) ? 2 : 5; }   // + 2 ordering kernels for small launches
-int mvp_backward_launch_count(uint32_t flags) { return (flags & MVP_FLAG_ACCEL_VALID) ? 2 : 5; }
+int mvp_forward_launch_count(uint32_t flags) { return (flags & MVP_FLAG_ACCEL_VALID) ? 2 : 6; }   // + 2 ordering kernels for small launches
+int mvp_backward_launch_count(uint32_t flags) { return (flags & MVP_FLAG_ACCEL_VALID) ? 2 : 6; }
 
 static inline bool misaligned(const void *p, uintptr_t a) { return p && ((uintptr_t)p & (a - 1)); }
 

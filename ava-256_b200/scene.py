@@ -70,6 +70,16 @@ def compute_raydirs_host(campos, camrot, focal, princpt, H, W, volradius=VOLRADI
     return rp.contiguous(), rd.contiguous(), tminmax.contiguous()
 
 
+def make_cameras(n_views, H, W, view_offset=0, view_ids=None):
+    """Camera parameters of the dome views in the form `compute_raydirs` takes them (fp32): viewpos [n,3] (mm), viewrot [n,3,3],
+    focal [n,2], princpt [n,2] -- what `make_rays` turns into rays on the host."""
+    campos, camrot = look_at_cameras(n_views, view_offset, view_ids)
+    ds = FULLRES_H / H
+    focal = torch.full((n_views, 2), FOCAL_FULLRES / ds, dtype=torch.float64)
+    princpt = torch.tensor([[W / 2.0, H / 2.0]], dtype=torch.float64).expand(n_views, 2)
+    return tuple(t.to(torch.float32).contiguous() for t in (campos, camrot, focal, princpt))
+
+
 def make_rays(n_views, H, W, view_offset=0, dtype=torch.float32, view_ids=None):
     """Rays of `n_views` dome cameras looking at the head: raypos, raydir [n,H,W,3], tminmax [n,H,W,2]."""
     campos, camrot = look_at_cameras(n_views, view_offset, view_ids)

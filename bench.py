@@ -435,7 +435,7 @@ def run_ours(args, rank, world):
     # gradient; it gets back the rendered images and the view-summed (all-reduced) primitive gradients.  Views are
     # streamed in chunks: H2D of chunk i+1 (copy stream) overlaps fwd+bwd of chunk i (compute stream) and D2H of chunk
     # i-1 (second copy stream) -- all inside the timed region.
-    e2e = None
+    e2e = e2e_cam = None
     if not args.no_e2e:
         host_in = {n: s[n].detach().cpu().pin_memory() for n in ("raypos", "raydir", "tminmax")}
         host_prim = {n: x.detach()[0].cpu().pin_memory() for n, x in zip(("primpos", "primrot", "primscale", "template"), leaves)}
@@ -458,7 +458,13 @@ def run_ours(args, rank, world):
         s_in, s_out, s_cmp = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.current_stream()
         cmp_done, flat_out_done = [None, None], [None, None]
 
-        def e2e_step(i):
+        from extensions.utils.utils import compute_raydirs
+        host_cam = [t.pin_memory() for t in scene.make_cameras(nv, h, w, view_ids=vids)]
+        dev_cam = [[torch.empty(t.shape, device=dev) for t in host_cam] for _ in range(2)]
+
+        def e2e_step(i, cams=False):
+            """cams=False: the host hands over the rays themselves.  cams=True: it hands over the camera parameters and the rays are
+            generated on the device by this repository's compute_raydirs, as models/autoencoder.py:240 does."""
             b_ = i & 1
             ev_in = []
             with torch.cuda.stream(s_in):
@@ -466,9 +472,13 @@ def run_ours(args, rank, world):
                     s_in.wait_event(cmp_done[b_])                  # step i-2 has finished reading this buffer set
                 for n in names:
                     dev_prim[b_][n].copy_(host_prim[n], non_blocking=True)
+                if cams:
+                    for d_, h_ in zip(dev_cam[b_], host_cam):
+                        d_.copy_(h_, non_blocking=True)
                 for (a0, a1) in bounds:
-                    for n in host_in:
-                        dev_in[b_][n][a0:a1].copy_(host_in[n][a0:a1], non_blocking=True)
+                    if not cams:
+                        for n in host_in:
+                            dev_in[b_][n][a0:a1].copy_(host_in[n][a0:a1], non_blocking=True)
                     dev_grad[b_][a0:a1].copy_(host_grad[a0:a1], non_blocking=True)
                     e = torch.cuda.Event()
                     e.record(s_in)
@@ -482,8 +492,12 @@ def run_ours(args, rank, world):
                 s_cmp.wait_event(ev_in[ci])
                 nvc = a1 - a0
                 lv = [pr[n][None].expand(nvc, *pr[n].shape).contiguous().requires_grad_(True) for n in names]
-                o_ = mvpraymarch(di["raypos"][a0:a1], di["raydir"][a0:a1], stepsize, di["tminmax"][a0:a1],
-                                 (lv[0], lv[1], lv[2]), lv[3], None)
+                if cams:
+                    cp_, cr_, cf_, cpp_ = (t[a0:a1] for t in dev_cam[b_])
+                    rp_, rd_, tm_ = compute_raydirs(cp_, cr_, cf_, cpp_, (w, h), scene.VOLRADIUS)
+                else:
+                    rp_, rd_, tm_ = di["raypos"][a0:a1], di["raydir"][a0:a1], di["tminmax"][a0:a1]
+                o_ = mvpraymarch(rp_, rd_, stepsize, tm_, (lv[0], lv[1], lv[2]), lv[3], None)
                 o_.backward(dev_grad[b_][a0:a1])
                 off = 0
                 for x in (lv[3], lv[0], lv[1], lv[2]):
@@ -530,6 +544,27 @@ def run_ours(args, rank, world):
         te = torch.tensor([a.elapsed_time(b) / nrep], device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        # same, with camera parameters instead of rays coming from the host (extra key, not the headline)
+        e2e_step(0, True)
+        e2e_step(1, True)
+        e2e_drain()
+        barrier()
+        a2, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a2.record()
+        for i in range(nrep):
+            e2e_step(i, True)
+        e2e_drain()
+        b2.record()
+        barrier()
+        tc_ = torch.tensor([a2.elapsed_time(b2) / nrep], device=dev)
+        if world > 1:
+            dist.all_reduce(tc_, op=dist.ReduceOp.MAX)
+        h2d_cam = sum(x.numel() * 4 for x in host_cam) + sum(x.numel() * 4 for x in host_prim.values()) + host_grad.numel() * 4
+        e2e_cam = {"value": views * h * w / (float(tc_.item()) * 1e-3) / 1e6, "unit": "MP/s", "ms_per_step": float(tc_.item()),
+                   "h2d_bytes_per_step": int(h2d_cam * world), "d2h_bytes_per_step": int(d2h * world),
+                   "what": "as e2e, but the host hands over camera parameters (viewpos, viewrot, focal, princpt) instead of rays; "
+                           "the rays are generated on the device by this repository's compute_raydirs (the reference pipeline, "
+                           "models/autoencoder.py:240)"}
         e2e = {"value": views * h * w / (float(te.item()) * 1e-3) / 1e6, "unit": "MP/s",
                "h2d_bytes_per_step": int(h2d * world), "d2h_bytes_per_step": int(d2h * world),
                "ms_per_step": float(te.item()), "steps": nrep,
@@ -580,7 +615,7 @@ def run_ours(args, rank, world):
         "scene": {"alpha_mu": ALPHA_MU, "alpha_sigma": ALPHA_SIGMA, "saturated_ray_frac": sat_frac, "covered_ray_frac": cover},
         "roofline": dominant, "roofline_forward": roof_f, "roofline_backward": roof_b,
         "cpu_baseline": cpu, "ref_cuda_baseline": ref_cuda, "parity_check": parity, "e2e": e2e, "clocks": clocks,
-        "shared_primitives_config": shared_cfg,
+        "shared_primitives_config": shared_cfg, "e2e_camera_inputs": e2e_cam,
         "gpu_launches": args.steps * (lib.LIB.mvp_forward_launch_count(0) + lib.LIB.mvp_backward_launch_count(lib.FLAG_ACCEL_VALID)),
         "kernel_ms": {"forward_all_views_per_rank": fwd_ms, "backward_all_views_per_rank": bwd_ms},
         "rank_ms_per_step": rank_ms, "allreduce_ms": allreduce_ms,
@@ -601,7 +636,7 @@ def main():
     ap.add_argument("--voxels", type=int, default=T)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--contiguous-views", action="store_true", help="contiguous view blocks per rank instead of interleaved")
-    ap.add_argument("--e2e-chunk", type=int, default=8, help="views per pipelined chunk in the e2e measurement")
+    ap.add_argument("--e2e-chunk", type=int, default=20, help="views per pipelined chunk in the e2e measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-shared-leg", action="store_true", help="skip the shared-primitive ([1,K,...]) configuration")
     ap.add_argument("--no-check", action="store_true", help="skip the reference-CUDA legs (ref_cuda_baseline, parity_check)")

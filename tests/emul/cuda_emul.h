@@ -263,6 +263,7 @@ inline int __reduce_add_sync(unsigned, int v) {
     return r;
 }
 inline void __syncthreads() { emul::block_barrier(0); }
+inline void __threadfence_block() {}
 inline int __syncthreads_or(int pred) { return emul::block_barrier(pred); }
 
 // ---- scalar intrinsics ---------------------------------------------------------------------------------------------

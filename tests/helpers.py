@@ -106,6 +106,9 @@ CASES = {
                                warp=make_warp(2, 8, 3, 4, 5, seed=5, amp=0.12)),
     "warp_head": lambda: dict(_head_case(1, 48, 32, 64, 8, stepsize=1.0 / 32, alpha_mu=2.0, alpha_sigma=2.0),
                               warp=make_warp(1, 64, 4, 4, 4, seed=9, amp=0.05)),
+    # 18 views in one launch: above MVP_CTA_ORDER_MAXVIEWS (16), i.e. the large-launch forms of the accel build (warp-per-row
+    # bucket kernel, plain grid order); every other case runs the small-launch forms
+    "many_views": lambda: gradcheck_like_scene(N=18, H=9, W=11, k3=2, M=3, seed=13, alpha_gain=20.0),
     "head_t16": lambda: _head_case(1, 48, 32, 16, 16, stepsize=1.0 / 32, view_offset=11, alpha_mu=0.5, alpha_sigma=1.0),
 }
 

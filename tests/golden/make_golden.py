@@ -19,9 +19,11 @@ from tests import refext  # noqa: E402
 from tests.helpers import CASES, build_case  # noqa: E402
 
 
-def main(outdir):
+def main(outdir, only=()):
     os.makedirs(outdir, exist_ok=True)
     for name in CASES:
+        if only and name not in only:
+            continue
         s, grad = build_case(name)
         dev = "cuda"
         t = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in s.items()}
@@ -39,4 +41,4 @@ def main(outdir):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden"))
+    main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden"), tuple(sys.argv[2:]))   # [outdir [case ...]]

@@ -53,9 +53,9 @@
 
 // C-ABI layout pins (the ctypes mirror in ava-256_b200/lib.py and INTEGRATION.md are checked against the same numbers)
 static_assert(sizeof(mvp_shape) == 28, "mvp_shape layout");
-static_assert(sizeof(mvp_forward_args) == 168 && offsetof(mvp_forward_args, raypos) == 48 && offsetof(mvp_forward_args, workspace_bytes) == 136 &&
+static_assert(sizeof(mvp_forward_args) == 184 && offsetof(mvp_forward_args, raypos) == 48 && offsetof(mvp_forward_args, workspace_bytes) == 136 &&
                   offsetof(mvp_forward_args, algo) == 164, "mvp_forward_args layout");
-static_assert(sizeof(mvp_backward_args) == 208 && offsetof(mvp_backward_args, grad_rayrgba) == 104 && offsetof(mvp_backward_args, workspace_bytes) == 168 &&
+static_assert(sizeof(mvp_backward_args) == 224 && offsetof(mvp_backward_args, grad_rayrgba) == 104 && offsetof(mvp_backward_args, workspace_bytes) == 168 &&
                   offsetof(mvp_backward_args, algo) == 204, "mvp_backward_args layout");
 
 // experiment knobs (defaults = measured best)
@@ -910,8 +910,10 @@ struct Params {
     // forward outputs
     float *rayrgba, *raysat;
     int4 *rayaux;
+    float *rgb_nchw, *alpha_nchw;          // optional image-plane outputs [N,3,H,W] / [N,1,H,W]
     // backward
     const float *grad_rayrgba;
+    const float *g_rgb_nchw, *g_alpha_nchw;   // the gradient as image planes (when grad_rayrgba is NULL)
     const float *raysat_in;
     const int4 *rayaux_in;
     float *g_primpos, *g_primrot, *g_primscale, *g_tplate;
@@ -1644,7 +1646,14 @@ __device__ __forceinline__ bool forward_tile(const Params &p, const int n, const
     complete();
 #endif
     if (c.inimg) {
-        reinterpret_cast<float4 *>(p.rayrgba)[r] = acc;
+        if (p.rayrgba) reinterpret_cast<float4 *>(p.rayrgba)[r] = acc;
+        if (p.rgb_nchw) {
+            // image planes for the caller (mvpraymarcher.py:50-51: permute + two contiguous copies, done here by the epilogue)
+            const size_t plane = (size_t)p.H * p.W, pix = r - (size_t)n * plane;
+            float *o = p.rgb_nchw + (size_t)n * 3 * plane + pix;
+            o[0] = acc.x; o[plane] = acc.y; o[2 * plane] = acc.z;
+            p.alpha_nchw[(size_t)n * plane + pix] = acc.w;
+        }
         if (kGrad) {
             p.raysat[r * 3 + 0] = sat0; p.raysat[r * 3 + 1] = sat1; p.raysat[r * 3 + 2] = sat2;
             p.rayaux[r] = make_int4(jsat, ranksat, __float_as_int(abefore), jlast);
@@ -1823,7 +1832,13 @@ __device__ __forceinline__ bool backward_tile(const Params &p, const int n, cons
     {
         // per-ray constants of the adjoint live in shared memory ([field][lane]: a batch reads them by owner lane,
         // conflict-free, instead of holding 9 registers per thread for the whole kernel)
-        const float4 dL = __ldg(reinterpret_cast<const float4 *>(p.grad_rayrgba) + r);
+        float4 dL;
+        if (p.grad_rayrgba) dL = __ldg(reinterpret_cast<const float4 *>(p.grad_rayrgba) + r);
+        else {
+            const size_t plane = (size_t)p.H * p.W, pix = r - (size_t)n * plane;
+            const float *gi = p.g_rgb_nchw + (size_t)n * 3 * plane + pix;
+            dL = make_float4(__ldg(gi), __ldg(gi + plane), __ldg(gi + 2 * plane), __ldg(p.g_alpha_nchw + (size_t)n * plane + pix));
+        }
         const float rs0 = __ldg(p.raysat_in + r * 3 + 0), rs1 = __ldg(p.raysat_in + r * 3 + 1), rs2 = __ldg(p.raysat_in + r * 3 + 2);
         const bool hassat = rs0 > -1.f;
         float *pr_ = sray;
@@ -2553,9 +2568,10 @@ static inline bool misaligned(const void *p, uintptr_t a) { return p && ((uintpt
 int mvp_raymarch_forward(const mvp_forward_args *a, void *stream) {
     if (!a) return MVP_ERR_NULL;
     if (a->struct_size != sizeof(mvp_forward_args)) return MVP_ERR_STRUCT;
-    if (!a->raypos || !a->raydir || !a->tminmax || !a->primpos || !a->primrot || !a->primscale || !a->tplate || !a->rayrgba ||
-        !a->workspace)
+    if (!a->raypos || !a->raydir || !a->tminmax || !a->primpos || !a->primrot || !a->primscale || !a->tplate || !a->workspace)
         return MVP_ERR_NULL;
+    if ((a->rayrgb_nchw == nullptr) != (a->rayalpha_nchw == nullptr)) return MVP_ERR_NULL;
+    if (!a->rayrgba && !a->rayrgb_nchw) return MVP_ERR_NULL;          // at least one form of the output
     if ((a->raysat == nullptr) != (a->rayaux == nullptr)) return MVP_ERR_NULL;
     int rc = check_shape(a->shape);
     if (rc != MVP_OK) return rc;
@@ -2567,7 +2583,8 @@ int mvp_raymarch_forward(const mvp_forward_args *a, void *stream) {
     // vector accesses: float4 (tplate, rayrgba), int4 (rayaux), float2 (tminmax); everything else is read as scalars
     if (misaligned(a->tplate, 16) || misaligned(a->rayrgba, 16) || misaligned(a->rayaux, 16) || misaligned(a->tminmax, 8) ||
         misaligned(a->raypos, 4) || misaligned(a->raydir, 4) || misaligned(a->primpos, 4) || misaligned(a->primrot, 4) ||
-        misaligned(a->primscale, 4) || misaligned(a->raysat, 4) || misaligned(a->warp, 4))
+        misaligned(a->primscale, 4) || misaligned(a->raysat, 4) || misaligned(a->warp, 4) || misaligned(a->rayrgb_nchw, 4) ||
+        misaligned(a->rayalpha_nchw, 4))
         return MVP_ERR_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
     char *ws = (char *)a->workspace;
@@ -2579,6 +2596,7 @@ int mvp_raymarch_forward(const mvp_forward_args *a, void *stream) {
     Params p{};
     fill_params(p, a->shape, a->stepsize, a->fadescale, a->fadeexp, ws, L);
     p.pview = pview;
+    p.rgb_nchw = a->rayrgb_nchw; p.alpha_nchw = a->rayalpha_nchw;
 #if MVP_LIST_REUSE
     if (a->flags & MVP_FLAG_TEST_TINY_LISTS) p.listlimit = p.listcap < 16 ? p.listcap : 16;
 #endif
@@ -2626,9 +2644,12 @@ int mvp_raymarch_backward(const mvp_backward_args *a, void *stream) {
     if (!a) return MVP_ERR_NULL;
     if (a->struct_size != sizeof(mvp_backward_args)) return MVP_ERR_STRUCT;
     if (!a->raypos || !a->raydir || !a->tminmax || !a->primpos || !a->primrot || !a->primscale || !a->tplate ||
-        !a->grad_rayrgba || !a->raysat || !a->rayaux || !a->grad_primpos || !a->grad_primrot || !a->grad_primscale ||
+        !a->raysat || !a->rayaux || !a->grad_primpos || !a->grad_primrot || !a->grad_primscale ||
         !a->grad_tplate || !a->workspace)
         return MVP_ERR_NULL;
+    // the image gradient: channels-last [N,H,W,4], or as image planes (both of them, and then not the other form)
+    if ((a->grad_rayrgb_nchw == nullptr) != (a->grad_rayalpha_nchw == nullptr)) return MVP_ERR_NULL;
+    if ((a->grad_rayrgba == nullptr) == (a->grad_rayrgb_nchw == nullptr)) return MVP_ERR_NULL;
     int rc = check_shape(a->shape);
     if (rc != MVP_OK) return rc;
     if (a->algo != 0 && a->algo != 1) return MVP_ERR_ALGO;
@@ -2639,7 +2660,8 @@ int mvp_raymarch_backward(const mvp_backward_args *a, void *stream) {
     if (misaligned(a->tplate, 16) || misaligned(a->grad_tplate, 16) || misaligned(a->grad_rayrgba, 16) || misaligned(a->rayaux, 16) ||
         misaligned(a->tminmax, 8) || misaligned(a->raypos, 4) || misaligned(a->raydir, 4) || misaligned(a->primpos, 4) ||
         misaligned(a->primrot, 4) || misaligned(a->primscale, 4) || misaligned(a->raysat, 4) || misaligned(a->grad_primpos, 4) ||
-        misaligned(a->grad_primrot, 4) || misaligned(a->grad_primscale, 4) || misaligned(a->warp, 4) || misaligned(a->grad_warp, 4))
+        misaligned(a->grad_primrot, 4) || misaligned(a->grad_primscale, 4) || misaligned(a->warp, 4) || misaligned(a->grad_warp, 4) ||
+        misaligned(a->grad_rayrgb_nchw, 4) || misaligned(a->grad_rayalpha_nchw, 4))
         return MVP_ERR_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
     char *ws = (char *)a->workspace;
@@ -2662,6 +2684,7 @@ int mvp_raymarch_backward(const mvp_backward_args *a, void *stream) {
     p.pview = pview;
     p.raypos = a->raypos; p.raydir = a->raydir; p.tminmax = a->tminmax; p.tplate = a->tplate;
     p.use_order = a->shape.N <= MVP_CTA_ORDER_MAXVIEWS;
+    p.g_rgb_nchw = a->grad_rayrgb_nchw; p.g_alpha_nchw = a->grad_rayalpha_nchw;
     p.grad_rayrgba = a->grad_rayrgba; p.raysat_in = a->raysat; p.rayaux_in = reinterpret_cast<const int4 *>(a->rayaux);
     p.g_primpos = a->grad_primpos; p.g_primrot = a->grad_primrot; p.g_primscale = a->grad_primscale; p.g_tplate = a->grad_tplate;
     p.warp = a->warp; p.g_warp = a->grad_warp; p.WD = a->WD; p.WH = a->WH; p.WW = a->WW;

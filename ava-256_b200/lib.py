@@ -25,6 +25,7 @@ class ForwardArgs(ctypes.Structure):
         ("rayrgba", c_f), ("raysat", c_f), ("rayaux", c_f),
         ("workspace", c_f), ("workspace_bytes", ctypes.c_size_t),
         ("warp", c_f), ("WD", ctypes.c_int32), ("WH", ctypes.c_int32), ("WW", ctypes.c_int32), ("algo", ctypes.c_int32),
+        ("rayrgb_nchw", c_f), ("rayalpha_nchw", c_f),
     ]
 
 
@@ -43,6 +44,7 @@ class BackwardArgs(ctypes.Structure):
         ("workspace", c_f), ("workspace_bytes", ctypes.c_size_t),
         ("warp", c_f), ("grad_warp", c_f), ("WD", ctypes.c_int32), ("WH", ctypes.c_int32), ("WW", ctypes.c_int32),
         ("algo", ctypes.c_int32),
+        ("grad_rayrgb_nchw", c_f), ("grad_rayalpha_nchw", c_f),
     ]
 
 
@@ -60,9 +62,9 @@ FLAG_ACCEL_VALID = 1
 FLAG_ZERO_GRADS = 2
 FLAG_SHARED_PRIMS = 4
 FLAG_TEST_TINY_LISTS = 0x100
-ABI_VERSION = 5
+ABI_VERSION = 6
 # layout pins, equal to the static_asserts in csrc/mvp_kernels.cu (tests/test_abi.py compares)
-SIZEOF = {"Shape": 28, "ForwardArgs": 168, "BackwardArgs": 208}
+SIZEOF = {"Shape": 28, "ForwardArgs": 184, "BackwardArgs": 224}
 
 EXPORTS = ("mvp_abi_version", "mvp_build_config", "mvp_error_string", "mvp_workspace_bytes", "mvp_build_accel", "mvp_raymarch_forward",
            "mvp_raymarch_backward", "mvp_compute_raydirs", "mvp_forward_launch_count", "mvp_backward_launch_count",

@@ -93,7 +93,13 @@ class MVPRaymarch(Function):
         with torch.cuda.device(dev):
             wsbytes = _lib.workspace_bytes(N, H, W, K, TD, TH, TW)
             workspace = torch.empty(wsbytes, dtype=torch.uint8, device=dev)
-            rayrgba = torch.empty((N, H, W, 4), dtype=torch.float32, device=dev)
+            planes = bool(options.get("_planes", False))   # image-plane outputs (MVPRaymarchPlanes below)
+            if planes:
+                rayrgba = None
+                rayrgb = torch.empty((N, 3, H, W), dtype=torch.float32, device=dev)
+                rayalpha = torch.empty((N, 1, H, W), dtype=torch.float32, device=dev)
+            else:
+                rayrgba = torch.empty((N, H, W, 4), dtype=torch.float32, device=dev)
             if gradmode:
                 raysat = torch.empty((N, H, W, 3), dtype=torch.float32, device=dev)
                 rayaux = torch.empty((N, H, W, 4), dtype=torch.int32, device=dev)
@@ -107,6 +113,8 @@ class MVPRaymarch(Function):
             a.primpos, a.primrot, a.primscale = _ptr(primpos), _ptr(primrot), _ptr(primscale)
             a.tplate = _ptr(template)
             a.rayrgba, a.raysat, a.rayaux = _ptr(rayrgba), _ptr(raysat), _ptr(rayaux)
+            if planes:
+                a.rayrgb_nchw, a.rayalpha_nchw = _ptr(rayrgb), _ptr(rayalpha)
             a.workspace, a.workspace_bytes = _ptr(workspace), wsbytes
             a.algo = 1 if usewarp else 0
             if usewarp:
@@ -120,10 +128,13 @@ class MVPRaymarch(Function):
             ctx.options = options
             ctx.stepsize = float(stepsize)
             ctx.shared = shared
+        if planes:
+            return rayrgb, rayalpha
         return rayrgba
 
     @staticmethod
-    def backward(ctx, grad_rayrgba):
+    def backward(ctx, grad_rayrgba, grad_rayalpha=None):
+        """grad_rayrgba [N,H,W,4]; or, for MVPRaymarchPlanes, (grad_rayrgb [N,3,H,W], grad_rayalpha [N,1,H,W])."""
         raypos, raydir, tminmax, primpos, primrot, primscale, template, raysat, rayaux, workspace, warp = ctx.saved_tensors
         options = ctx.options
         N, H, W = raypos.shape[:3]
@@ -131,7 +142,13 @@ class MVPRaymarch(Function):
         TD, TH, TW = template.shape[2:5]
         dev = raypos.device
         with torch.cuda.device(dev):
-            grad_rayrgba = _aligned(grad_rayrgba.contiguous(), 16)     # mvpraymarch.py:264
+            planes = bool(options.get("_planes", False))
+            if planes:
+                grad_rgb = grad_rayrgba.contiguous() if grad_rayrgba is not None else torch.zeros((N, 3, H, W), device=dev)
+                grad_alpha = grad_rayalpha.contiguous() if grad_rayalpha is not None else torch.zeros((N, 1, H, W), device=dev)
+                grad_rayrgba = None
+            else:
+                grad_rayrgba = _aligned(grad_rayrgba.contiguous(), 16)     # mvpraymarch.py:264
             # mvpraymarch.py:240-246 zeros_like's these; here the library zero-fills them on the stream (MVP_FLAG_ZERO_GRADS)
             grad_primpos = torch.empty_like(primpos)
             grad_primrot = torch.empty_like(primrot)
@@ -149,6 +166,8 @@ class MVPRaymarch(Function):
             a.primpos, a.primrot, a.primscale = _ptr(primpos), _ptr(primrot), _ptr(primscale)
             a.tplate = _ptr(template)
             a.grad_rayrgba, a.raysat, a.rayaux = _ptr(grad_rayrgba), _ptr(raysat), _ptr(rayaux)
+            if planes:
+                a.grad_rayrgb_nchw, a.grad_rayalpha_nchw = _ptr(grad_rgb), _ptr(grad_alpha)
             a.grad_primpos, a.grad_primrot, a.grad_primscale = _ptr(grad_primpos), _ptr(grad_primrot), _ptr(grad_primscale)
             a.grad_tplate = _ptr(grad_template)
             a.workspace, a.workspace_bytes = _ptr(workspace), workspace.numel()
@@ -159,6 +178,23 @@ class MVPRaymarch(Function):
             stream = torch.cuda.current_stream(dev).cuda_stream
             _lib.check(_lib.LIB.mvp_raymarch_backward(ctypes.byref(a), ctypes.c_void_p(stream)))
         return (None, None, None, None, grad_primpos, grad_primrot, grad_primscale, grad_template, grad_warp, None, None, None)
+
+
+class MVPRaymarchPlanes(MVPRaymarch):
+    """Same op with the outputs as the caller uses them: (rayrgb [N,3,H,W], rayalpha [N,1,H,W]), written by the render
+    kernel's epilogue, and the gradient taken as those two planes by the backward's prologue -- the permute + two
+    `.contiguous()` copies of models/raymarchers/mvpraymarcher.py:50-51 and the `.contiguous()` of the incoming gradient
+    (mvpraymarch.py:264) never run."""
+
+    @staticmethod
+    def forward(ctx, raypos, raydir, stepsize, tminmax, primpos, primrot, primscale, template, warp, rayterm, gradmode, options):
+        options = dict(options, _planes=True)
+        return MVPRaymarch.forward(ctx, raypos, raydir, stepsize, tminmax, primpos, primrot, primscale, template, warp, rayterm,
+                                   gradmode, options)
+
+    @staticmethod
+    def backward(ctx, grad_rayrgb, grad_rayalpha):
+        return MVPRaymarch.backward(ctx, grad_rayrgb, grad_rayalpha)
 
 
 def morton_codes(primpos):
@@ -248,5 +284,19 @@ def mvpraymarch(
         "fadeexp": fadeexp, "accum": accum, "termthresh": termthresh, "griddim": griddim, "blocksize": blocksize,
         "bwdblocksize": bwdblocksize,
     }
-    return MVPRaymarch.apply(raypos, raydir, stepsize, tminmax, primpos, primrot, primscale, template, warp, rayterm,
-                             torch.is_grad_enabled(), options)
+    fn = MVPRaymarchPlanes if _PLANES.get("on") else MVPRaymarch
+    return fn.apply(raypos, raydir, stepsize, tminmax, primpos, primrot, primscale, template, warp, rayterm,
+                    torch.is_grad_enabled(), options)
+
+
+_PLANES = {}
+
+
+def mvpraymarch_planes(*args, **kwargs):
+    """`mvpraymarch` with image-plane outputs: same parameters, returns (rayrgb [N,3,H,W], rayalpha [N,1,H,W]) instead of
+    rayrgba [N,H,W,4] (see MVPRaymarchPlanes; used by `ava256_b200.raymarcher.Raymarcher`)."""
+    _PLANES["on"] = True
+    try:
+        return mvpraymarch(*args, **kwargs)
+    finally:
+        _PLANES["on"] = False

@@ -1,27 +1,30 @@
-"""`Raymarcher`: host-side mirror of /root/reference/models/raymarchers/mvpraymarcher.py:17-54 (same constructor,
-same forward signature and return tuple) with the output split done by one kernel (`composite.split_rgba`) instead of a
-permute + two `.contiguous()` copies (:50-51)."""
+"""`Raymarcher`: host-side mirror of /root/reference/models/raymarchers/mvpraymarcher.py:17-54 (same constructor arguments,
+same forward signature and return tuple).  The image planes `rayrgb` / `rayalpha` come straight out of the render kernel's
+epilogue and their gradients go straight into the backward's prologue (`op.mvpraymarch_planes`); the reference makes them
+with a permute + two `.contiguous()` copies (:50-51)."""
 import torch.nn as nn
 
 from .composite import split_rgba
-from .op import mvpraymarch
+from .op import mvpraymarch, mvpraymarch_planes
 
 
 class Raymarcher(nn.Module):
-    def __init__(self, volradius, dt: float = 1.0):
+    def __init__(self, volradius, dt: float = 1.0, with_rgba: bool = False):
+        """with_rgba: also return the [N,4,H,W] view of the channels-last `rayrgba` as the third item, like the reference
+        (:50).  No caller in ava-256 reads it (models/autoencoder.py:246 drops it), so by default the channels-last image
+        is never written and the third item is None."""
         super().__init__()
         self.volume_radius = volradius
         self.dt = dt / self.volume_radius                       # mvpraymarcher.py:24
+        self.with_rgba = with_rgba
 
     def forward(self, raypos, raydir, tminmax, decout, renderoptions={}, rayterm=None, with_pos_img=None):
-        rayrgba = mvpraymarch(
-            raypos, raydir, self.dt, tminmax,
-            (decout["primpos"], decout["primrot"], decout["primscale"]),
-            template=decout["template"],
-            warp=decout["warp"] if "warp" in decout else None,
-            rayterm=rayterm,
-            **{k: v for k, v in renderoptions.items() if k in mvpraymarch.__code__.co_varnames},   # :45
-        )
-        assert rayrgba is not None
-        rayrgb, rayalpha = split_rgba(rayrgba)
-        return rayrgb, rayalpha, rayrgba.permute(0, 3, 1, 2), None   # third item is the permuted view, as in :50
+        args = (raypos, raydir, self.dt, tminmax, (decout["primpos"], decout["primrot"], decout["primscale"]))
+        kwargs = dict(template=decout["template"], warp=decout["warp"] if "warp" in decout else None, rayterm=rayterm,
+                      **{k: v for k, v in renderoptions.items() if k in mvpraymarch.__code__.co_varnames})   # :45
+        if self.with_rgba:
+            rayrgba = mvpraymarch(*args, **kwargs)
+            rayrgb, rayalpha = split_rgba(rayrgba)              # one kernel instead of the permute + two copies
+            return rayrgb, rayalpha, rayrgba.permute(0, 3, 1, 2), None
+        rayrgb, rayalpha = mvpraymarch_planes(*args, **kwargs)
+        return rayrgb, rayalpha, None, None

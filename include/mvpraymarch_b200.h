@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define MVP_ABI_VERSION 5
+#define MVP_ABI_VERSION 6
 
 #define MVP_OK 0
 #define MVP_ERR_NULL (-1)      /* a required pointer is NULL */
@@ -81,7 +81,7 @@ typedef struct mvp_forward_args {
     const float *raypos, *raydir, *tminmax;
     const float *primpos, *primrot, *primscale;
     const float *tplate;
-    float *rayrgba;          /* out */
+    float *rayrgba;          /* out; may be NULL when rayrgb_nchw / rayalpha_nchw are given */
     float *raysat;           /* out, NULL when no gradient will be taken (mvpraymarch.py:147-152) */
     int32_t *rayaux;         /* out, NULL iff raysat is NULL */
     void *workspace;         /* >= mvp_workspace_bytes(shape), 256-byte aligned */
@@ -91,6 +91,11 @@ typedef struct mvp_forward_args {
     const float *warp;
     int32_t WD, WH, WW;
     int32_t algo;            /* 0 or 1 (mvpraymarch.py:303) */
+    /* Optional image-plane outputs, written by the render kernel's epilogue (both or neither): rayrgb [N,3,H,W] and
+     * rayalpha [N,1,H,W] -- what models/raymarchers/mvpraymarcher.py:50-51 makes of rayrgba with a permute and two
+     * .contiguous() copies. */
+    float *rayrgb_nchw;
+    float *rayalpha_nchw;
 } mvp_forward_args;
 
 typedef struct mvp_backward_args {
@@ -104,7 +109,7 @@ typedef struct mvp_backward_args {
     const float *raypos, *raydir, *tminmax;
     const float *primpos, *primrot, *primscale;
     const float *tplate;
-    const float *grad_rayrgba; /* [N,H,W,4] */
+    const float *grad_rayrgba; /* [N,H,W,4]; NULL when the gradient comes as image planes (grad_rayrgb_nchw / grad_rayalpha_nchw) */
     const float *raysat;       /* from forward */
     const int32_t *rayaux;     /* from forward */
     float *grad_primpos, *grad_primrot, *grad_primscale; /* out, accumulated into: caller zero-fills (or MVP_FLAG_ZERO_GRADS) */
@@ -115,6 +120,10 @@ typedef struct mvp_backward_args {
     float *grad_warp;          /* algo 1 only; out, accumulated into: caller zero-fills */
     int32_t WD, WH, WW;
     int32_t algo;
+    /* The incoming gradient as image planes [N,3,H,W] + [N,1,H,W] (both, with grad_rayrgba == NULL), read by the kernel's
+     * prologue: the adjoint of the fused epilogue above; replaces the contiguous() copy of mvpraymarch.py:264. */
+    const float *grad_rayrgb_nchw;
+    const float *grad_rayalpha_nchw;
 } mvp_backward_args;
 
 int mvp_abi_version(void);

@@ -42,7 +42,7 @@ int main(int argc, char **argv) {
     a.stepsize = 0.1f;
     CHECK(fwd(NULL, NULL) == MVP_ERR_NULL);
     CHECK(fwd(&a, NULL) == MVP_ERR_STRUCT);                      /* struct_size not set */
-    a.struct_size = (uint32_t)sizeof a - 24;                      /* the ABI-v4 length: a stale caller */
+    a.struct_size = (uint32_t)sizeof a - 16;                      /* the ABI-v5 length: a stale caller */
     CHECK(fwd(&a, NULL) == MVP_ERR_STRUCT);
     a.struct_size = (uint32_t)sizeof a;
     CHECK(fwd(&a, NULL) == MVP_ERR_NULL);                        /* required pointers missing */
@@ -67,6 +67,9 @@ int main(int argc, char **argv) {
     a.tplate = (const float *)(uintptr_t)260;                    /* 4-byte aligned only */
     CHECK(fwd(&a, NULL) == MVP_ERR_ALIGN);
     a.tplate = dummy;
+    a.rayrgb_nchw = dummy;                                        /* image-plane outputs come in pairs */
+    CHECK(fwd(&a, NULL) == MVP_ERR_NULL);
+    a.rayrgb_nchw = NULL;
     a.raysat = dummy;                                             /* raysat without rayaux */
     CHECK(fwd(&a, NULL) == MVP_ERR_NULL);
 

@@ -57,7 +57,7 @@ def _f32(a):
 
 
 def forward_backward(raypos, raydir, stepsize, tminmax, primpos, primrot, primscale, template, grad_rayrgba=None, warp=None,
-                     fadescale=8.0, fadeexp=8.0, fwd_flags=0, bwd_flags=0):
+                     fadescale=8.0, fadeexp=8.0, fwd_flags=0, bwd_flags=0, planes=False):
     """Runs the emulated forward (and, when grad_rayrgba is given, backward) kernels.
     Returns (rayrgba, raysat, grads) with grads = [primpos, primrot, primscale, template(, warp)] or None."""
     L = load()
@@ -79,7 +79,11 @@ def forward_backward(raypos, raydir, stepsize, tminmax, primpos, primrot, primsc
     a.stepsize, a.fadescale, a.fadeexp, a.flags = float(stepsize), float(fadescale), float(fadeexp), fwd_flags
     a.raypos, a.raydir, a.tminmax = _p(raypos), _p(raydir), _p(tminmax)
     a.primpos, a.primrot, a.primscale, a.tplate = _p(primpos), _p(primrot), _p(primscale), _p(template)
-    a.rayrgba, a.raysat, a.rayaux = _p(rayrgba), _p(raysat), _p(rayaux)
+    rgb_p = np.full((N, 3, H, W), np.nan, np.float32) if planes else None
+    alpha_p = np.full((N, 1, H, W), np.nan, np.float32) if planes else None
+    a.rayrgba, a.raysat, a.rayaux = (None if planes else _p(rayrgba)), _p(raysat), _p(rayaux)
+    if planes:
+        a.rayrgb_nchw, a.rayalpha_nchw = _p(rgb_p), _p(alpha_p)
     a.workspace, a.workspace_bytes = _p(ws), wsb
     a.algo = 1 if warp is not None else 0
     if warp is not None:
@@ -87,6 +91,8 @@ def forward_backward(raypos, raydir, stepsize, tminmax, primpos, primrot, primsc
         a.WD, a.WH, a.WW = warp.shape[2:5]
     rc = L.mvp_raymarch_forward(ctypes.byref(a), None)
     assert rc == 0, rc
+    if planes:                      # hand back the same layout as the channels-last run, assembled from the planes
+        rayrgba = np.ascontiguousarray(np.concatenate([rgb_p, alpha_p], axis=1).transpose(0, 2, 3, 1))
     if not want_grad:
         return rayrgba, None, None
     grad_rayrgba = _f32(grad_rayrgba)
@@ -98,7 +104,11 @@ def forward_backward(raypos, raydir, stepsize, tminmax, primpos, primrot, primsc
     b.stepsize, b.fadescale, b.fadeexp, b.flags = float(stepsize), float(fadescale), float(fadeexp), _abi.FLAG_ACCEL_VALID | bwd_flags
     b.raypos, b.raydir, b.tminmax = _p(raypos), _p(raydir), _p(tminmax)
     b.primpos, b.primrot, b.primscale, b.tplate = _p(primpos), _p(primrot), _p(primscale), _p(template)
-    b.grad_rayrgba, b.raysat, b.rayaux = _p(grad_rayrgba), _p(raysat), _p(rayaux)
+    if planes:
+        g_rgb = np.ascontiguousarray(grad_rayrgba.transpose(0, 3, 1, 2)[:, :3])
+        g_alpha = np.ascontiguousarray(grad_rayrgba.transpose(0, 3, 1, 2)[:, 3:4])
+        b.grad_rayrgb_nchw, b.grad_rayalpha_nchw = _p(g_rgb), _p(g_alpha)
+    b.grad_rayrgba, b.raysat, b.rayaux = (None if planes else _p(grad_rayrgba)), _p(raysat), _p(rayaux)
     b.grad_primpos, b.grad_primrot, b.grad_primscale, b.grad_tplate = (_p(g) for g in grads)
     b.workspace, b.workspace_bytes = _p(ws), wsb
     b.algo = a.algo

@@ -150,6 +150,19 @@ def test_kernel_variants_match_the_default_build(kernels, name, variant):
                 assert loaded.value > 0 and rebuilt.value > 0             # tiny workspace: both paths in one launch
 
 
+@pytest.mark.parametrize("name", ["head_small", "gradcheck_ragged", "warp_small"])
+def test_emulated_image_plane_outputs(kernels, name):
+    """rayrgb [N,3,H,W] / rayalpha [N,1,H,W] written by the forward's epilogue and the gradient read as planes by the backward's
+    prologue (C-ABI 6) == the channels-last run, bit for bit in the forward."""
+    s, grad = build_case(name)
+    a, kw = scene_args_np(s)
+    out0, sat0, g0 = kernels.forward_backward(*a, grad_rayrgba=grad.numpy(), **kw)
+    out1, sat1, g1 = kernels.forward_backward(*a, grad_rayrgba=grad.numpy(), planes=True, **kw)
+    assert np.array_equal(out0, out1) and np.array_equal(sat0, sat1)
+    for x, y in zip(g0, g1):
+        assert relerr(x, y) <= 1e-5
+
+
 def test_emulated_runtime_flags(kernels):
     """C-ABI flags of the product library on the emulation: MVP_FLAG_TEST_TINY_LISTS (almost every tile takes the backward's
     rebuild path), MVP_FLAG_ZERO_GRADS (the library zero-fills NaN-initialised gradient buffers)."""

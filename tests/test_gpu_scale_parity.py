@@ -241,3 +241,41 @@ def test_unaligned_contiguous_views_are_accepted():
     a.primpos, a.primrot, a.primscale, a.tplate = P(s["primpos"]), P(s["primrot"]), P(s["primscale"]), P(s2["template"])
     a.rayrgba, a.workspace, a.workspace_bytes = P(rgba), P(ws), wsb
     assert lib.LIB.mvp_raymarch_forward(ctypes.byref(a), None) == -6          # MVP_ERR_ALIGN
+
+
+def test_image_plane_outputs_equal_channels_last_op():
+    """`mvpraymarch_planes` / the `Raymarcher` mirror: rayrgb [N,3,H,W] and rayalpha [N,1,H,W] straight from the render kernel,
+    gradients straight into the backward == the channels-last op followed by the reference's permute + contiguous copies
+    (models/raymarchers/mvpraymarcher.py:50-51), forward bit-identical."""
+    from ava256_b200 import scene
+    from ava256_b200.op import mvpraymarch_planes
+    from ava256_b200.raymarcher import Raymarcher
+    s = scene.make_scene(2, 160, 104, 1024, 8, alpha_mu=10.0, alpha_sigma=5.0, device="cuda")
+    g_rgb = torch.randn(2, 3, 160, 104, device="cuda", generator=torch.Generator(device="cuda").manual_seed(4))
+    g_alpha = torch.randn(2, 1, 160, 104, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5))
+    grad_nhwc = torch.cat([g_rgb, g_alpha], dim=1).permute(0, 2, 3, 1).contiguous()
+    out, grads = _ours(s, grad_nhwc)
+    lv = [s[n].detach().clone().requires_grad_(True) for n in NAMES]
+    rgb, alpha = mvpraymarch_planes(s["raypos"], s["raydir"], s["stepsize"], s["tminmax"], (lv[0], lv[1], lv[2]), lv[3], None)
+    assert rgb.shape == (2, 3, 160, 104) and alpha.shape == (2, 1, 160, 104) and rgb.is_contiguous() and alpha.is_contiguous()
+    ref = out.permute(0, 3, 1, 2)
+    assert torch.equal(rgb, ref[:, :3]) and torch.equal(alpha, ref[:, 3:4])
+    ((rgb * g_rgb).sum() + (alpha * g_alpha).sum()).backward()
+    for nm, x, g_ in zip(NAMES, lv, grads):
+        assert _trelerr(x.grad, g_) <= 1e-5, nm
+    # only one of the two outputs used downstream: the other gradient is None and must count as zero
+    lv2 = [s[n].detach().clone().requires_grad_(True) for n in NAMES]
+    rgb2, _ = mvpraymarch_planes(s["raypos"], s["raydir"], s["stepsize"], s["tminmax"], (lv2[0], lv2[1], lv2[2]), lv2[3], None)
+    (rgb2 * g_rgb).sum().backward()
+    g0 = torch.cat([g_rgb, torch.zeros_like(g_alpha)], dim=1).permute(0, 2, 3, 1).contiguous()
+    _, grads0 = _ours(s, g0)
+    for nm, x, g_ in zip(NAMES, lv2, grads0):
+        assert _trelerr(x.grad, g_) <= 1e-5, nm
+    # the module mirror
+    rm = Raymarcher(scene.VOLRADIUS)
+    decout = dict(primpos=s["primpos"], primrot=s["primrot"], primscale=s["primscale"], template=s["template"])
+    with torch.no_grad():
+        r1, a1, third, fourth = rm(s["raypos"], s["raydir"], s["tminmax"], decout)
+        r2, a2, full, _ = Raymarcher(scene.VOLRADIUS, with_rgba=True)(s["raypos"], s["raydir"], s["tminmax"], decout)
+    assert third is None and fourth is None and torch.equal(r1, rgb) and torch.equal(a1, alpha)
+    assert torch.equal(r2, rgb) and torch.equal(a2, alpha) and torch.equal(full, ref)

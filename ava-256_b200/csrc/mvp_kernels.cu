@@ -53,9 +53,9 @@
 
 // C-ABI layout pins (the ctypes mirror in ava-256_b200/lib.py and INTEGRATION.md are checked against the same numbers)
 static_assert(sizeof(mvp_shape) == 28, "mvp_shape layout");
-static_assert(sizeof(mvp_forward_args) == 184 && offsetof(mvp_forward_args, raypos) == 48 && offsetof(mvp_forward_args, workspace_bytes) == 136 &&
+static_assert(sizeof(mvp_forward_args) == 192 && offsetof(mvp_forward_args, raypos) == 48 && offsetof(mvp_forward_args, workspace_bytes) == 136 &&
                   offsetof(mvp_forward_args, algo) == 164, "mvp_forward_args layout");
-static_assert(sizeof(mvp_backward_args) == 224 && offsetof(mvp_backward_args, grad_rayrgba) == 104 && offsetof(mvp_backward_args, workspace_bytes) == 168 &&
+static_assert(sizeof(mvp_backward_args) == 232 && offsetof(mvp_backward_args, grad_rayrgba) == 104 && offsetof(mvp_backward_args, workspace_bytes) == 168 &&
                   offsetof(mvp_backward_args, algo) == 204, "mvp_backward_args layout");
 
 // experiment knobs (defaults = measured best)
@@ -170,7 +170,7 @@ struct Cam {          // 64 B per view
 struct __align__(8) RowEntry { int k; unsigned xr; };   // xr = x0 | x1 << 16  (pixels, inclusive)
 
 struct Layout {
-    size_t cam, bad, pack, rx, ry, rowcnt, rowlist, heavycnt, heavylist, ctaorder, ctahist, tilecnt, blky, tileclk, total;
+    size_t cam, bad, pack, rx, ry, rowcnt, rowlist, heavycnt, heavylist, ctaorder, ctahist, tilecnt, blky, rankof, tileclk, total;
     int R, rowcap;
 #if MVP_XBUCKETS
     size_t grphdr, grplist;
@@ -195,6 +195,7 @@ __host__ inline Layout make_layout(const mvp_shape &s) {
     L.rx = off;      off = align256(off + (size_t)s.N * s.K * 4);
     L.ry = off;      off = align256(off + (size_t)s.N * s.K * 4);
     L.blky = off;    off = align256(off + (size_t)s.N * ((s.K + 31) / 32) * 4);
+    L.rankof = off;  off = align256(off + (size_t)s.N * s.K * 4);
     L.rowcnt = off;  off = align256(off + (size_t)s.N * L.R * 4);
     L.rowlist = off; off = align256(off + (size_t)s.N * L.R * L.rowcap * sizeof(RowEntry));
     {
@@ -236,6 +237,29 @@ __host__ __device__ inline int dfs_kstart(int K) {
     int P = 1;
     while (P < K) P <<= 1;
     return P - K;
+}
+
+// Marching order of a view's slabs.  Default ("fixedorder"): the rotation above.  With an explicit order (usebvh=True: ascending
+// Morton code of the centres, the `sortedobjid` of mvpraymarch.py:46-55) leaf i of the heap holds slab order[i] (rankof = its
+// inverse) -- an indirection in the accel build and two lookups in the render kernels instead of gathering the primitive
+// tensors (134 MB of payload per view) into that order.
+__device__ __forceinline__ int slab_at_rank(const int *__restrict__ order, int K, int kstart, int j) {
+    int leaf = j + kstart;                       // DFS visits the leaves of the implicit heap in this rotated sequence ...
+    if (leaf >= K) leaf -= K;
+    return order ? order[leaf] : leaf;           // ... and leaf i holds slab sortedobjid[i]
+}
+__device__ __forceinline__ int rank_of_slab(const int *__restrict__ rankof, int K, int kstart, int k) {
+    int r = (rankof ? rankof[k] : k) - kstart;
+    if (r < 0) r += K;
+    return r;
+}
+
+// rankof[n][order[n][j]] = j
+__global__ void __launch_bounds__(256) invert_order_kernel(size_t NK, int K, const int *__restrict__ order, int *__restrict__ rankof) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NK) return;
+    const size_t n = i / (size_t)K;
+    rankof[n * K + order[i]] = (int)(i - n * K);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -403,7 +427,8 @@ __global__ void __launch_bounds__(128) prim_setup_kernel(int N, int K, int H, in
 // ------------------------------------------------------------------------------------------------------
 // y range (pixels) of every block of 32 slabs consecutive in DFS rank: the bucket kernels test a block before its slabs, so a
 // tile row only touches the ~10-20 % of the blocks that can reach it (slabs follow the UV grid: consecutive ranks are neighbours).
-__global__ void __launch_bounds__(256) block_ranges_kernel(int K, const unsigned *__restrict__ ry, unsigned *__restrict__ blky) {
+__global__ void __launch_bounds__(256) block_ranges_kernel(int K, const unsigned *__restrict__ ry, const int *__restrict__ order,
+                                                           int ostride, unsigned *__restrict__ blky) {
     const int lane = threadIdx.x & 31;
     const int NB = (K + 31) / 32;
     const int blk = blockIdx.x * 8 + (threadIdx.x >> 5), n = blockIdx.y;
@@ -412,7 +437,7 @@ __global__ void __launch_bounds__(256) block_ranges_kernel(int K, const unsigned
     const int j = blk * 32 + lane;
     int y0 = 0xffff, y1 = -1;
     if (j < K) {
-        int k = j + kstart; if (k >= K) k -= K;
+        const int k = slab_at_rank(order ? order + (size_t)n * ostride : nullptr, K, kstart, j);
         const unsigned yr = __ldg(ry + (size_t)n * K + k);
         const int a = (int)(yr & 0xffffu), b = (int)(yr >> 16);
         if (a <= b) { y0 = a; y1 = b; }
@@ -429,7 +454,7 @@ constexpr int kRowThreads = 256;          // 8 warps = 8 tile rows per CTA
 // spent its time in three __syncthreads per 256 slabs).  The 8 warps of a CTA read the same rectangle arrays (L1 hits).
 __global__ void __launch_bounds__(kRowThreads) row_lists_kernel(int K, int R, int rowcap, int TXn,
                                                                 const unsigned *__restrict__ rx, const unsigned *__restrict__ ry,
-                                                                const unsigned *__restrict__ blky,
+                                                                const unsigned *__restrict__ blky, const int *__restrict__ order, int ostride,
                                                                 int *__restrict__ rowcnt, RowEntry *__restrict__ rowlist
 #if MVP_XBUCKETS
                                                                 , int NG, int2 *__restrict__ grphdr, RowEntry *__restrict__ grplist,
@@ -443,6 +468,7 @@ __global__ void __launch_bounds__(kRowThreads) row_lists_kernel(int K, int R, in
     const unsigned *rxn = rx + (size_t)n * K, *ryn = ry + (size_t)n * K;
     RowEntry *out = rowlist + ((size_t)n * R + row) * rowcap;
     const int kstart = dfs_kstart(K);
+    const int *ordn = order ? order + (size_t)n * ostride : nullptr;
     const unsigned below = (1u << lane) - 1u;
     int total = 0;
     const int NB = (K + 31) / 32;
@@ -463,7 +489,7 @@ __global__ void __launch_bounds__(kRowThreads) row_lists_kernel(int K, int R, in
             int k = 0;
             unsigned xr = 0;
             if (j < K) {
-                k = j + kstart; if (k >= K) k -= K;
+                k = slab_at_rank(ordn, K, kstart, j);
                 const unsigned yr = __ldg(ryn + k);
                 const int y0 = (int)(yr & 0xffffu), y1 = (int)(yr >> 16);
                 in = (y0 <= y1) && (y0 <= yhi) && (y1 >= ylo);
@@ -534,7 +560,7 @@ __global__ void __launch_bounds__(kRowThreads) row_lists_kernel(int K, int R, in
 // an 8-GPU run), where it is 5x shorter; large launches are throughput-bound and keep the single-pass kernel above.
 __global__ void __launch_bounds__(kRowThreads) row_lists_cta_kernel(int K, int R, int rowcap, int TXn,
                                                                     const unsigned *__restrict__ rx, const unsigned *__restrict__ ry,
-                                                                    const unsigned *__restrict__ blky,
+                                                                    const unsigned *__restrict__ blky, const int *__restrict__ order, int ostride,
                                                                     int *__restrict__ rowcnt, RowEntry *__restrict__ rowlist
 #if MVP_XBUCKETS
                                                                     , int NG, int2 *__restrict__ grphdr, RowEntry *__restrict__ grplist,
@@ -548,6 +574,7 @@ __global__ void __launch_bounds__(kRowThreads) row_lists_cta_kernel(int K, int R
     const unsigned *rxn = rx + (size_t)n * K, *ryn = ry + (size_t)n * K;
     RowEntry *out = rowlist + ((size_t)n * R + row) * rowcap;
     const int kstart = dfs_kstart(K);
+    const int *ordn = order ? order + (size_t)n * ostride : nullptr;
     const unsigned below = (1u << lane) - 1u;
     __shared__ int s_cnt[NW];
     // the warp's segment of the rank-ordered sequence, in blocks of 32 slabs; only blocks whose y range reaches the row are read
@@ -559,7 +586,7 @@ __global__ void __launch_bounds__(kRowThreads) row_lists_cta_kernel(int K, int R
         in = false;
         k = 0;
         if (j < K) {
-            k = j + kstart; if (k >= K) k -= K;
+            k = slab_at_rank(ordn, K, kstart, j);
             const unsigned yr = __ldg(ryn + k);
             const int y0 = (int)(yr & 0xffffu), y1 = (int)(yr >> 16);
             in = (y0 <= y1) && (y0 <= yhi) && (y1 >= ylo);
@@ -888,6 +915,7 @@ struct Params {
     int R, rowcap;
     int TXn, TYn;
     unsigned slab_bytes;          // TD*TH*TW*16
+    const int *order, *rankof;    // explicit marching order (per view [K]) and its inverse, or NULL: the fixed-order rotation
     long long *tileclk;           // MVP_TILE_CLOCKS diagnostics
     int CXn, CYn;                 // CTAs (kBlkTX x kBlkTY tiles) per view in x / y
     int use_order;                // this launch follows ctaorder (else plain grid order)
@@ -1017,7 +1045,7 @@ __device__ __forceinline__ bool build_tile_list(const Params &p, float rdt, int 
                 k = e.k; xr = e.xr;
                 cand = true;
             } else {
-                k = idx + kstart; if (k >= p.K) k -= p.K;
+                k = slab_at_rank(p.order ? p.order + (size_t)(n * p.pview) * p.K : nullptr, p.K, kstart, idx);
                 xr = __ldg(rxn + k);
                 unsigned yr = __ldg(ryn + k);
                 int y0 = (int)(yr & 0xffffu), y1 = (int)(yr >> 16);
@@ -1424,8 +1452,7 @@ __device__ __forceinline__ bool forward_tile(const Params &p, const int n, const
                     sat = true;
                     if (kGrad) {
                         jsat = rm[b] + c.off;
-                        int rk = sk[(__float_as_int(rr.w) >> 5) & 1023] - kstart; if (rk < 0) rk += p.K;
-                        ranksat = rk;
+                        ranksat = rank_of_slab(p.rankof ? p.rankof + (size_t)(n * p.pview) * p.K : nullptr, p.K, kstart, sk[(__float_as_int(rr.w) >> 5) & 1023]);
                         abefore = acc.w;
                     }
                 }
@@ -1930,7 +1957,7 @@ __device__ __forceinline__ bool backward_tile(const Params &p, const int n, cons
                 word &= word - 1;
                 const int slot = w * 32 + bit;
                 const int k = sk[slot];
-                int rank = k - kstart; if (rank < 0) rank += p.K;
+                const int rank = rank_of_slab(p.rankof ? p.rankof + (size_t)(n * p.pview) * p.K : nullptr, p.K, kstart, k);
 #if MVP_BWD_SMEMREC
                 __syncwarp();                                  // the previous slab's last readers of the record are done
                 if (lane < 4) S->rec[lane] = __ldg(packn + (size_t)k * 4 + lane);
@@ -2358,8 +2385,9 @@ int check_shape(const mvp_shape &s) {
     return MVP_OK;
 }
 
-int launch_accel(const mvp_shape &s, int pview, const float *raypos, const float *raydir, const float *primpos, const float *primrot,
-                 const float *primscale, char *ws, const Layout &L, cudaStream_t st) {
+int launch_accel(const mvp_shape &s, int pview, const int *order, const float *raypos, const float *raydir, const float *primpos,
+                 const float *primrot, const float *primscale, char *ws, const Layout &L, cudaStream_t st) {
+    const int ostride = pview ? s.K : 0;      // the order belongs to the primitives: one per view, or one shared by all views
     Cam *cam = reinterpret_cast<Cam *>(ws + L.cam);
     int *bad = reinterpret_cast<int *>(ws + L.bad);
     cudaError_t e = cudaMemsetAsync(bad, 0, (size_t)s.N * sizeof(int), st);
@@ -2380,12 +2408,16 @@ int launch_accel(const mvp_shape &s, int pview, const float *raypos, const float
     MVP_LAUNCH(prim_setup_kernel, (unsigned)((NK + 127) / 128), 128, 0, st, s.N, s.K, s.H, s.W, pview, primpos, primrot, primscale, cam, bad,
                reinterpret_cast<float4 *>(ws + L.pack), reinterpret_cast<unsigned *>(ws + L.rx), reinterpret_cast<unsigned *>(ws + L.ry));
     const int TXn = (s.W + kTileW - 1) / kTileW;
+    if (order) {
+        const size_t nk = (size_t)(pview ? s.N : 1) * s.K;
+        MVP_LAUNCH(invert_order_kernel, (unsigned)((nk + 255) / 256), 256, 0, st, nk, s.K, order, reinterpret_cast<int *>(ws + L.rankof));
+    }
     MVP_LAUNCH(block_ranges_kernel, dim3(((s.K + 31) / 32 + 7) / 8, s.N), 256, 0, st, s.K, reinterpret_cast<const unsigned *>(ws + L.ry),
-               reinterpret_cast<unsigned *>(ws + L.blky));
+               order, ostride, reinterpret_cast<unsigned *>(ws + L.blky));
     if (small_launch)
         MVP_LAUNCH(row_lists_cta_kernel, dim3(L.R, s.N), kRowThreads, 0, st, s.K, L.R, L.rowcap, TXn,
                    reinterpret_cast<unsigned *>(ws + L.rx), reinterpret_cast<unsigned *>(ws + L.ry),
-                   reinterpret_cast<const unsigned *>(ws + L.blky), reinterpret_cast<int *>(ws + L.rowcnt),
+                   reinterpret_cast<const unsigned *>(ws + L.blky), order, ostride, reinterpret_cast<int *>(ws + L.rowcnt),
                    reinterpret_cast<RowEntry *>(ws + L.rowlist)
 #if MVP_XBUCKETS
                    , L.NG, reinterpret_cast<int2 *>(ws + L.grphdr), reinterpret_cast<RowEntry *>(ws + L.grplist),
@@ -2395,7 +2427,7 @@ int launch_accel(const mvp_shape &s, int pview, const float *raypos, const float
     else
         MVP_LAUNCH(row_lists_kernel, dim3((L.R + kRowThreads / 32 - 1) / (kRowThreads / 32), s.N), kRowThreads, 0, st, s.K, L.R, L.rowcap, TXn,
                    reinterpret_cast<unsigned *>(ws + L.rx), reinterpret_cast<unsigned *>(ws + L.ry),
-                   reinterpret_cast<const unsigned *>(ws + L.blky), reinterpret_cast<int *>(ws + L.rowcnt),
+                   reinterpret_cast<const unsigned *>(ws + L.blky), order, ostride, reinterpret_cast<int *>(ws + L.rowcnt),
                    reinterpret_cast<RowEntry *>(ws + L.rowlist)
 #if MVP_XBUCKETS
                    , L.NG, reinterpret_cast<int2 *>(ws + L.grphdr), reinterpret_cast<RowEntry *>(ws + L.grplist),
@@ -2409,12 +2441,17 @@ int launch_accel(const mvp_shape &s, int pview, const float *raypos, const float
         s.N, s.K, s.H, s.W, pview, primpos, primrot, primscale, cam, bad, reinterpret_cast<float4 *>(ws + L.pack),
         reinterpret_cast<unsigned *>(ws + L.rx), reinterpret_cast<unsigned *>(ws + L.ry));
     const int TXn = (s.W + kTileW - 1) / kTileW;
-    block_ranges_kernel<<<dim3(((s.K + 31) / 32 + 7) / 8, s.N), 256, 0, st>>>(s.K, reinterpret_cast<const unsigned *>(ws + L.ry),
-                                                                               reinterpret_cast<unsigned *>(ws + L.blky));
+    if (order) {
+        const size_t nk = (size_t)(pview ? s.N : 1) * s.K;
+        invert_order_kernel<<<(unsigned)((nk + 255) / 256), 256, 0, st>>>(nk, s.K, order, reinterpret_cast<int *>(ws + L.rankof));
+    }
+    block_ranges_kernel<<<dim3(((s.K + 31) / 32 + 7) / 8, s.N), 256, 0, st>>>(s.K, reinterpret_cast<const unsigned *>(ws + L.ry), order,
+                                                                               ostride, reinterpret_cast<unsigned *>(ws + L.blky));
     if (small_launch)
         row_lists_cta_kernel<<<dim3(L.R, s.N), kRowThreads, 0, st>>>(
             s.K, L.R, L.rowcap, TXn, reinterpret_cast<unsigned *>(ws + L.rx), reinterpret_cast<unsigned *>(ws + L.ry),
-            reinterpret_cast<const unsigned *>(ws + L.blky), reinterpret_cast<int *>(ws + L.rowcnt), reinterpret_cast<RowEntry *>(ws + L.rowlist)
+            reinterpret_cast<const unsigned *>(ws + L.blky), order, ostride, reinterpret_cast<int *>(ws + L.rowcnt),
+            reinterpret_cast<RowEntry *>(ws + L.rowlist)
 #if MVP_XBUCKETS
             , L.NG, reinterpret_cast<int2 *>(ws + L.grphdr), reinterpret_cast<RowEntry *>(ws + L.grplist),
             want_order ? reinterpret_cast<unsigned short *>(ws + L.tilecnt) : nullptr
@@ -2423,7 +2460,8 @@ int launch_accel(const mvp_shape &s, int pview, const float *raypos, const float
     else
         row_lists_kernel<<<dim3((L.R + kRowThreads / 32 - 1) / (kRowThreads / 32), s.N), kRowThreads, 0, st>>>(
             s.K, L.R, L.rowcap, TXn, reinterpret_cast<unsigned *>(ws + L.rx), reinterpret_cast<unsigned *>(ws + L.ry),
-            reinterpret_cast<const unsigned *>(ws + L.blky), reinterpret_cast<int *>(ws + L.rowcnt), reinterpret_cast<RowEntry *>(ws + L.rowlist)
+            reinterpret_cast<const unsigned *>(ws + L.blky), order, ostride, reinterpret_cast<int *>(ws + L.rowcnt),
+            reinterpret_cast<RowEntry *>(ws + L.rowlist)
 #if MVP_XBUCKETS
             , L.NG, reinterpret_cast<int2 *>(ws + L.grphdr), reinterpret_cast<RowEntry *>(ws + L.grplist),
             want_order ? reinterpret_cast<unsigned short *>(ws + L.tilecnt) : nullptr
@@ -2529,15 +2567,16 @@ size_t mvp_workspace_bytes(const mvp_shape *shape) {
     return make_layout(*shape).total;
 }
 
-int mvp_build_accel(const mvp_shape *shape, uint32_t flags, const float *raypos, const float *raydir, const float *primpos,
-                    const float *primrot, const float *primscale, void *workspace, size_t workspace_bytes, void *stream) {
+int mvp_build_accel(const mvp_shape *shape, uint32_t flags, const int32_t *order, const float *raypos, const float *raydir,
+                    const float *primpos, const float *primrot, const float *primscale, void *workspace, size_t workspace_bytes,
+                    void *stream) {
     if (!shape || !raypos || !raydir || !primpos || !primrot || !primscale || !workspace) return MVP_ERR_NULL;
     int rc = check_shape(*shape);
     if (rc != MVP_OK) return rc;
     const Layout L = make_layout(*shape);
     if (workspace_bytes < L.total || ((uintptr_t)workspace & 255)) return MVP_ERR_WORKSPACE;
-    return launch_accel(*shape, (flags & MVP_FLAG_SHARED_PRIMS) ? 0 : 1, raypos, raydir, primpos, primrot, primscale, (char *)workspace, L,
-                        (cudaStream_t)stream);
+    return launch_accel(*shape, (flags & MVP_FLAG_SHARED_PRIMS) ? 0 : 1, order, raypos, raydir, primpos, primrot, primscale,
+                        (char *)workspace, L, (cudaStream_t)stream);
 }
 
 int mvp_debug_saved_tiles(const mvp_shape *shape, const void *host_workspace_copy, int *saved, int *not_saved) {
@@ -2584,18 +2623,19 @@ int mvp_raymarch_forward(const mvp_forward_args *a, void *stream) {
     if (misaligned(a->tplate, 16) || misaligned(a->rayrgba, 16) || misaligned(a->rayaux, 16) || misaligned(a->tminmax, 8) ||
         misaligned(a->raypos, 4) || misaligned(a->raydir, 4) || misaligned(a->primpos, 4) || misaligned(a->primrot, 4) ||
         misaligned(a->primscale, 4) || misaligned(a->raysat, 4) || misaligned(a->warp, 4) || misaligned(a->rayrgb_nchw, 4) ||
-        misaligned(a->rayalpha_nchw, 4))
+        misaligned(a->rayalpha_nchw, 4) || misaligned(a->order, 4))
         return MVP_ERR_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
     char *ws = (char *)a->workspace;
     const int pview = (a->flags & MVP_FLAG_SHARED_PRIMS) ? 0 : 1;
     if (!(a->flags & MVP_FLAG_ACCEL_VALID)) {
-        rc = launch_accel(a->shape, pview, a->raypos, a->raydir, a->primpos, a->primrot, a->primscale, ws, L, st);
+        rc = launch_accel(a->shape, pview, a->order, a->raypos, a->raydir, a->primpos, a->primrot, a->primscale, ws, L, st);
         if (rc != MVP_OK) return rc;
     }
     Params p{};
     fill_params(p, a->shape, a->stepsize, a->fadescale, a->fadeexp, ws, L);
     p.pview = pview;
+    p.order = a->order; p.rankof = a->order ? reinterpret_cast<const int *>(ws + L.rankof) : nullptr;
     p.rgb_nchw = a->rayrgb_nchw; p.alpha_nchw = a->rayalpha_nchw;
 #if MVP_LIST_REUSE
     if (a->flags & MVP_FLAG_TEST_TINY_LISTS) p.listlimit = p.listcap < 16 ? p.listcap : 16;
@@ -2661,13 +2701,13 @@ int mvp_raymarch_backward(const mvp_backward_args *a, void *stream) {
         misaligned(a->tminmax, 8) || misaligned(a->raypos, 4) || misaligned(a->raydir, 4) || misaligned(a->primpos, 4) ||
         misaligned(a->primrot, 4) || misaligned(a->primscale, 4) || misaligned(a->raysat, 4) || misaligned(a->grad_primpos, 4) ||
         misaligned(a->grad_primrot, 4) || misaligned(a->grad_primscale, 4) || misaligned(a->warp, 4) || misaligned(a->grad_warp, 4) ||
-        misaligned(a->grad_rayrgb_nchw, 4) || misaligned(a->grad_rayalpha_nchw, 4))
+        misaligned(a->grad_rayrgb_nchw, 4) || misaligned(a->grad_rayalpha_nchw, 4) || misaligned(a->order, 4))
         return MVP_ERR_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
     char *ws = (char *)a->workspace;
     const int pview = (a->flags & MVP_FLAG_SHARED_PRIMS) ? 0 : 1;
     if (!(a->flags & MVP_FLAG_ACCEL_VALID)) {
-        rc = launch_accel(a->shape, pview, a->raypos, a->raydir, a->primpos, a->primrot, a->primscale, ws, L, st);
+        rc = launch_accel(a->shape, pview, a->order, a->raypos, a->raydir, a->primpos, a->primrot, a->primscale, ws, L, st);
         if (rc != MVP_OK) return rc;
     }
     if (a->flags & MVP_FLAG_ZERO_GRADS) {
@@ -2684,6 +2724,7 @@ int mvp_raymarch_backward(const mvp_backward_args *a, void *stream) {
     p.pview = pview;
     p.raypos = a->raypos; p.raydir = a->raydir; p.tminmax = a->tminmax; p.tplate = a->tplate;
     p.use_order = a->shape.N <= MVP_CTA_ORDER_MAXVIEWS;
+    p.order = a->order; p.rankof = a->order ? reinterpret_cast<const int *>(ws + L.rankof) : nullptr;
     p.g_rgb_nchw = a->grad_rayrgb_nchw; p.g_alpha_nchw = a->grad_rayalpha_nchw;
     p.grad_rayrgba = a->grad_rayrgba; p.raysat_in = a->raysat; p.rayaux_in = reinterpret_cast<const int4 *>(a->rayaux);
     p.g_primpos = a->grad_primpos; p.g_primrot = a->grad_primrot; p.g_primscale = a->grad_primscale; p.g_tplate = a->grad_tplate;

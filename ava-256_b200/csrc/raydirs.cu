@@ -49,7 +49,39 @@ __global__ void __launch_bounds__(256) compute_raydirs_kernel(int N, int H, int 
     tminmax[r] = make_float2(fmaxf(tmin, 0.f), tmax);
 }
 
+// ---- Morton codes of (normalised) slab centres: compute_morton of the reference (mvpraymarch.cpp:106-121; bvh.cu:20-57) ----
+// quantise each coordinate of a point of the unit cube to 10 bits and interleave them x | y | z from the top bit down
+__device__ __forceinline__ unsigned spread10(unsigned v) {
+    // 10 bits -> every third bit of 30: four shift-or-mask rounds (16, 8, 4, 2 positions), written as multiplies
+    v = (v | (v << 16)) & 0xFF0000FFu;
+    v = (v | (v << 8)) & 0x0F00F00Fu;
+    v = (v | (v << 4)) & 0xC30C30C3u;
+    v = (v | (v << 2)) & 0x49249249u;
+    return v;
+}
+__global__ void __launch_bounds__(256) compute_morton_kernel(size_t NK, const float *__restrict__ centre, int *__restrict__ code) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NK) return;
+    const float qx = fminf(fmaxf(centre[i * 3 + 0] * 1024.f, 0.f), 1023.f);
+    const float qy = fminf(fmaxf(centre[i * 3 + 1] * 1024.f, 0.f), 1023.f);
+    const float qz = fminf(fmaxf(centre[i * 3 + 2] * 1024.f, 0.f), 1023.f);
+    code[i] = (int)((spread10((unsigned)qx) << 2) | (spread10((unsigned)qy) << 1) | spread10((unsigned)qz));
+}
+
 }  // namespace
+
+extern "C" int mvp_compute_morton(int32_t N, int32_t K, const float *centre, int32_t *code, void *stream) {
+    if (!centre || !code) return MVP_ERR_NULL;
+    if (N < 1 || K < 1) return MVP_ERR_SHAPE;
+    const size_t NK = (size_t)N * K;
+#ifdef MVP_CPU_EMUL
+    MVP_LAUNCH(compute_morton_kernel, (unsigned)((NK + 255) / 256), 256, 0, stream, NK, centre, code);
+#else
+    compute_morton_kernel<<<(unsigned)((NK + 255) / 256), 256, 0, (cudaStream_t)stream>>>(NK, centre, code);
+#endif
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? MVP_OK : (int)e;
+}
 
 extern "C" int mvp_compute_raydirs(int32_t N, int32_t H, int32_t W, const float *viewpos, const float *viewrot, const float *focal,
                                    const float *princpt, const float *pixelcoords, float volradius, float *raypos, float *raydir,

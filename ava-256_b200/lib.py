@@ -25,7 +25,7 @@ class ForwardArgs(ctypes.Structure):
         ("rayrgba", c_f), ("raysat", c_f), ("rayaux", c_f),
         ("workspace", c_f), ("workspace_bytes", ctypes.c_size_t),
         ("warp", c_f), ("WD", ctypes.c_int32), ("WH", ctypes.c_int32), ("WW", ctypes.c_int32), ("algo", ctypes.c_int32),
-        ("rayrgb_nchw", c_f), ("rayalpha_nchw", c_f),
+        ("rayrgb_nchw", c_f), ("rayalpha_nchw", c_f), ("order", c_f),
     ]
 
 
@@ -44,7 +44,7 @@ class BackwardArgs(ctypes.Structure):
         ("workspace", c_f), ("workspace_bytes", ctypes.c_size_t),
         ("warp", c_f), ("grad_warp", c_f), ("WD", ctypes.c_int32), ("WH", ctypes.c_int32), ("WW", ctypes.c_int32),
         ("algo", ctypes.c_int32),
-        ("grad_rayrgb_nchw", c_f), ("grad_rayalpha_nchw", c_f),
+        ("grad_rayrgb_nchw", c_f), ("grad_rayalpha_nchw", c_f), ("order", c_f),
     ]
 
 
@@ -64,12 +64,12 @@ FLAG_SHARED_PRIMS = 4
 FLAG_TEST_TINY_LISTS = 0x100
 ABI_VERSION = 6
 # layout pins, equal to the static_asserts in csrc/mvp_kernels.cu (tests/test_abi.py compares)
-SIZEOF = {"Shape": 28, "ForwardArgs": 184, "BackwardArgs": 224}
+SIZEOF = {"Shape": 28, "ForwardArgs": 192, "BackwardArgs": 232}
 
 EXPORTS = ("mvp_abi_version", "mvp_build_config", "mvp_error_string", "mvp_workspace_bytes", "mvp_build_accel", "mvp_raymarch_forward",
            "mvp_raymarch_backward", "mvp_compute_raydirs", "mvp_forward_launch_count", "mvp_backward_launch_count",
            "mvp_composite_forward", "mvp_composite_backward", "mvp_assemble_payload_forward",
-           "mvp_assemble_payload_backward", "mvp_debug_saved_tiles")
+           "mvp_assemble_payload_backward", "mvp_debug_saved_tiles", "mvp_debug_tileclk_offset", "mvp_compute_morton")
 
 
 def _load():
@@ -95,7 +95,9 @@ def _load():
     lib.mvp_workspace_bytes.restype = ctypes.c_size_t
     lib.mvp_workspace_bytes.argtypes = [ctypes.POINTER(Shape)]
     lib.mvp_build_accel.restype = ctypes.c_int
-    lib.mvp_build_accel.argtypes = [ctypes.POINTER(Shape), ctypes.c_uint32] + [c_f] * 6 + [ctypes.c_size_t, c_f]
+    lib.mvp_build_accel.argtypes = [ctypes.POINTER(Shape), ctypes.c_uint32] + [c_f] * 7 + [ctypes.c_size_t, c_f]
+    lib.mvp_compute_morton.restype = ctypes.c_int
+    lib.mvp_compute_morton.argtypes = [ctypes.c_int32, ctypes.c_int32, c_f, c_f, c_f]
     lib.mvp_raymarch_forward.restype = ctypes.c_int
     lib.mvp_raymarch_forward.argtypes = [ctypes.POINTER(ForwardArgs), c_f]
     lib.mvp_raymarch_backward.restype = ctypes.c_int

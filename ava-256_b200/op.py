@@ -51,10 +51,9 @@ class MVPRaymarch(Function):
                                       "values, mvpraymarch_kernel.cu:104-105)")
         if algo == 1 and warp is None:
             raise RuntimeError("mvpraymarch_b200: algo=1 samples a warp field (PrimSamplerTW<true>); pass `warp`")
-        if options["usebvh"] != "fixedorder":                            # usebvh=True is resolved in mvpraymarch() below
-            raise NotImplementedError("mvpraymarch_b200: MVPRaymarch marches primitives in index order; use "
-                                      "mvpraymarch(usebvh=True) for Morton order.  usebvh=False passes a null BVH to "
-                                      "the reference kernels (mvpraymarch.py:132-134) and is not a usable mode there either")
+        if options["usebvh"] is False:
+            raise NotImplementedError("mvpraymarch_b200: usebvh=False passes a null BVH to the reference kernels "
+                                      "(mvpraymarch.py:132-134) and is not a usable mode there either")
         # same shape contract as mvpraymarch.py:112-127
         assert raypos.is_contiguous() and raypos.size(3) == 3
         assert raydir.is_contiguous() and raydir.size(3) == 3
@@ -115,6 +114,10 @@ class MVPRaymarch(Function):
             a.rayrgba, a.raysat, a.rayaux = _ptr(rayrgba), _ptr(raysat), _ptr(rayaux)
             if planes:
                 a.rayrgb_nchw, a.rayalpha_nchw = _ptr(rayrgb), _ptr(rayalpha)
+            order = options.get("_order")                              # [NP,K] int32 marching order (usebvh=True) or None
+            if order is not None:
+                assert order.dtype == torch.int32 and order.is_contiguous() and tuple(order.shape) == (NP, K)
+                a.order = _ptr(order)
             a.workspace, a.workspace_bytes = _ptr(workspace), wsbytes
             a.algo = 1 if usewarp else 0
             if usewarp:
@@ -125,6 +128,7 @@ class MVPRaymarch(Function):
 
         if gradmode:
             ctx.save_for_backward(raypos, raydir, tminmax, primpos, primrot, primscale, template, raysat, rayaux, workspace, warp)
+            ctx.order = order
             ctx.options = options
             ctx.stepsize = float(stepsize)
             ctx.shared = shared
@@ -168,6 +172,8 @@ class MVPRaymarch(Function):
             a.grad_rayrgba, a.raysat, a.rayaux = _ptr(grad_rayrgba), _ptr(raysat), _ptr(rayaux)
             if planes:
                 a.grad_rayrgb_nchw, a.grad_rayalpha_nchw = _ptr(grad_rgb), _ptr(grad_alpha)
+            if ctx.order is not None:
+                a.order = _ptr(ctx.order)
             a.grad_primpos, a.grad_primrot, a.grad_primscale = _ptr(grad_primpos), _ptr(grad_primrot), _ptr(grad_primscale)
             a.grad_tplate = _ptr(grad_template)
             a.workspace, a.workspace_bytes = _ptr(workspace), workspace.numel()
@@ -215,10 +221,25 @@ def morton_codes(primpos):
     return expand_bits(q[..., 0]) * 4 + expand_bits(q[..., 1]) * 2 + expand_bits(q[..., 2])   # bvh.cu:39
 
 
+def morton_codes_native(primpos):
+    """The same codes from the library's kernel (`mvp_compute_morton`, the reference's compute_morton): the normalisation to the
+    bounding box stays in torch like in the reference (mvpraymarch.py:46-50).  [N,K] int32."""
+    p = primpos.detach()
+    cmax = p.max(dim=1, keepdim=True)[0]
+    cmin = p.min(dim=1, keepdim=True)[0]
+    c = ((p - cmin) / (cmax - cmin).clamp(min=1e-8)).contiguous()
+    code = torch.empty(p.shape[:2], dtype=torch.int32, device=p.device)
+    with torch.cuda.device(p.device):
+        _lib.check(_lib.LIB.mvp_compute_morton(p.shape[0], p.shape[1], _ptr(c), _ptr(code),
+                                               ctypes.c_void_p(torch.cuda.current_stream(p.device).cuda_stream)))
+    return code
+
+
 def morton_order(primpos):
     """sortedobjid [N,K] (int64): primitive indices in ascending Morton code (mvpraymarch.py:54-55).  Ties keep index
     order (stable), where the reference's torch.sort leaves them unspecified."""
-    return torch.sort(morton_codes(primpos.detach()), dim=-1, stable=True)[1]
+    codes = morton_codes_native(primpos) if primpos.is_cuda else morton_codes(primpos.detach())
+    return torch.sort(codes, dim=-1, stable=True)[1]
 
 
 def _take(t, order):
@@ -261,9 +282,9 @@ def mvpraymarch(
 
     `usebvh="fixedorder"` (default) marches the primitives of a tile in index order.  `usebvh=True` marches them in
     Morton order of their centres -- the order the reference's LBVH branch computes (`sortedobjid`, mvpraymarch.py:46-55)
-    but its kernels never apply (they hard-code the implicit heap, utils.h:740-742) -- by
-    gathering the primitive tensors into that order first (one extra pass over the payload; gradients scatter back
-    through the gather).  The order only matters for rays that saturate.
+    but its kernels never apply (they hard-code the implicit heap, utils.h:740-742): codes from the
+    library's `mvp_compute_morton`, one `torch.sort`, and the order goes to the kernels as an indirection (no tensor is
+    gathered or copied).  The order only matters for rays that saturate.
     Returns rayrgba [N,H,W,4]."""
     if usebvh is False:
         raise NotImplementedError("mvpraymarch_b200: usebvh=False hands the reference kernels a null BVH "
@@ -274,15 +295,15 @@ def mvpraymarch(
         primpos = primtransf[:, :, 0, :].contiguous()
         primrot = primtransf[:, :, 1:4, :].contiguous()
         primscale = primtransf[:, :, 4, :].contiguous()
+    order = None
     if usebvh != "fixedorder":
-        order = morton_order(primpos)
-        primpos, primrot, primscale, template, warp = (_take(t, order) for t in (primpos, primrot, primscale, template, warp))
-        usebvh = "fixedorder"
+        # Morton order of the centres as an indirection inside the kernels (C-ABI `order`): nothing is gathered or copied
+        order = morton_order(primpos).to(torch.int32).contiguous()
     options = {
         "algo": algo, "usebvh": usebvh, "sortprims": sortprims, "randomorder": randomorder,
         "maxhitboxes": maxhitboxes, "synchitboxes": synchitboxes, "chlast": chlast, "fadescale": fadescale,
         "fadeexp": fadeexp, "accum": accum, "termthresh": termthresh, "griddim": griddim, "blocksize": blocksize,
-        "bwdblocksize": bwdblocksize,
+        "bwdblocksize": bwdblocksize, "_order": order,
     }
     fn = MVPRaymarchPlanes if _PLANES.get("on") else MVPRaymarch
     return fn.apply(raypos, raydir, stepsize, tminmax, primpos, primrot, primscale, template, warp, rayterm,

@@ -96,6 +96,11 @@ typedef struct mvp_forward_args {
      * .contiguous() copies. */
     float *rayrgb_nchw;
     float *rayalpha_nchw;
+    /* Optional marching order [N,K] int32 ([1,K] with MVP_FLAG_SHARED_PRIMS): order[n][j] = index of the slab marched j-th.
+     * NULL = the reference's fixed order (utils.h:740-742).  This is the `sortedobjid` of the reference's usebvh=True branch
+     * (mvpraymarch.py:46-55; codes from mvp_compute_morton) applied as an indirection instead of a gather of the primitive
+     * tensors.  Must be a permutation of 0..K-1 and the same in every call that shares the workspace. */
+    const int32_t *order;
 } mvp_forward_args;
 
 typedef struct mvp_backward_args {
@@ -124,6 +129,7 @@ typedef struct mvp_backward_args {
      * prologue: the adjoint of the fused epilogue above; replaces the contiguous() copy of mvpraymarch.py:264. */
     const float *grad_rayrgb_nchw;
     const float *grad_rayalpha_nchw;
+    const int32_t *order;      /* as in the forward call */
 } mvp_backward_args;
 
 int mvp_abi_version(void);
@@ -135,9 +141,14 @@ const char *mvp_error_string(int code);
 size_t mvp_workspace_bytes(const mvp_shape *shape);
 
 /* Build the acceleration structure (camera fit, primitive records, screen rectangles, tile-row lists). */
-int mvp_build_accel(const mvp_shape *shape, uint32_t flags, const float *raypos, const float *raydir,
+int mvp_build_accel(const mvp_shape *shape, uint32_t flags, const int32_t *order, const float *raypos, const float *raydir,
                     const float *primpos, const float *primrot, const float *primscale,
                     void *workspace, size_t workspace_bytes, void *stream);
+
+/* 30-bit Morton codes of slab centres that the caller has normalised to the unit cube (mvpraymarch.py:46-50):
+ * compute_morton of the reference (extensions/mvpraymarch/mvpraymarch.cpp:106-121, bvh.cu:20-57).
+ * centre [N,K,3] -> code [N,K] int32.  Sorting a view's codes gives the `order` the raymarch calls take. */
+int mvp_compute_morton(int32_t N, int32_t K, const float *centre, int32_t *code, void *stream);
 
 int mvp_raymarch_forward(const mvp_forward_args *args, void *stream);
 int mvp_raymarch_backward(const mvp_backward_args *args, void *stream);
@@ -177,6 +188,8 @@ int mvp_assemble_payload_backward(int32_t N, int32_t hb, int32_t wb, int32_t B, 
  * has filled, counts the tiles whose slab list the forward saved for the backward (`saved`, lists with >= 1 entry) and the
  * tiles it had to mark not-saved because the list storage was full (`not_saved`; the backward rebuilds those). */
 int mvp_debug_saved_tiles(const mvp_shape *shape, const void *host_workspace_copy, int *saved, int *not_saved);
+/* Diagnostics builds only (-DMVP_TILE_CLOCKS=1, scripts/tile_clocks.py): byte offset of the per-tile clock records in the workspace. */
+size_t mvp_debug_tileclk_offset(const mvp_shape *shape);
 
 /* Number of kernels the last forward / backward call of this shape launches (for bench.py's gpu_launches). */
 int mvp_forward_launch_count(uint32_t flags);

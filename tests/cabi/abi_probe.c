@@ -23,9 +23,9 @@ int main(int argc, char **argv) {
     size_t (*wsbytes)(const mvp_shape *) = (size_t (*)(const mvp_shape *))dlsym(h, "mvp_workspace_bytes");
     int (*fwd)(const mvp_forward_args *, void *) = (int (*)(const mvp_forward_args *, void *))dlsym(h, "mvp_raymarch_forward");
     int (*bwd)(const mvp_backward_args *, void *) = (int (*)(const mvp_backward_args *, void *))dlsym(h, "mvp_raymarch_backward");
-    int (*accel)(const mvp_shape *, uint32_t, const float *, const float *, const float *, const float *, const float *, void *, size_t,
-                 void *) = (int (*)(const mvp_shape *, uint32_t, const float *, const float *, const float *, const float *, const float *,
-                                    void *, size_t, void *))dlsym(h, "mvp_build_accel");
+    int (*accel)(const mvp_shape *, uint32_t, const int32_t *, const float *, const float *, const float *, const float *, const float *,
+                 void *, size_t, void *) = (int (*)(const mvp_shape *, uint32_t, const int32_t *, const float *, const float *,
+                                                    const float *, const float *, const float *, void *, size_t, void *))dlsym(h, "mvp_build_accel");
     CHECK(abi && errstr && wsbytes && fwd && bwd && accel);
     CHECK(abi() == MVP_ABI_VERSION);
     printf("abi %d\nsizeof_shape %zu\nsizeof_forward_args %zu\nsizeof_backward_args %zu\n", abi(), sizeof(mvp_shape),
@@ -42,7 +42,7 @@ int main(int argc, char **argv) {
     a.stepsize = 0.1f;
     CHECK(fwd(NULL, NULL) == MVP_ERR_NULL);
     CHECK(fwd(&a, NULL) == MVP_ERR_STRUCT);                      /* struct_size not set */
-    a.struct_size = (uint32_t)sizeof a - 16;                      /* the ABI-v5 length: a stale caller */
+    a.struct_size = (uint32_t)sizeof a - 24;                      /* the ABI-v5 length: a stale caller */
     CHECK(fwd(&a, NULL) == MVP_ERR_STRUCT);
     a.struct_size = (uint32_t)sizeof a;
     CHECK(fwd(&a, NULL) == MVP_ERR_NULL);                        /* required pointers missing */
@@ -78,7 +78,7 @@ int main(int argc, char **argv) {
     CHECK(bwd(&b, NULL) == MVP_ERR_STRUCT);
     b.struct_size = (uint32_t)sizeof b;
     CHECK(bwd(&b, NULL) == MVP_ERR_NULL);
-    CHECK(accel(&c3, 0, NULL, NULL, NULL, NULL, NULL, NULL, 0, NULL) == MVP_ERR_NULL);
+    CHECK(accel(&c3, 0, NULL, NULL, NULL, NULL, NULL, NULL, NULL, 0, NULL) == MVP_ERR_NULL);
     CHECK(strstr(errstr(MVP_ERR_WORKSPACE), "workspace") != NULL && strstr(errstr(MVP_ERR_STRUCT), "struct_size") != NULL);
     printf("ok 1\n");
     dlclose(h);

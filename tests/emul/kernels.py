@@ -57,7 +57,7 @@ def _f32(a):
 
 
 def forward_backward(raypos, raydir, stepsize, tminmax, primpos, primrot, primscale, template, grad_rayrgba=None, warp=None,
-                     fadescale=8.0, fadeexp=8.0, fwd_flags=0, bwd_flags=0, planes=False):
+                     fadescale=8.0, fadeexp=8.0, fwd_flags=0, bwd_flags=0, planes=False, order=None):
     """Runs the emulated forward (and, when grad_rayrgba is given, backward) kernels.
     Returns (rayrgba, raysat, grads) with grads = [primpos, primrot, primscale, template(, warp)] or None."""
     L = load()
@@ -84,6 +84,9 @@ def forward_backward(raypos, raydir, stepsize, tminmax, primpos, primrot, primsc
     a.rayrgba, a.raysat, a.rayaux = (None if planes else _p(rayrgba)), _p(raysat), _p(rayaux)
     if planes:
         a.rayrgb_nchw, a.rayalpha_nchw = _p(rgb_p), _p(alpha_p)
+    if order is not None:
+        order = np.ascontiguousarray(order, dtype=np.int32)
+        a.order = _p(order)
     a.workspace, a.workspace_bytes = _p(ws), wsb
     a.algo = 1 if warp is not None else 0
     if warp is not None:
@@ -110,6 +113,8 @@ def forward_backward(raypos, raydir, stepsize, tminmax, primpos, primrot, primsc
         b.grad_rayrgb_nchw, b.grad_rayalpha_nchw = _p(g_rgb), _p(g_alpha)
     b.grad_rayrgba, b.raysat, b.rayaux = (None if planes else _p(grad_rayrgba)), _p(raysat), _p(rayaux)
     b.grad_primpos, b.grad_primrot, b.grad_primscale, b.grad_tplate = (_p(g) for g in grads)
+    if order is not None:
+        b.order = _p(order)
     b.workspace, b.workspace_bytes = _p(ws), wsb
     b.algo = a.algo
     if warp is not None:

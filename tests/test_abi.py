@@ -53,7 +53,7 @@ def test_c_program_through_the_header_alone(tmp_path):
     # the stub printed in INTEGRATION.md states the same struct size
     doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
     assert "ctypes.sizeof(ForwardArgs) == %d" % lib.SIZEOF["ForwardArgs"] in doc
-    for field in ("struct_size", "workspace_bytes", '"warp"', '"WD"', '"WH"', '"WW"', '"algo"', '"rayrgb_nchw"', '"rayalpha_nchw"'):
+    for field in ("struct_size", "workspace_bytes", '"warp"', '"WD"', '"WH"', '"WW"', '"algo"', '"rayrgb_nchw"', '"rayalpha_nchw"', '"order"'):
         assert field in doc, field
 
 
@@ -61,7 +61,7 @@ def test_truncated_argument_struct_is_rejected():
     from ava256_b200 import lib
     a = lib.ForwardArgs()
     assert a.struct_size == ctypes.sizeof(lib.ForwardArgs)
-    a.struct_size -= 16                                                         # what an ABI-v5 caller would pass
+    a.struct_size -= 24                                                         # what an ABI-v5 caller would pass
     assert lib.LIB.mvp_raymarch_forward(ctypes.byref(a), None) == -7          # MVP_ERR_STRUCT
     b = lib.BackwardArgs()
     b.struct_size = 0

@@ -97,7 +97,7 @@ def test_standalone_accel_then_march_equals_one_shot():
     ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
     P = lambda x: ctypes.c_void_p(x.data_ptr())  # noqa: E731
     sh = lib.Shape(N, H, W, 256, 8, 8, 8)
-    lib.check(lib.LIB.mvp_build_accel(ctypes.byref(sh), 0, P(s["raypos"]), P(s["raydir"]), P(s["primpos"]), P(s["primrot"]),
+    lib.check(lib.LIB.mvp_build_accel(ctypes.byref(sh), 0, None, P(s["raypos"]), P(s["raydir"]), P(s["primpos"]), P(s["primrot"]),
                                       P(s["primscale"]), P(ws), wsb, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
     two, _ = _abi_forward(s, lib.FLAG_ACCEL_VALID, ws)
     assert torch.equal(one, two)

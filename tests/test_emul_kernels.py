@@ -163,6 +163,34 @@ def test_emulated_image_plane_outputs(kernels, name):
         assert relerr(x, y) <= 1e-5
 
 
+@pytest.mark.parametrize("seed", list(range(10)))
+def test_emulated_random_small_scenes_vs_oracle(kernels, seed):
+    """The seeded random shapes of tests/test_gpu_parity.py::test_random_small_scenes_vs_oracle on the CPU emulation."""
+    from oracle import oracle
+    from tests.helpers import gradcheck_like_scene
+    rng = np.random.default_rng(1000 + seed)
+    N = int(rng.integers(1, 4))
+    H, W = int(rng.integers(3, 30)), int(rng.integers(3, 40))
+    k3 = int(rng.integers(1, 5))
+    cubic = bool(rng.integers(0, 2))
+    M = int(rng.choice([2, 3, 4, 8]))
+    dims = None if cubic else (int(rng.integers(1, 6)), int(rng.integers(1, 6)), int(rng.integers(1, 6)))
+    s = gradcheck_like_scene(N=N, H=H, W=W, k3=k3, M=M, seed=50 + seed, alpha_gain=float(rng.choice([0.5, 8.0, 60.0])),
+                             scale=float(rng.uniform(0.9, 2.5)), dims=dims, fadescale=float(rng.uniform(4.0, 9.0)),
+                             fadeexp=float(rng.uniform(5.0, 9.0)))
+    s["stepsize"] = float(rng.choice([1.3, 0.39, 0.11, 0.03]))
+    grad = torch.randn(N, H, W, 4, generator=torch.Generator().manual_seed(seed))
+    a, kw = scene_args_np(s)
+    out, _, grads = kernels.forward_backward(*a, grad_rayrgba=grad.numpy(), **kw)
+    ref, raysat = oracle.forward(*a, **kw)
+    assert np.isfinite(out).all() and relerr(out, ref) <= FWD_TOL
+    gref = oracle.backward(*a, grad.numpy(), raysat, **kw)
+    for nm, g_, r in zip(("primpos", "primrot", "primscale", "template"), grads, gref):
+        assert np.isfinite(g_).all(), nm
+        if np.abs(r).max() > 0:
+            assert relerr(g_, r) <= BWD_TOL, nm
+
+
 @pytest.mark.parametrize("name", ["head_small", "gradcheck_ragged", "many_overlaps", "warp_small"])
 def test_emulated_marching_order_indirection(kernels, name):
     """An explicit marching order (C-ABI `order`, what usebvh=True passes) == the fixed-order kernels on primitive tensors

@@ -162,3 +162,32 @@ def test_usebvh_true_marches_in_morton_order(name):
     unsat = (out_f[..., 3] < 0.999) & (out_m[..., 3] < 0.999)
     assert unsat.any()
     assert float((out_f - out_m)[unsat].abs().max()) <= 1e-4 * float(out_f.abs().max())
+
+
+@pytest.mark.parametrize("seed", list(range(10)))
+def test_random_small_scenes_vs_oracle(seed):
+    """Seeded random shapes: image sizes that leave partial tiles, K that is not a power of two, cubic and non-cubic payloads,
+    several views, step sizes from a handful to hundreds of steps per ray, with and without saturation -- against the oracle."""
+    from oracle import oracle
+    from tests.helpers import gradcheck_like_scene
+    rng = np.random.default_rng(1000 + seed)
+    N = int(rng.integers(1, 4))
+    H, W = int(rng.integers(3, 30)), int(rng.integers(3, 40))
+    k3 = int(rng.integers(1, 5))
+    cubic = bool(rng.integers(0, 2))
+    M = int(rng.choice([2, 3, 4, 8]))
+    dims = None if cubic else (int(rng.integers(1, 6)), int(rng.integers(1, 6)), int(rng.integers(1, 6)))
+    s = gradcheck_like_scene(N=N, H=H, W=W, k3=k3, M=M, seed=50 + seed, alpha_gain=float(rng.choice([0.5, 8.0, 60.0])),
+                             scale=float(rng.uniform(0.9, 2.5)), dims=dims, fadescale=float(rng.uniform(4.0, 9.0)),
+                             fadeexp=float(rng.uniform(5.0, 9.0)))
+    s["stepsize"] = float(rng.choice([1.3, 0.39, 0.11, 0.03]))
+    grad = torch.randn(N, H, W, 4, generator=torch.Generator().manual_seed(seed))
+    out, grads = run_ours(s, grad)
+    a, kw = scene_args_np(s)
+    ref, raysat = oracle.forward(*a, **kw)
+    assert np.isfinite(out).all() and relerr(out, ref) <= FWD_TOL
+    gref = oracle.backward(*a, grad.numpy(), raysat, **kw)
+    for nm, g_, r in zip(("primpos", "primrot", "primscale", "template"), grads, gref):
+        assert np.isfinite(g_).all(), nm
+        if np.abs(r).max() > 0:
+            assert relerr(g_, r) <= BWD_TOL, nm

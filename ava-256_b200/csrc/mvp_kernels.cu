@@ -137,15 +137,6 @@ constexpr int kRing = 64;        // sample queue / ring per warp (forward and ba
 #define MVP_BWD_LANESMEM 0   // backward: per-lane state that is only touched between batches (ray origin / t-range, sweep limits, chunk
                              // base position, the 12 transform-gradient accumulators) lives in shared memory instead of registers
 #endif
-#ifndef MVP_FWD_ASYNC
-#define MVP_FWD_ASYNC 0   // 1: the forward's batch gathers go through cp.async (LDGSTS) into a per-warp staging area and are consumed one
-                          // batch later, so their L1/L2-miss latency overlaps the marching of the next batch instead of stalling the warp
-#endif
-#ifndef MVP_PF_CELL
-#define MVP_PF_CELL 0   // software prefetch of a queued sample's voxel cell at ENQUEUE time, so that the batch's corner gathers hit
-                        // (the gathers' L1/L2 misses are the top stall of both render kernels): 1 = L1 prefetch of the cell's 4
-                        // x-rows, 2 = of all 8 corners, 3 / 4 = the same into L2 only
-#endif
 #if MVP_XBUCKETS
 constexpr int kGrpTiles = 8;       // tile columns per x-group
 constexpr int kGrpCap = 1024;     // group-bucket entries per tile row; groups that do not fit keep using the row bucket
@@ -1245,32 +1236,6 @@ __device__ __forceinline__ float4 sample_slab(const float4 *__restrict__ slab, f
     return acc;
 }
 
-#if MVP_PF_CELL
-// Prefetch the voxel cell a valid sample at slab coordinate (y0, y1, y2) will gather (same cell arithmetic as sample_slab).
-template <int T>
-__device__ __forceinline__ void prefetch_cell(const float4 *__restrict__ slab, float y0, float y1, float y2, int TD, int TH, int TW) {
-#ifndef MVP_CPU_EMUL
-    const int td = T > 0 ? T : TD, th = T > 0 ? T : TH, tw = T > 0 ? T : TW;
-    const int ix = __float2int_rd(((y0 + 1.f) * 0.5f) * (float)(tw - 1)), iy = __float2int_rd(((y1 + 1.f) * 0.5f) * (float)(th - 1)),
-              iz = __float2int_rd(((y2 + 1.f) * 0.5f) * (float)(td - 1));
-    int cx, cy, cz;
-    if (T >= 2) { cx = min(ix, T - 2); cy = min(iy, T - 2); cz = min(iz, T - 2); }
-    else { cx = max(min(ix, tw - 2), 0); cy = max(min(iy, th - 2), 0); cz = max(min(iz, td - 2), 0); }
-    const int sx = tw > 1 ? 1 : 0, sy = th > 1 ? tw : 0, sz = td > 1 ? th * tw : 0;
-    const float4 *pc = slab + ((cz * th + cy) * tw + cx);
-#if MVP_PF_CELL <= 2
-#define MVP_PF_(a) asm volatile("prefetch.global.L1 [%0];" ::"l"(a))
-#else
-#define MVP_PF_(a) asm volatile("prefetch.global.L2 [%0];" ::"l"(a))
-#endif
-    MVP_PF_(pc); MVP_PF_(pc + sy); MVP_PF_(pc + sz); MVP_PF_(pc + sz + sy);
-#if MVP_PF_CELL == 2 || MVP_PF_CELL == 4
-    MVP_PF_(pc + sx); MVP_PF_(pc + sy + sx); MVP_PF_(pc + sz + sx); MVP_PF_(pc + sz + sy + sx);
-#endif
-#undef MVP_PF_
-#endif
-}
-#endif
 
 // ---- generic trilinear cell for an ARBITRARY position (utils.h:408-502: +-100 clamp, corners outside the grid
 //      contribute nothing); used by the warp-field path (algo 1), where the warped position may leave the slab ----
@@ -1335,45 +1300,16 @@ long long g_emul_fwd_stats[8];
 #define MVP_STAT(i, v) ((void)0)
 #endif
 
-#if MVP_FWD_ASYNC
-constexpr int kQOff = 32;            // ring[0, 32): the batch in flight; ring[32, 96): the sample queue
-constexpr int kFwdRing = 96;
-#else
-constexpr int kQOff = 0;
-constexpr int kFwdRing = kRing;
-#endif
 template <int CAP, bool kGrad>
 struct __align__(16) FwdWarpSmem {   // per-warp shared state of the forward kernel
-    float4 ring[kFwdRing];
-#if MVP_FWD_ASYNC
-    float4 gat[8 * 32];               // staged corner texels of the batch in flight: [corner][lane]
-#endif
+    float4 ring[kRing];
     RowEntry stage[2 * kStage];
     unsigned long long bar[2];
     int k[CAP];
     int iv[CAP];
     float ra[kRing];
-    int rm[kGrad ? kFwdRing : 1];
+    int rm[kGrad ? kRing : 1];
 };
-
-// cp.async (LDGSTS): 16-byte global -> shared copies that complete in the background (per-thread groups)
-__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src) {
-#ifdef MVP_CPU_EMUL
-    memcpy(dst_smem, src, 16);
-#else
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
-#endif
-}
-__device__ __forceinline__ void cp_async_commit() {
-#ifndef MVP_CPU_EMUL
-    asm volatile("cp.async.commit_group;" ::: "memory");
-#endif
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-#ifndef MVP_CPU_EMUL
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-#endif
-}
 
 // ------------------------------------------------------------------------------------------------------
 // 4. forward.  CAP = shared-memory list capacity per warp.  The CAP < 512 variant handles every tile whose list
@@ -1461,98 +1397,6 @@ __device__ __forceinline__ bool forward_tile(const Params &p, const int n, const
             }
         }
     };
-#if MVP_FWD_ASYNC
-    // Two-stage batches.  issue(): the first `cnt` queued samples become the batch in flight -- every lane computes the voxel
-    // cell and fade of one sample and starts 8 cp.async corner copies into its column of the staging area; complete(), one
-    // batch later: the copies have landed long ago, the lane interpolates from shared memory and every ray composites its
-    // samples of that batch in queue order.  A ray therefore learns that it saturated one batch later than in the synchronous
-    // scheme; what it queued in between is sampled in vain and ignored, exactly as before.
-    constexpr bool kAsync = (T == 8 || T == 16) && !kWarp;   // cell index packed in 3 x 4 bits of the entry's meta word
-    float4 *const gat = S->gat;
-    int pend = 0;
-    unsigned ownp = 0;
-    auto complete = [&]() {
-        if (pend == 0) return;   // warp-uniform
-        if (kAsync) {
-            cp_async_wait_all();
-            if (lane < pend) {
-                const float4 e = ring[lane];
-                const float fade = ra[lane];
-                const int meta = __float_as_int(e.w);
-                const int cx = (meta >> 15) & 15, cy = (meta >> 19) & 15, cz = (meta >> 23) & 15;
-                const float bx0 = e.x - (float)cx, bx1 = (float)(cx + 1) - e.x;
-                const float by0 = e.y - (float)cy, by1 = (float)(cy + 1) - e.y;
-                const float bz0 = e.z - (float)cz, bz1 = (float)(cz + 1) - e.z;
-                const float4 v000 = gat[0 * 32 + lane], v001 = gat[1 * 32 + lane], v010 = gat[2 * 32 + lane], v011 = gat[3 * 32 + lane];
-                const float4 v100 = gat[4 * 32 + lane], v101 = gat[5 * 32 + lane], v110 = gat[6 * 32 + lane], v111 = gat[7 * 32 + lane];
-                // same weights and accumulation order as sample_slab
-                const float w00 = bx1 * by1, w01 = bx0 * by1, w10 = bx1 * by0, w11 = bx0 * by0;
-                float4 a4;
-                float w;
-                w = w00 * bz1; a4.x = w * v000.x; a4.y = w * v000.y; a4.z = w * v000.z; a4.w = w * v000.w;
-                w = w01 * bz1; a4.x = __fmaf_rn(w, v001.x, a4.x); a4.y = __fmaf_rn(w, v001.y, a4.y); a4.z = __fmaf_rn(w, v001.z, a4.z); a4.w = __fmaf_rn(w, v001.w, a4.w);
-                w = w10 * bz1; a4.x = __fmaf_rn(w, v010.x, a4.x); a4.y = __fmaf_rn(w, v010.y, a4.y); a4.z = __fmaf_rn(w, v010.z, a4.z); a4.w = __fmaf_rn(w, v010.w, a4.w);
-                w = w11 * bz1; a4.x = __fmaf_rn(w, v011.x, a4.x); a4.y = __fmaf_rn(w, v011.y, a4.y); a4.z = __fmaf_rn(w, v011.z, a4.z); a4.w = __fmaf_rn(w, v011.w, a4.w);
-                w = w00 * bz0; a4.x = __fmaf_rn(w, v100.x, a4.x); a4.y = __fmaf_rn(w, v100.y, a4.y); a4.z = __fmaf_rn(w, v100.z, a4.z); a4.w = __fmaf_rn(w, v100.w, a4.w);
-                w = w01 * bz0; a4.x = __fmaf_rn(w, v101.x, a4.x); a4.y = __fmaf_rn(w, v101.y, a4.y); a4.z = __fmaf_rn(w, v101.z, a4.z); a4.w = __fmaf_rn(w, v101.w, a4.w);
-                w = w10 * bz0; a4.x = __fmaf_rn(w, v110.x, a4.x); a4.y = __fmaf_rn(w, v110.y, a4.y); a4.z = __fmaf_rn(w, v110.z, a4.z); a4.w = __fmaf_rn(w, v110.w, a4.w);
-                w = w11 * bz0; a4.x = __fmaf_rn(w, v111.x, a4.x); a4.y = __fmaf_rn(w, v111.y, a4.y); a4.z = __fmaf_rn(w, v111.z, a4.z); a4.w = __fmaf_rn(w, v111.w, a4.w);
-                ring[lane] = make_float4(a4.x, a4.y, a4.z, e.w);    // a lane only rewrites its own entry
-                ra[lane] = a4.w * fade;
-            }
-        }
-        __syncwarp();
-        composite(ownp);
-        __syncwarp();   // every lane is done with ring[0, 32) before the next issue() refills it
-        pend = 0;
-        if (sat) done = true;
-    };
-    auto issue = [&](int cnt) {
-        MVP_STAT(4, 1);
-        const bool act = lane < cnt;
-        const int n2 = qn - cnt;
-        float4 rec = make_float4(0.f, 0.f, 0.f, 0.f), mv = rec;
-        int recm = 0, mvm = 0;
-        if (act) { rec = ring[kQOff + lane]; if (kGrad) recm = rm[kQOff + lane]; }
-        if (lane < n2) { mv = ring[kQOff + cnt + lane]; if (kGrad) mvm = rm[kQOff + cnt + lane]; }
-        __syncwarp();
-        if (act) {
-            const int meta = __float_as_int(rec.w);
-            const int kk = sk[(meta >> 5) & 1023];
-            const float4 *slab = tpn + (size_t)kk * slabsz;
-            if (kAsync) {
-                constexpr int TT = T > 0 ? T : 2;
-                const float fade = __expf(-p.fadescale * (__powf(fabsf(rec.x), p.fadeexp) + __powf(fabsf(rec.y), p.fadeexp) + __powf(fabsf(rec.z), p.fadeexp)));
-                const float fx = ((rec.x + 1.f) * 0.5f) * (float)(TT - 1);
-                const float fy = ((rec.y + 1.f) * 0.5f) * (float)(TT - 1);
-                const float fz = ((rec.z + 1.f) * 0.5f) * (float)(TT - 1);
-                const int cx = min(__float2int_rd(fx), TT - 2), cy = min(__float2int_rd(fy), TT - 2), cz = min(__float2int_rd(fz), TT - 2);
-                const float4 *pc = slab + ((cz * TT + cy) * TT + cx);
-                float4 *g = gat + lane;
-                cp_async16(g + 0 * 32, pc); cp_async16(g + 1 * 32, pc + 1); cp_async16(g + 2 * 32, pc + TT); cp_async16(g + 3 * 32, pc + TT + 1);
-                cp_async16(g + 4 * 32, pc + TT * TT); cp_async16(g + 5 * 32, pc + TT * TT + 1);
-                cp_async16(g + 6 * 32, pc + TT * TT + TT); cp_async16(g + 7 * 32, pc + TT * TT + TT + 1);
-                ring[lane] = make_float4(fx, fy, fz, __int_as_float(meta | (cx << 15) | (cy << 19) | (cz << 23)));
-                ra[lane] = fade;
-            } else {
-                float4 sres;
-                if (kWarp) sres = sample_slab_warped(slab, p.warp + ((size_t)(n * p.pview) * p.K + kk) * ((size_t)p.WD * p.WH * p.WW * 3), rec.x, rec.y, rec.z, p);
-                else sres = sample_slab<T>(slab, rec.x, rec.y, rec.z, p.TD, p.TH, p.TW, p.fadescale, p.fadeexp);
-                ring[lane] = make_float4(sres.x, sres.y, sres.z, rec.w);
-                ra[lane] = sres.w;
-            }
-            if (kGrad) rm[lane] = recm;
-        }
-        if (lane < n2) { ring[kQOff + lane] = mv; if (kGrad) rm[kQOff + lane] = mvm; }
-        if (kAsync) cp_async_commit();
-        __syncwarp();
-        ownp = ownlo & (cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u));
-        ownlo = ownhi; ownhi = 0;
-        pend = cnt;
-        qn = n2;
-    };
-    auto flush = [&](int cnt) { complete(); issue(cnt); };
-#else
     auto flush = [&](int cnt) {
         MVP_STAT(4, 1);
         const bool act = lane < cnt;
@@ -1580,7 +1424,6 @@ __device__ __forceinline__ bool forward_tile(const Params &p, const int n, const
         qn = n2;
         if (sat) done = true;
     };
-#endif
 
     const int mstart = __reduce_min_sync(0xffffffffu, ms);
     if (nl > 0 && mstart < kBig) {
@@ -1623,11 +1466,8 @@ __device__ __forceinline__ bool forward_tile(const Params &p, const int n, const
                         MVP_STAT(2, 1); MVP_STAT(3, __popc(vm));
                         if (want) {
                             const int pos = qn + __popc(vm & ((1u << lane) - 1u));
-                            ring[kQOff + pos] = make_float4(y0, y1, y2, __int_as_float(lane | ((w * 32 + b) << 5)));
-                            if (kGrad) rm[kQOff + pos] = m;
-#if MVP_PF_CELL
-                            if (!kWarp) prefetch_cell<T>(tpn + (size_t)k * slabsz, y0, y1, y2, p.TD, p.TH, p.TW);
-#endif
+                            ring[pos] = make_float4(y0, y1, y2, __int_as_float(lane | ((w * 32 + b) << 5)));
+                            if (kGrad) rm[pos] = m;
                             if (pos < 32) ownlo |= 1u << pos; else ownhi |= 1u << (pos - 32);
                         }
                         qn += __popc(vm);
@@ -1669,9 +1509,6 @@ __device__ __forceinline__ bool forward_tile(const Params &p, const int n, const
         }
     }
     if (qn > 0) flush(qn);
-#if MVP_FWD_ASYNC
-    complete();
-#endif
     if (c.inimg) {
         if (p.rayrgba) reinterpret_cast<float4 *>(p.rayrgba)[r] = acc;
         if (p.rgb_nchw) {
@@ -2075,9 +1912,6 @@ __device__ __forceinline__ bool backward_tile(const Params &p, const int n, cons
                                 const int pos = (qhead + qn + __popc(vm & ((1u << lane) - 1u))) & (kRing - 1);
                                 const bool issat = (i == isat_i);
                                 ring[pos] = make_float4(xm, ym, zm, __int_as_float(lane | (issat ? 256 : 0)));
-#if MVP_PF_CELL
-                                if (!kWarp) prefetch_cell<T>(slab, y0, y1, y2, p.TD, p.TH, p.TW);
-#endif
                             }
                             qn += __popc(vm);
 #if defined(MVP_CPU_EMUL) && defined(MVP_EMUL_STATS)
@@ -2539,7 +2373,7 @@ int mvp_abi_version(void) { return MVP_ABI_VERSION; }
 #define MVP_STR(x) MVP_STR2(x)
 const char *mvp_build_config(void) {
     return "LIST_REUSE=" MVP_STR(MVP_LIST_REUSE)
-           " LIST_MARGIN=" MVP_STR(MVP_LIST_MARGIN) " XBUCKETS=" MVP_STR(MVP_XBUCKETS) " FASTCAP=" MVP_STR(MVP_FASTCAP) " PF_CELL=" MVP_STR(MVP_PF_CELL) " FWD_ASYNC=" MVP_STR(MVP_FWD_ASYNC) " BWD_SMEMREC=" MVP_STR(MVP_BWD_SMEMREC) " BWD_LANESMEM=" MVP_STR(MVP_BWD_LANESMEM) " CTA_ORDER=" MVP_STR(MVP_CTA_ORDER) " CTA_ORDER_MIN=" MVP_STR(MVP_CTA_ORDER_MIN)
+           " LIST_MARGIN=" MVP_STR(MVP_LIST_MARGIN) " XBUCKETS=" MVP_STR(MVP_XBUCKETS) " FASTCAP=" MVP_STR(MVP_FASTCAP) " BWD_SMEMREC=" MVP_STR(MVP_BWD_SMEMREC) " BWD_LANESMEM=" MVP_STR(MVP_BWD_LANESMEM) " CTA_ORDER=" MVP_STR(MVP_CTA_ORDER) " CTA_ORDER_MIN=" MVP_STR(MVP_CTA_ORDER_MIN)
            " CHUNK=" MVP_STR(MVP_CHUNK) " FWD_MINB=" MVP_STR(MVP_FWD_MINB) " BWD_MINB=" MVP_STR(MVP_BWD_MINB)
            " WARPS=" MVP_STR(MVP_WARPS) " BLK_TX=" MVP_STR(MVP_BLK_TX)
 #ifdef MVP_CPU_EMUL

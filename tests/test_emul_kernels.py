@@ -120,8 +120,6 @@ VARIANTS = {
     "bwd_regrecord": ("MVP_BWD_SMEMREC=0",),
     "grid_order": ("MVP_CTA_ORDER=0",),                                    # plain grid order instead of the cost-sorted CTA order
     "bwd_lanesmem": ("MVP_BWD_LANESMEM=1",),                               # per-lane between-batch state in shared memory                               # slab record in registers across the adjoint (round-1 form)
-    "fwd_async": ("MVP_FWD_ASYNC=1", "MVP_FASTCAP=128"),                   # cp.async-staged gathers, consumed one batch later
-    "fwd_sync": ("MVP_FWD_ASYNC=0",),
 }
 
 

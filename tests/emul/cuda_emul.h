@@ -205,6 +205,15 @@ inline T __shfl_xor_sync(unsigned, T v, int lanemask, int width = 32) {
     return emul::from_bits<T>(o[s]);
 }
 template <class T>
+inline T __shfl_up_sync(unsigned, T v, unsigned delta, int width = 32) {
+    unsigned long long o[32];
+    emul::warp_gather(emul::to_bits(v), o);
+    const int l = emul::g_blk->cur & 31;
+    int s = l - (int)delta;
+    if (s < 0 || (s & ~(width - 1)) != (l & ~(width - 1))) s = l;
+    return emul::from_bits<T>(o[s]);
+}
+template <class T>
 inline T __shfl_down_sync(unsigned, T v, unsigned delta, int width = 32) {
     unsigned long long o[32];
     emul::warp_gather(emul::to_bits(v), o);

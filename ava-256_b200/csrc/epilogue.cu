@@ -86,6 +86,22 @@ __global__ void __launch_bounds__(kThreads) payload_backward_kernel(PayloadArgs 
     if (e < total) payload_bwd<V, BT>(a, e);
 }
 
+// One subject's tensor written once per view: dst[v][i] = src[i].  Streaming stores; the source stays in L2.
+__global__ void __launch_bounds__(kThreads) expand_views_kernel(const float4 *__restrict__ src, float4 *__restrict__ dst, size_t count4,
+                                                                int n) {
+    const size_t e = (size_t)blockIdx.x * kThreads + threadIdx.x;
+    if (e >= count4) return;
+    const float4 v = __ldg(src + e);
+    for (int i = 0; i < n; ++i) __stcs(dst + (size_t)i * count4 + e, v);
+}
+__global__ void __launch_bounds__(kThreads) expand_views_scalar_kernel(const float *__restrict__ src, float *__restrict__ dst, size_t count,
+                                                                       int n) {
+    const size_t e = (size_t)blockIdx.x * kThreads + threadIdx.x;
+    if (e >= count) return;
+    const float v = __ldg(src + e);
+    for (int i = 0; i < n; ++i) dst[(size_t)i * count + e] = v;
+}
+
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 inline int finish() {
@@ -235,4 +251,19 @@ extern "C" int mvp_assemble_payload_backward(int32_t N, int32_t hb, int32_t wb, 
     a.tplate_in = tplate; a.grad_tplate = grad_tplate; a.grad_tex = grad_tex; a.grad_opacity = grad_opacity;
     const bool vec = B > 0 && B % 4 == 0 && aligned16(grad_tex) && aligned16(grad_opacity);
     return launch_payload<true>(N, hb, wb, B, a, vec, (cudaStream_t)stream);
+}
+
+extern "C" int mvp_expand_views(const float *src, float *dst, size_t count, int32_t n_views, void *stream) {
+    if (!src || !dst) return MVP_ERR_NULL;
+    if (n_views < 0) return MVP_ERR_SHAPE;
+    if (count == 0 || n_views == 0) return MVP_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (count % 4 == 0 && aligned16(src) && aligned16(dst)) {
+        const size_t c4 = count / 4;
+        expand_views_kernel<<<(unsigned)((c4 + kThreads - 1) / kThreads), kThreads, 0, st>>>(
+            reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), c4, n_views);
+    } else {
+        expand_views_scalar_kernel<<<(unsigned)((count + kThreads - 1) / kThreads), kThreads, 0, st>>>(src, dst, count, n_views);
+    }
+    return finish();
 }

@@ -60,3 +60,26 @@ def assemble_payload(tex, opacity, boxsize=8, rgb_scale=25.0, rgb_bias=100.0):
     """template [N, h*w, B, B, B, 4] from the decoders' images; defaults are the reference's hard-coded
     de-normalisation (assembler.py:261)."""
     return AssemblePayload.apply(tex, opacity, boxsize, rgb_scale, rgb_bias)
+
+
+class ExpandViews(Function):
+    @staticmethod
+    def forward(ctx, x, n_views):
+        _check_f32_cuda("x", x)
+        x = x.contiguous()
+        dev = x.device
+        with torch.cuda.device(dev):
+            out = torch.empty((int(n_views),) + tuple(x.shape), device=dev)
+            stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            _lib.check(_lib.LIB.mvp_expand_views(_ptr(x), _ptr(out), x.numel(), int(n_views), stream))
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        return grad.sum(dim=0), None
+
+
+def expand_views(x, n_views):
+    """[n_views, *x.shape] copies of one subject's tensor (`x[None].expand(n_views, ...).contiguous()` in one pass of
+    streaming stores, `mvp_expand_views`); the adjoint is the sum over the views."""
+    return ExpandViews.apply(x, n_views)

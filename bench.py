@@ -459,6 +459,7 @@ def run_ours(args, rank, world):
         cmp_done, flat_out_done = [None, None], [None, None]
 
         from extensions.utils.utils import compute_raydirs
+        from ava256_b200.payload import expand_views
         host_cam = [t.pin_memory() for t in scene.make_cameras(nv, h, w, view_ids=vids)]
         dev_cam = [[torch.empty(t.shape, device=dev) for t in host_cam] for _ in range(2)]
 
@@ -491,7 +492,7 @@ def run_ours(args, rank, world):
             for ci, (a0, a1) in enumerate(bounds):
                 s_cmp.wait_event(ev_in[ci])
                 nvc = a1 - a0
-                lv = [pr[n][None].expand(nvc, *pr[n].shape).contiguous().requires_grad_(True) for n in names]
+                lv = [expand_views(pr[n], nvc).requires_grad_(True) for n in names]     # the subject's primitives, per view
                 if cams:
                     cp_, cr_, cf_, cpp_ = (t[a0:a1] for t in dev_cam[b_])
                     rp_, rd_, tm_ = compute_raydirs(cp_, cr_, cf_, cpp_, (w, h), scene.VOLRADIUS)
@@ -568,7 +569,7 @@ def run_ours(args, rank, world):
         e2e = {"value": views * h * w / (float(te.item()) * 1e-3) / 1e6, "unit": "MP/s",
                "h2d_bytes_per_step": int(h2d * world), "d2h_bytes_per_step": int(d2h * world),
                "ms_per_step": float(te.item()), "steps": nrep,
-               "what": "every step: pinned host rays + one subject's primitives + grad_out -> device, per-view expand, op fwd+bwd, "
+               "what": "every step: pinned host rays + one subject's primitives + grad_out -> device, per-view expand (mvp_expand_views), op fwd+bwd, "
                        "view-sum (+all-reduce), rayrgba + reduced gradients -> pinned host; views streamed in chunks of %d, device "
                        "staging double-buffered so H2D of step i+1 / compute of step i / D2H of step i-1 overlap (three streams); "
                        "%d steps timed back to back, all copies inside the timed region" % (chunk, nrep)}

@@ -184,6 +184,12 @@ int mvp_assemble_payload_forward(int32_t N, int32_t hb, int32_t wb, int32_t B, c
 int mvp_assemble_payload_backward(int32_t N, int32_t hb, int32_t wb, int32_t B, const float *tplate, const float *grad_tplate,
                                   float rgb_scale, float *grad_tex, float *grad_opacity, void *stream);
 
+/* One subject's primitives materialised per view (what the decoders' batch dimension is in models/autoencoder.py:214-233
+ * when all items of a batch show the same subject): dst[v, i] = src[i] for v < n_views, i < count floats.  One pass of
+ * streaming 16-byte stores (scalar when count % 4 != 0 or a pointer is not 16-byte aligned); `expand().contiguous()` does the
+ * same at a quarter of the rate.  count < 2^32 * 1024. */
+int mvp_expand_views(const float *src, float *dst, size_t count, int32_t n_views, void *stream);
+
 /* Test / diagnostics helper (host only, no device work): given a HOST copy of a workspace that a gradient-mode forward
  * has filled, counts the tiles whose slab list the forward saved for the backward (`saved`, lists with >= 1 entry) and the
  * tiles it had to mark not-saved because the list storage was full (`not_saved`; the backward rebuilds those). */

@@ -159,6 +159,9 @@ def test_epilogue_argument_errors_do_not_need_a_device():
     assert L.mvp_assemble_payload_forward(1, 2, 2, 8, p, p, 25.0, 100.0, odd, None) == -6
     assert L.mvp_assemble_payload_backward(1, 2, 2, 8, p, p, 25.0, p, None, None) == -1
     assert L.mvp_assemble_payload_backward(1, 0, 2, 8, p, p, 25.0, p, p, None) == -2
+    assert L.mvp_expand_views(None, p, 16, 2, None) == -1
+    assert L.mvp_expand_views(p, p, 16, -1, None) == -2
+    assert L.mvp_expand_views(p, p, 0, 2, None) == 0                                        # nothing to do, no launch
     assert b"aligned" in L.mvp_error_string(-6)
 
 
@@ -268,3 +271,19 @@ def test_gpu_payload_golden_and_feeds_the_raymarcher():
     assert torch.equal(rgb, rgb2) and torch.equal(alpha, alpha2)
     torch.testing.assert_close(tex.grad, tex2.grad, rtol=1e-3, atol=1e-3 * float(tex2.grad.abs().max()))
     torch.testing.assert_close(opa.grad, opa2.grad, rtol=1e-3, atol=1e-3 * float(opa2.grad.abs().max()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,n", [((5, 3), 4), ((7,), 3), ((16, 8, 8, 8, 4), 6), ((1, 1, 2), 1)])
+def test_gpu_expand_views_equals_expand_contiguous(shape, n):
+    """One subject's tensor materialised per view (`mvp_expand_views`): bit-identical to expand().contiguous(), vector and
+    scalar (count % 4 != 0, unaligned slice) paths; the adjoint is the sum over the views."""
+    from ava256_b200.payload import expand_views
+    x = torch.randn(*shape, device="cuda", requires_grad=True)
+    y = expand_views(x, n)
+    assert y.shape == (n,) + tuple(shape) and torch.equal(y, x[None].expand(n, *shape).contiguous())
+    g = torch.randn_like(y)
+    y.backward(g)
+    assert torch.allclose(x.grad, g.sum(0), rtol=1e-6, atol=1e-6)
+    flat = torch.randn(4 * 33 + 1, device="cuda")[1:]                                       # 4-byte aligned only
+    assert torch.equal(expand_views(flat, 3), flat[None].expand(3, -1).contiguous())

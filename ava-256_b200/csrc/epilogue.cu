@@ -260,10 +260,15 @@ extern "C" int mvp_expand_views(const float *src, float *dst, size_t count, int3
     cudaStream_t st = (cudaStream_t)stream;
     if (count % 4 == 0 && aligned16(src) && aligned16(dst)) {
         const size_t c4 = count / 4;
-        expand_views_kernel<<<(unsigned)((c4 + kThreads - 1) / kThreads), kThreads, 0, st>>>(
-            reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), c4, n_views);
+        const dim3 grid((unsigned)((c4 + kThreads - 1) / kThreads));
+#define MVP_EPI_KERNEL expand_views_kernel
+        MVP_EPI_LAUNCH(grid, st, reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), c4, (int)n_views);
+#undef MVP_EPI_KERNEL
     } else {
-        expand_views_scalar_kernel<<<(unsigned)((count + kThreads - 1) / kThreads), kThreads, 0, st>>>(src, dst, count, n_views);
+        const dim3 grid((unsigned)((count + kThreads - 1) / kThreads));
+#define MVP_EPI_KERNEL expand_views_scalar_kernel
+        MVP_EPI_LAUNCH(grid, st, src, dst, count, (int)n_views);
+#undef MVP_EPI_KERNEL
     }
     return finish();
 }

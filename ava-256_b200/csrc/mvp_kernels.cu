@@ -53,7 +53,7 @@
 
 // C-ABI layout pins (the ctypes mirror in ava-256_b200/lib.py and INTEGRATION.md are checked against the same numbers)
 static_assert(sizeof(mvp_shape) == 28, "mvp_shape layout");
-static_assert(sizeof(mvp_forward_args) == 192 && offsetof(mvp_forward_args, raypos) == 48 && offsetof(mvp_forward_args, workspace_bytes) == 136 &&
+static_assert(sizeof(mvp_forward_args) == 232 && offsetof(mvp_forward_args, raypos) == 48 && offsetof(mvp_forward_args, workspace_bytes) == 136 &&
                   offsetof(mvp_forward_args, algo) == 164, "mvp_forward_args layout");
 static_assert(sizeof(mvp_backward_args) == 232 && offsetof(mvp_backward_args, grad_rayrgba) == 104 && offsetof(mvp_backward_args, workspace_bytes) == 168 &&
                   offsetof(mvp_backward_args, algo) == 204, "mvp_backward_args layout");
@@ -893,6 +893,7 @@ struct TileCtx {
     int nl;             // list length
 };
 
+constexpr int kClearBufs = 5;
 struct Params {
     int N, H, W, K, TD, TH, TW;
     int pview;                    // 1: primitive tensors are per view [N,K,...]; 0: one set [1,K,...] shared by all views
@@ -940,6 +941,10 @@ struct Params {
     const float *warp;
     float *g_warp;
     int WD, WH, WW;
+    // gradient buffers the gradient-mode forward zero-fills for the coming backward (mvp_forward_args::clear_grad_*): base (or NULL),
+    // floats, and float4s per warp of the fast render launch
+    float *clr[kClearBufs];
+    unsigned long long clrn[kClearBufs], clrper[kClearBufs];
 };
 
 #if defined(MVP_CPU_EMUL) && defined(MVP_EMUL_STATS)
@@ -1546,6 +1551,22 @@ __device__ __forceinline__ FwdWarpSmem<CAP, kGrad> *pinned_warp_record(FwdWarpSm
 #endif
 }
 
+// The gradient buffers of the coming backward, zero-filled on the side: warp g of the G warps of the fast render launch clears the g-th
+// slice of each buffer with streaming 16-byte stores before it renders its tile.  The render kernel is issue bound with the DRAM
+// write path idle, and 134 MB per view is 12 store instructions per warp -- a separate memset pass costs 1.4 ms per 80 views.
+__device__ __forceinline__ void clear_grad_slices(const Params &p, size_t g, int lane) {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int b = 0; b < kClearBufs; ++b) {
+        float *const base = p.clr[b];
+        if (!base) continue;
+        const size_t n4 = p.clrn[b] >> 2, lo = g * p.clrper[b];
+        const size_t hi = lo + p.clrper[b] < n4 ? lo + p.clrper[b] : n4;
+        for (size_t i = lo + lane; i < hi; i += 32) __stcs(reinterpret_cast<float4 *>(base) + i, z);
+        if (g == 0 && lane < (int)(p.clrn[b] & 3)) base[(n4 << 2) + lane] = 0.f;
+    }
+}
+
 template <int T, bool kGrad, int CAP, bool kWarp>
 __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_FWD_MINB * 4) / kWarps : 16 / kWarps) render_forward_kernel(const Params p) {
     __shared__ FwdWarpSmem<CAP, kGrad> s_w[kWarps];
@@ -1562,6 +1583,7 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
         }
     } else {
 #if MVP_CTA_ORDER
+        if (kGrad) clear_grad_slices(p, (size_t)blockIdx.x * kWarps + warp, lane);
         // 1-D grid; CTA b renders the b-th most expensive 2x2-tile block of the launch (order_ctas_kernel), or block b
         const int cid = p.use_order ? p.ctaorder[blockIdx.x] : (int)blockIdx.x;
         const int bx = cid % p.CXn, by = (cid / p.CXn) % p.CYn, n = cid / (p.CXn * p.CYn);
@@ -2457,7 +2479,9 @@ int mvp_raymarch_forward(const mvp_forward_args *a, void *stream) {
     if (misaligned(a->tplate, 16) || misaligned(a->rayrgba, 16) || misaligned(a->rayaux, 16) || misaligned(a->tminmax, 8) ||
         misaligned(a->raypos, 4) || misaligned(a->raydir, 4) || misaligned(a->primpos, 4) || misaligned(a->primrot, 4) ||
         misaligned(a->primscale, 4) || misaligned(a->raysat, 4) || misaligned(a->warp, 4) || misaligned(a->rayrgb_nchw, 4) ||
-        misaligned(a->rayalpha_nchw, 4) || misaligned(a->order, 4))
+        misaligned(a->rayalpha_nchw, 4) || misaligned(a->order, 4) || misaligned(a->clear_grad_primpos, 16) ||
+        misaligned(a->clear_grad_primrot, 16) || misaligned(a->clear_grad_primscale, 16) || misaligned(a->clear_grad_tplate, 16) ||
+        misaligned(a->clear_grad_warp, 16))
         return MVP_ERR_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
     char *ws = (char *)a->workspace;
@@ -2487,6 +2511,24 @@ int mvp_raymarch_forward(const mvp_forward_args *a, void *stream) {
     {
         cudaError_t e0 = cudaMemsetAsync(p.heavycnt, 0, sizeof(int), st);
         if (e0 != cudaSuccess) return (int)e0;
+    }
+    if (a->raysat) {
+        // gradient buffers to clear for the coming backward: in the fast render kernel (one slice per warp), see clear_grad_slices
+        const size_t nk = (size_t)(pview ? a->shape.N : 1) * a->shape.K;
+        float *const bufs[kClearBufs] = {a->clear_grad_primpos, a->clear_grad_primrot, a->clear_grad_primscale, a->clear_grad_tplate,
+                                         a->algo == 1 ? a->clear_grad_warp : nullptr};
+        const size_t floats[kClearBufs] = {nk * 3, nk * 9, nk * 3, nk * a->shape.TD * a->shape.TH * a->shape.TW * 4,
+                                           a->algo == 1 ? nk * a->WD * a->WH * a->WW * 3 : 0};
+        for (int b = 0; b < kClearBufs; ++b) {
+            if (!bufs[b]) continue;
+#if MVP_CTA_ORDER
+            const size_t G = (size_t)grid.x * kWarps, n4 = floats[b] / 4;
+            p.clr[b] = bufs[b]; p.clrn[b] = floats[b]; p.clrper[b] = (n4 + G - 1) / G;
+#else
+            cudaError_t z = cudaMemsetAsync(bufs[b], 0, floats[b] * sizeof(float), st);
+            if (z != cudaSuccess) return (int)z;
+#endif
+        }
     }
 #if MVP_LIST_REUSE
     if (a->raysat) {

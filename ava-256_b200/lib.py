@@ -26,6 +26,8 @@ class ForwardArgs(ctypes.Structure):
         ("workspace", c_f), ("workspace_bytes", ctypes.c_size_t),
         ("warp", c_f), ("WD", ctypes.c_int32), ("WH", ctypes.c_int32), ("WW", ctypes.c_int32), ("algo", ctypes.c_int32),
         ("rayrgb_nchw", c_f), ("rayalpha_nchw", c_f), ("order", c_f),
+        ("clear_grad_primpos", c_f), ("clear_grad_primrot", c_f), ("clear_grad_primscale", c_f), ("clear_grad_tplate", c_f),
+        ("clear_grad_warp", c_f),
     ]
 
 
@@ -62,9 +64,9 @@ FLAG_ACCEL_VALID = 1
 FLAG_ZERO_GRADS = 2
 FLAG_SHARED_PRIMS = 4
 FLAG_TEST_TINY_LISTS = 0x100
-ABI_VERSION = 6
+ABI_VERSION = 7
 # layout pins, equal to the static_asserts in csrc/mvp_kernels.cu (tests/test_abi.py compares)
-SIZEOF = {"Shape": 28, "ForwardArgs": 192, "BackwardArgs": 232}
+SIZEOF = {"Shape": 28, "ForwardArgs": 232, "BackwardArgs": 232}
 
 EXPORTS = ("mvp_abi_version", "mvp_build_config", "mvp_error_string", "mvp_workspace_bytes", "mvp_build_accel", "mvp_raymarch_forward",
            "mvp_raymarch_backward", "mvp_compute_raydirs", "mvp_forward_launch_count", "mvp_backward_launch_count",

@@ -123,10 +123,19 @@ class MVPRaymarch(Function):
             if usewarp:
                 a.warp = _ptr(warp)
                 a.WD, a.WH, a.WW = warp.shape[2:5]
+            grads = None
+            if gradmode:
+                # The gradient buffers of the backward (mvpraymarch.py:240-246 zeros_like's them there) are made now and zero-filled
+                # by the forward's render kernel on the side (mvp_forward_args::clear_grad_*): no memset pass in the step.
+                grads = [torch.empty_like(primpos), torch.empty_like(primrot), torch.empty_like(primscale), torch.empty_like(template),
+                         torch.empty_like(warp) if usewarp else None]
+                a.clear_grad_primpos, a.clear_grad_primrot, a.clear_grad_primscale = _ptr(grads[0]), _ptr(grads[1]), _ptr(grads[2])
+                a.clear_grad_tplate, a.clear_grad_warp = _ptr(grads[3]), _ptr(grads[4])
             stream = torch.cuda.current_stream(dev).cuda_stream
             _lib.check(_lib.LIB.mvp_raymarch_forward(ctypes.byref(a), ctypes.c_void_p(stream)))
 
         if gradmode:
+            ctx.grads = grads
             ctx.save_for_backward(raypos, raydir, tminmax, primpos, primrot, primscale, template, raysat, rayaux, workspace, warp)
             ctx.order = order
             ctx.options = options
@@ -153,19 +162,19 @@ class MVPRaymarch(Function):
                 grad_rayrgba = None
             else:
                 grad_rayrgba = _aligned(grad_rayrgba.contiguous(), 16)     # mvpraymarch.py:264
-            # mvpraymarch.py:240-246 zeros_like's these; here the library zero-fills them on the stream (MVP_FLAG_ZERO_GRADS)
-            grad_primpos = torch.empty_like(primpos)
-            grad_primrot = torch.empty_like(primrot)
-            grad_primscale = torch.empty_like(primscale)
-            grad_template = torch.empty_like(template)
             usewarp = options["algo"] == 1
-            grad_warp = None
-            if warp is not None:                                       # mvpraymarch.py:246 (zero when algo 0 ignores it)
-                grad_warp = torch.empty_like(warp) if usewarp else torch.zeros_like(warp)
+            grads, ctx.grads = ctx.grads, None
+            fresh = grads is not None          # the forward's render kernel zero-filled them; a second backward through the
+            if not fresh:                      # same graph (retain_graph) gets new ones, zero-filled by the library
+                grads = [torch.empty_like(primpos), torch.empty_like(primrot), torch.empty_like(primscale), torch.empty_like(template),
+                         torch.empty_like(warp) if usewarp else None]
+            grad_primpos, grad_primrot, grad_primscale, grad_template, grad_warp = grads
+            if warp is not None and not usewarp:                       # mvpraymarch.py:246 (zero when algo 0 ignores it)
+                grad_warp = torch.zeros_like(warp)
             a = _lib.BackwardArgs()
             a.shape = _lib.Shape(N, H, W, K, TD, TH, TW)
             a.stepsize, a.fadescale, a.fadeexp = ctx.stepsize, float(options["fadescale"]), float(options["fadeexp"])
-            a.flags = _lib.FLAG_ACCEL_VALID | _lib.FLAG_ZERO_GRADS | (_lib.FLAG_SHARED_PRIMS if ctx.shared else 0)
+            a.flags = _lib.FLAG_ACCEL_VALID | (0 if fresh else _lib.FLAG_ZERO_GRADS) | (_lib.FLAG_SHARED_PRIMS if ctx.shared else 0)
             a.raypos, a.raydir, a.tminmax = _ptr(raypos), _ptr(raydir), _ptr(tminmax)
             a.primpos, a.primrot, a.primscale = _ptr(primpos), _ptr(primrot), _ptr(primscale)
             a.tplate = _ptr(template)

@@ -352,6 +352,7 @@ def run_ours(args, rank, world):
     fa.stepsize, fa.fadescale, fa.fadeexp, fa.flags = stepsize, 8.0, 8.0, 0
     P = lambda x: ctypes.c_void_p(x.data_ptr())  # noqa: E731
     tl = [x.detach() for x in leaves]
+    clear_gb = sum(g.numel() for g in tl) * 4 / 1e9
     fa.raypos, fa.raydir, fa.tminmax = P(s["raypos"]), P(s["raydir"]), P(s["tminmax"])
     fa.primpos, fa.primrot, fa.primscale, fa.tplate = P(tl[0]), P(tl[1]), P(tl[2]), P(tl[3])
     fa.rayrgba, fa.raysat, fa.rayaux, fa.workspace, fa.workspace_bytes = P(rgba), P(rsat), P(raux), P(ws), wsb
@@ -359,6 +360,8 @@ def run_ours(args, rank, world):
     lib.check(lib.LIB.mvp_raymarch_forward(ctypes.byref(fa), stream))          # builds accel
     fa.flags = lib.FLAG_ACCEL_VALID
     gs = [torch.zeros_like(x) for x in tl]
+    # the timed forward is the one the op runs: it also zero-fills the backward's gradient buffers on the side
+    fa.clear_grad_primpos, fa.clear_grad_primrot, fa.clear_grad_primscale, fa.clear_grad_tplate = P(gs[0]), P(gs[1]), P(gs[2]), P(gs[3])
     ba = lib.BackwardArgs()
     ba.shape, ba.stepsize, ba.fadescale, ba.fadeexp, ba.flags = fa.shape, stepsize, 8.0, 8.0, lib.FLAG_ACCEL_VALID
     ba.raypos, ba.raydir, ba.tminmax = fa.raypos, fa.raydir, fa.tminmax
@@ -618,7 +621,9 @@ def run_ours(args, rank, world):
         "cpu_baseline": cpu, "ref_cuda_baseline": ref_cuda, "parity_check": parity, "e2e": e2e, "clocks": clocks,
         "shared_primitives_config": shared_cfg, "e2e_camera_inputs": e2e_cam,
         "gpu_launches": args.steps * (lib.LIB.mvp_forward_launch_count(0) + lib.LIB.mvp_backward_launch_count(lib.FLAG_ACCEL_VALID)),
-        "kernel_ms": {"forward_all_views_per_rank": fwd_ms, "backward_all_views_per_rank": bwd_ms},
+        "kernel_ms": {"forward_all_views_per_rank": fwd_ms, "backward_all_views_per_rank": bwd_ms,
+                      "note": "the forward launch also zero-fills the backward's gradient buffers (clear_grad_*, %.1f GB per rank) "
+                              "on the side; those bytes are not counted as algorithmic" % clear_gb},
         "rank_ms_per_step": rank_ms, "allreduce_ms": allreduce_ms,
     }
     print(json.dumps(line), flush=True)

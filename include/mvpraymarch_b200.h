@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define MVP_ABI_VERSION 6
+#define MVP_ABI_VERSION 7
 
 #define MVP_OK 0
 #define MVP_ERR_NULL (-1)      /* a required pointer is NULL */
@@ -101,6 +101,13 @@ typedef struct mvp_forward_args {
      * (mvpraymarch.py:46-55; codes from mvp_compute_morton) applied as an indirection instead of a gather of the primitive
      * tensors.  Must be a permutation of 0..K-1 and the same in every call that shares the workspace. */
     const int32_t *order;
+    /* Optional (each may be NULL): the gradient buffers of the mvp_raymarch_backward call that will follow, shapes as in
+     * mvp_backward_args.  A gradient-mode forward (raysat != NULL) zero-fills them from inside its render kernel -- every warp
+     * clears one slice with streaming stores before it renders its tile; the kernel is issue bound and the DRAM write path idle,
+     * so the 134 MB per view cost nothing measurable, where a memset pass (MVP_FLAG_ZERO_GRADS in the backward, or the caller's
+     * zeros_like of mvpraymarch.py:265-268) costs 1.4 ms per 80 views.  16-byte aligned; ignored when raysat is NULL;
+     * clear_grad_warp is used for algo 1 only. */
+    float *clear_grad_primpos, *clear_grad_primrot, *clear_grad_primscale, *clear_grad_tplate, *clear_grad_warp;
 } mvp_forward_args;
 
 typedef struct mvp_backward_args {

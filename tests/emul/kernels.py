@@ -56,10 +56,21 @@ def _f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 
 
+def _nan_like16(x):
+    """NaN-filled array of x's shape whose data pointer is 16-byte aligned."""
+    raw = np.empty(x.size + 4, np.float32)
+    off = (-raw.ctypes.data // 4) % 4
+    out = raw[off:off + x.size].reshape(x.shape)
+    out[...] = np.nan
+    return out
+
+
 def forward_backward(raypos, raydir, stepsize, tminmax, primpos, primrot, primscale, template, grad_rayrgba=None, warp=None,
-                     fadescale=8.0, fadeexp=8.0, fwd_flags=0, bwd_flags=0, planes=False, order=None):
+                     fadescale=8.0, fadeexp=8.0, fwd_flags=0, bwd_flags=0, planes=False, order=None, clear_in_forward=False):
     """Runs the emulated forward (and, when grad_rayrgba is given, backward) kernels.
-    Returns (rayrgba, raysat, grads) with grads = [primpos, primrot, primscale, template(, warp)] or None."""
+    Returns (rayrgba, raysat, grads) with grads = [primpos, primrot, primscale, template(, warp)] or None.
+    clear_in_forward: the gradient buffers are handed to the forward NaN-filled (mvp_forward_args::clear_grad_*), which must leave
+    them zero; the backward then runs without MVP_FLAG_ZERO_GRADS."""
     L = load()
     raypos, raydir, tminmax, primpos, primrot, primscale, template = map(_f32, (raypos, raydir, tminmax, primpos, primrot, primscale, template))
     warp = None if warp is None else _f32(warp)
@@ -92,16 +103,24 @@ def forward_backward(raypos, raydir, stepsize, tminmax, primpos, primrot, primsc
     if warp is not None:
         a.warp = _p(warp)
         a.WD, a.WH, a.WW = warp.shape[2:5]
+    pre = None
+    if clear_in_forward:
+        assert want_grad and not (bwd_flags & _abi.FLAG_ZERO_GRADS)
+        pre = [_nan_like16(x) for x in (primpos, primrot, primscale, template)] + [_nan_like16(warp) if warp is not None else None]
+        a.clear_grad_primpos, a.clear_grad_primrot, a.clear_grad_primscale, a.clear_grad_tplate = (_p(g) for g in pre[:4])
+        a.clear_grad_warp = _p(pre[4])
     rc = L.mvp_raymarch_forward(ctypes.byref(a), None)
     assert rc == 0, rc
+    if pre is not None:
+        assert all(g is None or not g.any() for g in pre), "the forward must leave the clear_grad_* buffers zero"
     if planes:                      # hand back the same layout as the channels-last run, assembled from the planes
         rayrgba = np.ascontiguousarray(np.concatenate([rgb_p, alpha_p], axis=1).transpose(0, 2, 3, 1))
     if not want_grad:
         return rayrgba, None, None
     grad_rayrgba = _f32(grad_rayrgba)
     fill = np.nan if (bwd_flags & _abi.FLAG_ZERO_GRADS) else 0.0           # ZERO_GRADS: the library must overwrite the NaNs
-    grads = [np.full_like(x, fill) for x in (primpos, primrot, primscale, template)]
-    gwarp = np.full_like(warp, fill) if warp is not None else None
+    grads = pre[:4] if pre is not None else [np.full_like(x, fill) for x in (primpos, primrot, primscale, template)]
+    gwarp = pre[4] if pre is not None else (np.full_like(warp, fill) if warp is not None else None)
     b = _abi.BackwardArgs()
     b.shape = shape
     b.stepsize, b.fadescale, b.fadeexp, b.flags = float(stepsize), float(fadescale), float(fadeexp), _abi.FLAG_ACCEL_VALID | bwd_flags

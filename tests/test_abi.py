@@ -27,7 +27,7 @@ def test_header_symbols_are_exported():
     for n in names:
         assert hasattr(lib.LIB, n), n
     assert sorted(names) == sorted(lib.EXPORTS)
-    assert lib.LIB.mvp_abi_version() == 6
+    assert lib.LIB.mvp_abi_version() == 7
     cfg = lib.LIB.mvp_build_config().decode()
     assert "LIST_REUSE=" in cfg and "FASTCAP=" in cfg and "CPU_EMUL" not in cfg
 

@@ -217,6 +217,28 @@ def test_emulated_marching_order_indirection(kernels, name):
     assert not np.array_equal(order, np.arange(order.shape[1])[None].repeat(order.shape[0], 0))
 
 
+@pytest.mark.parametrize("name", ["head_small", "warp_head", "many_views", "odd_k"])
+def test_emulated_forward_clears_gradient_buffers(kernels, name):
+    """mvp_forward_args::clear_grad_*: the gradient-mode forward leaves the (NaN-filled) gradient buffers zero -- every float of
+    every buffer, also when the count is not a multiple of 4 or of the warps of the launch -- and the backward that follows
+    without MVP_FLAG_ZERO_GRADS returns the same gradients."""
+    if name == "odd_k":                                   # K = 9: 54 / 162 floats, tails and empty slices
+        from ava256_b200 import scene
+        sc = scene.make_scene(2, 24, 40, 9, 8, seed=5)
+        a = (sc["raypos"].numpy(), sc["raydir"].numpy(), sc["stepsize"], sc["tminmax"].numpy(), sc["primpos"].numpy(),
+             sc["primrot"].numpy(), sc["primscale"].numpy(), sc["template"].numpy())
+        kw = {}
+        grad = torch.randn(2, 24, 40, 4, generator=torch.Generator().manual_seed(3))
+    else:
+        s, grad = build_case(name)
+        a, kw = scene_args_np(s)
+    out0, sat0, g0 = kernels.forward_backward(*a, grad_rayrgba=grad.numpy(), **kw)
+    out1, sat1, g1 = kernels.forward_backward(*a, grad_rayrgba=grad.numpy(), clear_in_forward=True, **kw)
+    assert np.array_equal(out0, out1) and np.array_equal(sat0, sat1)
+    for x, y in zip(g0, g1):
+        assert np.isfinite(y).all() and relerr(x, y) <= 1e-5
+
+
 def test_emulated_runtime_flags(kernels):
     """C-ABI flags of the product library on the emulation: MVP_FLAG_TEST_TINY_LISTS (almost every tile takes the backward's
     rebuild path), MVP_FLAG_ZERO_GRADS (the library zero-fills NaN-initialised gradient buffers)."""

@@ -118,6 +118,25 @@ def test_emul_payload_matches_eager_torch(emul, N, hb, wb, B, V, BT):
     assert np.array_equal(grad_op, gop.numpy())
 
 
+@pytest.mark.parametrize("count,off", [(4 * 700, 0), (4 * 700 + 3, 0), (256, 1)])
+def test_emul_expand_views(count, off):
+    """mvp_expand_views on the emulation: 16-byte path, scalar path for a count that is not a multiple of 4 and for a source
+    that is only 4-byte aligned; untouched guard floats either side of the destination."""
+    from tests.emul.build import build_aux
+    emul = ctypes.CDLL(build_aux())                          # raydirs.cu + epilogue.cu on the CPU emulation
+    emul.mvp_expand_views.argtypes = [F32P, F32P, ctypes.c_size_t, ctypes.c_int32, ctypes.c_void_p]
+    n = 3
+    raw = np.random.default_rng(count).standard_normal(count + 8).astype(np.float32)
+    base = (-raw.ctypes.data // 4) % 4                       # index of a 16-byte aligned float
+    src = raw[base + off:base + off + count]
+    draw = np.full(n * count + 12, 7.0, np.float32)
+    dbase = (-draw.ctypes.data // 4) % 4 + 4
+    dst = draw[dbase:dbase + n * count]
+    assert emul.mvp_expand_views(_np_ptr(src), _np_ptr(dst), count, n, None) == 0
+    assert np.array_equal(dst.reshape(n, count), np.broadcast_to(src, (n, count)))
+    assert (draw[:dbase] == 7.0).all() and (draw[dbase + n * count:] == 7.0).all()
+
+
 def test_restatement_matches_reference_golden():
     """oracle/epilogue_ref.py against vectors produced with the reference's own Colorcal module / literal statements."""
     z = np.load(os.path.join(HERE, "golden", "epilogue_composite.npz"))

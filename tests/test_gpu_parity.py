@@ -191,3 +191,32 @@ def test_random_small_scenes_vs_oracle(seed):
         assert np.isfinite(g_).all(), nm
         if np.abs(r).max() > 0:
             assert relerr(g_, r) <= BWD_TOL, nm
+
+
+@pytest.mark.parametrize("name", ["head_small", "warp_small"])
+def test_gradient_buffers_cleared_by_the_forward_and_second_backward(name):
+    """The op hands the gradient buffers to the forward, whose render kernel zero-fills them (mvp_forward_args::clear_grad_*),
+    and the backward runs without a memset pass; a second backward through the same graph (retain_graph) takes the library's
+    zero-fill path instead.  Both give the same gradients, and they do not depend on what the allocator's blocks held before."""
+    from extensions.mvpraymarch.mvpraymarch import mvpraymarch
+    s, grad = build_case(name)
+    t = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in s.items()}
+    junk = [torch.full((1 << 22,), float("nan"), device="cuda") for _ in range(4)]    # poison the allocator's free blocks
+    del junk
+    leaves = [t[k].clone().requires_grad_(True) for k in ("primpos", "primrot", "primscale", "template")]
+    warp = t.get("warp")
+    if warp is not None:
+        warp = warp.clone().requires_grad_(True)
+        leaves.append(warp)
+    out = mvpraymarch(t["raypos"], t["raydir"], t["stepsize"], t["tminmax"], (leaves[0], leaves[1], leaves[2]), leaves[3], warp,
+                      algo=1 if warp is not None else 0, fadescale=s.get("fadescale", 8.0), fadeexp=s.get("fadeexp", 8.0))
+    g = grad.cuda()
+    out.backward(g, retain_graph=True)
+    first = [x.grad.clone() for x in leaves]
+    for x in leaves:
+        x.grad = None
+    out.backward(g)
+    _, ref = run_ours(s, grad)
+    for a, b, c in zip(first, leaves, ref):
+        assert torch.isfinite(a).all() and relerr(a.cpu().numpy(), c) <= 1e-5
+        assert relerr(b.grad.cpu().numpy(), c) <= 1e-5

@@ -12,7 +12,8 @@ SRC = [os.path.join(HERE, "csrc", n) for n in ("mvp_kernels.cu", "raydirs.cu", "
 # raydirs.cu mirrors the reference's utils extension, which is NOT built with -use_fast_math; epilogue.cu replaces
 # eager PyTorch expressions and keeps their IEEE single-rounding arithmetic
 NO_FAST_MATH = {"raydirs.cu", "epilogue.cu"}
-HDR = [os.path.join(ROOT, "include", "mvpraymarch_b200.h"), os.path.join(HERE, "csrc", "epilogue_body.h")]
+HDR = [os.path.join(ROOT, "include", "mvpraymarch_b200.h"), os.path.join(HERE, "csrc", "epilogue_body.h"),
+       os.path.join(HERE, "csrc", "raygen.h")]
 LIB = os.path.join(HERE, "libmvpraymarch_b200.so")
 
 NVCC_FLAGS = [

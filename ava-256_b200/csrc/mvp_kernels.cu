@@ -49,13 +49,15 @@
 #include <stdlib.h>
 
 #include "mvpraymarch_b200.h"
+#include "raygen.h"
 #include <stddef.h>
 
 // C-ABI layout pins (the ctypes mirror in ava-256_b200/lib.py and INTEGRATION.md are checked against the same numbers)
 static_assert(sizeof(mvp_shape) == 28, "mvp_shape layout");
-static_assert(sizeof(mvp_forward_args) == 232 && offsetof(mvp_forward_args, raypos) == 48 && offsetof(mvp_forward_args, workspace_bytes) == 136 &&
+static_assert(sizeof(mvp_camera) == 40, "mvp_camera layout");
+static_assert(sizeof(mvp_forward_args) == 272 && offsetof(mvp_forward_args, camera) == 232 && offsetof(mvp_forward_args, raypos) == 48 && offsetof(mvp_forward_args, workspace_bytes) == 136 &&
                   offsetof(mvp_forward_args, algo) == 164, "mvp_forward_args layout");
-static_assert(sizeof(mvp_backward_args) == 232 && offsetof(mvp_backward_args, grad_rayrgba) == 104 && offsetof(mvp_backward_args, workspace_bytes) == 168 &&
+static_assert(sizeof(mvp_backward_args) == 272 && offsetof(mvp_backward_args, camera) == 232 && offsetof(mvp_backward_args, grad_rayrgba) == 104 && offsetof(mvp_backward_args, workspace_bytes) == 168 &&
                   offsetof(mvp_backward_args, algo) == 204, "mvp_backward_args layout");
 
 // experiment knobs (defaults = measured best)
@@ -161,7 +163,7 @@ struct Cam {          // 64 B per view
 struct __align__(8) RowEntry { int k; unsigned xr; };   // xr = x0 | x1 << 16  (pixels, inclusive)
 
 struct Layout {
-    size_t cam, bad, pack, rx, ry, rowcnt, rowlist, heavycnt, heavylist, ctaorder, ctahist, tilecnt, blky, rankof, tileclk, total;
+    size_t cam, raycam, bad, pack, rx, ry, rowcnt, rowlist, heavycnt, heavylist, ctaorder, ctahist, tilecnt, blky, rankof, tileclk, total;
     int R, rowcap;
 #if MVP_XBUCKETS
     size_t grphdr, grplist;
@@ -181,6 +183,7 @@ __host__ inline Layout make_layout(const mvp_shape &s) {
     L.rowcap = ((s.K < kRowCapMax ? s.K : kRowCapMax) + 1) & ~1;   // even: 16-byte aligned buckets (TMA bulk copies)
     size_t off = 0;
     L.cam = off;     off = align256(off + (size_t)s.N * sizeof(Cam));
+    L.raycam = off;  off = align256(off + (size_t)s.N * 4 * sizeof(float4));
     L.bad = off;     off = align256(off + (size_t)s.N * sizeof(int));
     L.pack = off;    off = align256(off + (size_t)s.N * s.K * 64);
     L.rx = off;      off = align256(off + (size_t)s.N * s.K * 4);
@@ -349,6 +352,50 @@ __global__ void __launch_bounds__(kFitThreads) fit_camera_kernel(int H, int W, c
             cam[n] = c;
         }
     }
+}
+
+// 1b. The same record from the camera parameters themselves (mvp_camera): D(w,h) = row2 + row0 (w - cx) / fx + row1 (h - cy) / fy is a
+//     pinhole grid by construction, so there is nothing to fit and nothing to verify -- no pass over a ray field that, in this mode,
+//     does not exist.  Also writes the record the render kernels generate their rays from (raygen.h).  One thread per view.
+__global__ void __launch_bounds__(128) cam_params_kernel(int N, const float *__restrict__ viewpos, const float *__restrict__ viewrot,
+                                                         const float *__restrict__ focal, const float *__restrict__ princpt, float volradius,
+                                                         Cam *cam, int *bad, float4 *raycam) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const float *R = viewrot + (size_t)n * 9;
+    const float fx = focal[n * 2 + 0], fy = focal[n * 2 + 1], cx = princpt[n * 2 + 0], cy = princpt[n * 2 + 1];
+    Cam c;
+    // ray origin exactly as the generator computes it (utils_kernel.cu:32)
+    c.o[0] = __fdiv_rn(viewpos[n * 3 + 0], volradius); c.o[1] = __fdiv_rn(viewpos[n * 3 + 1], volradius); c.o[2] = __fdiv_rn(viewpos[n * 3 + 2], volradius);
+    raycam[(size_t)n * 4 + 0] = make_float4(c.o[0], c.o[1], c.o[2], R[0]);
+    raycam[(size_t)n * 4 + 1] = make_float4(R[1], R[2], R[3], R[4]);
+    raycam[(size_t)n * 4 + 2] = make_float4(R[5], R[6], R[7], R[8]);
+    raycam[(size_t)n * 4 + 3] = make_float4(cx, cy, fx, fy);
+    int ok = 1;
+    double mi[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    double A[3], B[3], C[3];
+    for (int i = 0; i < 3; ++i) {
+        B[i] = (double)R[i] / (double)fx;
+        C[i] = (double)R[3 + i] / (double)fy;
+        A[i] = (double)R[6 + i] - B[i] * (double)cx - C[i] * (double)cy;
+    }
+    // M = [B C A] (columns); pixel (w, h, 1) ~ M^-1 (P - o)
+    const double M[9] = {B[0], C[0], A[0], B[1], C[1], A[1], B[2], C[2], A[2]};
+    const double dm = M[0] * (M[4] * M[8] - M[5] * M[7]) - M[1] * (M[3] * M[8] - M[5] * M[6]) + M[2] * (M[3] * M[7] - M[4] * M[6]);
+    if (!(fabs(dm) > 1e-30) || !isfinite(dm)) ok = 0;
+    else {
+        const double im = 1.0 / dm;
+        mi[0] = (M[4] * M[8] - M[5] * M[7]) * im; mi[1] = (M[2] * M[7] - M[1] * M[8]) * im; mi[2] = (M[1] * M[5] - M[2] * M[4]) * im;
+        mi[3] = (M[5] * M[6] - M[3] * M[8]) * im; mi[4] = (M[0] * M[8] - M[2] * M[6]) * im; mi[5] = (M[2] * M[3] - M[0] * M[5]) * im;
+        mi[6] = (M[3] * M[7] - M[4] * M[6]) * im; mi[7] = (M[1] * M[6] - M[0] * M[7]) * im; mi[8] = (M[0] * M[4] - M[1] * M[3]) * im;
+        for (int i = 0; i < 9; ++i) if (!isfinite(mi[i])) ok = 0;
+    }
+    if (!isfinite(c.o[0]) || !isfinite(c.o[1]) || !isfinite(c.o[2])) ok = 0;
+    c.ok = ok;
+    for (int i = 0; i < 9; ++i) c.minv[i] = (float)mi[i];
+    c.pad[0] = c.pad[1] = c.pad[2] = 0.f;
+    cam[n] = c;
+    bad[n] = ok ? 0 : 1;          // a degenerate camera (focal 0, non-finite) falls back to "every slab is a candidate", like a failed fit
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -883,6 +930,29 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
 }
 #endif
 
+// This lane's ray: read from the caller's ray tensors, or -- mvp_camera -- generated from the view's camera record with the arithmetic
+// of mvp_compute_raydirs (raygen.h; utils_kernel.cu:32-46), in which case raypos / raydir / tminmax are never touched.
+__device__ __forceinline__ Ray fetch_ray(const float *__restrict__ raypos, const float *__restrict__ raydir, const float *__restrict__ tminmax,
+                                         const float4 *__restrict__ raycam, int n, size_t r, int cx, int cy) {
+    Ray ray;
+    if (raycam) {
+        const float4 q0 = __ldg(raycam + (size_t)n * 4), q1 = __ldg(raycam + (size_t)n * 4 + 1), q2 = __ldg(raycam + (size_t)n * 4 + 2),
+                     q3 = __ldg(raycam + (size_t)n * 4 + 3);
+        MvpRayCam c;
+        c.ox = q0.x; c.oy = q0.y; c.oz = q0.z;
+        c.R[0] = q0.w; c.R[1] = q1.x; c.R[2] = q1.y; c.R[3] = q1.z; c.R[4] = q1.w; c.R[5] = q2.x; c.R[6] = q2.y; c.R[7] = q2.z; c.R[8] = q2.w;
+        c.pcx = q3.x; c.pcy = q3.y; c.fx = q3.z; c.fy = q3.w;
+        ray.ox = c.ox; ray.oy = c.oy; ray.oz = c.oz;
+        mvp_gen_ray(c, (float)cx, (float)cy, ray.dx, ray.dy, ray.dz, ray.tmin, ray.tmax);
+    } else {
+        ray.ox = __ldg(raypos + r * 3 + 0); ray.oy = __ldg(raypos + r * 3 + 1); ray.oz = __ldg(raypos + r * 3 + 2);
+        ray.dx = __ldg(raydir + r * 3 + 0); ray.dy = __ldg(raydir + r * 3 + 1); ray.dz = __ldg(raydir + r * 3 + 2);
+        const float2 tmm = __ldg(reinterpret_cast<const float2 *>(tminmax) + r);
+        ray.tmin = tmm.x; ray.tmax = tmm.y;
+    }
+    return ray;
+}
+
 struct TileCtx {
     // per-lane
     Ray ray;
@@ -899,6 +969,7 @@ struct Params {
     int pview;                    // 1: primitive tensors are per view [N,K,...]; 0: one set [1,K,...] shared by all views
     float dt, fadescale, fadeexp;
     const float *raypos, *raydir, *tminmax;
+    const float4 *raycam;         // per view 4 x float4 (raygen.h): the rays are generated from it instead of read (mvp_camera); or NULL
     const float *tplate;
     const float4 *pack;
     const unsigned *rx, *ry;
@@ -952,6 +1023,18 @@ long long g_emul_list_chunks;   // 32-entry bucket chunks scanned by build_tile_
 long long g_emul_bwd_stats[8];  // see render_backward_kernel
 #endif
 
+// No slab rectangle reaches this tile (three quarters of the tiles of a head-and-shoulders view): its rays hit nothing, whatever they
+// are -- the render kernels neither read nor generate them.
+__device__ __forceinline__ bool tile_bucket_empty(const Params &p, int n, int tx, int ty) {
+    const int cnt = p.rowcnt[(size_t)n * p.R + ty];
+    if (cnt > p.rowcap) return false;          // overflowed row bucket: the tile scans all slabs
+#if MVP_XBUCKETS
+    const int2 gh = __ldg(p.grphdr + ((size_t)n * p.R + ty) * p.NG + tx / kGrpTiles);
+    if (gh.y >= 0) return gh.y == 0;
+#endif
+    return cnt == 0;
+}
+
 // Builds the warp's slab list (rank order, at most CAP entries in shared memory), each slab's warp step interval and
 // each lane's rtminmax, in one pass over the tile row's bucket.
 //
@@ -970,10 +1053,7 @@ __device__ __forceinline__ bool build_tile_list(const Params &p, float rdt, int 
     c.inimg = (px < p.W) && (py < p.H);
     const int cx = min(px, p.W - 1), cy = min(py, p.H - 1);
     const size_t r = ((size_t)n * p.H + cy) * p.W + cx;
-    c.ray.ox = __ldg(p.raypos + r * 3 + 0); c.ray.oy = __ldg(p.raypos + r * 3 + 1); c.ray.oz = __ldg(p.raypos + r * 3 + 2);
-    c.ray.dx = __ldg(p.raydir + r * 3 + 0); c.ray.dy = __ldg(p.raydir + r * 3 + 1); c.ray.dz = __ldg(p.raydir + r * 3 + 2);
-    const float2 tmm = __ldg(reinterpret_cast<const float2 *>(p.tminmax) + r);
-    c.ray.tmin = tmm.x; c.ray.tmax = tmm.y;
+    c.ray = fetch_ray(p.raypos, p.raydir, p.tminmax, p.raycam, n, r, cx, cy);
     c.rt0 = CUDART_INF_F; c.rt1 = -CUDART_INF_F;
 
     const float tsteps = c.ray.tmin * rdt;            // lattice origin of this lane, in steps
@@ -1165,14 +1245,12 @@ __device__ __forceinline__ int load_saved_tile_list(const Params &p, float rdt, 
 #endif
     if (hdr.y < 0) return 0;
     if (hdr.y > CAP) return 2;
+    if (hdr.y == 0) { c.nl = 0; return 1; }   // nothing to march: the caller returns before it looks at anything else
     const int px = tx * kTileW + (lane & 7), py = ty * kTileH + (lane >> 3);
     c.inimg = (px < p.W) && (py < p.H);
     const int cx = min(px, p.W - 1), cy = min(py, p.H - 1);
     const size_t r = ((size_t)n * p.H + cy) * p.W + cx;
-    c.ray.ox = __ldg(p.raypos + r * 3 + 0); c.ray.oy = __ldg(p.raypos + r * 3 + 1); c.ray.oz = __ldg(p.raypos + r * 3 + 2);
-    c.ray.dx = __ldg(p.raydir + r * 3 + 0); c.ray.dy = __ldg(p.raydir + r * 3 + 1); c.ray.dz = __ldg(p.raydir + r * 3 + 2);
-    const float2 tmm = __ldg(reinterpret_cast<const float2 *>(p.tminmax) + r);
-    c.ray.tmin = tmm.x; c.ray.tmax = tmm.y;
+    c.ray = fetch_ray(p.raypos, p.raydir, p.tminmax, p.raycam, n, r, cx, cy);
     const float tsteps = c.ray.tmin * rdt;
     float tref = c.inimg ? tsteps : CUDART_INF_F;
 #pragma unroll
@@ -1330,6 +1408,32 @@ __device__ __forceinline__ bool forward_tile(const Params &p, const int n, const
     float4 *const ring = S->ring;
     float *const ra = S->ra;
 
+    if (tile_bucket_empty(p, n, tx, ty)) {
+        // background tile: what the general path below writes for rays without a hit, without touching the rays
+        const int px = tx * kTileW + (lane & 7), py = ty * kTileH + (lane >> 3);
+        const bool inimg = (px < p.W) && (py < p.H);
+        const size_t r = ((size_t)n * p.H + min(py, p.H - 1)) * p.W + min(px, p.W - 1);
+#if MVP_LIST_REUSE
+        if (kGrad) {
+            if (lane == 0) p.tilehdr[((size_t)n * p.TYn + ty) * p.TXn + tx] = make_int2(0, 0);
+            if (inimg) p.rayj0[r] = kNoHitJ0;
+        }
+#endif
+        if (inimg) {
+            if (p.rayrgba) reinterpret_cast<float4 *>(p.rayrgba)[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.rgb_nchw) {
+                const size_t plane = (size_t)p.H * p.W, pix = r - (size_t)n * plane;
+                float *o = p.rgb_nchw + (size_t)n * 3 * plane + pix;
+                o[0] = 0.f; o[plane] = 0.f; o[2 * plane] = 0.f;
+                p.alpha_nchw[(size_t)n * plane + pix] = 0.f;
+            }
+            if (kGrad) {
+                p.raysat[r * 3 + 0] = -1.f; p.raysat[r * 3 + 1] = -1.f; p.raysat[r * 3 + 2] = -1.f;
+                p.rayaux[r] = make_int4(0x7fffffff, 0, 0, 0x7ffffffe);   // (no saturating sample, -, -, first step - 1 of a ray with no first step)
+            }
+        }
+        return true;
+    }
     const float rdt = fast_rcp(p.dt);   // MUFU.RCP(stepsize), as the reference (SASS 0x16c0)
     TileCtx c;
     float t, x, y, z, r1e;
@@ -2241,8 +2345,9 @@ int check_shape(const mvp_shape &s) {
     return MVP_OK;
 }
 
-int launch_accel(const mvp_shape &s, int pview, const int *order, const float *raypos, const float *raydir, const float *primpos,
-                 const float *primrot, const float *primscale, char *ws, const Layout &L, cudaStream_t st) {
+// camera: NULL or a checked mvp_camera (then raypos / raydir are not used)
+int launch_accel(const mvp_shape &s, int pview, const int *order, const float *raypos, const float *raydir, const mvp_camera *camera,
+                 const float *primpos, const float *primrot, const float *primscale, char *ws, const Layout &L, cudaStream_t st) {
     const int ostride = pview ? s.K : 0;      // the order belongs to the primitives: one per view, or one shared by all views
     Cam *cam = reinterpret_cast<Cam *>(ws + L.cam);
     int *bad = reinterpret_cast<int *>(ws + L.bad);
@@ -2259,7 +2364,11 @@ int launch_accel(const mvp_shape &s, int pview, const int *order, const float *r
     const size_t HW = (size_t)s.H * s.W;
     dim3 gfit((unsigned)((HW + kFitThreads * kFitRaysPerThread - 1) / (kFitThreads * kFitRaysPerThread)), s.N);
 #ifdef MVP_CPU_EMUL
-    MVP_LAUNCH(fit_camera_kernel, gfit, kFitThreads, 0, st, s.H, s.W, raypos, raydir, cam, bad);
+    if (camera)
+        MVP_LAUNCH(cam_params_kernel, (unsigned)((s.N + 127) / 128), 128, 0, st, s.N, camera->viewpos, camera->viewrot, camera->focal,
+                   camera->princpt, camera->volradius, cam, bad, reinterpret_cast<float4 *>(ws + L.raycam));
+    else
+        MVP_LAUNCH(fit_camera_kernel, gfit, kFitThreads, 0, st, s.H, s.W, raypos, raydir, cam, bad);
     const size_t NK = (size_t)s.N * s.K;
     MVP_LAUNCH(prim_setup_kernel, (unsigned)((NK + 127) / 128), 128, 0, st, s.N, s.K, s.H, s.W, pview, primpos, primrot, primscale, cam, bad,
                reinterpret_cast<float4 *>(ws + L.pack), reinterpret_cast<unsigned *>(ws + L.rx), reinterpret_cast<unsigned *>(ws + L.ry));
@@ -2291,7 +2400,11 @@ int launch_accel(const mvp_shape &s, int pview, const int *order, const float *r
 #endif
                    );
 #else
-    fit_camera_kernel<<<gfit, kFitThreads, 0, st>>>(s.H, s.W, raypos, raydir, cam, bad);
+    if (camera)
+        cam_params_kernel<<<(unsigned)((s.N + 127) / 128), 128, 0, st>>>(s.N, camera->viewpos, camera->viewrot, camera->focal, camera->princpt,
+                                                                         camera->volradius, cam, bad, reinterpret_cast<float4 *>(ws + L.raycam));
+    else
+        fit_camera_kernel<<<gfit, kFitThreads, 0, st>>>(s.H, s.W, raypos, raydir, cam, bad);
     const size_t NK = (size_t)s.N * s.K;
     prim_setup_kernel<<<(unsigned)((NK + 127) / 128), 128, 0, st>>>(
         s.N, s.K, s.H, s.W, pview, primpos, primrot, primscale, cam, bad, reinterpret_cast<float4 *>(ws + L.pack),
@@ -2414,6 +2527,7 @@ const char *mvp_error_string(int code) {
         case MVP_ERR_ALGO: return "unsupported algo";
         case MVP_ERR_ALIGN: return "misaligned buffer (tplate/rayrgba/grad_rayrgba/grad_tplate/rayaux: 16 bytes, tminmax: 8, others: 4)";
         case MVP_ERR_STRUCT: return "args->struct_size does not match this library's argument struct (ABI mismatch)";
+        case MVP_ERR_CAMERA: return "camera.volradius must be finite and > 0";
         default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
     }
 }
@@ -2431,7 +2545,30 @@ int mvp_build_accel(const mvp_shape *shape, uint32_t flags, const int32_t *order
     if (rc != MVP_OK) return rc;
     const Layout L = make_layout(*shape);
     if (workspace_bytes < L.total || ((uintptr_t)workspace & 255)) return MVP_ERR_WORKSPACE;
-    return launch_accel(*shape, (flags & MVP_FLAG_SHARED_PRIMS) ? 0 : 1, order, raypos, raydir, primpos, primrot, primscale,
+    return launch_accel(*shape, (flags & MVP_FLAG_SHARED_PRIMS) ? 0 : 1, order, raypos, raydir, nullptr, primpos, primrot, primscale,
+                        (char *)workspace, L, (cudaStream_t)stream);
+}
+
+// mvp_camera of an argument struct: 0 = absent, 1 = present and well-formed, < 0 = error code
+static int check_camera(const mvp_camera &c) {
+    const int have = (c.viewpos != nullptr) + (c.viewrot != nullptr) + (c.focal != nullptr) + (c.princpt != nullptr);
+    if (have == 0) return 0;
+    if (have != 4) return MVP_ERR_NULL;                                       // all four or none
+    if (!(c.volradius > 0.f) || !(c.volradius < 3.0e38f)) return MVP_ERR_CAMERA;
+    if (((uintptr_t)c.viewpos | (uintptr_t)c.viewrot | (uintptr_t)c.focal | (uintptr_t)c.princpt) & 3) return MVP_ERR_ALIGN;
+    return 1;
+}
+
+int mvp_build_accel_camera(const mvp_shape *shape, uint32_t flags, const int32_t *order, const mvp_camera *camera, const float *primpos,
+                           const float *primrot, const float *primscale, void *workspace, size_t workspace_bytes, void *stream) {
+    if (!shape || !camera || !primpos || !primrot || !primscale || !workspace) return MVP_ERR_NULL;
+    int rc = check_shape(*shape);
+    if (rc != MVP_OK) return rc;
+    rc = check_camera(*camera);
+    if (rc <= 0) return rc == 0 ? MVP_ERR_NULL : rc;
+    const Layout L = make_layout(*shape);
+    if (workspace_bytes < L.total || ((uintptr_t)workspace & 255)) return MVP_ERR_WORKSPACE;
+    return launch_accel(*shape, (flags & MVP_FLAG_SHARED_PRIMS) ? 0 : 1, order, nullptr, nullptr, camera, primpos, primrot, primscale,
                         (char *)workspace, L, (cudaStream_t)stream);
 }
 
@@ -2463,7 +2600,10 @@ static inline bool misaligned(const void *p, uintptr_t a) { return p && ((uintpt
 int mvp_raymarch_forward(const mvp_forward_args *a, void *stream) {
     if (!a) return MVP_ERR_NULL;
     if (a->struct_size != sizeof(mvp_forward_args)) return MVP_ERR_STRUCT;
-    if (!a->raypos || !a->raydir || !a->tminmax || !a->primpos || !a->primrot || !a->primscale || !a->tplate || !a->workspace)
+    const int camrc = check_camera(a->camera);
+    if (camrc < 0) return camrc;
+    const mvp_camera *const camera = camrc ? &a->camera : nullptr;      // rays generated in the kernels: the ray tensors are not read
+    if ((!camera && (!a->raypos || !a->raydir || !a->tminmax)) || !a->primpos || !a->primrot || !a->primscale || !a->tplate || !a->workspace)
         return MVP_ERR_NULL;
     if ((a->rayrgb_nchw == nullptr) != (a->rayalpha_nchw == nullptr)) return MVP_ERR_NULL;
     if (!a->rayrgba && !a->rayrgb_nchw) return MVP_ERR_NULL;          // at least one form of the output
@@ -2487,12 +2627,13 @@ int mvp_raymarch_forward(const mvp_forward_args *a, void *stream) {
     char *ws = (char *)a->workspace;
     const int pview = (a->flags & MVP_FLAG_SHARED_PRIMS) ? 0 : 1;
     if (!(a->flags & MVP_FLAG_ACCEL_VALID)) {
-        rc = launch_accel(a->shape, pview, a->order, a->raypos, a->raydir, a->primpos, a->primrot, a->primscale, ws, L, st);
+        rc = launch_accel(a->shape, pview, a->order, a->raypos, a->raydir, camera, a->primpos, a->primrot, a->primscale, ws, L, st);
         if (rc != MVP_OK) return rc;
     }
     Params p{};
     fill_params(p, a->shape, a->stepsize, a->fadescale, a->fadeexp, ws, L);
     p.pview = pview;
+    p.raycam = camera ? reinterpret_cast<const float4 *>(ws + L.raycam) : nullptr;
     p.order = a->order; p.rankof = a->order ? reinterpret_cast<const int *>(ws + L.rankof) : nullptr;
     p.rgb_nchw = a->rayrgb_nchw; p.alpha_nchw = a->rayalpha_nchw;
 #if MVP_LIST_REUSE
@@ -2559,7 +2700,10 @@ int mvp_raymarch_forward(const mvp_forward_args *a, void *stream) {
 int mvp_raymarch_backward(const mvp_backward_args *a, void *stream) {
     if (!a) return MVP_ERR_NULL;
     if (a->struct_size != sizeof(mvp_backward_args)) return MVP_ERR_STRUCT;
-    if (!a->raypos || !a->raydir || !a->tminmax || !a->primpos || !a->primrot || !a->primscale || !a->tplate ||
+    const int camrc = check_camera(a->camera);
+    if (camrc < 0) return camrc;
+    const mvp_camera *const camera = camrc ? &a->camera : nullptr;
+    if ((!camera && (!a->raypos || !a->raydir || !a->tminmax)) || !a->primpos || !a->primrot || !a->primscale || !a->tplate ||
         !a->raysat || !a->rayaux || !a->grad_primpos || !a->grad_primrot || !a->grad_primscale ||
         !a->grad_tplate || !a->workspace)
         return MVP_ERR_NULL;
@@ -2583,7 +2727,7 @@ int mvp_raymarch_backward(const mvp_backward_args *a, void *stream) {
     char *ws = (char *)a->workspace;
     const int pview = (a->flags & MVP_FLAG_SHARED_PRIMS) ? 0 : 1;
     if (!(a->flags & MVP_FLAG_ACCEL_VALID)) {
-        rc = launch_accel(a->shape, pview, a->order, a->raypos, a->raydir, a->primpos, a->primrot, a->primscale, ws, L, st);
+        rc = launch_accel(a->shape, pview, a->order, a->raypos, a->raydir, camera, a->primpos, a->primrot, a->primscale, ws, L, st);
         if (rc != MVP_OK) return rc;
     }
     if (a->flags & MVP_FLAG_ZERO_GRADS) {
@@ -2598,6 +2742,7 @@ int mvp_raymarch_backward(const mvp_backward_args *a, void *stream) {
     Params p{};
     fill_params(p, a->shape, a->stepsize, a->fadescale, a->fadeexp, ws, L);
     p.pview = pview;
+    p.raycam = camera ? reinterpret_cast<const float4 *>(ws + L.raycam) : nullptr;
     p.raypos = a->raypos; p.raydir = a->raydir; p.tminmax = a->tminmax; p.tplate = a->tplate;
     p.use_order = a->shape.N <= MVP_CTA_ORDER_MAXVIEWS;
     p.order = a->order; p.rankof = a->order ? reinterpret_cast<const int *>(ws + L.rankof) : nullptr;

@@ -3,8 +3,10 @@
 // (compute_raydirs_forward_kernel); the reference's backward kernel is an empty stub and its Python backward returns
 // None for every input (extensions/utils/utils.py:45-46), so there is nothing else to build.
 //
-// Compiled WITHOUT -use_fast_math, like the reference's utils extension (extensions/utils/setup.py has no such flag):
-// IEEE division, rnorm3df for the normalisation.  Pure streaming kernel: 32 B written per ray, no reads to speak of
+// Compiled WITHOUT -use_fast_math, like the reference's utils extension (extensions/utils/setup.py has no such flag).
+// The per-ray arithmetic is raygen.h's mvp_gen_ray -- explicitly rounded operations only, because the render kernels' prologue
+// (mvp_kernels.cu, compiled WITH -use_fast_math) generates the same rays from the same function and must get the same bits.
+// Pure streaming kernel: 32 B written per ray, no reads to speak of
 // -> HBM-write bound; one thread per ray, x fastest for coalesced 12/12/8-byte stores.
 #ifdef MVP_CPU_EMUL   // test-only host build on the CPU emulation (tests/emul/), see mvp_kernels.cu
 #include "cuda_emul.h"
@@ -14,6 +16,7 @@
 #include <stdint.h>
 
 #include "mvpraymarch_b200.h"
+#include "raygen.h"
 
 namespace {
 
@@ -26,27 +29,20 @@ __global__ void __launch_bounds__(256) compute_raydirs_kernel(int N, int H, int 
     const int h = blockIdx.y;
     const int n = blockIdx.z;
     if (w >= W) return;
+    MvpRayCam c;
     // raypos = viewpos / volradius                                           utils_kernel.cu:32
-    const float rx = viewpos[n * 3 + 0] / volradius, ry = viewpos[n * 3 + 1] / volradius, rz = viewpos[n * 3 + 2] / volradius;
-    const float *R = viewrot + n * 9;
+    c.ox = __fdiv_rn(viewpos[n * 3 + 0], volradius); c.oy = __fdiv_rn(viewpos[n * 3 + 1], volradius); c.oz = __fdiv_rn(viewpos[n * 3 + 2], volradius);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) c.R[i] = viewrot[n * 9 + i];
+    c.pcx = princpt[n * 2 + 0]; c.pcy = princpt[n * 2 + 1]; c.fx = focal[n * 2 + 0]; c.fy = focal[n * 2 + 1];
     const size_t r = ((size_t)n * H + h) * W + w;
-    float2 pc = pixelcoords ? __ldg(pixelcoords + r) : make_float2((float)w, (float)h);
-    pc.x = (pc.x - princpt[n * 2 + 0]) / focal[n * 2 + 0];                    // :36-37
-    pc.y = (pc.y - princpt[n * 2 + 1]) / focal[n * 2 + 1];
-    // raydir = viewrot0 * x + viewrot1 * y + viewrot2 * 1                     :38-39
-    float dx = R[0] * pc.x + R[3] * pc.y + R[6] * 1.f;
-    float dy = R[1] * pc.x + R[4] * pc.y + R[7] * 1.f;
-    float dz = R[2] * pc.x + R[5] * pc.y + R[8] * 1.f;
-    const float inv = rnorm3df(dx, dy, dz);                                    // :40 normalize = v * rnorm(v)
-    dx *= inv; dy *= inv; dz *= inv;
-    // unit-cube slab test                                                     :42-46
-    const float t1x = (-1.f - rx) / dx, t1y = (-1.f - ry) / dy, t1z = (-1.f - rz) / dz;
-    const float t2x = (1.f - rx) / dx, t2y = (1.f - ry) / dy, t2z = (1.f - rz) / dz;
-    const float tmin = fmaxf(fminf(t1x, t2x), fmaxf(fminf(t1y, t2y), fminf(t1z, t2z)));
-    const float tmax = fminf(fmaxf(t1x, t2x), fminf(fmaxf(t1y, t2y), fmaxf(t1z, t2z)));
+    const float2 pc = pixelcoords ? __ldg(pixelcoords + r) : make_float2((float)w, (float)h);
+    float dx, dy, dz, tmin, tmax;
+    mvp_gen_ray(c, pc.x, pc.y, dx, dy, dz, tmin, tmax);                       // :36-46, shared with the render kernels' prologue
+    const float rx = c.ox, ry = c.oy, rz = c.oz;
     raypos[r * 3 + 0] = rx; raypos[r * 3 + 1] = ry; raypos[r * 3 + 2] = rz;
     raydir[r * 3 + 0] = dx; raydir[r * 3 + 1] = dy; raydir[r * 3 + 2] = dz;
-    tminmax[r] = make_float2(fmaxf(tmin, 0.f), tmax);
+    tminmax[r] = make_float2(tmin, tmax);
 }
 
 // ---- Morton codes of (normalised) slab centres: compute_morton of the reference (mvpraymarch.cpp:106-121; bvh.cu:20-57) ----

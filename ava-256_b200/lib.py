@@ -12,6 +12,12 @@ class Shape(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ("N", "H", "W", "K", "TD", "TH", "TW")]
 
 
+class Camera(ctypes.Structure):
+    """struct mvp_camera: the arguments of the reference's compute_raydirs on the integer pixel grid; viewpos == NULL = absent."""
+    _fields_ = [("viewpos", c_f), ("viewrot", c_f), ("focal", c_f), ("princpt", c_f), ("volradius", ctypes.c_float),
+                ("reserved", ctypes.c_uint32)]
+
+
 class ForwardArgs(ctypes.Structure):
     """struct mvp_forward_args; the constructor fills struct_size."""
     _fields_ = [
@@ -28,6 +34,7 @@ class ForwardArgs(ctypes.Structure):
         ("rayrgb_nchw", c_f), ("rayalpha_nchw", c_f), ("order", c_f),
         ("clear_grad_primpos", c_f), ("clear_grad_primrot", c_f), ("clear_grad_primscale", c_f), ("clear_grad_tplate", c_f),
         ("clear_grad_warp", c_f),
+        ("camera", Camera),
     ]
 
 
@@ -47,6 +54,7 @@ class BackwardArgs(ctypes.Structure):
         ("warp", c_f), ("grad_warp", c_f), ("WD", ctypes.c_int32), ("WH", ctypes.c_int32), ("WW", ctypes.c_int32),
         ("algo", ctypes.c_int32),
         ("grad_rayrgb_nchw", c_f), ("grad_rayalpha_nchw", c_f), ("order", c_f),
+        ("camera", Camera),
     ]
 
 
@@ -64,11 +72,12 @@ FLAG_ACCEL_VALID = 1
 FLAG_ZERO_GRADS = 2
 FLAG_SHARED_PRIMS = 4
 FLAG_TEST_TINY_LISTS = 0x100
-ABI_VERSION = 7
+ABI_VERSION = 8
 # layout pins, equal to the static_asserts in csrc/mvp_kernels.cu (tests/test_abi.py compares)
-SIZEOF = {"Shape": 28, "ForwardArgs": 232, "BackwardArgs": 232}
+SIZEOF = {"Shape": 28, "Camera": 40, "ForwardArgs": 272, "BackwardArgs": 272}
 
-EXPORTS = ("mvp_abi_version", "mvp_build_config", "mvp_error_string", "mvp_workspace_bytes", "mvp_build_accel", "mvp_raymarch_forward",
+EXPORTS = ("mvp_abi_version", "mvp_build_config", "mvp_error_string", "mvp_workspace_bytes", "mvp_build_accel", "mvp_build_accel_camera",
+           "mvp_raymarch_forward",
            "mvp_raymarch_backward", "mvp_compute_raydirs", "mvp_forward_launch_count", "mvp_backward_launch_count",
            "mvp_composite_forward", "mvp_composite_backward", "mvp_assemble_payload_forward",
            "mvp_assemble_payload_backward", "mvp_debug_saved_tiles", "mvp_debug_tileclk_offset", "mvp_compute_morton",
@@ -99,6 +108,8 @@ def _load():
     lib.mvp_workspace_bytes.argtypes = [ctypes.POINTER(Shape)]
     lib.mvp_build_accel.restype = ctypes.c_int
     lib.mvp_build_accel.argtypes = [ctypes.POINTER(Shape), ctypes.c_uint32] + [c_f] * 7 + [ctypes.c_size_t, c_f]
+    lib.mvp_build_accel_camera.restype = ctypes.c_int
+    lib.mvp_build_accel_camera.argtypes = [ctypes.POINTER(Shape), ctypes.c_uint32, c_f, ctypes.POINTER(Camera)] + [c_f] * 4 + [ctypes.c_size_t, c_f]
     lib.mvp_compute_morton.restype = ctypes.c_int
     lib.mvp_compute_morton.argtypes = [ctypes.c_int32, ctypes.c_int32, c_f, c_f, c_f]
     lib.mvp_raymarch_forward.restype = ctypes.c_int
@@ -123,7 +134,7 @@ def _load():
     lib.mvp_backward_launch_count.argtypes = [ctypes.c_uint32]
     if lib.mvp_abi_version() != ABI_VERSION:
         raise RuntimeError("mvpraymarch_b200: ABI version mismatch (library %d, binding %d)" % (lib.mvp_abi_version(), ABI_VERSION))
-    for cls in (Shape, ForwardArgs, BackwardArgs):
+    for cls in (Shape, Camera, ForwardArgs, BackwardArgs):
         assert ctypes.sizeof(cls) == SIZEOF[cls.__name__], cls.__name__
     return lib
 

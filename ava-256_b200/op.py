@@ -54,10 +54,18 @@ class MVPRaymarch(Function):
         if options["usebvh"] is False:
             raise NotImplementedError("mvpraymarch_b200: usebvh=False passes a null BVH to the reference kernels "
                                       "(mvpraymarch.py:132-134) and is not a usable mode there either")
-        # same shape contract as mvpraymarch.py:112-127
-        assert raypos.is_contiguous() and raypos.size(3) == 3
-        assert raydir.is_contiguous() and raydir.size(3) == 3
-        assert tminmax.is_contiguous() and tminmax.size(3) == 2
+        camera = options.get("_camera")        # (viewpos, viewrot, focal, princpt, volradius, H, W): rays generated in the kernels
+        if camera is not None:
+            assert raypos is None and raydir is None and tminmax is None
+            viewpos, viewrot, focal, princpt, volradius, camH, camW = camera
+            for name, t, tail in (("viewpos", viewpos, (3,)), ("viewrot", viewrot, (3, 3)), ("focal", focal, (2,)), ("princpt", princpt, (2,))):
+                _check_f32_cuda(name, t)                                  # utils.py:24-25 / utils.cpp CHECK_CUDA
+                assert t.shape == (viewpos.size(0),) + tail, "%s must be [N,%s]" % (name, ",".join(map(str, tail)))
+        else:
+            # same shape contract as mvpraymarch.py:112-127
+            assert raypos.is_contiguous() and raypos.size(3) == 3
+            assert raydir.is_contiguous() and raydir.size(3) == 3
+            assert tminmax.is_contiguous() and tminmax.size(3) == 2
         assert primpos.is_contiguous() and primpos.size(2) == 3
         assert primrot.is_contiguous() and primrot.size(2) == 3
         assert primscale.is_contiguous() and primscale.size(2) == 3
@@ -65,22 +73,27 @@ class MVPRaymarch(Function):
             "channels-last template [N,K,TD,TH,TW,4] required (the reference sampler is always channels-last, primsampler.h:16)"
         for name, t in (("raypos", raypos), ("raydir", raydir), ("tminmax", tminmax), ("primpos", primpos),
                         ("primrot", primrot), ("primscale", primscale), ("template", template)):
-            _check_f32_cuda(name, t)
+            if t is not None:
+                _check_f32_cuda(name, t)
         if warp is not None:                                           # mvpraymarch.py:124
             assert warp.is_contiguous() and warp.dim() == 6 and warp.size(-1) == 3, \
                 "channels-last warp field [N,K,WD,WH,WW,3] required"
             _check_f32_cuda("warp", warp)
         usewarp = algo == 1                                            # algo 0 ignores a warp field, like the reference
 
-        N, H, W = raypos.shape[:3]
+        if camera is not None:
+            N, H, W = viewpos.size(0), int(camH), int(camW)
+        else:
+            N, H, W = raypos.shape[:3]
         K = primpos.size(1)
         TD, TH, TW = template.shape[2:5]
-        dev = raypos.device
+        dev = primpos.device
         # The reference never checks that the leading dimensions agree (a mismatch reads out of bounds there).  Here:
         # rays and tminmax must agree; the primitive tensors must agree with each other and have a batch of N, or of 1
         # = one set of primitives shared by all N views (extension, SURVEY.md section 8e "optional fast path":
         # nothing is replicated in HBM and the gradients of all views accumulate into the one set).
-        assert raydir.shape[:3] == (N, H, W) and tminmax.shape[:3] == (N, H, W), "raypos / raydir / tminmax disagree on [N,H,W]"
+        if camera is None:
+            assert raydir.shape[:3] == (N, H, W) and tminmax.shape[:3] == (N, H, W), "raypos / raydir / tminmax disagree on [N,H,W]"
         NP = primpos.size(0)
         assert NP in (N, 1), "primitive batch (%d) must equal the number of views (%d) or be 1 (shared)" % (NP, N)
         assert primrot.shape[:2] == (NP, K) and primscale.shape[:2] == (NP, K) and template.shape[:2] == (NP, K), \
@@ -109,6 +122,8 @@ class MVPRaymarch(Function):
             a.stepsize, a.fadescale, a.fadeexp = float(stepsize), float(options["fadescale"]), float(options["fadeexp"])
             a.flags = _lib.FLAG_SHARED_PRIMS if shared else 0
             a.raypos, a.raydir, a.tminmax = _ptr(raypos), _ptr(raydir), _ptr(tminmax)
+            if camera is not None:
+                a.camera = _lib.Camera(_ptr(viewpos), _ptr(viewrot), _ptr(focal), _ptr(princpt), float(volradius), 0)
             a.primpos, a.primrot, a.primscale = _ptr(primpos), _ptr(primrot), _ptr(primscale)
             a.tplate = _ptr(template)
             a.rayrgba, a.raysat, a.rayaux = _ptr(rayrgba), _ptr(raysat), _ptr(rayaux)
@@ -137,6 +152,8 @@ class MVPRaymarch(Function):
         if gradmode:
             ctx.grads = grads
             ctx.save_for_backward(raypos, raydir, tminmax, primpos, primrot, primscale, template, raysat, rayaux, workspace, warp)
+            ctx.camera = camera                # camera tensors are plain inputs without gradients (utils.py:45-46 returns None for all)
+            ctx.nhw = (N, H, W)
             ctx.order = order
             ctx.options = options
             ctx.stepsize = float(stepsize)
@@ -150,10 +167,10 @@ class MVPRaymarch(Function):
         """grad_rayrgba [N,H,W,4]; or, for MVPRaymarchPlanes, (grad_rayrgb [N,3,H,W], grad_rayalpha [N,1,H,W])."""
         raypos, raydir, tminmax, primpos, primrot, primscale, template, raysat, rayaux, workspace, warp = ctx.saved_tensors
         options = ctx.options
-        N, H, W = raypos.shape[:3]
+        N, H, W = ctx.nhw
         K = primpos.size(1)
         TD, TH, TW = template.shape[2:5]
-        dev = raypos.device
+        dev = primpos.device
         with torch.cuda.device(dev):
             planes = bool(options.get("_planes", False))
             if planes:
@@ -176,6 +193,9 @@ class MVPRaymarch(Function):
             a.stepsize, a.fadescale, a.fadeexp = ctx.stepsize, float(options["fadescale"]), float(options["fadeexp"])
             a.flags = _lib.FLAG_ACCEL_VALID | (0 if fresh else _lib.FLAG_ZERO_GRADS) | (_lib.FLAG_SHARED_PRIMS if ctx.shared else 0)
             a.raypos, a.raydir, a.tminmax = _ptr(raypos), _ptr(raydir), _ptr(tminmax)
+            if ctx.camera is not None:
+                viewpos, viewrot, focal, princpt, volradius = ctx.camera[:5]
+                a.camera = _lib.Camera(_ptr(viewpos), _ptr(viewrot), _ptr(focal), _ptr(princpt), float(volradius), 0)
             a.primpos, a.primrot, a.primscale = _ptr(primpos), _ptr(primrot), _ptr(primscale)
             a.tplate = _ptr(template)
             a.grad_rayrgba, a.raysat, a.rayaux = _ptr(grad_rayrgba), _ptr(raysat), _ptr(rayaux)
@@ -314,12 +334,15 @@ def mvpraymarch(
         "fadeexp": fadeexp, "accum": accum, "termthresh": termthresh, "griddim": griddim, "blocksize": blocksize,
         "bwdblocksize": bwdblocksize, "_order": order,
     }
+    if _CAMERA.get("cam") is not None:
+        options["_camera"] = _CAMERA["cam"]
     fn = MVPRaymarchPlanes if _PLANES.get("on") else MVPRaymarch
     return fn.apply(raypos, raydir, stepsize, tminmax, primpos, primrot, primscale, template, warp, rayterm,
                     torch.is_grad_enabled(), options)
 
 
 _PLANES = {}
+_CAMERA = {}
 
 
 def mvpraymarch_planes(*args, **kwargs):
@@ -330,3 +353,28 @@ def mvpraymarch_planes(*args, **kwargs):
         return mvpraymarch(*args, **kwargs)
     finally:
         _PLANES["on"] = False
+
+
+def mvpraymarch_camera(viewpos, viewrot, focal, princpt, pixelcoords, volradius, stepsize, primtransf, template, warp, planes=False,
+                       **kwargs):
+    """`compute_raydirs` + `mvpraymarch` of models/autoencoder.py:240-252 as ONE call: the first six parameters are those of the
+    reference's compute_raydirs (extensions/utils/utils.py:48-51), the rest those of `mvpraymarch` after its ray arguments.
+
+    With `pixelcoords` given as the `(W, H)` tuple (the integer pixel grid, utils.py:28-30) the rays never exist in memory: the
+    render kernels generate each tile's rays in their prologue from the camera (C-ABI `mvp_camera`), bit-identical to what
+    `compute_raydirs` would have written -- 32 bytes per ray that are neither written by a generation pass nor read by forward
+    and backward -- and the accel build takes the camera as it is instead of fitting one to the ray field.  With a `pixelcoords`
+    tensor (arbitrary sample positions) the two calls are made one after the other, as in the reference.
+    No gradients flow to the camera (the reference's compute_raydirs backward returns None for every input, utils.py:45-46).
+    Returns rayrgba [N,H,W,4], or (rayrgb [N,3,H,W], rayalpha [N,1,H,W]) with planes=True."""
+    march = mvpraymarch_planes if planes else mvpraymarch
+    if not isinstance(pixelcoords, tuple):
+        from .raydirs import compute_raydirs
+        raypos, raydir, tminmax = compute_raydirs(viewpos, viewrot, focal, princpt, pixelcoords, volradius)
+        return march(raypos, raydir, stepsize, tminmax, primtransf, template, warp, **kwargs)
+    W, H = pixelcoords
+    _CAMERA["cam"] = (viewpos, viewrot, focal, princpt, float(volradius), int(H), int(W))
+    try:
+        return march(None, None, stepsize, None, primtransf, template, warp, **kwargs)
+    finally:
+        _CAMERA["cam"] = None

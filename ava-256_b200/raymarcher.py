@@ -5,7 +5,7 @@ with a permute + two `.contiguous()` copies (:50-51)."""
 import torch.nn as nn
 
 from .composite import split_rgba
-from .op import mvpraymarch, mvpraymarch_planes
+from .op import mvpraymarch, mvpraymarch_camera, mvpraymarch_planes
 
 
 class Raymarcher(nn.Module):
@@ -28,3 +28,16 @@ class Raymarcher(nn.Module):
             return rayrgb, rayalpha, rayrgba.permute(0, 3, 1, 2), None
         rayrgb, rayalpha = mvpraymarch_planes(*args, **kwargs)
         return rayrgb, rayalpha, None, None
+
+    def forward_camera(self, viewpos, viewrot, focal, princpt, pixelcoords, decout, renderoptions={}, rayterm=None):
+        """`compute_raydirs(viewpos, viewrot, focal, princpt, pixelcoords, volradius)` followed by `forward(raypos, raydir, tminmax,
+        ...)` -- models/autoencoder.py:240-252 -- as one call.  With `pixelcoords = (W, H)` the rays are generated inside the render
+        kernels and never stored (`op.mvpraymarch_camera`); same return tuple as `forward`."""
+        kwargs = dict(rayterm=rayterm, **{k: v for k, v in renderoptions.items() if k in mvpraymarch.__code__.co_varnames})
+        out = mvpraymarch_camera(viewpos, viewrot, focal, princpt, pixelcoords, self.volume_radius, self.dt,
+                                 (decout["primpos"], decout["primrot"], decout["primscale"]), decout["template"],
+                                 decout["warp"] if "warp" in decout else None, planes=not self.with_rgba, **kwargs)
+        if self.with_rgba:
+            rayrgb, rayalpha = split_rgba(out)
+            return rayrgb, rayalpha, out.permute(0, 3, 1, 2), None
+        return out[0], out[1], None, None

@@ -257,7 +257,7 @@ def ref_cuda_leg(s, stepsize, grad_out, out, grads, chunk=16, reps=7, warm=2):
 # ----------------------------------------------------------------------------------------------------------------
 def run_ours(args, rank, world):
     from ava256_b200 import lib, parallel, scene
-    from ava256_b200.op import mvpraymarch
+    from ava256_b200.op import mvpraymarch, mvpraymarch_camera
     import ctypes
 
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -384,6 +384,16 @@ def run_ours(args, rank, world):
     reps = max(2, min(args.steps, 5))
     fwd_ms = time_kernel(lambda: lib.check(lib.LIB.mvp_raymarch_forward(ctypes.byref(fa), stream)), reps)
     bwd_ms = time_kernel(lambda: lib.check(lib.LIB.mvp_raymarch_backward(ctypes.byref(ba), stream)), reps)
+    # the same two launches with the rays generated in the kernels' prologue from the camera parameters (mvp_camera) instead of read
+    cams_dev = [c_.to(dev) for c_ in scene.make_cameras(nv, h, w, view_ids=vids)]
+    cam_struct = lib.Camera(P(cams_dev[0]), P(cams_dev[1]), P(cams_dev[2]), P(cams_dev[3]), scene.VOLRADIUS, 0)
+    fa.camera, ba.camera = cam_struct, cam_struct
+    fa.raypos = fa.raydir = fa.tminmax = ba.raypos = ba.raydir = ba.tminmax = None
+    fa.flags = 0
+    lib.check(lib.LIB.mvp_raymarch_forward(ctypes.byref(fa), stream))          # accel from the camera
+    fa.flags = lib.FLAG_ACCEL_VALID
+    fwd_cam_ms = time_kernel(lambda: lib.check(lib.LIB.mvp_raymarch_forward(ctypes.byref(fa), stream)), reps)
+    bwd_cam_ms = time_kernel(lambda: lib.check(lib.LIB.mvp_raymarch_backward(ctypes.byref(ba), stream)), reps)
     del gs, ws
     log("kernel-only: fwd %.2f ms, bwd %.2f ms per launch (%d views)" % (fwd_ms, bwd_ms, nv))
 
@@ -424,6 +434,50 @@ def run_ours(args, rank, world):
         del sh, o_sh
         log("shared-primitive configuration: %.2f ms per step" % shared_cfg["ms_per_step"])
 
+    # ---- third configuration (not the headline either): rays generated inside the render kernels from the camera parameters
+    # (op.mvpraymarch_camera): raypos / raydir / tminmax never exist, no camera fit over a ray field ----
+    camera_cfg = None
+    if not args.no_shared_leg:
+        def camera_step():
+            for x in leaves:
+                x.grad = None
+            o_ = mvpraymarch_camera(cams_dev[0], cams_dev[1], cams_dev[2], cams_dev[3], (w, h), scene.VOLRADIUS, stepsize,
+                                    (leaves[0], leaves[1], leaves[2]), leaves[3], None)
+            o_.backward(grad_out)
+            red.reduce(leaves[3].grad, leaves[0].grad, leaves[1].grad, leaves[2].grad)
+            return o_
+
+        o_cam = camera_step()
+        red.finish()
+        torch.cuda.synchronize()
+        # the bench scene's ray tensors come from the torch formula on the host (scene.compute_raydirs_host), the kernels' rays from
+        # the reference kernel's arithmetic: last-place differences in the rays, so the images agree closely but not bit for bit
+        # (bit identity holds against rays from mvp_compute_raydirs: tests/test_gpu_camera_rays.py)
+        cam_img_diff = float((o_cam.detach() - out.detach()).abs().max()) / max(float(out.detach().abs().max()), 1e-30)
+        barrier()
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ncm = max(2, min(args.steps, 10))
+        ea.record()
+        for _ in range(ncm):
+            camera_step()
+        red.finish()
+        eb.record()
+        barrier()
+        tcm = torch.tensor([ea.elapsed_time(eb) / ncm], device=dev)
+        if world > 1:
+            dist.all_reduce(tcm, op=dist.ReduceOp.MAX)
+        camera_cfg = {"what": "same views and per-view primitives as the headline, the rays generated in the render kernels' prologue from "
+                              "(viewpos, viewrot, focal, princpt) (mvp_camera; reference: compute_raydirs, utils_kernel.cu:32-46) instead of "
+                              "read from raypos / raydir / tminmax; NOT the headline configuration",
+                      "ms_per_step": float(tcm.item()), "value": views * h * w / (float(tcm.item()) * 1e-3) / 1e6, "unit": "MP/s",
+                      "image_max_rel_diff_vs_host_formula_rays": cam_img_diff,
+                      "kernel_ms": {"forward_all_views_per_rank": fwd_cam_ms, "backward_all_views_per_rank": bwd_cam_ms}}
+        del o_cam
+        out = step()                 # the leaves' gradients are those of the headline configuration again (the parity leg reads them)
+        red.finish()
+        torch.cuda.synchronize()
+        log("camera-ray configuration: %.2f ms per step (kernels %.2f + %.2f)" % (camera_cfg["ms_per_step"], fwd_cam_ms, bwd_cam_ms))
+
     # ---- checker legs (rank 0, single GPU): reference CUDA kernels on the same tensors: timing + parity of view 0 ----
     ref_cuda = parity = None
     if world == 1 and not args.no_check:
@@ -461,14 +515,13 @@ def run_ours(args, rank, world):
         s_in, s_out, s_cmp = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.current_stream()
         cmp_done, flat_out_done = [None, None], [None, None]
 
-        from extensions.utils.utils import compute_raydirs
         from ava256_b200.payload import expand_views
         host_cam = [t.pin_memory() for t in scene.make_cameras(nv, h, w, view_ids=vids)]
         dev_cam = [[torch.empty(t.shape, device=dev) for t in host_cam] for _ in range(2)]
 
         def e2e_step(i, cams=False):
-            """cams=False: the host hands over the rays themselves.  cams=True: it hands over the camera parameters and the rays are
-            generated on the device by this repository's compute_raydirs, as models/autoencoder.py:240 does."""
+            """cams=False: the host hands over the rays themselves.  cams=True: it hands over the camera parameters (what
+            models/autoencoder.py:240 gives compute_raydirs) and the render kernels generate the rays (op.mvpraymarch_camera)."""
             b_ = i & 1
             ev_in = []
             with torch.cuda.stream(s_in):
@@ -497,11 +550,11 @@ def run_ours(args, rank, world):
                 nvc = a1 - a0
                 lv = [expand_views(pr[n], nvc).requires_grad_(True) for n in names]     # the subject's primitives, per view
                 if cams:
-                    cp_, cr_, cf_, cpp_ = (t[a0:a1] for t in dev_cam[b_])
-                    rp_, rd_, tm_ = compute_raydirs(cp_, cr_, cf_, cpp_, (w, h), scene.VOLRADIUS)
+                    cp_, cr_, cf_, cpp_ = (t[a0:a1].contiguous() for t in dev_cam[b_])
+                    o_ = mvpraymarch_camera(cp_, cr_, cf_, cpp_, (w, h), scene.VOLRADIUS, stepsize, (lv[0], lv[1], lv[2]), lv[3], None)
                 else:
                     rp_, rd_, tm_ = di["raypos"][a0:a1], di["raydir"][a0:a1], di["tminmax"][a0:a1]
-                o_ = mvpraymarch(rp_, rd_, stepsize, tm_, (lv[0], lv[1], lv[2]), lv[3], None)
+                    o_ = mvpraymarch(rp_, rd_, stepsize, tm_, (lv[0], lv[1], lv[2]), lv[3], None)
                 o_.backward(dev_grad[b_][a0:a1])
                 off = 0
                 for x in (lv[3], lv[0], lv[1], lv[2]):
@@ -567,8 +620,8 @@ def run_ours(args, rank, world):
         e2e_cam = {"value": views * h * w / (float(tc_.item()) * 1e-3) / 1e6, "unit": "MP/s", "ms_per_step": float(tc_.item()),
                    "h2d_bytes_per_step": int(h2d_cam * world), "d2h_bytes_per_step": int(d2h * world),
                    "what": "as e2e, but the host hands over camera parameters (viewpos, viewrot, focal, princpt) instead of rays; "
-                           "the rays are generated on the device by this repository's compute_raydirs (the reference pipeline, "
-                           "models/autoencoder.py:240)"}
+                           "the render kernels generate the rays in their prologue (op.mvpraymarch_camera: compute_raydirs of "
+                           "models/autoencoder.py:240 fused into the raymarcher, no ray tensors in HBM)"}
         e2e = {"value": views * h * w / (float(te.item()) * 1e-3) / 1e6, "unit": "MP/s",
                "h2d_bytes_per_step": int(h2d * world), "d2h_bytes_per_step": int(d2h * world),
                "ms_per_step": float(te.item()), "steps": nrep,
@@ -619,7 +672,7 @@ def run_ours(args, rank, world):
         "scene": {"alpha_mu": ALPHA_MU, "alpha_sigma": ALPHA_SIGMA, "saturated_ray_frac": sat_frac, "covered_ray_frac": cover},
         "roofline": dominant, "roofline_forward": roof_f, "roofline_backward": roof_b,
         "cpu_baseline": cpu, "ref_cuda_baseline": ref_cuda, "parity_check": parity, "e2e": e2e, "clocks": clocks,
-        "shared_primitives_config": shared_cfg, "e2e_camera_inputs": e2e_cam,
+        "shared_primitives_config": shared_cfg, "camera_rays_config": camera_cfg, "e2e_camera_inputs": e2e_cam,
         "gpu_launches": args.steps * (lib.LIB.mvp_forward_launch_count(0) + lib.LIB.mvp_backward_launch_count(lib.FLAG_ACCEL_VALID)),
         "kernel_ms": {"forward_all_views_per_rank": fwd_ms, "backward_all_views_per_rank": bwd_ms,
                       "note": "the forward launch also zero-fills the backward's gradient buffers (clear_grad_*, %.1f GB per rank) "

@@ -14,6 +14,9 @@
  *   mvp_workspace_bytes    <- the tensors build_accel allocates, extensions/mvpraymarch/mvpraymarch.py:21-84
  *   mvp_compute_raydirs    <- compute_raydirs_forward  extensions/utils/utils.cpp:46-82 (pybind module `utilslib`;
  *                             the step right before the raymarcher)
+ *   mvp_camera (struct)    <- the same call fused away: given the camera parameters compute_raydirs takes
+ *                             (models/autoencoder.py:240), the render kernels generate each tile's rays in their prologue
+ *                             (extensions/utils/utils_kernel.cu:32-46) and raypos / raydir / tminmax never exist in HBM
  *
  * and two entry points that replace eager PyTorch chains of the callers either side of the path (no native reference
  * counterpart):
@@ -46,7 +49,7 @@
 extern "C" {
 #endif
 
-#define MVP_ABI_VERSION 7
+#define MVP_ABI_VERSION 8
 
 #define MVP_OK 0
 #define MVP_ERR_NULL (-1)      /* a required pointer is NULL */
@@ -57,6 +60,7 @@ extern "C" {
 #define MVP_ERR_ALIGN (-6)     /* a vector-accessed buffer is misaligned: tplate, rayrgba, grad_rayrgba, grad_tplate, rayaux
                                 * need 16 bytes, tminmax 8, everything else 4 */
 #define MVP_ERR_STRUCT (-7)    /* args->struct_size != sizeof(the struct this library was built with) */
+#define MVP_ERR_CAMERA (-8)    /* camera.volradius must be finite and > 0 */
 
 typedef struct mvp_shape {
     int32_t N, H, W, K, TD, TH, TW;
@@ -73,12 +77,28 @@ typedef struct mvp_shape {
 #define MVP_FLAG_TEST_TINY_LISTS 0x100u /* test hook: forward keeps at most 16 saved tile-list entries per view, so almost
                                  * every tile takes the backward's rebuild path */
 
+/* The pinhole cameras of the N views, exactly the arguments of the reference's compute_raydirs (extensions/utils/utils.py:21-51,
+ * kernel utils_kernel.cu:12-52) on the integer pixel grid (its `pixelcoords` = (W, H) tuple form): ray (n, h, w) starts at
+ * viewpos[n] / volradius and points along normalize(viewrot[n]^T ((w - princpt.x) / focal.x, (h - princpt.y) / focal.y, 1)).
+ * A call that gets a camera (viewpos != NULL) generates the rays inside the kernels -- bit-identical to what
+ * mvp_compute_raydirs writes -- and ignores raypos / raydir / tminmax, which may then be NULL: 32 bytes per ray that are neither
+ * written by a ray-generation pass nor read by forward and backward, and no camera fit over the ray field in the accel build.
+ * All four pointers or none; volradius finite and > 0.  Must be the same in every call that shares a workspace. */
+typedef struct mvp_camera {
+    const float *viewpos;    /* [N,3]   camera centres (same unit as volradius) */
+    const float *viewrot;    /* [N,3,3] row-major; rows = camera x, y, z axes in world coordinates */
+    const float *focal;      /* [N,2]   focal lengths in pixels (x, y) */
+    const float *princpt;    /* [N,2]   principal point in pixels (x, y) */
+    float volradius;         /* world units of the unit cube's half edge (models/autoencoder.py: self.volradius) */
+    uint32_t reserved;       /* 0 */
+} mvp_camera;
+
 typedef struct mvp_forward_args {
     uint32_t struct_size;    /* = sizeof(mvp_forward_args); a truncated or stale caller-side struct is rejected */
     mvp_shape shape;
     float stepsize, fadescale, fadeexp;
     uint32_t flags;
-    const float *raypos, *raydir, *tminmax;
+    const float *raypos, *raydir, *tminmax;   /* may be NULL when `camera` is given */
     const float *primpos, *primrot, *primscale;
     const float *tplate;
     float *rayrgba;          /* out; may be NULL when rayrgb_nchw / rayalpha_nchw are given */
@@ -108,6 +128,7 @@ typedef struct mvp_forward_args {
      * zeros_like of mvpraymarch.py:265-268) costs 1.4 ms per 80 views.  16-byte aligned; ignored when raysat is NULL;
      * clear_grad_warp is used for algo 1 only. */
     float *clear_grad_primpos, *clear_grad_primrot, *clear_grad_primscale, *clear_grad_tplate, *clear_grad_warp;
+    mvp_camera camera;       /* optional (camera.viewpos != NULL): rays generated in the kernels, see mvp_camera */
 } mvp_forward_args;
 
 typedef struct mvp_backward_args {
@@ -137,6 +158,7 @@ typedef struct mvp_backward_args {
     const float *grad_rayrgb_nchw;
     const float *grad_rayalpha_nchw;
     const int32_t *order;      /* as in the forward call */
+    mvp_camera camera;         /* as in the forward call */
 } mvp_backward_args;
 
 int mvp_abi_version(void);
@@ -151,6 +173,10 @@ size_t mvp_workspace_bytes(const mvp_shape *shape);
 int mvp_build_accel(const mvp_shape *shape, uint32_t flags, const int32_t *order, const float *raypos, const float *raydir,
                     const float *primpos, const float *primrot, const float *primscale,
                     void *workspace, size_t workspace_bytes, void *stream);
+/* The same from the camera parameters instead of the ray field (see mvp_camera): no pass over the rays at all. */
+int mvp_build_accel_camera(const mvp_shape *shape, uint32_t flags, const int32_t *order, const mvp_camera *camera,
+                           const float *primpos, const float *primrot, const float *primscale,
+                           void *workspace, size_t workspace_bytes, void *stream);
 
 /* 30-bit Morton codes of slab centres that the caller has normalised to the unit cube (mvpraymarch.py:46-50):
  * compute_morton of the reference (extensions/mvpraymarch/mvpraymarch.cpp:106-121, bvh.cu:20-57).

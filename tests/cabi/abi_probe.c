@@ -26,10 +26,13 @@ int main(int argc, char **argv) {
     int (*accel)(const mvp_shape *, uint32_t, const int32_t *, const float *, const float *, const float *, const float *, const float *,
                  void *, size_t, void *) = (int (*)(const mvp_shape *, uint32_t, const int32_t *, const float *, const float *,
                                                     const float *, const float *, const float *, void *, size_t, void *))dlsym(h, "mvp_build_accel");
-    CHECK(abi && errstr && wsbytes && fwd && bwd && accel);
+    int (*accel_cam)(const mvp_shape *, uint32_t, const int32_t *, const mvp_camera *, const float *, const float *, const float *, void *, size_t,
+                     void *) = (int (*)(const mvp_shape *, uint32_t, const int32_t *, const mvp_camera *, const float *, const float *,
+                                        const float *, void *, size_t, void *))dlsym(h, "mvp_build_accel_camera");
+    CHECK(abi && errstr && wsbytes && fwd && bwd && accel && accel_cam);
     CHECK(abi() == MVP_ABI_VERSION);
-    printf("abi %d\nsizeof_shape %zu\nsizeof_forward_args %zu\nsizeof_backward_args %zu\n", abi(), sizeof(mvp_shape),
-           sizeof(mvp_forward_args), sizeof(mvp_backward_args));
+    printf("abi %d\nsizeof_shape %zu\nsizeof_forward_args %zu\nsizeof_backward_args %zu\nsizeof_camera %zu\n", abi(), sizeof(mvp_shape),
+           sizeof(mvp_forward_args), sizeof(mvp_backward_args), sizeof(mvp_camera));
 
     mvp_shape c3 = {80, 1024, 667, 16384, 8, 8, 8}, bad = {1, 0, 8, 4, 2, 2, 2};
     size_t ws = wsbytes(&c3);
@@ -42,7 +45,7 @@ int main(int argc, char **argv) {
     a.stepsize = 0.1f;
     CHECK(fwd(NULL, NULL) == MVP_ERR_NULL);
     CHECK(fwd(&a, NULL) == MVP_ERR_STRUCT);                      /* struct_size not set */
-    a.struct_size = (uint32_t)sizeof a - 24;                      /* the ABI-v5 length: a stale caller */
+    a.struct_size = (uint32_t)sizeof a - (uint32_t)sizeof(mvp_camera);   /* the ABI-v7 length: a stale caller */
     CHECK(fwd(&a, NULL) == MVP_ERR_STRUCT);
     a.struct_size = (uint32_t)sizeof a;
     CHECK(fwd(&a, NULL) == MVP_ERR_NULL);                        /* required pointers missing */
@@ -72,6 +75,22 @@ int main(int argc, char **argv) {
     a.rayrgb_nchw = NULL;
     a.raysat = dummy;                                             /* raysat without rayaux */
     CHECK(fwd(&a, NULL) == MVP_ERR_NULL);
+    a.raysat = NULL;
+    /* rays from the camera (mvp_camera): the ray tensors may be NULL, the four camera arrays come together, volradius > 0 */
+    a.raypos = a.raydir = a.tminmax = NULL;
+    CHECK(fwd(&a, NULL) == MVP_ERR_NULL);
+    a.camera.viewpos = dummy;
+    CHECK(fwd(&a, NULL) == MVP_ERR_NULL);                        /* viewrot / focal / princpt missing */
+    a.camera.viewrot = a.camera.focal = a.camera.princpt = dummy;
+    CHECK(fwd(&a, NULL) == MVP_ERR_CAMERA);                      /* volradius = 0 */
+    a.camera.volradius = 256.f;
+    a.stepsize = 0.f;
+    CHECK(fwd(&a, NULL) == MVP_ERR_STEPSIZE);                    /* i.e. the camera was accepted in place of the ray tensors */
+    {
+        mvp_camera cam0;
+        memset(&cam0, 0, sizeof cam0);
+        CHECK(accel_cam(&c3, 0, NULL, &cam0, dummy, dummy, dummy, dummy, (size_t)1 << 40, NULL) == MVP_ERR_NULL);
+    }
 
     mvp_backward_args b;
     memset(&b, 0, sizeof b);

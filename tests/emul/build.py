@@ -20,6 +20,7 @@ def build():
 
 KSRC = [os.path.join(HERE, "mvp_emul.cpp"), os.path.join(HERE, "cuda_emul.cpp")]
 KDEP = KSRC + [os.path.join(HERE, "cuda_emul.h"), os.path.join(ROOT, "ava-256_b200", "csrc", "mvp_kernels.cu"),
+               os.path.join(ROOT, "ava-256_b200", "csrc", "raygen.h"),
                os.path.join(ROOT, "include", "mvpraymarch_b200.h")]
 KLIB = os.path.join(HERE, "libmvp_emul.so")
 
@@ -33,7 +34,8 @@ def build_kernels(defines=(), opt="-O1"):
         return lib
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
     subprocess.check_call(["g++", "-std=c++20", opt, "-g", "-ffp-contract=off", "-shared", "-fPIC", "-pthread", "-Wno-attributes",
-                           "-Wno-unknown-pragmas", "-I" + cuda_inc, "-I" + HERE, "-I" + os.path.join(ROOT, "include")] +
+                           "-Wno-unknown-pragmas", "-I" + cuda_inc, "-I" + HERE, "-I" + os.path.join(ROOT, "include"),
+                           "-I" + os.path.join(ROOT, "ava-256_b200", "csrc")] +
                           ["-D" + d for d in defines] + KSRC + ["-o", lib])
     return lib
 
@@ -45,7 +47,7 @@ def build_aux():
     """libaux_emul.so: raydirs.cu + epilogue.cu compiled for the host on the CPU emulation."""
     src = [os.path.join(HERE, "aux_emul.cpp"), os.path.join(HERE, "cuda_emul.cpp")]
     dep = src + [os.path.join(HERE, "cuda_emul.h"), BODY, os.path.join(ROOT, "ava-256_b200", "csrc", "raydirs.cu"),
-                 os.path.join(ROOT, "ava-256_b200", "csrc", "epilogue.cu"), os.path.join(ROOT, "include", "mvpraymarch_b200.h")]
+                 os.path.join(ROOT, "ava-256_b200", "csrc", "raygen.h"), os.path.join(ROOT, "ava-256_b200", "csrc", "epilogue.cu"), os.path.join(ROOT, "include", "mvpraymarch_b200.h")]
     if os.path.exists(ALIB) and all(os.path.getmtime(ALIB) >= os.path.getmtime(f) for f in dep + [__file__]):
         return ALIB
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")

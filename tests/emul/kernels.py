@@ -66,15 +66,25 @@ def _nan_like16(x):
 
 
 def forward_backward(raypos, raydir, stepsize, tminmax, primpos, primrot, primscale, template, grad_rayrgba=None, warp=None,
-                     fadescale=8.0, fadeexp=8.0, fwd_flags=0, bwd_flags=0, planes=False, order=None, clear_in_forward=False):
+                     fadescale=8.0, fadeexp=8.0, fwd_flags=0, bwd_flags=0, planes=False, order=None, clear_in_forward=False, camera=None):
     """Runs the emulated forward (and, when grad_rayrgba is given, backward) kernels.
     Returns (rayrgba, raysat, grads) with grads = [primpos, primrot, primscale, template(, warp)] or None.
     clear_in_forward: the gradient buffers are handed to the forward NaN-filled (mvp_forward_args::clear_grad_*), which must leave
-    them zero; the backward then runs without MVP_FLAG_ZERO_GRADS."""
+    them zero; the backward then runs without MVP_FLAG_ZERO_GRADS.
+    camera = (viewpos, viewrot, focal, princpt, volradius, H, W): the kernels generate the rays (mvp_camera); raypos / raydir / tminmax
+    must then be None and are passed as NULL."""
     L = load()
-    raypos, raydir, tminmax, primpos, primrot, primscale, template = map(_f32, (raypos, raydir, tminmax, primpos, primrot, primscale, template))
+    primpos, primrot, primscale, template = map(_f32, (primpos, primrot, primscale, template))
     warp = None if warp is None else _f32(warp)
-    N, H, W = raypos.shape[:3]
+    cam = None
+    if camera is not None:
+        assert raypos is None and raydir is None and tminmax is None
+        camarrs = [_f32(x) for x in camera[:4]]
+        cam = _abi.Camera(_p(camarrs[0]), _p(camarrs[1]), _p(camarrs[2]), _p(camarrs[3]), float(camera[4]), 0)
+        N, H, W = camarrs[0].shape[0], int(camera[5]), int(camera[6])
+    else:
+        raypos, raydir, tminmax = map(_f32, (raypos, raydir, tminmax))
+        N, H, W = raypos.shape[:3]
     K = primpos.shape[1]
     TD, TH, TW = template.shape[2:5]
     shape = _abi.Shape(N, H, W, K, TD, TH, TW)
@@ -89,6 +99,8 @@ def forward_backward(raypos, raydir, stepsize, tminmax, primpos, primrot, primsc
     a.shape = shape
     a.stepsize, a.fadescale, a.fadeexp, a.flags = float(stepsize), float(fadescale), float(fadeexp), fwd_flags
     a.raypos, a.raydir, a.tminmax = _p(raypos), _p(raydir), _p(tminmax)
+    if cam is not None:
+        a.camera = cam
     a.primpos, a.primrot, a.primscale, a.tplate = _p(primpos), _p(primrot), _p(primscale), _p(template)
     rgb_p = np.full((N, 3, H, W), np.nan, np.float32) if planes else None
     alpha_p = np.full((N, 1, H, W), np.nan, np.float32) if planes else None
@@ -125,6 +137,8 @@ def forward_backward(raypos, raydir, stepsize, tminmax, primpos, primrot, primsc
     b.shape = shape
     b.stepsize, b.fadescale, b.fadeexp, b.flags = float(stepsize), float(fadescale), float(fadeexp), _abi.FLAG_ACCEL_VALID | bwd_flags
     b.raypos, b.raydir, b.tminmax = _p(raypos), _p(raydir), _p(tminmax)
+    if cam is not None:
+        b.camera = cam
     b.primpos, b.primrot, b.primscale, b.tplate = _p(primpos), _p(primrot), _p(primscale), _p(template)
     if planes:
         g_rgb = np.ascontiguousarray(grad_rayrgba.transpose(0, 3, 1, 2)[:, :3])

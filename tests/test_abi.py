@@ -27,7 +27,7 @@ def test_header_symbols_are_exported():
     for n in names:
         assert hasattr(lib.LIB, n), n
     assert sorted(names) == sorted(lib.EXPORTS)
-    assert lib.LIB.mvp_abi_version() == 7
+    assert lib.LIB.mvp_abi_version() == 8
     cfg = lib.LIB.mvp_build_config().decode()
     assert "LIST_REUSE=" in cfg and "FASTCAP=" in cfg and "CPU_EMUL" not in cfg
 
@@ -49,11 +49,12 @@ def test_c_program_through_the_header_alone(tmp_path):
     assert int(facts["sizeof_shape"]) == ctypes.sizeof(lib.Shape) == lib.SIZEOF["Shape"]
     assert int(facts["sizeof_forward_args"]) == ctypes.sizeof(lib.ForwardArgs) == lib.SIZEOF["ForwardArgs"]
     assert int(facts["sizeof_backward_args"]) == ctypes.sizeof(lib.BackwardArgs) == lib.SIZEOF["BackwardArgs"]
+    assert int(facts["sizeof_camera"]) == ctypes.sizeof(lib.Camera) == lib.SIZEOF["Camera"]
     assert int(facts["workspace_bytes_c3"]) == lib.workspace_bytes(80, 1024, 667, 16384, 8, 8, 8)
     # the stub printed in INTEGRATION.md states the same struct size
     doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
     assert "ctypes.sizeof(ForwardArgs) == %d" % lib.SIZEOF["ForwardArgs"] in doc
-    for field in ("struct_size", "workspace_bytes", '"warp"', '"WD"', '"WH"', '"WW"', '"algo"', '"rayrgb_nchw"', '"rayalpha_nchw"', '"order"'):
+    for field in ("struct_size", "workspace_bytes", '"warp"', '"WD"', '"WH"', '"WW"', '"algo"', '"rayrgb_nchw"', '"rayalpha_nchw"', '"order"', '"camera"'):
         assert field in doc, field
 
 
@@ -61,7 +62,7 @@ def test_truncated_argument_struct_is_rejected():
     from ava256_b200 import lib
     a = lib.ForwardArgs()
     assert a.struct_size == ctypes.sizeof(lib.ForwardArgs)
-    a.struct_size -= 24                                                         # what an ABI-v5 caller would pass
+    a.struct_size -= 40                                                         # what an ABI-v7 caller (no `camera`) would pass
     assert lib.LIB.mvp_raymarch_forward(ctypes.byref(a), None) == -7          # MVP_ERR_STRUCT
     b = lib.BackwardArgs()
     b.struct_size = 0

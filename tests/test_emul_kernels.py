@@ -324,7 +324,14 @@ def test_emulated_raydirs_kernel(aux, with_pixelcoords):
     assert aux.mvp_compute_raydirs(n, H, W, _ptr(campos), _ptr(camrot), _ptr(focal), _ptr(princpt), _ptr(pc), scene.VOLRADIUS,
                                    _ptr(rp), _ptr(rd), _ptr(tmm), None) == 0
     hp, hd, ht = scene.compute_raydirs_host(campos, camrot, focal, princpt, H, W)
-    assert relerr(rp.numpy(), hp.numpy()) < 1e-6 and relerr(rd.numpy(), hd.numpy()) < 1e-6 and relerr(tmm.numpy(), ht.numpy()) < 1e-5
+    assert relerr(rp.numpy(), hp.numpy()) < 1e-6 and relerr(rd.numpy(), hd.numpy()) < 1e-6
+    # clip range: rays that cross the cube to 1e-5; a ray that misses it parallel to a face has a clip distance of 1 / (a direction
+    # component that nearly cancels), which follows the kernel's fused multiply-adds (raygen.h), not torch's separate roundings
+    hit = (ht[..., 0] < ht[..., 1]).numpy()
+    assert hit.mean() > 0.05
+    assert relerr(tmm.numpy()[hit], ht.numpy()[hit]) < 1e-5
+    assert np.array_equal(tmm.numpy()[..., 0] < tmm.numpy()[..., 1], hit)
+    assert relerr(tmm.numpy()[~hit], ht.numpy()[~hit]) < 1e-2
 
 
 @pytest.mark.parametrize("shape", [(3, 6, 10), (2, 7, 9), (2, 33, 67), (1, 64, 48)])
@@ -416,3 +423,69 @@ def test_emulated_row_bucket_overflow_falls_back_to_all_slabs(kernels):
     gref = oracle.backward(*a, grad.numpy(), raysat, **kw)
     for nm, g_, r in zip(("primpos", "primrot", "primscale", "template"), grads, gref):
         assert relerr(g_, r) <= BWD_TOL, nm
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# rays generated in the render kernels' prologue from the camera (mvp_camera) must be the rays
+# mvp_compute_raydirs writes, and the images / gradients those of the two-call form
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,H,W,K,T,planes", [(2, 64, 42, 64, 8, False), (1, 13, 19, 16, 4, True), (3, 30, 50, 64, 8, False)])
+def test_emulated_camera_rays_match_ray_tensors(kernels, aux, n, H, W, K, T, planes):
+    from ava256_b200 import scene
+    viewpos, viewrot, focal, princpt = scene.make_cameras(n, H, W, view_offset=3)
+    rp, rd, tmm = torch.full((n, H, W, 3), float("nan")), torch.full((n, H, W, 3), float("nan")), torch.full((n, H, W, 2), float("nan"))
+    assert aux.mvp_compute_raydirs(n, H, W, _ptr(viewpos), _ptr(viewrot), _ptr(focal), _ptr(princpt), None, scene.VOLRADIUS,
+                                   _ptr(rp), _ptr(rd), _ptr(tmm), None) == 0
+    s = scene.make_scene(n, H, W, K, T, view_offset=3, alpha_mu=1.0, alpha_sigma=2.0, share_primitives=False)
+    g = torch.randn(n, H, W, 4, generator=torch.Generator().manual_seed(5)).numpy()
+    prim = (s["primpos"].numpy(), s["primrot"].numpy(), s["primscale"].numpy(), s["template"].numpy())
+    step = 1.0 / 64
+    out_t, sat_t, g_t = kernels.forward_backward(rp.numpy(), rd.numpy(), step, tmm.numpy(), *prim, grad_rayrgba=g, planes=planes)
+    cam = (viewpos.numpy(), viewrot.numpy(), focal.numpy(), princpt.numpy(), scene.VOLRADIUS, H, W)
+    out_c, sat_c, g_c = kernels.forward_backward(None, None, step, None, *prim, grad_rayrgba=g, planes=planes, camera=cam)
+    assert float(out_t[..., 3].max()) > 0.05
+    assert np.array_equal(out_t, out_c) and np.array_equal(sat_t, sat_c)
+    for x, y in zip(g_t, g_c):
+        assert relerr(y, x) <= 1e-6
+    # inference mode (no raysat / rayaux) through the same prologue
+    out_i, _, _ = kernels.forward_backward(None, None, step, None, *prim, camera=cam)
+    assert np.array_equal(out_i, out_c)
+
+
+def test_emulated_camera_argument_errors(kernels):
+    import ctypes
+    from ava256_b200 import lib as abi
+    L = kernels.load()
+    a = abi.ForwardArgs()
+    a.shape = abi.Shape(1, 8, 8, 4, 2, 2, 2)
+    a.stepsize = 0.1
+    dummy = ctypes.c_void_p(256)
+    for f in ("primpos", "primrot", "primscale", "tplate", "rayrgba", "workspace"):
+        setattr(a, f, dummy)
+    a.workspace_bytes = 1 << 30
+    assert L.mvp_raymarch_forward(ctypes.byref(a), None) == -1                 # neither rays nor a camera
+    a.camera = abi.Camera(dummy, dummy, dummy, None, 256.0, 0)
+    assert L.mvp_raymarch_forward(ctypes.byref(a), None) == -1                 # three of the four camera arrays
+    a.camera = abi.Camera(dummy, dummy, dummy, dummy, 0.0, 0)
+    assert L.mvp_raymarch_forward(ctypes.byref(a), None) == -8                 # MVP_ERR_CAMERA
+    a.camera = abi.Camera(dummy, dummy, dummy, ctypes.c_void_p(258), 256.0, 0)
+    assert L.mvp_raymarch_forward(ctypes.byref(a), None) == -6                 # MVP_ERR_ALIGN
+
+
+def test_emulated_degenerate_camera_falls_back(kernels):
+    """focal = 0 for one view: its rays are not finite and nothing can be projected -- the view is flagged like a failed camera fit
+    (every slab a candidate, no hits) and the other view renders as before."""
+    from ava256_b200 import scene
+    n, H, W, K, T = 2, 16, 20, 16, 4
+    viewpos, viewrot, focal, princpt = scene.make_cameras(n, H, W)
+    s = scene.make_scene(n, H, W, K, T, alpha_mu=2.0, alpha_sigma=2.0, share_primitives=False)
+    prim = (s["primpos"].numpy(), s["primrot"].numpy(), s["primscale"].numpy(), s["template"].numpy())
+    good, _, _ = kernels.forward_backward(None, None, 1.0 / 32, None, *prim,
+                                          camera=(viewpos.numpy(), viewrot.numpy(), focal.numpy(), princpt.numpy(), scene.VOLRADIUS, H, W))
+    bad_focal = focal.clone()
+    bad_focal[1] = 0.0
+    out, _, _ = kernels.forward_backward(None, None, 1.0 / 32, None, *prim,
+                                         camera=(viewpos.numpy(), viewrot.numpy(), bad_focal.numpy(), princpt.numpy(), scene.VOLRADIUS, H, W))
+    assert float(good[0, ..., 3].max()) > 0.0
+    assert np.array_equal(out[0], good[0])
+    assert not out[1].any()

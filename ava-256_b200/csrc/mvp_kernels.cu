@@ -1378,9 +1378,14 @@ __device__ __forceinline__ float4 sample_slab_warped(const float4 *__restrict__ 
 // events, [2] events with at least one valid lane, [3] valid lanes (= samples queued), [4] flushes, [5] tiles with a list,
 // [6] events with a lane geometrically inside the slab (whether or not it still marches), [7] such lanes
 long long g_emul_fwd_stats[8];
+// second set: [0] sweep steps executed by the step loop, [1] steps run through by the skip loop, [2] events whose slab is the slab of the
+// tile's previous event, [3] ballot words with two or more active slabs, [4] events in such words
+long long g_emul_fwd_stats2[8];
 #define MVP_STAT(i, v) do { if (lane == 0) stat_[i] += (v); } while (0)
+#define MVP_STAT2(i, v) do { if (lane == 0) stat2_[i] += (v); } while (0)
 #else
 #define MVP_STAT(i, v) ((void)0)
+#define MVP_STAT2(i, v) ((void)0)
 #endif
 
 template <int CAP, bool kGrad>
@@ -1458,7 +1463,8 @@ __device__ __forceinline__ bool forward_tile(const Params &p, const int n, const
 
     const int nl = c.nl;
 #if defined(MVP_CPU_EMUL) && defined(MVP_EMUL_STATS)
-    long long stat_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long stat_[8] = {0, 0, 0, 0, 0, 0, 0, 0}, stat2_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int prevk_ = -1;
     if (nl > 0) MVP_STAT(5, 1);
 #endif
     const int nwords = (nl + 31) >> 5;
@@ -1543,6 +1549,7 @@ __device__ __forceinline__ bool forward_tile(const Params &p, const int n, const
         for (int m = mstart;; ++m) {
             const bool on = !done && (m >= ms);
             bool anyslab = false;
+            MVP_STAT2(0, 1);
             for (int w = 0; w < nwords; ++w) {
                 bool a;
                 if (w == 0) a = (lo0 <= m) && (m <= hi0);
@@ -1554,11 +1561,16 @@ __device__ __forceinline__ bool forward_tile(const Params &p, const int n, const
                 unsigned word = __ballot_sync(0xffffffffu, a);
                 anyslab |= (word != 0);
                 MVP_STAT(0, 1);
+                if (__popc(word) >= 2) { MVP_STAT2(3, 1); MVP_STAT2(4, __popc(word)); }
                 while (word) {
                     const int b = __ffs(word) - 1;
                     word &= word - 1;
                     MVP_STAT(1, 1);
                     const int k = list_k(w * 32 + b);
+#if defined(MVP_CPU_EMUL) && defined(MVP_EMUL_STATS)
+                    if (k == prevk_) MVP_STAT2(2, 1);
+                    prevk_ = k;
+#endif
                     const Prim q = load_prim(packn, k);
                     // primtransf.h:119-132
                     const float xm = x - q.px, ym = y - q.py, zm = z - q.pz;
@@ -1605,6 +1617,7 @@ __device__ __forceinline__ bool forward_tile(const Params &p, const int n, const
                 nxt = __reduce_min_sync(0xffffffffu, nxt);
                 if (nxt == kBig) break;          // no slab starts later: nothing left to sample for any lane
                 for (int mm = m + 1; mm < nxt; ++mm) {
+                    MVP_STAT2(1, 1);
                     if (!done && (mm >= ms)) {
                         if (kGrad && (t < r1e)) jlast = mm + c.off;
                         t = __fadd_rn(t, p.dt);
@@ -1634,6 +1647,7 @@ __device__ __forceinline__ bool forward_tile(const Params &p, const int n, const
     }
 #if defined(MVP_CPU_EMUL) && defined(MVP_EMUL_STATS)
     if (lane == 0) for (int i = 0; i < 8; ++i) if (stat_[i]) std::atomic_ref<long long>(g_emul_fwd_stats[i]).fetch_add(stat_[i]);
+    if (lane == 0) for (int i = 0; i < 8; ++i) if (stat2_[i]) std::atomic_ref<long long>(g_emul_fwd_stats2[i]).fetch_add(stat2_[i]);
 #endif
     return true;
 }
@@ -2778,6 +2792,9 @@ int mvp_raymarch_backward(const mvp_backward_args *a, void *stream) {
 #if defined(MVP_CPU_EMUL) && defined(MVP_EMUL_STATS)
 void mvp_emul_fwd_stats(long long *out) {
     for (int i = 0; i < 8; ++i) { out[i] = g_emul_fwd_stats[i]; g_emul_fwd_stats[i] = 0; }
+}
+void mvp_emul_fwd_stats2(long long *out) {
+    for (int i = 0; i < 8; ++i) { out[i] = g_emul_fwd_stats2[i]; g_emul_fwd_stats2[i] = 0; }
 }
 void mvp_emul_bwd_stats(long long *out) {
     for (int i = 0; i < 8; ++i) { out[i] = g_emul_bwd_stats[i]; g_emul_bwd_stats[i] = 0; }

@@ -33,6 +33,9 @@ for tag, defs in VARIANTS:
     L.mvp_emul_list_chunks.restype = ctypes.c_longlong
     chunks = L.mvp_emul_list_chunks()
     print("%-9s %6.1fs  " % (tag, dt) + "  ".join("%s=%d" % (n, v) for n, v in zip(NAMES, st)) + "  list_chunks=%d" % chunks)
+    s2 = (ctypes.c_longlong * 8)()
+    L.mvp_emul_fwd_stats2(s2)
+    print("          forward loop: " + "  ".join("%s=%d" % (n, v) for n, v in zip(("sweep_steps", "skipped_steps", "events_same_slab_as_previous", "words_with_2plus_slabs", "events_in_such_words"), s2)))
     bs = (ctypes.c_longlong * 8)()
     L.mvp_emul_bwd_stats(bs)
     print("          backward: " + "  ".join("%s=%d" % (n, v) for n, v in zip(("slab_visits", "visits_with_work", "warp_steps", "lane_steps", "samples", "batches", "carry_steps"), bs)))

@@ -143,7 +143,26 @@ constexpr int kRing = 64;        // sample queue / ring per warp (forward and ba
 constexpr int kGrpTiles = 8;       // tile columns per x-group
 constexpr int kGrpCap = 1024;     // group-bucket entries per tile row; groups that do not fit keep using the row bucket
 #endif
-constexpr int kFastCap = MVP_FASTCAP;   // shared-memory list capacity of the common-case render kernels
+#ifndef MVP_FWD_FASTCAP
+#define MVP_FWD_FASTCAP MVP_FASTCAP
+#endif
+#ifndef MVP_BWD_FASTCAP
+#define MVP_BWD_FASTCAP MVP_FASTCAP
+#endif
+constexpr int kFastCapF = MVP_FWD_FASTCAP;   // shared-memory list capacity of the common-case render kernels (forward / backward); a tile whose
+constexpr int kFastCapB = MVP_BWD_FASTCAP;   // list is longer goes to the 512-entry kernel of that pass (the backward's may be the smaller one)
+#ifndef MVP_SMEM_UNION
+#define MVP_SMEM_UNION 1   // 1: the bucket staging buffer (used only while a tile's list is built) shares its shared memory with the sample
+                           // queue (used only afterwards): 512 bytes less per warp.  Measured on B200 (round 2): forward 2.096 vs 2.120 ms per
+                           // 8 views, 10.475 vs 10.610 per 40; backward unchanged
+#endif
+#ifndef MVP_FWD_CARVEOUT
+#define MVP_FWD_CARVEOUT 0   // > 0: preferred shared-memory carve-out (percent of the maximum, cudaFuncAttributePreferredSharedMemoryCarveout) of the
+#endif                       // fast render kernels; 0 leaves the driver's choice.  The kernels live off L1 hits: what is not carved out is L1
+#ifndef MVP_BWD_CARVEOUT
+#define MVP_BWD_CARVEOUT 43   // 100 KB of shared memory (4 CTAs need 81): the driver's own choice is 132 KB.  Measured: backward 2.821 vs 2.835 ms
+#endif                        // per 8 views, 14.187 vs 14.257 per 40.  The carve-out matters little either way (forward at 100 KB instead of
+                              // 132: +-0; at 164 KB: +2 %; backward at 64 KB: +-0): the kernels are issue bound, not L1-capacity bound
 constexpr int kBig = 1 << 30;
 constexpr int kCostClasses = 64;   // cost classes of the CTA ordering (counting sort)
 #ifndef MVP_BWD_MINB
@@ -1390,8 +1409,15 @@ long long g_emul_fwd_stats2[8];
 
 template <int CAP, bool kGrad>
 struct __align__(16) FwdWarpSmem {   // per-warp shared state of the forward kernel
+#if MVP_SMEM_UNION
+    union {
+        float4 ring[kRing];            // sample queue of the march ...
+        RowEntry stage[2 * kStage];    // ... bucket chunks while the list is built (every bulk copy has been waited for before the march starts)
+    };
+#else
     float4 ring[kRing];
     RowEntry stage[2 * kStage];
+#endif
     unsigned long long bar[2];
     int k[CAP];
     int iv[CAP];
@@ -1466,6 +1492,9 @@ __device__ __forceinline__ bool forward_tile(const Params &p, const int n, const
     long long stat_[8] = {0, 0, 0, 0, 0, 0, 0, 0}, stat2_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int prevk_ = -1;
     if (nl > 0) MVP_STAT(5, 1);
+    if (nl > 128) MVP_STAT2(5, 1);      // list-length tail: [5] > 128, [6] > 160, [7] > 192 entries
+    if (nl > 160) MVP_STAT2(6, 1);
+    if (nl > 192) MVP_STAT2(7, 1);
 #endif
     const int nwords = (nl + 31) >> 5;
     const float4 *packn = p.pack + (size_t)(n * p.pview) * p.K * 4;
@@ -1772,8 +1801,15 @@ __device__ __forceinline__ float3 index_grad_general(const float4 *pc, int sx, i
 
 template <int CAP>
 struct __align__(16) BwdWarpSmem {   // per-warp shared state of the backward kernel
+#if MVP_SMEM_UNION
+    union {
+        float4 q[kRing];
+        RowEntry stage[2 * kStage];    // only the list rebuild uses it, before the first sample is queued
+    };
+#else
     float4 q[kRing];
     RowEntry stage[2 * kStage];
+#endif
     unsigned long long bar[2];
     int k[CAP];
     int iv[CAP];
@@ -2349,6 +2385,15 @@ __global__ void __launch_bounds__(kWarps * 32, (CAP < kMaxHit && !kWarp) ? (MVP_
 #define MVP_LAUNCH_FAST(...) __VA_ARGS__<<<grid, kWarps * 32, 0, st>>>(p)
 #define MVP_LAUNCH_HEAVY(...) __VA_ARGS__<<<kHeavyGrid, kWarps * 32, 0, st>>>(p)
 #endif
+// shared-memory carve-out preference of a fast render kernel (a per-function attribute: no allocation, no synchronisation)
+#ifdef MVP_CPU_EMUL
+#define MVP_CARVE(pct, ...) ((void)0)
+#else
+#define MVP_CARVE(pct, ...)                                                                                          \
+    do {                                                                                                             \
+        if ((pct) > 0) cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributePreferredSharedMemoryCarveout, (pct));     \
+    } while (0)
+#endif
 
 int check_shape(const mvp_shape &s) {
     if (s.N < 1 || s.H < 1 || s.W < 1 || s.K < 1 || s.TD < 1 || s.TH < 1 || s.TW < 1) return MVP_ERR_SHAPE;
@@ -2522,7 +2567,7 @@ int mvp_abi_version(void) { return MVP_ABI_VERSION; }
 #define MVP_STR(x) MVP_STR2(x)
 const char *mvp_build_config(void) {
     return "LIST_REUSE=" MVP_STR(MVP_LIST_REUSE)
-           " LIST_MARGIN=" MVP_STR(MVP_LIST_MARGIN) " XBUCKETS=" MVP_STR(MVP_XBUCKETS) " FASTCAP=" MVP_STR(MVP_FASTCAP) " BWD_SMEMREC=" MVP_STR(MVP_BWD_SMEMREC) " BWD_LANESMEM=" MVP_STR(MVP_BWD_LANESMEM) " CTA_ORDER=" MVP_STR(MVP_CTA_ORDER) " CTA_ORDER_MIN=" MVP_STR(MVP_CTA_ORDER_MIN)
+           " LIST_MARGIN=" MVP_STR(MVP_LIST_MARGIN) " XBUCKETS=" MVP_STR(MVP_XBUCKETS) " FASTCAP=" MVP_STR(MVP_FWD_FASTCAP) "/" MVP_STR(MVP_BWD_FASTCAP) " SMEM_UNION=" MVP_STR(MVP_SMEM_UNION) " CARVEOUT=" MVP_STR(MVP_FWD_CARVEOUT) "/" MVP_STR(MVP_BWD_CARVEOUT) " BWD_SMEMREC=" MVP_STR(MVP_BWD_SMEMREC) " BWD_LANESMEM=" MVP_STR(MVP_BWD_LANESMEM) " CTA_ORDER=" MVP_STR(MVP_CTA_ORDER) " CTA_ORDER_MIN=" MVP_STR(MVP_CTA_ORDER_MIN)
            " CHUNK=" MVP_STR(MVP_CHUNK) " FWD_MINB=" MVP_STR(MVP_FWD_MINB) " BWD_MINB=" MVP_STR(MVP_BWD_MINB)
            " WARPS=" MVP_STR(MVP_WARPS) " BLK_TX=" MVP_STR(MVP_BLK_TX)
 #ifdef MVP_CPU_EMUL
@@ -2695,10 +2740,12 @@ int mvp_raymarch_forward(const mvp_forward_args *a, void *stream) {
 #define MVP_LAUNCH_FWD(TT, WW_)                                                                              \
     do {                                                                                                     \
         if (a->raysat) {                                                                                     \
-            MVP_LAUNCH_FAST(render_forward_kernel<TT, true, kFastCap, WW_>);                                 \
+            MVP_CARVE(MVP_FWD_CARVEOUT, render_forward_kernel<TT, true, kFastCapF, WW_>);                    \
+            MVP_LAUNCH_FAST(render_forward_kernel<TT, true, kFastCapF, WW_>);                                \
             MVP_LAUNCH_HEAVY(render_forward_kernel<TT, true, kMaxHit, WW_>);                                 \
         } else {                                                                                             \
-            MVP_LAUNCH_FAST(render_forward_kernel<TT, false, kFastCap, WW_>);                                \
+            MVP_CARVE(MVP_FWD_CARVEOUT, render_forward_kernel<TT, false, kFastCapF, WW_>);                   \
+            MVP_LAUNCH_FAST(render_forward_kernel<TT, false, kFastCapF, WW_>);                               \
             MVP_LAUNCH_HEAVY(render_forward_kernel<TT, false, kMaxHit, WW_>);                                \
         }                                                                                                    \
     } while (0)
@@ -2777,7 +2824,8 @@ int mvp_raymarch_backward(const mvp_backward_args *a, void *stream) {
     const int cubic = (a->shape.TD == a->shape.TH && a->shape.TH == a->shape.TW) ? a->shape.TD : 0;
 #define MVP_LAUNCH_BWD(TT, WW_)                                                                  \
     do {                                                                                         \
-        MVP_LAUNCH_FAST(render_backward_kernel<TT, kFastCap, WW_>);                              \
+        MVP_CARVE(MVP_BWD_CARVEOUT, render_backward_kernel<TT, kFastCapB, WW_>);                 \
+        MVP_LAUNCH_FAST(render_backward_kernel<TT, kFastCapB, WW_>);                             \
         MVP_LAUNCH_HEAVY(render_backward_kernel<TT, kMaxHit, WW_>);                              \
     } while (0)
     if (a->algo == 1) MVP_LAUNCH_BWD(0, true);

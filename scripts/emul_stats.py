@@ -35,7 +35,7 @@ for tag, defs in VARIANTS:
     print("%-9s %6.1fs  " % (tag, dt) + "  ".join("%s=%d" % (n, v) for n, v in zip(NAMES, st)) + "  list_chunks=%d" % chunks)
     s2 = (ctypes.c_longlong * 8)()
     L.mvp_emul_fwd_stats2(s2)
-    print("          forward loop: " + "  ".join("%s=%d" % (n, v) for n, v in zip(("sweep_steps", "skipped_steps", "events_same_slab_as_previous", "words_with_2plus_slabs", "events_in_such_words"), s2)))
+    print("          forward loop: " + "  ".join("%s=%d" % (n, v) for n, v in zip(("sweep_steps", "skipped_steps", "events_same_slab_as_previous", "words_with_2plus_slabs", "events_in_such_words", "tiles_list_gt128", "tiles_list_gt160", "tiles_list_gt192"), s2)))
     bs = (ctypes.c_longlong * 8)()
     L.mvp_emul_bwd_stats(bs)
     print("          backward: " + "  ".join("%s=%d" % (n, v) for n, v in zip(("slab_visits", "visits_with_work", "warp_steps", "lane_steps", "samples", "batches", "carry_steps"), bs)))

@@ -812,6 +812,26 @@ __global__ void __launch_bounds__(256) order_ctas_kernel(int pass, int N, int CX
 // ------------------------------------------------------------------------------------------------------
 // device helpers shared by forward and backward
 // ------------------------------------------------------------------------------------------------------
+// bits of the lanes below this one (one special-register read; (1u << lane) - 1u is re-derived from %tid under a tight register cap)
+__device__ __forceinline__ unsigned lanemask_lt() {
+#ifdef MVP_CPU_EMUL
+    return (1u << (threadIdx.x & 31)) - 1u;
+#else
+    unsigned m;
+    asm volatile("mov.u32 %0, %%lanemask_lt;" : "=r"(m));   // volatile: read where it is used, not hoisted into a register that lives across the kernel
+    return m;
+#endif
+}
+
+// strictly inside the slab, |y_i| < 1 for all three (primsampler.h:46): the magnitudes compared as integers -- one 3-input maximum and one
+// compare instead of three float compares and their predicate logic (forward event loop; with the constant slab size and lanemask_lt():
+// -2.8 % instructions, -1 % time on B200).  Same decisions: below 1.0 the order of non-negative floats is the
+// order of their bit patterns, a NaN's pattern is above 1.0's (invalid, as with the float compare), and flushing denormals changes nothing.
+__device__ __forceinline__ bool inside_unit(float y0, float y1, float y2) {
+    const unsigned a = __float_as_uint(y0) & 0x7fffffffu, b = __float_as_uint(y1) & 0x7fffffffu, c = __float_as_uint(y2) & 0x7fffffffu;
+    return max(max(a, b), c) < 0x3f800000u;
+}
+
 struct Prim {
     float px, py, pz;
     float r00, r01, r02, r10, r11, r12, r20, r21, r22;
@@ -1498,7 +1518,9 @@ __device__ __forceinline__ bool forward_tile(const Params &p, const int n, const
 #endif
     const int nwords = (nl + 31) >> 5;
     const float4 *packn = p.pack + (size_t)(n * p.pview) * p.K * 4;
-    const size_t slabsz = (size_t)p.TD * p.TH * p.TW;
+    // voxels per slab: a compile-time constant for the cubic 8^3 / 16^3 specialisations, so that a slab's address is a shift and an add
+    // wherever the register cap makes the compiler re-derive it (it was ~30 of the 159 instructions of a batch gather)
+    const size_t slabsz = T > 0 ? (size_t)(T * T * T) : (size_t)p.TD * p.TH * p.TW;
     const float4 *tpn = reinterpret_cast<const float4 *>(p.tplate) + (size_t)(n * p.pview) * p.K * slabsz;
     const int kstart = dfs_kstart(p.K);
     {
@@ -1606,7 +1628,7 @@ __device__ __forceinline__ bool forward_tile(const Params &p, const int n, const
                     const float y0 = __fmul_rn(q.sx, rowdot(q.r00, xm, q.r10, ym, q.r20, zm));
                     const float y1 = __fmul_rn(q.sy, rowdot(q.r01, xm, q.r11, ym, q.r21, zm));
                     const float y2 = __fmul_rn(q.sz, rowdot(q.r02, xm, q.r12, ym, q.r22, zm));
-                    const bool valid = (fabsf(y0) < 1.f) && (fabsf(y1) < 1.f) && (fabsf(y2) < 1.f);
+                    const bool valid = inside_unit(y0, y1, y2);
                     const bool want = valid && on && !sat && (t < r1e);
                     const unsigned vm = __ballot_sync(0xffffffffu, want);
 #if defined(MVP_CPU_EMUL) && defined(MVP_EMUL_STATS)
@@ -1615,7 +1637,7 @@ __device__ __forceinline__ bool forward_tile(const Params &p, const int n, const
                     if (vm) {
                         MVP_STAT(2, 1); MVP_STAT(3, __popc(vm));
                         if (want) {
-                            const int pos = qn + __popc(vm & ((1u << lane) - 1u));
+                            const int pos = qn + __popc(vm & lanemask_lt());
                             ring[pos] = make_float4(y0, y1, y2, __int_as_float(lane | ((w * 32 + b) << 5)));
                             if (kGrad) rm[pos] = m;
                             if (pos < 32) ownlo |= 1u << pos; else ownhi |= 1u << (pos - 32);
@@ -1898,7 +1920,7 @@ __device__ __forceinline__ bool backward_tile(const Params &p, const int n, cons
     if (wlast < wfirst || wfirst >= kBig) return true;
 
     const float4 *packn = p.pack + (size_t)(n * p.pview) * p.K * 4;
-    const size_t slabsz = (size_t)p.TD * p.TH * p.TW;
+    const size_t slabsz = (size_t)p.TD * p.TH * p.TW;   // (a compile-time T^3 here makes the compiler keep slab addresses in registers: 64 B of spills)
     // bases of the primitive tensors are re-derived from the parameter block where they are used (cheap constant-bank
     // arithmetic) instead of living in a dozen registers for the whole tile
     const size_t pvK = (size_t)(n * p.pview) * p.K;
@@ -2081,7 +2103,7 @@ __device__ __forceinline__ bool backward_tile(const Params &p, const int n, cons
                         const float y0 = __fmul_rn(q.sx, rowdot(q.r00, xm, q.r10, ym, q.r20, zm));
                         const float y1 = __fmul_rn(q.sy, rowdot(q.r01, xm, q.r11, ym, q.r21, zm));
                         const float y2 = __fmul_rn(q.sz, rowdot(q.r02, xm, q.r12, ym, q.r22, zm));
-                        const bool valid = live && (fabsf(y0) < 1.f) && (fabsf(y1) < 1.f) && (fabsf(y2) < 1.f);
+                        const bool valid = live && (fabsf(y0) < 1.f) && (fabsf(y1) < 1.f) && (fabsf(y2) < 1.f);   // (inside_unit here: +1.7 % instructions)
                         const unsigned vm = __ballot_sync(0xffffffffu, valid);
                         if (vm) {
                             if (valid) {

@@ -654,6 +654,11 @@ def run_ours(args, rank, world):
             per_view = tj.get(r_["kernel"], {}).get("dram_bytes_per_view")
             if per_view and (h, w, k, t) == tuple(tj.get("shape", ())) and same_build:
                 r_["traffic"] = per_view * nv
+                zf = tj.get(r_["kernel"], {}).get("of_which_gradient_zero_fill_per_view")
+                if zf:
+                    r_["traffic_note"] = ("includes %.1f MB per view of gradient-buffer zero-fill the gradient-mode forward does on the side "
+                                          "(clear_grad_*; formerly a memset pass), not algorithmic bytes: %.1f MB per view without it"
+                                          % (zf / 1e6, (per_view - zf) / 1e6))
                 r_["traffic_source"] = "committed ncu capture %s (per view x %d views), not this run" % (tj.get("source", "profiles/traffic.json"), nv)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

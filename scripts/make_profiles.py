@@ -62,6 +62,13 @@ for r in rows[2:]:
     if ", 256," in name or "256, 0>" in name or "(int)256" in name:
         key = "render_forward_kernel" if "forward" in name else "render_backward_kernel"
         traffic[key] = {"dram_bytes_per_view": dram / views, "warp_instructions_per_view": inst / views}
+        if key == "render_forward_kernel":
+            # the captured forward runs in gradient mode: it also zero-fills the coming backward's gradient buffers (clear_grad_*:
+            # K * (T^3 * 4 + 15) floats per view), bytes that used to be a separate memset pass and are not part of the
+            # algorithmic traffic of SURVEY 8d
+            clear = 16384 * (8 ** 3 * 4 + 15) * 4.0
+            traffic[key]["of_which_gradient_zero_fill_per_view"] = clear
+            traffic[key]["dram_bytes_per_view_without_zero_fill"] = dram / views - clear
 open(os.path.join(ROOT, "profiles", "%s_render_kernels_full.txt" % tag), "w").write("\n".join(out))
 json.dump(traffic, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
 print("\n".join(out[:3]))

@@ -102,6 +102,34 @@ __global__ void __launch_bounds__(kThreads) expand_views_scalar_kernel(const flo
     for (int i = 0; i < n; ++i) dst[(size_t)i * count + e] = v;
 }
 
+// The adjoint: dst[i] = sum over the views of src[v][i], added up in view order (deterministic).  Every source byte is read once
+// (streaming loads, eight views in flight per thread), the sum is written once.
+__global__ void __launch_bounds__(kThreads) sum_views_kernel(const float4 *__restrict__ src, float4 *__restrict__ dst, size_t count4, int n) {
+    const size_t e = (size_t)blockIdx.x * kThreads + threadIdx.x;
+    if (e >= count4) return;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int i = 0;
+    for (; i + 8 <= n; i += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __ldcs(src + (size_t)(i + j) * count4 + e);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
+    }
+    for (; i < n; ++i) {
+        const float4 v = __ldcs(src + (size_t)i * count4 + e);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    dst[e] = acc;
+}
+__global__ void __launch_bounds__(kThreads) sum_views_scalar_kernel(const float *__restrict__ src, float *__restrict__ dst, size_t count, int n) {
+    const size_t e = (size_t)blockIdx.x * kThreads + threadIdx.x;
+    if (e >= count) return;
+    float acc = 0.f;
+    for (int i = 0; i < n; ++i) acc += src[(size_t)i * count + e];
+    dst[e] = acc;
+}
+
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 inline int finish() {
@@ -267,6 +295,26 @@ extern "C" int mvp_expand_views(const float *src, float *dst, size_t count, int3
     } else {
         const dim3 grid((unsigned)((count + kThreads - 1) / kThreads));
 #define MVP_EPI_KERNEL expand_views_scalar_kernel
+        MVP_EPI_LAUNCH(grid, st, src, dst, count, (int)n_views);
+#undef MVP_EPI_KERNEL
+    }
+    return finish();
+}
+
+extern "C" int mvp_sum_views(const float *src, float *dst, size_t count, int32_t n_views, void *stream) {
+    if (!src || !dst) return MVP_ERR_NULL;
+    if (n_views < 1) return MVP_ERR_SHAPE;
+    if (count == 0) return MVP_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (count % 4 == 0 && aligned16(src) && aligned16(dst)) {
+        const size_t c4 = count / 4;
+        const dim3 grid((unsigned)((c4 + kThreads - 1) / kThreads));
+#define MVP_EPI_KERNEL sum_views_kernel
+        MVP_EPI_LAUNCH(grid, st, reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), c4, (int)n_views);
+#undef MVP_EPI_KERNEL
+    } else {
+        const dim3 grid((unsigned)((count + kThreads - 1) / kThreads));
+#define MVP_EPI_KERNEL sum_views_scalar_kernel
         MVP_EPI_LAUNCH(grid, st, src, dst, count, (int)n_views);
 #undef MVP_EPI_KERNEL
     }

@@ -81,7 +81,7 @@ EXPORTS = ("mvp_abi_version", "mvp_build_config", "mvp_error_string", "mvp_works
            "mvp_raymarch_backward", "mvp_compute_raydirs", "mvp_forward_launch_count", "mvp_backward_launch_count",
            "mvp_composite_forward", "mvp_composite_backward", "mvp_assemble_payload_forward",
            "mvp_assemble_payload_backward", "mvp_debug_saved_tiles", "mvp_debug_tileclk_offset", "mvp_compute_morton",
-           "mvp_expand_views")
+           "mvp_expand_views", "mvp_sum_views")
 
 
 def _load():
@@ -124,6 +124,8 @@ def _load():
     lib.mvp_composite_backward.argtypes = [ctypes.c_int32] * 3 + [c_f] * 10
     lib.mvp_expand_views.restype = ctypes.c_int
     lib.mvp_expand_views.argtypes = [c_f, c_f, ctypes.c_size_t, ctypes.c_int32, c_f]
+    lib.mvp_sum_views.restype = ctypes.c_int
+    lib.mvp_sum_views.argtypes = [c_f, c_f, ctypes.c_size_t, ctypes.c_int32, c_f]
     lib.mvp_assemble_payload_forward.restype = ctypes.c_int
     lib.mvp_assemble_payload_forward.argtypes = [ctypes.c_int32] * 4 + [c_f] * 2 + [ctypes.c_float] * 2 + [c_f] * 2
     lib.mvp_assemble_payload_backward.restype = ctypes.c_int

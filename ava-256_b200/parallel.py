@@ -25,6 +25,16 @@ def rank_views(n_views, rank, world, interleave=True):
     return list(range(lo, hi))
 
 
+def _sum_views(p, out):
+    """out[...] = sum over the local views of p [nv, ...]: the library's one-pass kernel on the GPU (`mvp_sum_views`), torch.sum for
+    host tensors (the world-size-2 gloo tests of this module's logic run on the CPU)."""
+    if p.is_cuda:
+        from .payload import sum_views
+        sum_views(p, out)
+    else:
+        torch.sum(p.reshape(p.shape[0], -1), dim=0, out=out)
+
+
 def flat_grad_numel(K, TD, TH, TW):
     return K * TD * TH * TW * 4 + K * 15
 
@@ -44,7 +54,7 @@ def reduce_primitive_grads(grad_template, grad_primpos, grad_primrot, grad_prims
     views = []
     for p in parts:
         n = p[0].numel()
-        torch.sum(p.reshape(nv, n), dim=0, out=flat[o:o + n])
+        _sum_views(p, flat[o:o + n])
         views.append(flat[o:o + n].view(p.shape[1:]))
         o += n
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
@@ -86,7 +96,7 @@ class GradReducer:
         o = 0
         for p in parts:
             n = p[0].numel()
-            torch.sum(p.reshape(nv, n), dim=0, out=flat[o:o + n])
+            _sum_views(p, flat[o:o + n])
             o += n
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             self.work[i] = dist.all_reduce(flat, group=self.group, async_op=True)

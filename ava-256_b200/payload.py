@@ -76,7 +76,23 @@ class ExpandViews(Function):
 
     @staticmethod
     def backward(ctx, grad):
-        return grad.sum(dim=0), None
+        return sum_views(grad), None
+
+
+def sum_views(x, out=None):
+    """x [n_views, ...] -> sum over the views [...] in one pass (`mvp_sum_views`; view order, deterministic).  `out`: optional
+    contiguous destination with x[0].numel() elements (e.g. a slice of a flat all-reduce buffer)."""
+    _check_f32_cuda("x", x)
+    x = x.contiguous()
+    n, count = x.shape[0], x[0].numel()
+    dev = x.device
+    with torch.cuda.device(dev):
+        if out is None:
+            out = torch.empty(tuple(x.shape[1:]), device=dev)
+        assert out.is_cuda and out.is_contiguous() and out.dtype == torch.float32 and out.numel() == count
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(_lib.LIB.mvp_sum_views(_ptr(x), _ptr(out), count, int(n), stream))
+    return out
 
 
 def expand_views(x, n_views):

@@ -515,7 +515,7 @@ def run_ours(args, rank, world):
         s_in, s_out, s_cmp = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.current_stream()
         cmp_done, flat_out_done = [None, None], [None, None]
 
-        from ava256_b200.payload import expand_views
+        from ava256_b200.payload import expand_views, sum_views
         host_cam = [t.pin_memory() for t in scene.make_cameras(nv, h, w, view_ids=vids)]
         dev_cam = [[torch.empty(t.shape, device=dev) for t in host_cam] for _ in range(2)]
 
@@ -559,7 +559,7 @@ def run_ours(args, rank, world):
                 off = 0
                 for x in (lv[3], lv[0], lv[1], lv[2]):
                     n_ = x[0].numel()
-                    flat_[off:off + n_] += x.grad.view(nvc, n_).sum(dim=0)
+                    flat_[off:off + n_] += sum_views(x.grad).view(-1)
                     off += n_
                 od = o_.detach()
                 e = torch.cuda.Event()
@@ -626,7 +626,7 @@ def run_ours(args, rank, world):
                "h2d_bytes_per_step": int(h2d * world), "d2h_bytes_per_step": int(d2h * world),
                "ms_per_step": float(te.item()), "steps": nrep,
                "what": "every step: pinned host rays + one subject's primitives + grad_out -> device, per-view expand (mvp_expand_views), op fwd+bwd, "
-                       "view-sum (+all-reduce), rayrgba + reduced gradients -> pinned host; views streamed in chunks of %d, device "
+                       "view-sum (mvp_sum_views) (+all-reduce), rayrgba + reduced gradients -> pinned host; views streamed in chunks of %d, device "
                        "staging double-buffered so H2D of step i+1 / compute of step i / D2H of step i-1 overlap (three streams); "
                        "%d steps timed back to back, all copies inside the timed region" % (chunk, nrep)}
 

@@ -222,6 +222,10 @@ int mvp_assemble_payload_backward(int32_t N, int32_t hb, int32_t wb, int32_t B, 
  * streaming 16-byte stores (scalar when count % 4 != 0 or a pointer is not 16-byte aligned); `expand().contiguous()` does the
  * same at a quarter of the rate.  count < 2^32 * 1024. */
 int mvp_expand_views(const float *src, float *dst, size_t count, int32_t n_views, void *stream);
+/* Its adjoint, and the local step of the per-subject gradient reduction (the views of a step share one
+ * subject's primitives, their gradients are summed before the one all-reduce): dst[i] = sum over v < n_views of src[v, i], added
+ * in view order (deterministic), one pass over the per-view gradients.  Same alignment rule as mvp_expand_views; n_views >= 1. */
+int mvp_sum_views(const float *src, float *dst, size_t count, int32_t n_views, void *stream);
 
 /* Test / diagnostics helper (host only, no device work): given a HOST copy of a workspace that a gradient-mode forward
  * has filled, counts the tiles whose slab list the forward saved for the backward (`saved`, lists with >= 1 entry) and the

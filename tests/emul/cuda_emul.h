@@ -278,6 +278,7 @@ inline int __syncthreads_or(int pred) { return emul::block_barrier(pred); }
 // ---- scalar intrinsics ---------------------------------------------------------------------------------------------
 template <class T> inline T __ldg(const T *p) { return *p; }
 template <class T> inline void __stcs(T *p, const T &v) { *p = v; }
+template <class T> inline T __ldcs(const T *p) { return *p; }
 inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
 inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }

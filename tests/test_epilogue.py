@@ -137,6 +137,29 @@ def test_emul_expand_views(count, off):
     assert (draw[:dbase] == 7.0).all() and (draw[dbase + n * count:] == 7.0).all()
 
 
+@pytest.mark.parametrize("count,off,n", [(4 * 700, 0, 19), (4 * 700 + 3, 0, 3), (256, 1, 8), (64, 0, 1)])
+def test_emul_sum_views(count, off, n):
+    """mvp_sum_views on the emulation: dst = sum over the views in view order -- the 16-byte path (8 views per round + tail), the
+    scalar path for a count that is not a multiple of 4 and for a 4-byte aligned destination; guard floats stay untouched."""
+    from tests.emul.build import build_aux
+    emul = ctypes.CDLL(build_aux())
+    emul.mvp_sum_views.argtypes = [F32P, F32P, ctypes.c_size_t, ctypes.c_int32, ctypes.c_void_p]
+    raw = np.random.default_rng(count + n).standard_normal(n * count + 8).astype(np.float32)
+    base = (-raw.ctypes.data // 4) % 4
+    src = raw[base:base + n * count]
+    draw = np.full(count + 12, 7.0, np.float32)
+    dbase = (-draw.ctypes.data // 4) % 4 + 4 + off
+    dst = draw[dbase:dbase + count]
+    assert emul.mvp_sum_views(_np_ptr(src), _np_ptr(dst), count, n, None) == 0
+    ref = np.zeros(count, np.float32)
+    for v in range(n):                                        # same order, same single roundings
+        ref = (ref + src[v * count:(v + 1) * count]).astype(np.float32)
+    assert np.array_equal(dst, ref)
+    assert (draw[:dbase] == 7.0).all() and (draw[dbase + count:] == 7.0).all()
+    assert emul.mvp_sum_views(_np_ptr(src), _np_ptr(dst), count, 0, None) == -2
+    assert emul.mvp_sum_views(None, _np_ptr(dst), count, 1, None) == -1
+
+
 def test_restatement_matches_reference_golden():
     """oracle/epilogue_ref.py against vectors produced with the reference's own Colorcal module / literal statements."""
     z = np.load(os.path.join(HERE, "golden", "epilogue_composite.npz"))
@@ -306,3 +329,21 @@ def test_gpu_expand_views_equals_expand_contiguous(shape, n):
     assert torch.allclose(x.grad, g.sum(0), rtol=1e-6, atol=1e-6)
     flat = torch.randn(4 * 33 + 1, device="cuda")[1:]                                       # 4-byte aligned only
     assert torch.equal(expand_views(flat, 3), flat[None].expand(3, -1).contiguous())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,n", [((5, 3), 4), ((64, 8, 8, 8, 4), 19), ((1024, 9), 10), ((7,), 1)])
+def test_gpu_sum_views_equals_sequential_sum(shape, n):
+    """`mvp_sum_views` (the local step of the per-subject gradient reduction, parallel.GradReducer): the sum over the views added
+    in view order, bit for bit; into a fresh tensor and into a slice of a flat buffer (4-byte aligned: the scalar path)."""
+    from ava256_b200.payload import sum_views
+    x = torch.randn(n, *shape, device="cuda")
+    ref = torch.zeros(*shape, device="cuda")
+    for v in range(n):
+        ref = ref + x[v]
+    assert torch.equal(sum_views(x), ref)
+    assert torch.allclose(sum_views(x), x.sum(0), rtol=1e-5, atol=1e-5)
+    cnt = ref.numel()
+    flat = torch.full((cnt + 9,), 7.0, device="cuda")
+    sum_views(x, flat[5:5 + cnt])
+    assert torch.equal(flat[5:5 + cnt].view(*shape), ref) and bool((flat[:5] == 7.0).all()) and bool((flat[5 + cnt:] == 7.0).all())

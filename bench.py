@@ -678,7 +678,8 @@ def run_ours(args, rank, world):
         "roofline": dominant, "roofline_forward": roof_f, "roofline_backward": roof_b,
         "cpu_baseline": cpu, "ref_cuda_baseline": ref_cuda, "parity_check": parity, "e2e": e2e, "clocks": clocks,
         "shared_primitives_config": shared_cfg, "camera_rays_config": camera_cfg, "e2e_camera_inputs": e2e_cam,
-        "gpu_launches": args.steps * (lib.LIB.mvp_forward_launch_count(0) + lib.LIB.mvp_backward_launch_count(lib.FLAG_ACCEL_VALID)),
+        # this repository's kernels per timed step: accel build + render pair (forward), render pair (backward), 4 x mvp_sum_views
+        "gpu_launches": args.steps * (lib.LIB.mvp_forward_launch_count(0) + lib.LIB.mvp_backward_launch_count(lib.FLAG_ACCEL_VALID) + 4),
         "kernel_ms": {"forward_all_views_per_rank": fwd_ms, "backward_all_views_per_rank": bwd_ms,
                       "note": "the forward launch also zero-fills the backward's gradient buffers (clear_grad_*, %.1f GB per rank) "
                               "on the side; those bytes are not counted as algorithmic" % clear_gb},

@@ -129,6 +129,24 @@ def test_op_rejects_cpu_tensors_loudly():
                     s["template"], None)
 
 
+def test_camera_entry_point_has_no_cpu_path_either():
+    """mvpraymarch_camera (compute_raydirs + mvpraymarch as one call): host tensors raise like the reference's CHECK_CUDA /
+    AT_ASSERTM, for the fused form ((W, H) pixel grid) and for the two-call form (pixelcoords tensor) alike; the parameter list
+    starts with compute_raydirs' own (extensions/utils/utils.py:48-51)."""
+    from ava256_b200 import scene
+    from ava256_b200.op import mvpraymarch_camera
+    from tests.helpers import build_case
+    s, _ = build_case("gradcheck_ragged")
+    H, W = s["raypos"].shape[1:3]
+    cams = scene.make_cameras(1, H, W)
+    prim = (s["primpos"], s["primrot"], s["primscale"])
+    assert list(inspect.signature(mvpraymarch_camera).parameters)[:6] == ["viewpos", "viewrot", "focal", "princpt", "pixelcoords", "volradius"]
+    with pytest.raises(RuntimeError, match="CUDA"):
+        mvpraymarch_camera(*cams, (W, H), 256.0, s["stepsize"], prim, s["template"], None)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        mvpraymarch_camera(*cams, torch.zeros(1, H, W, 2), 256.0, s["stepsize"], prim, s["template"], None)
+
+
 def test_unsupported_modes_raise():
     from extensions.mvpraymarch.mvpraymarch import mvpraymarch
     from tests.helpers import build_case

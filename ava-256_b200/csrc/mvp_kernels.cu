@@ -156,6 +156,11 @@ constexpr int kFastCapB = MVP_BWD_FASTCAP;   // list is longer goes to the 512-e
                            // queue (used only afterwards): 512 bytes less per warp.  Measured on B200 (round 2): forward 2.096 vs 2.120 ms per
                            // 8 views, 10.475 vs 10.610 per 40; backward unchanged
 #endif
+#ifndef MVP_FWD_RING
+#define MVP_FWD_RING 1   // 1: the forward's sample queue is a ring of two 32-entry halves -- a flush always takes exactly one half, so the
+                          // head alternates between 0 and 32 and nothing is ever moved; 0: the queue is compacted to the front after every
+                          // flush (two shared-memory passes and three warp barriers per batch)
+#endif
 #ifndef MVP_FWD_CARVEOUT
 #define MVP_FWD_CARVEOUT 0   // > 0: preferred shared-memory carve-out (percent of the maximum, cudaFuncAttributePreferredSharedMemoryCarveout) of the
 #endif                       // fast render kernels; 0 leaves the driver's choice.  The kernels live off L1 hits: what is not carved out is L1
@@ -1539,10 +1544,15 @@ __device__ __forceinline__ bool forward_tile(const Params &p, const int n, const
     // sampled in vain and then ignored.  (Measured: neutral at 8^3 / K=16384, -15 % forward time at 16^3 / K=4096.)
     int qn = 0;
     unsigned ownlo = 0, ownhi = 0;   // queue positions (0..63) holding this lane's pending samples
-    // primaccum.h:63-79 for this ray's samples among the first sampled entries of the ring (bit b of `mine` = ring[b])
+#if MVP_FWD_RING
+    int qhead = 0;                   // 0 or 32: the half of the ring the next flush takes (ownlo / ownhi belong to halves 0 / 1)
+#else
+    constexpr int qhead = 0;
+#endif
+    // primaccum.h:63-79 for this ray's samples among the sampled entries of the flushed half (bit b of `mine` = ring[qhead + b])
     auto composite = [&](unsigned mine) {
         while (mine) {
-            const int b = __ffs(mine) - 1;
+            const int b = qhead + __ffs(mine) - 1;
             mine &= mine - 1;
             if (!sat) {
                 const float4 rr = ring[b];
@@ -1566,7 +1576,7 @@ __device__ __forceinline__ bool forward_tile(const Params &p, const int n, const
     auto flush = [&](int cnt) {
         MVP_STAT(4, 1);
         const bool act = lane < cnt;
-        const float4 rec = ring[act ? lane : 0];
+        const float4 rec = ring[qhead + (act ? lane : 0)];
         float4 sres = make_float4(0.f, 0.f, 0.f, 0.f);
         if (act) {
             const int kk = sk[(__float_as_int(rec.w) >> 5) & 1023];
@@ -1574,8 +1584,17 @@ __device__ __forceinline__ bool forward_tile(const Params &p, const int n, const
             else sres = sample_slab<T>(tpn + (size_t)kk * slabsz, rec.x, rec.y, rec.z, p.TD, p.TH, p.TW, p.fadescale, p.fadeexp);
         }
         __syncwarp();
-        if (act) { ring[lane] = make_float4(sres.x, sres.y, sres.z, rec.w); ra[lane] = sres.w; }
+        if (act) { ring[qhead + lane] = make_float4(sres.x, sres.y, sres.z, rec.w); ra[qhead + lane] = sres.w; }
         __syncwarp();
+#if MVP_FWD_RING
+        composite((qhead ? ownhi : ownlo) & (cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u)));
+        __syncwarp();                  // the half is free again before anything is queued into it
+        if (qhead) ownhi = 0; else ownlo = 0;
+        qhead ^= 32;
+        qn -= cnt;
+        if (sat) done = true;
+    };
+#else
         composite(ownlo & (cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u)));
         __syncwarp();
         // move what is left of the queue to the front
@@ -1590,6 +1609,7 @@ __device__ __forceinline__ bool forward_tile(const Params &p, const int n, const
         qn = n2;
         if (sat) done = true;
     };
+#endif
 
     const int mstart = __reduce_min_sync(0xffffffffu, ms);
     if (nl > 0 && mstart < kBig) {
@@ -1637,7 +1657,7 @@ __device__ __forceinline__ bool forward_tile(const Params &p, const int n, const
                     if (vm) {
                         MVP_STAT(2, 1); MVP_STAT(3, __popc(vm));
                         if (want) {
-                            const int pos = qn + __popc(vm & lanemask_lt());
+                            const int pos = (qhead + qn + __popc(vm & lanemask_lt())) & (kRing - 1);
                             ring[pos] = make_float4(y0, y1, y2, __int_as_float(lane | ((w * 32 + b) << 5)));
                             if (kGrad) rm[pos] = m;
                             if (pos < 32) ownlo |= 1u << pos; else ownhi |= 1u << (pos - 32);
@@ -2589,7 +2609,7 @@ int mvp_abi_version(void) { return MVP_ABI_VERSION; }
 #define MVP_STR(x) MVP_STR2(x)
 const char *mvp_build_config(void) {
     return "LIST_REUSE=" MVP_STR(MVP_LIST_REUSE)
-           " LIST_MARGIN=" MVP_STR(MVP_LIST_MARGIN) " XBUCKETS=" MVP_STR(MVP_XBUCKETS) " FASTCAP=" MVP_STR(MVP_FWD_FASTCAP) "/" MVP_STR(MVP_BWD_FASTCAP) " SMEM_UNION=" MVP_STR(MVP_SMEM_UNION) " CARVEOUT=" MVP_STR(MVP_FWD_CARVEOUT) "/" MVP_STR(MVP_BWD_CARVEOUT) " BWD_SMEMREC=" MVP_STR(MVP_BWD_SMEMREC) " BWD_LANESMEM=" MVP_STR(MVP_BWD_LANESMEM) " CTA_ORDER=" MVP_STR(MVP_CTA_ORDER) " CTA_ORDER_MIN=" MVP_STR(MVP_CTA_ORDER_MIN)
+           " LIST_MARGIN=" MVP_STR(MVP_LIST_MARGIN) " XBUCKETS=" MVP_STR(MVP_XBUCKETS) " FASTCAP=" MVP_STR(MVP_FWD_FASTCAP) "/" MVP_STR(MVP_BWD_FASTCAP) " SMEM_UNION=" MVP_STR(MVP_SMEM_UNION) " CARVEOUT=" MVP_STR(MVP_FWD_CARVEOUT) "/" MVP_STR(MVP_BWD_CARVEOUT) " FWD_RING=" MVP_STR(MVP_FWD_RING) " BWD_SMEMREC=" MVP_STR(MVP_BWD_SMEMREC) " BWD_LANESMEM=" MVP_STR(MVP_BWD_LANESMEM) " CTA_ORDER=" MVP_STR(MVP_CTA_ORDER) " CTA_ORDER_MIN=" MVP_STR(MVP_CTA_ORDER_MIN)
            " CHUNK=" MVP_STR(MVP_CHUNK) " FWD_MINB=" MVP_STR(MVP_FWD_MINB) " BWD_MINB=" MVP_STR(MVP_BWD_MINB)
            " WARPS=" MVP_STR(MVP_WARPS) " BLK_TX=" MVP_STR(MVP_BLK_TX)
 #ifdef MVP_CPU_EMUL

@@ -119,6 +119,7 @@ VARIANTS = {
     "fastcap_small": ("MVP_FASTCAP=8",),                                   # most tiles overflow the fast list -> handed to the 512-entry kernel
     "bwd_regrecord": ("MVP_BWD_SMEMREC=0",),
     "grid_order": ("MVP_CTA_ORDER=0",),                                    # plain grid order instead of the cost-sorted CTA order
+    "queue_compaction": ("MVP_FWD_RING=0",),                                # forward sample queue compacted to the front after every flush (the former form)
     "separate_stage": ("MVP_SMEM_UNION=0",),                               # bucket staging buffer not overlaid on the sample queue (the former layout)
     "split_fastcaps": ("MVP_FWD_FASTCAP=16", "MVP_BWD_FASTCAP=8"),         # backward's fast list shorter than the forward's: saved lists that only fit the forward's
     "bwd_lanesmem": ("MVP_BWD_LANESMEM=1",),                               # per-lane between-batch state in shared memory                               # slab record in registers across the adjoint (round-1 form)

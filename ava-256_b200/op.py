@@ -61,6 +61,8 @@ class MVPRaymarch(Function):
             for name, t, tail in (("viewpos", viewpos, (3,)), ("viewrot", viewrot, (3, 3)), ("focal", focal, (2,)), ("princpt", princpt, (2,))):
                 _check_f32_cuda(name, t)                                  # utils.py:24-25 / utils.cpp CHECK_CUDA
                 assert t.shape == (viewpos.size(0),) + tail, "%s must be [N,%s]" % (name, ",".join(map(str, tail)))
+                assert t.device == primpos.device, "%s must be on the primitives' device" % name
+            assert int(camH) >= 1 and int(camW) >= 1 and float(volradius) > 0.0
         else:
             # same shape contract as mvpraymarch.py:112-127
             assert raypos.is_contiguous() and raypos.size(3) == 3

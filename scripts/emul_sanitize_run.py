@@ -18,3 +18,17 @@ for kind in EDGE_KINDS:
     grad = torch.randn(*s["raypos"].shape[:3], 4)
     out, sat, g = kernels.forward_backward(*a, grad_rayrgba=grad.numpy(), **kw)
     print(kind, "ok", flush=True)
+# rays generated in the kernels from the camera (mvp_camera), incl. a ragged image and a degenerate camera
+from ava256_b200 import scene
+for (n, H, W, K, T) in ((2, 64, 42, 64, 8), (1, 13, 19, 16, 4)):
+    cams = [c.numpy() for c in scene.make_cameras(n, H, W)]
+    sc = scene.make_scene(n, H, W, K, T, alpha_mu=1.0, alpha_sigma=2.0, share_primitives=False)
+    prim = (sc["primpos"].numpy(), sc["primrot"].numpy(), sc["primscale"].numpy(), sc["template"].numpy())
+    grad = torch.randn(n, H, W, 4).numpy()
+    for bad in (False, True):
+        f = cams[2].copy()
+        if bad:
+            f[-1] = 0.0
+        out, sat, g = kernels.forward_backward(None, None, 1.0 / 64, None, *prim, grad_rayrgba=grad,
+                                               camera=(cams[0], cams[1], f, cams[3], scene.VOLRADIUS, H, W), clear_in_forward=True)
+        print("camera %dx%d%s" % (H, W, " (one degenerate view)" if bad else ""), "ok", float(np.abs(out).max()), flush=True)
